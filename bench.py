@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- cell-RK-stage updates per second of the fvs2d hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c3|naca|vortex]
+
+One "step" = one full RK time step (4 stages: gradient -> Roe flux gather -> residual -> RK update, plus
+the per-step residual / vortex-error norms) of `time_integration` over the whole mesh.
+Metric = ncells * 4 * K / seconds (BASELINE.json: "cell-RK-stage updates/sec").
+
+Workloads:
+  c4     (default) synthetic mixed tri/quad vortex mesh, 8.64 M cells per GPU (9600 x 600*N background quads;
+         N=8 is the 69.12 M-cell C4 mesh), GGCB, RK4, dt=4e-4 -- weak scaling
+  c3     synthetic 4.0 M-triangle vortex mesh (2000 x 1000 split quads), GGCB, RK4, dt=0.002 (single GPU)
+  naca   tests/golden/naca_mesh.npz, LSQ-nn + Venkatakrishnan, SSPRK steady (C2)
+  vortex tests/golden/vortex_mesh.npz as shipped (C1)
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from fvs2d_b200 import config as fcfg  # noqa: E402
+from fvs2d_b200 import meshgen, meshio  # noqa: E402
+
+# algorithmic bytes per cell-stage, SURVEY.md section 8(d): (pass A, pass B)
+B_ALG = {"tri_ggcb": (180, 332), "quad_ggcb": (200, 360), "tri_lsqfn": (156, 332), "quad_lsqnn_venk_steady": (336, 376)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_workload(name: str, ngpus: int, scale: float = 1.0):
+    """-> (mesh, RunInput, description, (bytes_passA, bytes_passB) per cell-stage)"""
+    golden = os.path.join(ROOT, "tests", "golden")
+    if name == "c4":
+        nx = int(round(9600 * scale))
+        ny = int(round(600 * scale)) * ngpus
+        mesh = meshgen.make_mesh(nx, ny, 20.0, 10.0, (nx // 4, 3 * nx // 4))
+        run = fcfg.RunInput(grad_cellcntr_imethd=1, lvortex=True, dt=4e-4 / scale)
+        ft = mesh.ntri / mesh.ncells
+        ba = ft * B_ALG["tri_ggcb"][0] + (1 - ft) * B_ALG["quad_ggcb"][0]
+        bb = ft * B_ALG["tri_ggcb"][1] + (1 - ft) * B_ALG["quad_ggcb"][1]
+        desc = f"C4 synthetic mixed tri/quad vortex mesh {nx}x{ny} background quads, GGCB, upwind-2nd, Roe, RK4"
+        return mesh, run, desc, (ba, bb)
+    if name == "c3":
+        nx = int(round(2000 * scale))
+        mesh = meshgen.vortex_tri_mesh(nx)
+        run = fcfg.RunInput(grad_cellcntr_imethd=1, lvortex=True, dt=0.002 / scale)
+        return mesh, run, f"C3 synthetic triangle vortex mesh {nx}x{nx // 2} split quads, GGCB, upwind-2nd, Roe, RK4", B_ALG["tri_ggcb"]
+    inp = json.load(open(os.path.join(golden, "inputs.json")))
+    if name == "naca":
+        mesh = meshio.load_npz(os.path.join(golden, "naca_mesh.npz"))
+        d = inp["naca"]
+        run = fcfg.RunInput(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in d.items()})
+        run.grad_limiter_imethd = 1
+        return mesh, run, "C2 naca0012_ogrid, LSQ-nn + Venkatakrishnan, SSPRK(4,2) steady CFL 1.25", B_ALG["quad_lsqnn_venk_steady"]
+    if name == "vortex":
+        mesh = meshio.load_npz(os.path.join(golden, "vortex_mesh.npz"))
+        d = inp["vortex"]
+        run = fcfg.RunInput(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in d.items()})
+        return mesh, run, "C1 isentropic_vortex example as shipped, LSQ-fn, RK4", B_ALG["tri_lsqfn"]
+    raise SystemExit(f"unknown workload {name}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.stop, self.index = [], False, index
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows if len(r) > 3 + k)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "samples": len(self.rows),
+                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons}
+
+
+def cpu_baseline(name: str, run, steps: int, warmup: int = 0):
+    """The CPU oracle (C restatement of the reference algorithm, -Ofast, ONE thread: the reference's only
+    multi-thread mode is racy, src/residual.f90:65) on a bounded sample of the workload."""
+    from oracle.oracle import Oracle, build
+    build()
+    if name in ("c4", "c3"):
+        mesh, run_s, desc, _ = make_workload(name, 1, scale=0.25)
+        sample = f"1/16-size sibling of the workload ({mesh.ncells} cells, same generator/seed/scheme), {steps} RK4 steps"
+    else:
+        mesh, run_s, desc, _ = make_workload(name, 1)
+        sample = f"the full {name} mesh ({mesh.ncells} cells), {steps} steps"
+    orc = Oracle(mesh, run_s.to_config(), fast=True)
+    orc.initialize_solution()
+    if warmup:
+        orc.time_integration(0.0, warmup)
+    orc.reset_timers()
+    t0 = time.perf_counter()
+    orc.time_integration(warmup * run_s.dt, steps)
+    dt = time.perf_counter() - t0
+    tm = orc.timers()
+    return {"value": mesh.ncells * 4 * steps / dt, "unit": "cell-RK-stage updates/s", "cores": 1, "kind": "port",
+            "sample": sample, "seconds": dt, "host_cores_available": os.cpu_count(),
+            "buckets_s": {k: round(v, 4) for k, v in tm.items()}}, dt / steps * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4")
+    ap.add_argument("--scale", type=float, default=1.0, help="mesh refinement factor relative to the named workload")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    K, W = args.steps, max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "cell-RK-stage updates/sec"
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        desc = {"c4": "C4 synthetic mixed tri/quad vortex mesh, GGCB, upwind-2nd, Roe, RK4", "c3": "C3 synthetic triangle vortex mesh, GGCB, upwind-2nd, Roe, RK4",
+                "naca": "C2 naca0012_ogrid, LSQ-nn + Venkatakrishnan, SSPRK(4,2) steady CFL 1.25", "vortex": "C1 isentropic_vortex example as shipped"}[args.workload]
+        cb, ms_step = cpu_baseline(args.workload, None, max(K, 1), W)
+        line = {"metric": metric, "value": cb["value"], "unit": "cell-stage updates/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "impl": "reference",
+                "config": {"workload": desc, "note": "reference algorithm on host cores (C restatement, oracle/; the Fortran "
+                           "reference cannot be compiled in this image); each step is a bounded sample: " + cb["sample"]},
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "cell-stage updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    import torch.distributed as dist
+    from fvs2d_b200 import solver
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(solver.Fvs2dGpu.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        comm = (rank, world, bytes(uid.cpu().numpy().tobytes()))
+    ngpus = world
+
+    t_setup = time.perf_counter()
+    mesh, run, desc, (bA, bB) = make_workload(args.workload, ngpus, args.scale)
+    cfg = run.to_config(ngpus)
+    gpu = solver.Fvs2dGpu(cfg, device=local_rank, comm=comm)
+    gpu.set_mesh(mesh)
+    gpu.initialize_solution()
+    sizes, scal = gpu.sizes(), gpu.scalars()
+    ncells = mesh.ncells
+    t_setup = time.perf_counter() - t_setup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    dt = run.dt
+    t_sim = 0.0
+    gpu.set_option("timing", 1)
+    # warm-up (untimed)
+    if W:
+        gpu.time_integration(t_sim, W, logs=False)
+        t_sim += W * dt
+    # ---- timed region: exactly K steps, state resident in HBM, device time from CUDA events on the
+    # library's stream (recorded around the K steps inside fvs2d_gpu_time_integration), max over ranks
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        w0 = time.perf_counter()
+        gpu.time_integration(t_sim, K, logs=False)
+        barrier()
+        wall = time.perf_counter() - w0
+    tm = gpu.last_timing()
+    t_sim += K * dt
+    dev_ms = max_over_ranks(tm["total_ms"])
+    value = ncells * 4 * K / (dev_ms * 1e-3)
+    flux_ms = max_over_ranks(tm["flux_ms"]) / (4 * K)   # average k_flux_rk launch
+    grad_ms = max_over_ranks(tm["grad_ms"]) / (4 * K)   # average k_gradient launch
+    launches = tm["launches"]
+    gpu.set_option("timing", 0)
+
+    # ---- end to end through the C-ABI with HOST buffers: every step uploads cvar(4,ncells) from pinned
+    # host memory, runs one time step, downloads cvar and the 4 residual norms
+    e2e = None
+    if not args.no_e2e:
+        q_host = torch.empty((ncells, 4), dtype=torch.float64).pin_memory()
+        gpu.get_state(q_host)
+        ke = min(K, 5)
+        barrier()
+        e0 = time.perf_counter()
+        for s in range(ke):
+            gpu.set_state(q_host)
+            gpu.time_integration(t_sim + s * dt, 1, logs=True)
+            gpu.get_state(q_host)
+        barrier()
+        e_s = max_over_ranks(time.perf_counter() - e0)
+        # amortised variant: the seam as the reference calls it (one call per save interval)
+        gpu.set_state(q_host)
+        barrier()
+        a0 = time.perf_counter()
+        gpu.set_state(q_host)
+        gpu.time_integration(t_sim, K, logs=True)
+        gpu.get_state(q_host)
+        barrier()
+        a_s = max_over_ranks(time.perf_counter() - a0)
+        e2e = {"value": ncells * 4 * ke / e_s, "unit": "cell-stage updates/s", "h2d_bytes_per_step": ncells * 32 * world,
+               "d2h_bytes_per_step": (ncells * 32 + 32 + 16 * 8) * world, "steps": ke,
+               "note": "per step: fvs2d_gpu_set_state(pinned host cvar) + fvs2d_gpu_time_integration(1 step, logs) + fvs2d_gpu_get_state",
+               "amortized_value": ncells * 4 * K / a_s,
+               "amortized_note": f"one seam call as the reference makes it: set_state + time_integration({K} steps) + get_state"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = load_peaks()
+    n_own = sizes["ncells_own"]
+    roof = {"bound": "hbm", "kernel": "k_flux_rk (pass B: face-flux gather + residual + RK update)",
+            "achieved": bB * n_own / (flux_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+            "alg_bytes_per_cell": bB, "avg_launch_ms": flux_ms, "traffic": None}
+    roof["frac"] = roof["achieved"] / peak
+    stage = {"alg_bytes_per_cell_stage": bA + bB, "achieved_GBs": (bA + bB) * ncells * 4 * K / (dev_ms * 1e-3) / 1e9}
+    stage["frac"] = stage["achieved_GBs"] / (peak * world)
+    gradk = {"kernel": "k_gradient (pass A)", "alg_bytes_per_cell": bA, "avg_launch_ms": grad_ms,
+             "achieved_GBs": bA * n_own / (grad_ms * 1e-3) / 1e9 if grad_ms > 0 else None}
+    line = {"metric": metric, "value": value, "unit": "cell-stage updates/s", "n_gpus": ngpus, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": desc, "ncells": ncells, "ncells_per_gpu": n_own, "dt": dt, "l2": "inputs larger than L2 "
+                       f"({scal['device_bytes'] / 1e9:.2f} GB resident per GPU vs 126 MB L2)", "parallelism": f"dd{ngpus}",
+                       "setup_s": round(t_setup, 1)},
+            "roofline": roof, "stage_roofline": stage, "gradient_kernel": gradk,
+            "wall_ms_per_step": wall * 1e3 / K, "gpu_launches": launches, "clocks": clk.summary(), "e2e": e2e}
+    if not args.no_cpu_baseline:
+        cb, _ = cpu_baseline(args.workload, run, 4 if args.workload in ("c3", "c4") else 50)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line))
+    gpu.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,783 @@
+// api.cu -- context and C-ABI of libfvs2d_gpu.so (include/fvs2d_gpu.h).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fvs2d_gpu.h"
+#include "host_mesh.hpp"
+#include "kernels.cuh"
+#include "layout.hpp"
+
+using namespace fvs2d;
+
+namespace {
+
+// ---- NCCL, resolved lazily so that single-GPU use has no NCCL dependency ------------------------
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string &err) {
+    if (lib) return true;
+    const char *names[] = {"libnccl.so.2", "/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl/lib/libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+#define SYM(f) f = (decltype(f))dlsym(lib, "nccl" #f); if (!f) { err = "libnccl lacks nccl" #f; return false; }
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(Send) SYM(Recv) SYM(AllReduce) SYM(AllGather) SYM(GroupStart) SYM(GroupEnd) SYM(GetErrorString)
+#undef SYM
+    return true;
+  }
+};
+NcclApi g_nccl;
+
+struct Ctx {
+  bool inited = false, has_mesh = false, has_state = false;
+  fvs2d_config cfg{};
+  int device = 0;
+  cudaStream_t st = nullptr;
+  // communicator
+  int rank = 0, nranks = 1;
+  ncclComm_t comm = nullptr;
+  // host products
+  HostMesh mesh;
+  GradOp grad;
+  Layout L;
+  // device
+  std::vector<void *> allocs;
+  size_t bytes = 0;
+  DevMesh dm{};
+  Phys phys{};
+  int np = 0, nblocks = 0;
+  int recon = RC_K0;
+  double *q = nullptr, *f = nullptr, *pa = nullptr, *pb = nullptr, *g = nullptr, *phi = nullptr, *dtl = nullptr;
+  double *resid = nullptr, *ws = nullptr, *bc = nullptr, *partial = nullptr, *vpartial = nullptr;
+  int *vbest = nullptr;
+  double *stage_aos = nullptr;  // nc_global*8 doubles staging for AoS <-> SoA
+  size_t stage_aos_len = 0;
+  double *logbuf = nullptr; int *logid = nullptr; size_t log_cap = 0;
+  int *send_idx = nullptr; double *sendbuf = nullptr;
+  bool bc_static_done = false;
+  double rk_coef[4], h_rk[4], dts[4], dte[4];
+  // timing
+  int opt_timing = 0;
+  double last_ms[4] = {0, 0, 0, 0};
+  long last_launches = 0;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<int, int>> ev_spans[3];
+  size_t ev_used = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+Ctx *C = nullptr;
+std::string g_err;
+
+int fail(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CUDA_OK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #x); } while (0)
+#define NCCL_OK(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) return fail("NCCL error %s at %s:%d", g_nccl.GetErrorString(r_), __FILE__, __LINE__); } while (0)
+#define NEED(cond, msg) do { if (!(cond)) return fail("%s", msg); } while (0)
+
+template <class T>
+int dev_alloc(T *&p, size_t n) {
+  p = nullptr;
+  if (n == 0) n = 1;
+  CUDA_OK(cudaMalloc((void **)&p, n * sizeof(T)));
+  C->allocs.push_back(p);
+  C->bytes += n * sizeof(T);
+  return 0;
+}
+template <class T>
+int dev_upload(const T *&p, const std::vector<T> &h) {
+  T *d;
+  if (dev_alloc(d, h.size())) return 1;
+  if (!h.empty()) CUDA_OK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  p = d;
+  return 0;
+}
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+void free_device() {
+  for (void *p : C->allocs) cudaFree(p);
+  C->allocs.clear();
+  C->bytes = 0;
+  C->stage_aos = nullptr; C->stage_aos_len = 0;
+  C->logbuf = nullptr; C->log_cap = 0;
+}
+
+// ---- event-based kernel timing (option "timing") ------------------------------------------------
+struct Span {
+  int bucket, a = -1;
+  Span(int b) : bucket(b) {
+    if (!C->opt_timing) return;
+    if (C->ev_used + 2 > C->ev_pool.size()) return;
+    a = (int)C->ev_used;
+    C->ev_used += 2;
+    cudaEventRecord(C->ev_pool[a], C->st);
+  }
+  ~Span() {
+    if (a < 0) return;
+    cudaEventRecord(C->ev_pool[a + 1], C->st);
+    C->ev_spans[bucket].push_back({a, a + 1});
+  }
+};
+
+int rk_setup() {  // src/runge_kutta.f90:25-88
+  const fvs2d_config &c = C->cfg;
+  const double dt = c.dt;
+  NEED(c.rk_nstages == 4, "only rk_nstages==4 is coded (src/runge_kutta.f90:36)");
+  double a, b, cc, d;
+  switch (c.rk_order) {
+    case 1: a = 3.60897; b = 2.04; cc = 0.34206; d = 0.00897; break;
+    case 2: a = 0.11; b = 3.92; cc = 1.86; d = 0.11; break;
+    case 3: a = 0.65; b = 2.7; cc = 2.0; d = 0.65; break;
+    case 4: a = 1.0; b = 2.0; cc = 2.0; d = 1.0; break;
+    default: return fail("rk_order must be 1..4");
+  }
+  C->h_rk[0] = dt / 2.0; C->rk_coef[0] = a;
+  C->h_rk[1] = dt / 2.0; C->rk_coef[1] = b;
+  C->h_rk[2] = dt;       C->rk_coef[2] = cc;
+  C->h_rk[3] = dt / 6.0; C->rk_coef[3] = d;
+  for (int k = 0; k < 4; k++) C->dts[k] = C->dte[k] = 0;
+  if (c.ssprk) {
+    NEED(c.rk_order == 2, "SSPRK is coded only for 4 stages, order 2 (src/runge_kutta.f90:56)");
+    for (int k = 0; k < 3; k++) { C->h_rk[k] = dt / 3.0; C->rk_coef[k] = 1.0; }
+    C->h_rk[3] = dt / 4.0; C->rk_coef[3] = 1.0;
+    C->dts[0] = 0.0;            C->dte[0] = dt / 3.0;
+    C->dts[1] = dt / 3.0;       C->dte[1] = dt * 2.0 / 3.0;
+    C->dts[2] = dt * 2.0 / 3.0; C->dte[2] = dt;
+    C->dts[3] = dt;             C->dte[3] = dt;
+  }
+  return 0;
+}
+
+// ---- halo exchange: owned send-cells -> the peers' ghost runs, nv variables of SoA array a ---------
+struct HaloItem { double *a; int nv; };
+int halo_exchange(const HaloItem *items, int nitems) {
+  if (C->nranks == 1) return 0;
+  const Layout &L = C->L;
+  const int nsend = L.send_ptr.empty() ? 0 : L.send_ptr.back();
+  // pack: sendbuf layout [item][var][all send cells]
+  size_t boff = 0;
+  for (int it = 0; it < nitems; it++) {
+    if (nsend) k_pack<<<cdiv(nsend, 256), 256, 0, C->st>>>(nsend, items[it].nv, C->np, C->send_idx, items[it].a, C->sendbuf + boff);
+    C->last_launches++;
+    boff += (size_t)items[it].nv * nsend;
+  }
+  NCCL_OK(g_nccl.GroupStart());
+  boff = 0;
+  for (int it = 0; it < nitems; it++) {
+    for (size_t pi = 0; pi < L.peers.size(); pi++) {
+      const int peer = L.peers[pi];
+      const int s0 = L.send_ptr[pi], sn = L.send_ptr[pi + 1] - s0;
+      for (int v = 0; v < items[it].nv; v++) {
+        if (sn) NCCL_OK(g_nccl.Send(C->sendbuf + boff + (size_t)v * nsend + s0, sn, ncclDouble, peer, C->comm, C->st));
+        if (L.recv_count[pi]) NCCL_OK(g_nccl.Recv(items[it].a + (size_t)v * C->np + L.recv_begin[pi], L.recv_count[pi], ncclDouble, peer, C->comm, C->st));
+      }
+    }
+    boff += (size_t)items[it].nv * nsend;
+  }
+  NCCL_OK(g_nccl.GroupEnd());
+  return 0;
+}
+
+int ensure_stage(size_t ndoubles) {
+  if (C->stage_aos_len >= ndoubles) return 0;
+  if (C->stage_aos) {
+    cudaFree(C->stage_aos);
+    C->allocs.erase(std::remove(C->allocs.begin(), C->allocs.end(), (void *)C->stage_aos), C->allocs.end());
+    C->bytes -= C->stage_aos_len * 8;
+  }
+  C->stage_aos_len = 0;
+  if (dev_alloc(C->stage_aos, ndoubles)) return 1;
+  C->stage_aos_len = ndoubles;
+  return 0;
+}
+
+// device SoA (local numbering, owned cells) -> caller AoS (original numbering)
+int download_aos(const double *soa, int nvar, double *host_out) {
+  const size_t ng = (size_t)C->L.nc_global * nvar;
+  if (ensure_stage(ng)) return 1;
+  k_gather_out<<<cdiv(C->L.n_own, 256), 256, 0, C->st>>>(C->L.n_own, C->np, nvar, C->dm.orig_id, soa, C->stage_aos);
+  CUDA_OK(cudaGetLastError());
+  if (C->nranks == 1) {
+    CUDA_OK(cudaMemcpyAsync(host_out, C->stage_aos, ng * 8, cudaMemcpyDeviceToHost, C->st));
+    CUDA_OK(cudaStreamSynchronize(C->st));
+  } else {
+    std::vector<double> tmp(ng);
+    CUDA_OK(cudaMemcpyAsync(tmp.data(), C->stage_aos, ng * 8, cudaMemcpyDeviceToHost, C->st));
+    CUDA_OK(cudaStreamSynchronize(C->st));
+    for (int i = 0; i < C->L.n_own; i++) {
+      const size_t o = C->L.orig_id[i];
+      for (int v = 0; v < nvar; v++) host_out[o * nvar + v] = tmp[o * nvar + v];
+    }
+  }
+  return 0;
+}
+
+int launch_gradient(const double *p) {
+  if (C->recon == RC_FIRST) return 0;
+  Span sp(1);
+  const bool lim = C->cfg.limiter > 0;
+  double *gx = C->g, *gy = C->g + 4 * (size_t)C->np;
+  const int nb = C->nblocks;
+  if (C->L.g_form == 0) {
+    if (lim) k_gradient<0, true><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, gx, gy, C->phi);
+    else k_gradient<0, false><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, gx, gy, C->phi);
+  } else {
+    if (lim) k_gradient<1, true><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, gx, gy, C->phi);
+    else k_gradient<1, false><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, gx, gy, C->phi);
+  }
+  C->last_launches++;
+  return 0;
+}
+
+template <int UM, bool STEADY>
+void launch_flux_rc(const StageParams &S, const double *pin, double *pout) {
+  const double *gx = C->g, *gy = C->g + 4 * (size_t)C->np;
+  const int nb = C->nblocks;
+#define GO(RC) k_flux_rk<UM, STEADY, RC><<<nb, kBlock, 0, C->st>>>(C->dm, C->phys, S, pin, gx, gy, C->phi, C->bc, C->q, C->f, pout, C->dtl, C->resid, C->ws, C->partial)
+  switch (C->recon) {
+    case RC_FIRST: GO(RC_FIRST); break;
+    case RC_K0: GO(RC_K0); break;
+    case RC_K0_PHI: GO(RC_K0_PHI); break;
+    default: GO(RC_GENERAL); break;
+  }
+#undef GO
+}
+
+int launch_flux(int um, const StageParams &S, const double *pin, double *pout) {
+  Span sp(2);
+  const bool steady = C->cfg.steady != 0;
+  if (um == UM_RESID) launch_flux_rc<UM_RESID, false>(S, pin, pout);
+  else if (um == UM_RK) { if (steady) launch_flux_rc<UM_RK, true>(S, pin, pout); else launch_flux_rc<UM_RK, false>(S, pin, pout); }
+  else { if (steady) launch_flux_rc<UM_SSPRK, true>(S, pin, pout); else launch_flux_rc<UM_SSPRK, false>(S, pin, pout); }
+  C->last_launches++;
+  return 0;
+}
+
+int launch_bc(double time) {
+  if (C->L.nbf == 0) return 0;
+  const bool time_dep = C->cfg.lvortex != 0;
+  if (!time_dep && C->bc_static_done) return 0;
+  Span sp(0);
+  k_bc_state<<<cdiv(C->L.nbf, 128), 128, 0, C->st>>>(C->dm, C->phys, time, C->bc);
+  C->last_launches++;
+  C->bc_static_done = true;
+  return 0;
+}
+
+// one residual evaluation's worth of pass A (+ halo) for state p
+int pass_a(const double *p) {
+  if (launch_gradient(p)) return 1;
+  if (C->nranks > 1 && C->recon != RC_FIRST) {
+    Span sp(0);
+    HaloItem it[2] = {{C->g, 8}, {C->phi, 1}};
+    if (halo_exchange(it, C->cfg.limiter > 0 ? 2 : 1)) return 1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *fvs2d_gpu_last_error(void) { return g_err.c_str(); }
+
+int fvs2d_gpu_init(const fvs2d_config *cfg, int device) {
+  NEED(cfg != nullptr, "fvs2d_gpu_init: null config");
+  if (C) fvs2d_gpu_finalize();
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail("fvs2d_gpu_init: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0) {
+    const char *lr = getenv("LOCAL_RANK");
+    device = lr ? atoi(lr) % ndev : 0;
+  }
+  NEED(device < ndev, "fvs2d_gpu_init: device index out of range");
+  C = new Ctx();
+  C->cfg = *cfg;
+  C->device = device;
+  CUDA_OK(cudaSetDevice(device));
+  CUDA_OK(cudaStreamCreateWithFlags(&C->st, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreate(&C->ev0));
+  CUDA_OK(cudaEventCreate(&C->ev1));
+  // scheme validation: the stop conditions of src/input.f90:181-277 and the limiter/LSQ coupling
+  NEED(cfg->grad_method >= 1 && cfg->grad_method <= 3, "check cell-center gradient scheme in input file");
+  NEED(cfg->limiter >= 0 && cfg->limiter <= 3, "check gradient limiter scheme in input file");
+  NEED(cfg->recon >= 1 && cfg->recon <= 3, "check face reconstruction scheme in input file");
+  NEED(cfg->flux == 1, "check inviscid flux discretization scheme in input file");
+  if (cfg->limiter > 0 && cfg->recon != 1)
+    NEED(cfg->grad_method == 3, "gradient limiter needs the LSQ stencil (src/gradient_limiter.f90:54-58): use grad_method 3");
+  if (rk_setup()) return 1;
+  const double kap = cfg->recon == 3 ? cfg->umuscl_cst : 0.0;  // src/input.f90:248-254
+  if (cfg->recon == 1) C->recon = RC_FIRST;
+  else if (kap == 0.0) C->recon = cfg->limiter > 0 ? RC_K0_PHI : RC_K0;
+  else C->recon = RC_GENERAL;
+  Phys &P = C->phys;
+  P.gamma = cfg->gamma; P.kappa = kap; P.cfl = cfg->cfl_user;
+  for (int i = 0; i < 4; i++) { P.pinf[i] = cfg->pvar_inf[i]; P.vinf[i] = cfg->vortex_inf[i]; }
+  P.vpos[0] = cfg->vortex_pos[0]; P.vpos[1] = cfg->vortex_pos[1]; P.vkap = cfg->vortex_kappa;
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) P.mms[i][j] = cfg->mms_c[i][j];
+  P.lvortex = cfg->lvortex; P.limiter = cfg->limiter;
+  C->inited = true;
+  return 0;
+}
+
+int fvs2d_gpu_comm_unique_id(char id[128]) {
+  if (!g_nccl.load(g_err)) return 1;
+  ncclUniqueId u;
+  NCCL_OK(g_nccl.GetUniqueId(&u));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(id, &u, 128);
+  return 0;
+}
+
+int fvs2d_gpu_comm_init(int rank, int nranks, const char id[128]) {
+  NEED(C && C->inited, "fvs2d_gpu_comm_init: call fvs2d_gpu_init first");
+  NEED(!C->has_mesh, "fvs2d_gpu_comm_init: must precede fvs2d_gpu_set_mesh");
+  NEED(nranks >= 1 && rank >= 0 && rank < nranks, "fvs2d_gpu_comm_init: bad rank");
+  if (nranks == 1) { C->rank = 0; C->nranks = 1; return 0; }
+  if (!g_nccl.load(g_err)) return 1;
+  ncclUniqueId u;
+  memcpy(&u, id, 128);
+  NCCL_OK(g_nccl.CommInitRank(&C->comm, nranks, u, rank));
+  C->rank = rank; C->nranks = nranks;
+  return 0;
+}
+
+}  // extern "C"
+
+namespace {
+// host half of set_mesh: connectivity, geometry, gradient operator, renumbering, layout (no CUDA calls)
+int host_build(int nnodes, int ntri, int nquad, const double *node_xy, const int *cell_ptr, const int *cell_node,
+               int nb, const int *b_ncells, const int *b_type, const int *b_cell) {
+  NEED(nnodes > 0 && ntri >= 0 && nquad >= 0 && ntri + nquad > 0, "fvs2d_gpu_set_mesh: empty mesh");
+  NEED(node_xy && cell_ptr && cell_node, "fvs2d_gpu_set_mesh: null array");
+  NEED(nb == 0 || (b_ncells && b_type && b_cell), "fvs2d_gpu_set_mesh: null boundary array");
+  C->has_mesh = C->has_state = false;
+  C->bc_static_done = false;
+  HostMesh &m = C->mesh;
+  m = HostMesh();
+  const int nc = ntri + nquad;
+  m.nnodes = nnodes; m.ntri = ntri; m.nquad = nquad; m.ncells = nc;
+  m.xn.resize(nnodes); m.yn.resize(nnodes);
+  for (int i = 0; i < nnodes; i++) { m.xn[i] = node_xy[2 * (size_t)i]; m.yn[i] = node_xy[2 * (size_t)i + 1]; }
+  m.cptr.assign(cell_ptr, cell_ptr + nc + 1);
+  NEED(m.cptr[0] == 0 && m.cptr[nc] == 3 * ntri + 4 * nquad, "fvs2d_gpu_set_mesh: cell_ptr inconsistent with ncells_tri/ncells_quad");
+  m.cnode.assign(cell_node, cell_node + m.cptr[nc]);
+  m.nb = nb;
+  m.b_ncells.assign(b_ncells, b_ncells + nb);
+  m.b_type.assign(b_type, b_type + nb);
+  size_t nbc = 0;
+  for (int ib = 0; ib < nb; ib++) {
+    NEED(b_type[ib] == FVS2D_BC_FREESTREAM || b_type[ib] == FVS2D_BC_SLIP_WALL || b_type[ib] == FVS2D_BC_DIRICHLET,
+         "Boundary condition not implemented (src/residual.f90:206-216)");
+    nbc += b_ncells[ib];
+  }
+  m.b_cell.assign(b_cell, b_cell + nbc);
+  std::string err = build_mesh(m);
+  if (!err.empty()) return fail("%s", err.c_str());
+  err = build_gradient(m, C->cfg.grad_method, C->cfg.lsq_stencil, C->cfg.lsq_pow, C->grad);
+  if (!err.empty()) return fail("%s", err.c_str());
+  std::vector<int> perm;
+  hilbert_order(m, perm);
+  err = build_layout(m, C->grad, perm, C->rank, C->nranks, C->L);
+  if (!err.empty()) return fail("%s", err.c_str());
+  C->has_mesh = true;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int fvs2d_host_build(const fvs2d_config *cfg, int rank, int nranks, int nnodes, int ntri, int nquad, const double *node_xy,
+                     const int *cell_ptr, const int *cell_node, int nb, const int *b_ncells, const int *b_type, const int *b_cell) {
+  NEED(cfg != nullptr, "fvs2d_host_build: null config");
+  NEED(nranks >= 1 && rank >= 0 && rank < nranks, "fvs2d_host_build: bad rank");
+  if (C) fvs2d_gpu_finalize();
+  C = new Ctx();
+  C->cfg = *cfg;
+  C->rank = rank; C->nranks = nranks;
+  return host_build(nnodes, ntri, nquad, node_xy, cell_ptr, cell_node, nb, b_ncells, b_type, b_cell);
+}
+
+int fvs2d_gpu_set_mesh(int nnodes, int ntri, int nquad, const double *node_xy, const int *cell_ptr, const int *cell_node,
+                       int nb, const int *b_ncells, const int *b_type, const int *b_cell) {
+  NEED(C && C->inited, "fvs2d_gpu_set_mesh: call fvs2d_gpu_init first");
+  free_device();
+  if (host_build(nnodes, ntri, nquad, node_xy, cell_ptr, cell_node, nb, b_ncells, b_type, b_cell)) return 1;
+  C->has_mesh = false;
+
+  // ---- upload
+  const Layout &L = C->L;
+  DevMesh &d = C->dm;
+  d.n_own = L.n_own; d.n_loc = L.n_loc; d.nbf = L.nbf;
+  C->np = d.np = (L.n_loc + 31) / 32 * 32;
+  C->nblocks = cdiv(L.n_own, kBlock);
+  if (dev_upload(d.f_off, L.f_off) || dev_upload(d.f_nbr, L.f_nbr) || dev_upload(d.f_edge, L.f_edge)) return 1;
+  if (dev_upload(d.ex, L.ex) || dev_upload(d.ey, L.ey) || dev_upload(d.ea, L.ea) || dev_upload(d.enx, L.enx) || dev_upload(d.eny, L.eny)) return 1;
+  if (dev_upload(d.xc, L.xc) || dev_upload(d.yc, L.yc) || dev_upload(d.vol, L.vol)) return 1;
+  if (dev_upload(d.g_off, L.g_off) || dev_upload(d.g_idx, L.g_idx) || dev_upload(d.g_cx, L.g_cx) || dev_upload(d.g_cy, L.g_cy)) return 1;
+  if (dev_upload(d.c0x, L.c0x) || dev_upload(d.c0y, L.c0y)) return 1;
+  if (dev_upload(d.bf_type, L.bf_type) || dev_upload(d.bf_edge, L.bf_edge)) return 1;
+  if (dev_upload(d.is_intr, L.is_intr) || dev_upload(d.orig_id, L.orig_id)) return 1;
+  const size_t np = C->np;
+  if (dev_alloc(C->q, 4 * np) || dev_alloc(C->f, 4 * np) || dev_alloc(C->pa, 4 * np) || dev_alloc(C->pb, 4 * np)) return 1;
+  if (dev_alloc(C->g, 8 * np) || dev_alloc(C->phi, np)) return 1;
+  if (C->cfg.steady && dev_alloc(C->dtl, np)) return 1;
+  if (dev_alloc(C->bc, 4 * (size_t)std::max(1, L.nbf))) return 1;
+  if (dev_alloc(C->partial, (size_t)C->nblocks * 4) || dev_alloc(C->vpartial, (size_t)C->nblocks * 13) || dev_alloc(C->vbest, (size_t)C->nblocks)) return 1;
+  CUDA_OK(cudaMemset(C->q, 0, 4 * np * 8));
+  CUDA_OK(cudaMemset(C->f, 0, 4 * np * 8));
+  CUDA_OK(cudaMemset(C->pa, 0, 4 * np * 8));
+  CUDA_OK(cudaMemset(C->pb, 0, 4 * np * 8));
+  CUDA_OK(cudaMemset(C->g, 0, 8 * np * 8));
+  {  // phi == 1 unless the limiter kernel overwrites it (src/gradient_limiter.f90:36-39)
+    std::vector<double> ones(np, 1.0);
+    CUDA_OK(cudaMemcpy(C->phi, ones.data(), np * 8, cudaMemcpyHostToDevice));
+  }
+  if (C->nranks > 1) {
+    const int nsend = L.send_ptr.empty() ? 0 : L.send_ptr.back();
+    const int *si;
+    if (dev_upload(si, L.send_idx)) return 1;
+    C->send_idx = const_cast<int *>(si);
+    if (dev_alloc(C->sendbuf, (size_t)std::max(1, nsend) * 9)) return 1;
+  }
+  C->ev_pool.resize(8192);
+  for (auto &e : C->ev_pool) CUDA_OK(cudaEventCreate(&e));
+  C->has_mesh = true;
+  return 0;
+}
+
+int fvs2d_gpu_set_state(const double *cvar) {
+  NEED(C && C->has_mesh, "fvs2d_gpu_set_state: no mesh");
+  NEED(cvar != nullptr, "fvs2d_gpu_set_state: null cvar");
+  const size_t ng = (size_t)C->L.nc_global * 4;
+  if (ensure_stage(ng)) return 1;
+  CUDA_OK(cudaMemcpyAsync(C->stage_aos, cvar, ng * 8, cudaMemcpyHostToDevice, C->st));
+  k_scatter_in<<<cdiv(C->L.n_loc, 256), 256, 0, C->st>>>(C->L.n_loc, C->np, 4, C->dm.orig_id, C->stage_aos, C->q);
+  k_prim<<<cdiv(C->L.n_loc, 256), 256, 0, C->st>>>(C->L.n_loc, C->np, C->cfg.gamma, C->q, C->pa);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(C->st));
+  C->has_state = true;
+  return 0;
+}
+
+int fvs2d_gpu_get_state(double *cvar) {
+  NEED(C && C->has_state, "fvs2d_gpu_get_state: no state");
+  NEED(cvar != nullptr, "fvs2d_gpu_get_state: null cvar");
+  return download_aos(C->q, 4, cvar);
+}
+
+int fvs2d_gpu_initialize_solution(void) {
+  NEED(C && C->has_mesh, "fvs2d_gpu_initialize_solution: no mesh");
+  const fvs2d_config &c = C->cfg;
+  NEED(c.ntstart <= 1, "fvs2d_gpu_initialize_solution: ntstart>1 is a restart; pass cont.s8's cvar to fvs2d_gpu_set_state");
+  const HostMesh &m = C->mesh;
+  const int nc = m.ncells;
+  std::vector<double> cv(4 * (size_t)nc);
+  const double pi = std::acos(-1.0), g = c.gamma;
+  const double t0 = (double)(c.ntstart - 1) * c.dt;
+#pragma omp parallel for schedule(static)
+  for (int ic = 0; ic < nc; ic++) {
+    double pv[4];
+    const double x = m.xc[ic], y = m.yc[ic];
+    if (c.ntstart == 1 && c.lvortex) {  // src/mms.f90:219-265
+      const double ri = c.vortex_inf[0], ui = c.vortex_inf[1], vi = c.vortex_inf[2], p_i = c.vortex_inf[3];
+      const double dx = x - (c.vortex_pos[0] + ui * t0), dy = y - (c.vortex_pos[1] + vi * t0);
+      const double r = std::sqrt(dx * dx + dy * dy), kk = c.vortex_kappa / (2.0 * pi);
+      pv[1] = ui - kk * dy * std::exp(0.5 * (1.0 - r * r));
+      pv[2] = vi + kk * dx * std::exp(0.5 * (1.0 - r * r));
+      const double temp = p_i / ri - kk * kk * (g - 1.0) / (2.0 * g) * std::exp(1.0 - r * r);
+      pv[0] = std::pow(temp, 1.0 / (g - 1.0));
+      pv[3] = std::pow(pv[0], g);
+    } else if (c.ntstart == 1) {
+      for (int v = 0; v < 4; v++) pv[v] = c.pvar_inf[v];
+    } else {  // manufactured solution, src/mms.f90:137-146
+      for (int v = 0; v < 4; v++) pv[v] = c.mms_c[v][0] + c.mms_c[v][1] * std::sin(c.mms_c[v][2] * x + c.mms_c[v][3] * y);
+    }
+    double *q = &cv[4 * (size_t)ic];  // pvar2cvar, src/data_solution.f90:92-106
+    q[0] = pv[0]; q[1] = pv[0] * pv[1]; q[2] = pv[0] * pv[2];
+    q[3] = pv[3] / (g - 1.0) + 0.5 * pv[0] * (pv[1] * pv[1] + pv[2] * pv[2]);
+  }
+  return fvs2d_gpu_set_state(cv.data());
+}
+
+int fvs2d_gpu_compute_residual(double time, double *resid, double *ws_nrml) {
+  NEED(C && C->has_state, "fvs2d_gpu_compute_residual: no state");
+  const size_t np = C->np;
+  if (!C->resid && (dev_alloc(C->resid, 4 * np) || dev_alloc(C->ws, np))) return 1;
+  C->last_launches = 0;
+  if (launch_bc(time)) return 1;
+  if (pass_a(C->pa)) return 1;
+  StageParams S{0, 0, 0.0, 0.0, C->cfg.dt};
+  if (launch_flux(UM_RESID, S, C->pa, C->pb)) return 1;
+  CUDA_OK(cudaGetLastError());
+  if (resid && download_aos(C->resid, 4, resid)) return 1;
+  if (ws_nrml && download_aos(C->ws, 1, ws_nrml)) return 1;
+  CUDA_OK(cudaStreamSynchronize(C->st));
+  return 0;
+}
+
+int fvs2d_gpu_get_aux(double *pvar, double *grad, double *phi_lim) {
+  NEED(C && C->has_state, "fvs2d_gpu_get_aux: no state");
+  if (pvar && download_aos(C->pa, 4, pvar)) return 1;
+  if (phi_lim && download_aos(C->phi, 1, phi_lim)) return 1;
+  if (grad) {  // Fortran grad(ivar,ic,idim): two planes of (4,ncells)
+    const size_t plane = 4 * (size_t)C->L.nc_global;
+    if (download_aos(C->g, 4, grad)) return 1;
+    if (download_aos(C->g + 4 * (size_t)C->np, 4, grad + plane)) return 1;
+  }
+  return 0;
+}
+
+int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vortex_err, double *vortex_err_xy) {
+  NEED(C && C->has_state, "fvs2d_gpu_time_integration: no state");
+  NEED(nsub >= 0, "fvs2d_gpu_time_integration: nsub < 0");
+  const fvs2d_config &c = C->cfg;
+  const int um = c.ssprk ? UM_SSPRK : UM_RK;
+  const double dt = c.dt;
+  const bool vort = c.lvortex != 0;
+  // device log: per step 4 sums of squares, 13 vortex numbers, 1 id
+  const size_t per = 4 + 13;
+  if (C->log_cap < (size_t)nsub) {
+    if (dev_alloc(C->logbuf, per * (size_t)nsub) || dev_alloc(C->logid, (size_t)nsub)) return 1;
+    C->log_cap = nsub;
+  }
+  C->last_launches = 0;
+  C->ev_used = 0;
+  for (auto &s : C->ev_spans) s.clear();
+  CUDA_OK(cudaEventRecord(C->ev0, C->st));
+  for (int istep = 1; istep <= nsub; istep++) {
+    const double told = t1 + (double)(istep - 1) * dt;  // src/runge_kutta.f90:135-139
+    const double t12 = told + 0.5 * dt, tnew = told + dt;
+    const double tstart[4] = {told, t12, t12, tnew};
+    double tend = tnew;
+    for (int rk = 0; rk < 4; rk++) {
+      const double ts = c.ssprk ? told + C->dts[rk] : tstart[rk];
+      if (c.ssprk) tend = told + C->dte[rk];
+      StageParams S;
+      S.stage = rk; S.last = rk == 3; S.c = C->rk_coef[rk]; S.dt = dt;
+      if (c.steady) S.h = c.ssprk ? (rk == 3 ? 1.0 / 4.0 : 1.0 / 3.0) : (rk == 2 ? 1.0 : rk == 3 ? 1.0 / 6.0 : 1.0 / 2.0);
+      else S.h = C->h_rk[rk];
+      if (launch_bc(ts)) return 1;
+      if (pass_a(C->pa)) return 1;
+      if (launch_flux(um, S, C->pa, C->pb)) return 1;
+      if (C->nranks > 1) {
+        Span sp(0);
+        HaloItem it{C->pb, 4};
+        if (halo_exchange(&it, 1)) return 1;
+      }
+      std::swap(C->pa, C->pb);
+    }
+    {
+      Span sp(0);
+      double *lg = C->logbuf + per * (size_t)(istep - 1);
+      k_finish_sum<4><<<1, 256, 0, C->st>>>(C->partial, C->nblocks, lg);
+      C->last_launches++;
+      if (vort) {
+        k_vortex_err<<<C->nblocks, kBlock, 0, C->st>>>(C->dm, C->phys, tend, C->q, C->vpartial, C->vbest);
+        k_finish_vortex<<<1, 256, 0, C->st>>>(C->vpartial, C->vbest, C->nblocks, lg + 4, C->logid + (istep - 1));
+        C->last_launches += 2;
+      }
+    }
+  }
+  CUDA_OK(cudaEventRecord(C->ev1, C->st));
+  CUDA_OK(cudaGetLastError());
+  // ---- logs back to the host (the only device->host traffic of the call)
+  std::vector<double> lg(per * (size_t)nsub);
+  std::vector<int> ids(nsub);
+  if (nsub > 0 && (res_l2 || vortex_err || vortex_err_xy)) {
+    CUDA_OK(cudaMemcpyAsync(lg.data(), C->logbuf, lg.size() * 8, cudaMemcpyDeviceToHost, C->st));
+    CUDA_OK(cudaMemcpyAsync(ids.data(), C->logid, ids.size() * 4, cudaMemcpyDeviceToHost, C->st));
+  }
+  CUDA_OK(cudaStreamSynchronize(C->st));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, C->ev0, C->ev1));
+  C->last_ms[0] = ms;
+  for (int b = 0; b < 3; b++) {
+    double acc = 0;
+    for (auto &pr : C->ev_spans[b]) { float t = 0; cudaEventElapsedTime(&t, C->ev_pool[pr.first], C->ev_pool[pr.second]); acc += t; }
+    C->last_ms[b == 0 ? 3 : b] = acc;
+  }
+  if (nsub == 0 || !(res_l2 || vortex_err || vortex_err_xy)) return 0;
+
+  // ---- combine across ranks (sums / maxima are tiny: 17 doubles per step)
+  const int nr = C->nranks;
+  std::vector<double> all;  // [rank][step][per]
+  std::vector<int> allid;
+  if (nr > 1) {
+    double *dall; int *dallid;
+    CUDA_OK(cudaMalloc(&dall, lg.size() * 8 * nr));
+    CUDA_OK(cudaMalloc(&dallid, ids.size() * 4 * nr));
+    NCCL_OK(g_nccl.AllGather(C->logbuf, dall, lg.size(), ncclDouble, C->comm, C->st));
+    NCCL_OK(g_nccl.AllGather(C->logid, dallid, ids.size(), ncclInt, C->comm, C->st));
+    all.resize(lg.size() * nr); allid.resize(ids.size() * nr);
+    CUDA_OK(cudaMemcpyAsync(all.data(), dall, all.size() * 8, cudaMemcpyDeviceToHost, C->st));
+    CUDA_OK(cudaMemcpyAsync(allid.data(), dallid, allid.size() * 4, cudaMemcpyDeviceToHost, C->st));
+    CUDA_OK(cudaStreamSynchronize(C->st));
+    cudaFree(dall); cudaFree(dallid);
+  } else { all = lg; allid = ids; }
+  const double ncg = (double)C->L.nc_global, nin = (double)C->mesh.ncells_intr;
+  for (int s = 0; s < nsub; s++) {
+    double sum4[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, best = -1.0;
+    int bid = 0x7fffffff;
+    for (int r = 0; r < nr; r++) {
+      const double *a = &all[((size_t)r * nsub + s) * per];
+      for (int v = 0; v < 4; v++) { sum4[v] += a[v]; mx[v] = std::max(mx[v], a[4 + v]); s1[v] += a[8 + v]; s2[v] += a[12 + v]; }
+      const int id = allid[(size_t)r * nsub + s];
+      if (a[16] > best || (a[16] == best && id < bid)) { best = a[16]; bid = id; }
+    }
+    if (res_l2) for (int v = 0; v < 4; v++) res_l2[4 * s + v] = std::sqrt(sum4[v] / ncg);  // src/runge_kutta.f90:172-181
+    if (vort && vortex_err) {  // the 14 columns of src/mms.f90:357-361
+      double *o = &vortex_err[14 * (size_t)s];
+      const double told = t1 + (double)s * dt;
+      o[0] = c.ssprk ? told + C->dte[3] : told + dt;
+      for (int v = 0; v < 4; v++) { o[1 + 3 * v] = mx[v]; o[2 + 3 * v] = s1[v] / nin; o[3 + 3 * v] = std::sqrt(s2[v] / nin); }
+      o[13] = std::sqrt((s2[0] + s2[1] + s2[2] + s2[3]) / nin);
+    }
+    if (vort && vortex_err_xy) {
+      // maxloc(erho) (src/mms.f90:363): first cell of the maximum; cell 1 when every error is zero
+      const int cell = (best > 0.0 && bid != 0x7fffffff) ? bid : 0;
+      vortex_err_xy[2 * s] = C->mesh.xc[cell];
+      vortex_err_xy[2 * s + 1] = C->mesh.yc[cell];
+    }
+  }
+  return 0;
+}
+
+int fvs2d_gpu_test_resid(int corrected, double l2[4], double linf[4]) {
+  NEED(C && C->has_state, "fvs2d_gpu_test_resid: no state");
+  NEED(!C->cfg.lvortex, "test_resid needs mms_source, which exists only when lvortex is false (src/mms.f90:45-66)");
+  NEED(C->nranks == 1, "fvs2d_gpu_test_resid: single GPU only");
+  const HostMesh &m = C->mesh;
+  std::vector<double> r(4 * (size_t)m.ncells);
+  if (fvs2d_gpu_compute_residual(0.0, r.data(), nullptr)) return 1;
+  const fvs2d_config &c = C->cfg;
+  const double g = c.gamma;
+  for (int v = 0; v < 4; v++) { l2[v] = 0; linf[v] = 0; }
+  for (int i = 0; i < m.ncells_intr; i++) {
+    const int ic = m.cell_intr[i];
+    const double x = m.xc[ic], y = m.yc[ic];
+    // src/mms.f90:124-181
+    double f0[4], fx[4], fy[4];
+    for (int v = 0; v < 4; v++) {
+      const double a0 = c.mms_c[v][0], as = c.mms_c[v][1], ax = c.mms_c[v][2], ay = c.mms_c[v][3];
+      f0[v] = a0 + as * std::sin(ax * x + ay * y);
+      fx[v] = ax * as * std::cos(ax * x + ay * y);
+      fy[v] = ay * as * std::cos(ax * x + ay * y);
+    }
+    const double rr = f0[0], u = f0[1], vv = f0[2], p = f0[3];
+    const double rx = fx[0], ux = fx[1], vx = fx[2], px = fx[3], ry = fy[0], uy = fy[1], vy = fy[2], py = fy[3];
+    const double rH = g / (g - 1.0) * p + rr * u * u / 2.0 + rr * vv * vv / 2.0;
+    const double rHx = g / (g - 1.0) * px + rx * (u * u + vv * vv) / 2.0 + rr * (u * ux + vv * vx);
+    const double rHy = g / (g - 1.0) * py + ry * (u * u + vv * vv) / 2.0 + rr * (u * uy + vv * vy);
+    double rhs[4];
+    rhs[0] = corrected ? rx * u + rr * ux + ry * vv + rr * vy : rx * u + u * rx + ry * vv + rr * vy;  // :169 typo kept
+    rhs[1] = rx * u * u + 2.0 * rr * u * ux + ry * u * vv + rr * uy * vv + rr * u * vy + px;
+    rhs[2] = rx * u * vv + rr * ux * vv + rr * u * vx + ry * vv * vv + 2.0 * rr * vv * vy + py;
+    rhs[3] = u * rHx + ux * rH + vv * rHy + vy * rH;
+    for (int v = 0; v < 4; v++) {
+      const double e = r[4 * (size_t)ic + v] + rhs[v];
+      l2[v] += e * e;
+      linf[v] = std::max(linf[v], std::fabs(e));
+    }
+  }
+  for (int v = 0; v < 4; v++) l2[v] = std::sqrt(l2[v] / (double)m.ncells_intr);
+  return 0;
+}
+
+int fvs2d_gpu_sizes(int s[10]) {
+  NEED(C && C->has_mesh, "fvs2d_gpu_sizes: no mesh");
+  const HostMesh &m = C->mesh;
+  s[0] = m.nnodes; s[1] = m.ncells; s[2] = m.nedges; s[3] = m.nedges_intr; s[4] = m.nedges_bndr;
+  s[5] = m.ncells_intr; s[6] = m.ncells_bndr; s[7] = C->L.n_own; s[8] = C->L.n_loc; s[9] = C->L.nedges;
+  return 0;
+}
+
+int fvs2d_gpu_scalars(double s[6]) {
+  NEED(C && C->has_mesh, "fvs2d_gpu_scalars: no mesh");
+  const HostMesh &m = C->mesh;
+  s[0] = m.heff1; s[1] = m.heff2; s[2] = m.vol_sum; s[3] = m.vol_green; s[4] = C->grad.verify_err; s[5] = (double)C->bytes;
+  return 0;
+}
+
+long fvs2d_gpu_mesh_array(const char *name, void *out) {
+  if (!C || !C->has_mesh) { fail("fvs2d_gpu_mesh_array: no mesh"); return -1; }
+  const HostMesh &m = C->mesh;
+  const std::string n = name;
+#define RET(nm, vec) if (n == nm) { if (out) memcpy(out, (vec).data(), (vec).size() * sizeof((vec)[0])); return (long)(vec).size(); }
+  RET("xc", m.xc) RET("yc", m.yc) RET("vol", m.vol) RET("ex", m.ex) RET("ey", m.ey) RET("ea", m.ea) RET("enx", m.enx) RET("eny", m.eny)
+  RET("en1", m.en1) RET("en2", m.en2) RET("ec1", m.ec1) RET("ec2", m.ec2) RET("cedge", m.cedge) RET("nghbre", m.nghbre)
+  RET("cell_intr", m.cell_intr) RET("b_edge", m.b_edge) RET("b_edge_ptr", m.b_edge_ptr) RET("perm", C->L.perm)
+  RET("loc2new", C->L.loc2new) RET("peers", C->L.peers) RET("send_ptr", C->L.send_ptr) RET("send_idx", C->L.send_idx)
+  RET("recv_begin", C->L.recv_begin) RET("recv_count", C->L.recv_count)
+  RET("f_off", C->L.f_off) RET("f_nbr", C->L.f_nbr) RET("f_edge", C->L.f_edge) RET("g_off", C->L.g_off) RET("g_idx", C->L.g_idx)
+  RET("g_cx", C->L.g_cx) RET("g_cy", C->L.g_cy) RET("orig_id", C->L.orig_id) RET("bf_type", C->L.bf_type) RET("bf_edge", C->L.bf_edge)
+  RET("lex", C->L.ex) RET("ley", C->L.ey) RET("is_intr", C->L.is_intr)
+  RET("grad_idx", C->grad.idx) RET("grad_cx", C->grad.cx) RET("grad_cy", C->grad.cy) RET("grad_c0x", C->grad.c0x) RET("grad_c0y", C->grad.c0y)
+#undef RET
+  if (n == "grad_ptr") {
+    if (out) for (size_t i = 0; i < C->grad.ptr.size(); i++) ((int *)out)[i] = (int)C->grad.ptr[i];
+    return (long)C->grad.ptr.size();
+  }
+  fail("fvs2d_gpu_mesh_array: unknown array '%s'", name);
+  return -1;
+}
+
+int fvs2d_gpu_last_timing(double ms[4], long *launches) {
+  NEED(C != nullptr, "fvs2d_gpu_last_timing: not initialised");
+  for (int i = 0; i < 4; i++) ms[i] = C->last_ms[i];
+  if (launches) *launches = C->last_launches;
+  return 0;
+}
+
+int fvs2d_gpu_set_option(const char *key, int value) {
+  NEED(C != nullptr, "fvs2d_gpu_set_option: not initialised");
+  const std::string k = key ? key : "";
+  if (k == "timing") { C->opt_timing = value; return 0; }
+  return fail("fvs2d_gpu_set_option: unknown option '%s'", key);
+}
+
+int fvs2d_gpu_finalize(void) {
+  if (!C) return 0;
+  if (C->inited) {
+    cudaSetDevice(C->device);
+    if (C->st) cudaStreamSynchronize(C->st);
+    free_device();
+  }
+  for (auto &e : C->ev_pool) cudaEventDestroy(e);
+  if (C->ev0) cudaEventDestroy(C->ev0);
+  if (C->ev1) cudaEventDestroy(C->ev1);
+  if (C->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(C->comm);
+  if (C->st) cudaStreamDestroy(C->st);
+  delete C;
+  C = nullptr;
+  return 0;
+}
+
+}  // extern "C"

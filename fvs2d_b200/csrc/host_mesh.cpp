@@ -1,0 +1,552 @@
+// host_mesh.cpp -- host-side (CPU, runs once) mesh pre-processing for the GPU hot path.
+//
+// What: the products of the reference's grid_data (src/grid_procs.f90:170-794) and of the three
+// gradient set-ups (src/gradient_ggcb.f90:48-110, src/gradient_ggnb.f90:49-177,
+// src/gradient_lsq.f90:70-365) with the reference's numbering (edge ids, c1<c2, normal c1->c2,
+// boundary-edge list order), because the device accumulates face fluxes in the reference's order.
+// How: not the reference's algorithms -- counting sorts, prefix sums and independent per-cell loops
+// (OpenMP), so a 69 M-cell mesh is processed in seconds rather than minutes.
+#include "host_mesh.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+namespace fvs2d {
+
+static inline double tri_area(double x1, double x2, double x3, double y1, double y2, double y3) {
+  return 0.5 * (x1 * (y2 - y3) + x2 * (y3 - y1) + x3 * (y1 - y2));  // src/grid_procs.f90:800-808
+}
+
+std::string build_mesh(HostMesh &m) {
+  const int nc = m.ncells = m.ntri + m.nquad;
+  const int nn = m.nnodes;
+  if ((int)m.cptr.size() != nc + 1) return "build_mesh: cell_ptr has the wrong length";
+  const int nslots = m.cptr[nc];
+  for (int ic = 0; ic < nc; ic++) {
+    int nv = m.cptr[ic + 1] - m.cptr[ic];
+    if (nv != (ic < m.ntri ? 3 : 4)) return "build_mesh: cells must be listed triangles first, then quads";
+  }
+  for (int s = 0; s < nslots; s++)
+    if (m.cnode[s] < 0 || m.cnode[s] >= nn) return "build_mesh: node id out of range";
+
+  // -- centroids and volumes (src/grid_procs.f90:185-227)
+  m.xc.resize(nc); m.yc.resize(nc); m.vol.resize(nc);
+#pragma omp parallel for schedule(static)
+  for (int ic = 0; ic < nc; ic++) {
+    const int *nd = &m.cnode[m.cptr[ic]];
+    const int nv = m.nvrt(ic);
+    double xc = 0, yc = 0;
+    for (int iv = 0; iv < nv; iv++) { xc = xc + m.xn[nd[iv]]; yc = yc + m.yn[nd[iv]]; }
+    m.xc[ic] = xc / (double)nv;
+    m.yc[ic] = yc / (double)nv;
+    double x1 = m.xn[nd[0]], y1 = m.yn[nd[0]], x2 = m.xn[nd[1]], y2 = m.yn[nd[1]], x3 = m.xn[nd[2]], y3 = m.yn[nd[2]];
+    double v = tri_area(x1, x2, x3, y1, y2, y3);
+    if (nv == 4) { double x4 = m.xn[nd[3]], y4 = m.yn[nd[3]]; v = v + tri_area(x1, x3, x4, y1, y3, y4); }
+    m.vol[ic] = v;
+  }
+  {  // effective lengths, sequential sums as in src/grid_procs.f90:233-243
+    double at = 0, as = 0;
+    for (int ic = 0; ic < nc; ic++) { at += m.vol[ic]; as += std::sqrt(m.vol[ic]); }
+    m.vol_sum = at;
+    m.heff1 = std::sqrt(at / (double)nc);
+    m.heff2 = as / (double)nc;
+  }
+
+  // -- node -> cell by counting sort; ascending cell id per node like src/grid_procs.f90:291-299
+  m.n2c_ptr.assign(nn + 1, 0);
+  for (int s = 0; s < nslots; s++) m.n2c_ptr[m.cnode[s] + 1]++;
+  for (int i = 0; i < nn; i++) m.n2c_ptr[i + 1] += m.n2c_ptr[i];
+  m.n2c.resize(nslots);
+  {
+    std::vector<int> fill(m.n2c_ptr.begin(), m.n2c_ptr.end() - 1);
+    for (int ic = 0; ic < nc; ic++)
+      for (int s = m.cptr[ic]; s < m.cptr[ic + 1]; s++) m.n2c[fill[m.cnode[s]]++] = ic;
+  }
+
+  // -- face neighbours: the cell around v_k that holds the reversed edge (v_k+1 -> v_k)
+  m.nghbre.assign(nslots, -1);
+#pragma omp parallel for schedule(static)
+  for (int ic = 0; ic < nc; ic++) {
+    const int nv = m.nvrt(ic);
+    const int *nd = &m.cnode[m.cptr[ic]];
+    for (int e = 0; e < nv; e++) {
+      const int vR = nd[e], vL = nd[(e + 1) % nv];
+      int found = -1;
+      for (int j = m.n2c_ptr[vR]; j < m.n2c_ptr[vR + 1] && found < 0; j++) {
+        const int jc = m.n2c[j];
+        const int nvj = m.nvrt(jc);
+        const int *ndj = &m.cnode[m.cptr[jc]];
+        for (int ii = 0; ii < nvj; ii++)
+          if (ndj[ii] == vR && ndj[(ii + nvj - 1) % nvj] == vL) { found = jc; break; }
+      }
+      m.nghbre[m.cptr[ic] + e] = found;
+    }
+  }
+
+  // -- global edges: cell order, local-edge order, owner = lower cell id (src/grid_procs.f90:403-624)
+  std::vector<int> estart(nc + 1, 0);
+#pragma omp parallel for schedule(static)
+  for (int ic = 0; ic < nc; ic++) {
+    int cnt = 0;
+    for (int s = m.cptr[ic]; s < m.cptr[ic + 1]; s++)
+      if (m.nghbre[s] > ic || m.nghbre[s] < 0) cnt++;
+    estart[ic + 1] = cnt;
+  }
+  for (int ic = 0; ic < nc; ic++) estart[ic + 1] += estart[ic];
+  const int ne = m.nedges = estart[nc];
+  m.en1.resize(ne); m.en2.resize(ne); m.ec1.resize(ne); m.ec2.resize(ne);
+  m.cedge.assign(nslots, -1);
+  int bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+  for (int ic = 0; ic < nc; ic++) {
+    const int nv = m.nvrt(ic), b = m.cptr[ic];
+    const int *nd = &m.cnode[b];
+    int own = 0;
+    for (int e = 0; e < nv; e++) {
+      const int jc = m.nghbre[b + e];
+      if (jc > ic || jc < 0) {
+        const int id = estart[ic] + own++;
+        m.en1[id] = nd[e]; m.en2[id] = nd[(e + 1) % nv];
+        m.ec1[id] = ic; m.ec2[id] = jc;
+        m.cedge[b + e] = id;
+      } else {
+        // the reference scans jc's nghbr slots k=1..nvrt for ic and maps slot -> local edge (k-2)
+        const int nvj = m.nvrt(jc), bj = m.cptr[jc];
+        int ej = -1;
+        for (int k = 0; k < nvj && ej < 0; k++) {
+          const int e2 = (k + nvj - 2) % nvj;
+          if (m.nghbre[bj + e2] == ic) ej = e2;
+        }
+        if (ej < 0) { bad++; continue; }
+        int rank = 0;
+        for (int e2 = 0; e2 < ej; e2++)
+          if (m.nghbre[bj + e2] > jc || m.nghbre[bj + e2] < 0) rank++;
+        m.cedge[b + e] = estart[jc] + rank;
+      }
+    }
+  }
+  if (bad) return "build_mesh: inconsistent face neighbours (non-conforming mesh?)";
+
+  // -- edge geometry (src/grid_procs.f90:630-647)
+  m.ex.resize(ne); m.ey.resize(ne); m.ea.resize(ne); m.enx.resize(ne); m.eny.resize(ne);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < ne; i++) {
+    const int v1 = m.en1[i], v2 = m.en2[i];
+    const double dx = m.xn[v2] - m.xn[v1], dy = m.yn[v2] - m.yn[v1];
+    const double a = std::sqrt(dx * dx + dy * dy);
+    m.ea[i] = a;
+    m.ex[i] = 0.5 * (m.xn[v1] + m.xn[v2]);
+    m.ey[i] = 0.5 * (m.yn[v1] + m.yn[v2]);
+    m.enx[i] = dy / a;
+    m.eny[i] = -dx / a;
+  }
+
+  // -- interior / boundary cells and edges (src/grid_procs.f90:697-763)
+  m.cell_intr.clear();
+  m.cell_intr.reserve(nc);
+  for (int ic = 0; ic < nc; ic++) {
+    bool intr = true;
+    for (int s = m.cptr[ic]; s < m.cptr[ic + 1]; s++) intr = intr && m.nghbre[s] >= 0;
+    if (intr) m.cell_intr.push_back(ic);
+  }
+  m.ncells_intr = (int)m.cell_intr.size();
+  m.ncells_bndr = nc - m.ncells_intr;
+  m.b_cell_ptr.assign(m.nb + 1, 0);
+  for (int ib = 0; ib < m.nb; ib++) m.b_cell_ptr[ib + 1] = m.b_cell_ptr[ib] + m.b_ncells[ib];
+  if (m.ncells_bndr != m.b_cell_ptr[m.nb]) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "#s of boundary cells does not match (determined %d, .bc file %d)", m.ncells_bndr, m.b_cell_ptr[m.nb]);
+    return buf;
+  }
+  m.nedges_bndr = 0;
+  for (int ie = 0; ie < ne; ie++) m.nedges_bndr += m.ec2[ie] < 0;
+  m.nedges_intr = ne - m.nedges_bndr;
+
+  // -- boundary edge lists (src/grid_procs.f90:765-791)
+  m.edge_bc.assign(ne, -1);
+  m.b_edge_ptr.assign(m.nb + 1, 0);
+  m.b_edge.clear();
+  for (int ib = 0; ib < m.nb; ib++) {
+    for (int i = m.b_cell_ptr[ib]; i < m.b_cell_ptr[ib + 1]; i++) {
+      const int ic = m.b_cell[i];
+      if (ic < 0 || ic >= nc) return "build_mesh: boundary cell id out of range";
+      for (int s = m.cptr[ic]; s < m.cptr[ic + 1]; s++) {
+        const int je = m.cedge[s];
+        if (m.ec1[je] == ic && m.ec2[je] < 0) {
+          m.b_edge.push_back(je);
+          m.edge_bc[je] = ib;
+        }
+      }
+    }
+    m.b_edge_ptr[ib + 1] = (int)m.b_edge.size();
+  }
+  if ((int)m.b_edge.size() != m.nedges_bndr) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "#s of boundary edges/faces does not match (determined %d, read %d)", m.nedges_bndr, (int)m.b_edge.size());
+    return buf;
+  }
+  for (int ie = 0; ie < ne; ie++)
+    if (m.ec2[ie] < 0 && m.edge_bc[ie] < 0) return "build_mesh: a boundary edge belongs to no boundary of the .bc file";
+
+  // -- Green-theorem volume (src/grid_procs.f90:831-840), logged only
+  double vg = 0;
+#pragma omp parallel for schedule(static) reduction(+ : vg)
+  for (int ic = 0; ic < nc; ic++) {
+    double v = 0;
+    for (int s = m.cptr[ic]; s < m.cptr[ic + 1]; s++) {
+      const int je = m.cedge[s];
+      const double sgn = m.ec1[je] == ic ? 1.0 : -1.0;
+      v += m.enx[je] * sgn * m.ex[je] * m.ea[je];
+    }
+    vg += v;
+  }
+  m.vol_green = vg;
+  return "";
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact k-nearest centroids on a uniform bucket grid (replaces kdtree2 for the LSQ-fn boundary cells,
+// src/gradient_lsq.f90:85,108; ties broken by lower cell id)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct BucketGrid {
+  double x0, y0, h;
+  int nx, ny;
+  std::vector<int> ptr, item;
+  void build(const std::vector<double> &x, const std::vector<double> &y) {
+    const int n = (int)x.size();
+    double x1 = -1e300, y1 = -1e300;
+    x0 = y0 = 1e300;
+    for (int i = 0; i < n; i++) { x0 = std::min(x0, x[i]); x1 = std::max(x1, x[i]); y0 = std::min(y0, y[i]); y1 = std::max(y1, y[i]); }
+    const double area = std::max((x1 - x0) * (y1 - y0), 1e-300);
+    h = std::sqrt(area / std::max(1.0, n / 2.0));
+    nx = std::max(1, std::min(1 << 14, (int)((x1 - x0) / h) + 1));
+    ny = std::max(1, std::min(1 << 14, (int)((y1 - y0) / h) + 1));
+    h = std::max((x1 - x0) / nx, (y1 - y0) / ny) * (1.0 + 1e-12) + 1e-300;
+    ptr.assign((size_t)nx * ny + 1, 0);
+    std::vector<int> b(n);
+    for (int i = 0; i < n; i++) { b[i] = bucket(x[i], y[i]); ptr[b[i] + 1]++; }
+    for (size_t k = 0; k + 1 < ptr.size(); k++) ptr[k + 1] += ptr[k];
+    item.resize(n);
+    std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+    for (int i = 0; i < n; i++) item[fill[b[i]]++] = i;
+  }
+  int bx(double x) const { return std::max(0, std::min(nx - 1, (int)((x - x0) / h))); }
+  int by(double y) const { return std::max(0, std::min(ny - 1, (int)((y - y0) / h))); }
+  int bucket(double x, double y) const { return by(y) * nx + bx(x); }
+};
+struct Near { double d2; int idx; };
+inline bool nearer(const Near &a, const Near &b) { return a.d2 < b.d2 || (a.d2 == b.d2 && a.idx < b.idx); }
+
+void knn(const BucketGrid &g, const std::vector<double> &x, const std::vector<double> &y, int q, int k, Near *out) {
+  for (int i = 0; i < k; i++) out[i] = {HUGE_VAL, 0x7fffffff};
+  const int cx = g.bx(x[q]), cy = g.by(y[q]);
+  const int rmax = std::max(g.nx, g.ny);
+  for (int r = 0; r <= rmax; r++) {
+    // every bucket at Chebyshev ring r is at least (r-1)*h away from the query
+    if (r >= 2) { double dmin = (r - 1) * g.h; if (dmin * dmin > out[k - 1].d2) break; }
+    for (int j = cy - r; j <= cy + r; j++) {
+      if (j < 0 || j >= g.ny) continue;
+      const bool edge_row = (j == cy - r || j == cy + r);
+      for (int i = cx - r; i <= cx + r; i += (edge_row ? 1 : 2 * r > 0 ? 2 * r : 1)) {
+        if (i < 0 || i >= g.nx) continue;
+        const int b = j * g.nx + i;
+        for (int t = g.ptr[b]; t < g.ptr[b + 1]; t++) {
+          const int c = g.item[t];
+          const double dx = x[c] - x[q], dy = y[c] - y[q];
+          Near cand{dx * dx + dy * dy, c};
+          if (nearer(cand, out[k - 1])) {
+            int p = k - 1;
+            while (p > 0 && nearer(cand, out[p - 1])) { out[p] = out[p - 1]; p--; }
+            out[p] = cand;
+          }
+        }
+      }
+    }
+  }
+}
+}  // namespace
+
+std::string build_gradient(const HostMesh &m, int grad_method, int lsq_stencil, double lsq_pow, GradOp &g) {
+  const int nc = m.ncells;
+  g = GradOp();
+  g.ptr.assign(nc + 1, 0);
+  if (grad_method == 1) {
+    // ---- Green-Gauss cell-based: one entry per face; a boundary face points back at the cell itself
+    g.form = 0;
+    for (int ic = 0; ic < nc; ic++) g.ptr[ic + 1] = m.cptr[ic + 1];
+    const int64_t tot = g.ptr[nc];
+    g.idx.resize(tot); g.cx.resize(tot); g.cy.resize(tot); g.c0x.resize(nc); g.c0y.resize(nc);
+#pragma omp parallel for schedule(static)
+    for (int ic = 0; ic < nc; ic++) {
+      const double xc = m.xc[ic], yc = m.yc[ic], vol = m.vol[ic];
+      double c0x = 0, c0y = 0;
+      for (int s = m.cptr[ic]; s < m.cptr[ic + 1]; s++) {
+        const int je = m.cedge[s];
+        const double sgn = m.ec1[je] == ic ? 1.0 : -1.0;
+        const double af = m.ea[je], nxf = m.enx[je] * sgn, nyf = m.eny[je] * sgn, xf = m.ex[je], yf = m.ey[je];
+        double dx = xf - xc, dy = yf - yc;
+        const double d0 = std::sqrt(dx * dx + dy * dy);
+        const int jc = m.nghbre[s] >= 0 ? m.nghbre[s] : ic;
+        dx = xf - m.xc[jc]; dy = yf - m.yc[jc];
+        const double d1 = std::sqrt(dx * dx + dy * dy);
+        c0x = c0x + d1 / (d0 + d1) * nxf * af;
+        c0y = c0y + d1 / (d0 + d1) * nyf * af;
+        g.idx[s] = jc;
+        g.cx[s] = d0 / (d0 + d1) * nxf * af / vol;
+        g.cy[s] = d0 / (d0 + d1) * nyf * af / vol;
+      }
+      g.c0x[ic] = c0x / vol;
+      g.c0y[ic] = c0y / vol;
+    }
+    return "";
+  }
+  if (grad_method == 2) {
+    // ---- Green-Gauss node-based: inverse-distance cell->node interpolation folded into per-cell
+    // coefficients; entries of the same neighbour (shared through two vertices) are merged.
+    g.form = 0;
+    const int nn = m.nnodes;
+    std::vector<double> idw(nn);
+#pragma omp parallel for schedule(static)
+    for (int in = 0; in < nn; in++) {
+      double idt = 0;
+      for (int j = m.n2c_ptr[in]; j < m.n2c_ptr[in + 1]; j++) {
+        const int ic = m.n2c[j];
+        const double dx = m.xc[ic] - m.xn[in], dy = m.yc[ic] - m.yn[in];
+        idt = idt + 1.0 / std::sqrt(dx * dx + dy * dy);
+      }
+      idw[in] = 1.0 / idt;
+    }
+    // pass 1: unique neighbour count per cell; pass 2: fill
+    std::vector<int> cnt(nc);
+    auto gather = [&](int ic, int *ids, double *wx, double *wy, double &c0x, double &c0y) {
+      const int nv = m.nvrt(ic), b = m.cptr[ic];
+      const double xc = m.xc[ic], yc = m.yc[ic];
+      double ex[4] = {0, 0, 0, 0}, ey[4] = {0, 0, 0, 0};  // coefedg per vertex: sum over the two touching edges of n*a/2
+      c0x = c0y = 0;
+      for (int e = 0; e < nv; e++) {
+        const int je = m.cedge[b + e];
+        const double sgn = m.ec1[je] == ic ? 1.0 : -1.0;
+        const double af = m.ea[je], nxf = m.enx[je] * sgn, nyf = m.eny[je] * sgn;
+        const int iv1 = m.en1[je], iv2 = m.en2[je];
+        double dx = xc - m.xn[iv1], dy = yc - m.yn[iv1];
+        const double w1 = 1.0 / std::sqrt(dx * dx + dy * dy);
+        dx = xc - m.xn[iv2]; dy = yc - m.yn[iv2];
+        const double w2 = 1.0 / std::sqrt(dx * dx + dy * dy);
+        c0x = c0x + af * nxf / 2.0 * (w1 * idw[iv1] + w2 * idw[iv2]);
+        c0y = c0y + af * nyf / 2.0 * (w1 * idw[iv1] + w2 * idw[iv2]);
+        for (int v = 0; v < nv; v++) {
+          const int iv = m.cnode[b + v];
+          if (iv == iv1) { ex[v] += af * nxf / 2.0; ey[v] += af * nyf / 2.0; }
+          if (iv == iv2) { ex[v] += af * nxf / 2.0; ey[v] += af * nyf / 2.0; }
+        }
+      }
+      int n = 0;
+      for (int v = 0; v < nv; v++) {
+        const int iv = m.cnode[b + v];
+        for (int j = m.n2c_ptr[iv]; j < m.n2c_ptr[iv + 1]; j++) {
+          const int jc = m.n2c[j];
+          if (jc == ic) continue;  // coefnb = 0 for the cell itself (src/gradient_ggnb.f90:145)
+          const double dx = m.xc[jc] - m.xn[iv], dy = m.yc[jc] - m.yn[iv];
+          const double cnb = idw[iv] / std::sqrt(dx * dx + dy * dy);
+          int p = 0;
+          while (p < n && ids[p] != jc) p++;
+          if (p == n) { ids[n] = jc; wx[n] = 0; wy[n] = 0; n++; }
+          wx[p] += ex[v] * cnb;
+          wy[p] += ey[v] * cnb;
+        }
+      }
+      return n;
+    };
+    int overflow = 0;
+#pragma omp parallel for schedule(static) reduction(+ : overflow)
+    for (int ic = 0; ic < nc; ic++) {
+      int tot = 0;
+      for (int s = m.cptr[ic]; s < m.cptr[ic + 1]; s++) tot += m.n2c_ptr[m.cnode[s] + 1] - m.n2c_ptr[m.cnode[s]];
+      if (tot > 256) { overflow++; cnt[ic] = 0; continue; }
+      int ids[256]; double wx[256], wy[256], a, b2;
+      cnt[ic] = gather(ic, ids, wx, wy, a, b2);
+    }
+    if (overflow) return "build_gradient: node valence too high for the GGNB stencil buffer";
+    for (int ic = 0; ic < nc; ic++) g.ptr[ic + 1] = g.ptr[ic] + cnt[ic];
+    const int64_t tot = g.ptr[nc];
+    g.idx.resize(tot); g.cx.resize(tot); g.cy.resize(tot); g.c0x.resize(nc); g.c0y.resize(nc);
+#pragma omp parallel for schedule(static)
+    for (int ic = 0; ic < nc; ic++) {
+      int ids[256]; double wx[256], wy[256], c0x, c0y;
+      const int n = gather(ic, ids, wx, wy, c0x, c0y);
+      const double vol = m.vol[ic];
+      g.c0x[ic] = c0x / vol; g.c0y[ic] = c0y / vol;
+      // ascending neighbour id: deterministic and memory-friendly
+      int ord[256];
+      for (int i = 0; i < n; i++) ord[i] = i;
+      std::sort(ord, ord + n, [&](int a, int b) { return ids[a] < ids[b]; });
+      for (int i = 0; i < n; i++) {
+        g.idx[g.ptr[ic] + i] = ids[ord[i]];
+        g.cx[g.ptr[ic] + i] = wx[ord[i]] / vol;
+        g.cy[g.ptr[ic] + i] = wy[ord[i]] / vol;
+      }
+    }
+    return "";
+  }
+  if (grad_method != 3) return "check cell-center gradient scheme in input file";
+
+  // ---- least squares: stencil first
+  g.form = 1;
+  std::vector<int> sten;
+  if (lsq_stencil == 0) {
+    // fn: face neighbours; each boundary slot (in nghbr slot order) takes the next nearest centroid
+    // that is neither the cell nor a face neighbour (src/gradient_lsq.f90:88-131)
+    for (int ic = 0; ic < nc; ic++) g.ptr[ic + 1] = m.cptr[ic + 1];
+    sten.assign(g.ptr[nc], -1);
+    std::vector<int> bcells;
+    int too_many = 0;
+    for (int ic = 0; ic < nc; ic++) {
+      const int nv = m.nvrt(ic);
+      int izb = 0;
+      for (int k = 0; k < nv; k++) {
+        const int jc = m.nghbr(ic, k);
+        sten[m.cptr[ic] + k] = jc;
+        izb += jc < 0;
+      }
+      if (izb > 2) too_many++;
+      else if (izb > 0) bcells.push_back(ic);
+    }
+    if (too_many) return "error in gradient_lsq, sub: setup_fn: #s of edges on the boundary>2!";
+    if (!bcells.empty()) {
+      BucketGrid bg;
+      bg.build(m.xc, m.yc);
+      int fail = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : fail)
+      for (int t = 0; t < (int)bcells.size(); t++) {
+        const int ic = bcells[t], nv = m.nvrt(ic), b = m.cptr[ic];
+        Near near[8];
+        knn(bg, m.xc, m.yc, ic, 8, near);
+        int slot = 0;
+        for (int i = 0; i < 8; i++) {
+          while (slot < nv && sten[b + slot] >= 0) slot++;
+          if (slot == nv) break;
+          const int jc = near[i].idx;
+          if (jc == ic || jc == 0x7fffffff) continue;
+          bool isnb = false;
+          for (int k = 0; k < nv; k++) isnb = isnb || m.nghbr(ic, k) == jc;
+          if (!isnb) sten[b + slot] = jc;
+        }
+        for (int k = 0; k < nv; k++) fail += sten[b + k] < 0;
+      }
+      if (fail) return "gradient_lsq setup_fn: could not complete a boundary-cell stencil from the 8 nearest cells";
+    }
+  } else {
+    // nn: sorted unique cells sharing a vertex (src/gradient_lsq.f90:227-271)
+    std::vector<int> cnt(nc);
+    auto collect = [&](int ic, int *tmp) {
+      int nt = 0;
+      for (int s = m.cptr[ic]; s < m.cptr[ic + 1]; s++) {
+        const int iv = m.cnode[s];
+        for (int j = m.n2c_ptr[iv]; j < m.n2c_ptr[iv + 1]; j++)
+          if (m.n2c[j] != ic && nt < 256) tmp[nt++] = m.n2c[j];
+      }
+      std::sort(tmp, tmp + nt);
+      return (int)(std::unique(tmp, tmp + nt) - tmp);
+    };
+#pragma omp parallel for schedule(static)
+    for (int ic = 0; ic < nc; ic++) { int tmp[256]; cnt[ic] = collect(ic, tmp); }
+    for (int ic = 0; ic < nc; ic++) g.ptr[ic + 1] = g.ptr[ic] + cnt[ic];
+    sten.resize(g.ptr[nc]);
+#pragma omp parallel for schedule(static)
+    for (int ic = 0; ic < nc; ic++) { int tmp[256]; int n = collect(ic, tmp); std::copy(tmp, tmp + n, sten.begin() + g.ptr[ic]); }
+  }
+  // ---- normal equations per cell (src/gradient_lsq.f90:137-203 / 281-347)
+  const int64_t tot = g.ptr[nc];
+  g.idx = sten;
+  g.cx.resize(tot); g.cy.resize(tot);
+  double verr = 0;
+  int singular = 0;
+#pragma omp parallel for schedule(static) reduction(max : verr) reduction(+ : singular)
+  for (int ic = 0; ic < nc; ic++) {
+    const double xc = m.xc[ic], yc = m.yc[ic];
+    const int64_t b = g.ptr[ic];
+    const int n = (int)(g.ptr[ic + 1] - b);
+    double g11 = 0, g12 = 0, g21 = 0, g22 = 0;
+    double dxw[256], dyw[256], w[256];
+    for (int i = 0; i < n && i < 256; i++) {
+      const int jc = sten[b + i];
+      const double ddx = m.xc[jc] - xc, ddy = m.yc[jc] - yc;
+      const double dis = std::sqrt(ddx * ddx + ddy * ddy);
+      w[i] = dis > 0.0 ? 1.0 / std::pow(dis, lsq_pow) : 0.0;
+      dxw[i] = w[i] * ddx; dyw[i] = w[i] * ddy;
+    }
+    for (int i = 0; i < n; i++) { g11 += dxw[i] * dxw[i]; g12 += dxw[i] * dyw[i]; g21 += dyw[i] * dxw[i]; g22 += dyw[i] * dyw[i]; }
+    const double det = g11 * g22 - g12 * g21;
+    if (!(std::fabs(det) > 0)) singular++;
+    const double i11 = 1.0 / det * g22, i22 = 1.0 / det * g11, i12 = -1.0 / det * g12, i21 = -1.0 / det * g21;
+    double dfx = 0, dfy = 0;
+    for (int i = 0; i < n; i++) {
+      const double c1 = i11 * dxw[i] + i12 * dyw[i], c2 = i21 * dxw[i] + i22 * dyw[i];
+      g.cx[b + i] = c1 * w[i];  // w folded in: grad = sum coef*w*(p_j - p_i)
+      g.cy[b + i] = c2 * w[i];
+      // linear-exactness self check with f = 2x + y (src/gradient_lsq.f90:490-529)
+      const int jc = sten[b + i];
+      const double diff = 1.0 * m.yc[jc] + 2.0 * m.xc[jc] - (1.0 * yc + 2.0 * xc);
+      dfx += c1 * diff * w[i];
+      dfy += c2 * diff * w[i];
+    }
+    verr = std::max(verr, std::max(std::fabs(dfx - 2.0), std::fabs(dfy - 1.0)));
+  }
+  g.verify_err = verr;
+  if (singular) return "gradient_lsq: singular least-squares system";
+  if (!(verr <= 1.0e-10)) return " LSQ coefficients are not correct";
+  return "";
+}
+
+// ------------------------------------------------------------------------------------------------
+// Hilbert ordering
+// ------------------------------------------------------------------------------------------------
+static inline uint64_t hilbert_d(uint32_t x, uint32_t y, int bits) {
+  uint64_t d = 0;
+  const uint32_t n1 = (1u << bits) - 1;
+  for (uint32_t s = 1u << (bits - 1); s > 0; s >>= 1) {
+    const uint32_t rx = (x & s) ? 1 : 0, ry = (y & s) ? 1 : 0;
+    d += (uint64_t)s * s * ((3 * rx) ^ ry);
+    if (ry == 0) {  // rotate the quadrant; only the bits below s are looked at afterwards
+      if (rx == 1) { x = n1 - x; y = n1 - y; }
+      const uint32_t t = x; x = y; y = t;
+    }
+  }
+  return d;
+}
+
+void hilbert_order(const HostMesh &m, std::vector<int> &perm) {
+  const int nc = m.ncells;
+  const int bits = 20;
+  double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+  for (int i = 0; i < nc; i++) { x0 = std::min(x0, m.xc[i]); x1 = std::max(x1, m.xc[i]); y0 = std::min(y0, m.yc[i]); y1 = std::max(y1, m.yc[i]); }
+  const double span = std::max(std::max(x1 - x0, y1 - y0), 1e-300);
+  const double scale = ((double)(1u << bits) - 1.0) / span;
+  std::vector<uint64_t> key(nc), key2(nc);
+  std::vector<int> idx2(nc);
+  perm.resize(nc);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < nc; i++) {
+    const uint32_t ix = (uint32_t)((m.xc[i] - x0) * scale), iy = (uint32_t)((m.yc[i] - y0) * scale);
+    key[i] = hilbert_d(ix, iy, bits);
+    perm[i] = i;
+  }
+  // LSD radix sort, 5 passes of 8 bits over the 40-bit key; stable, so ties keep the original order
+  for (int pass = 0; pass < 5; pass++) {
+    const int sh = 8 * pass;
+    size_t cnt[257] = {0};
+    for (int i = 0; i < nc; i++) cnt[((key[i] >> sh) & 255) + 1]++;
+    for (int b = 0; b < 256; b++) cnt[b + 1] += cnt[b];
+    for (int i = 0; i < nc; i++) {
+      const size_t p = cnt[(key[i] >> sh) & 255]++;
+      key2[p] = key[i]; idx2[p] = perm[i];
+    }
+    key.swap(key2); perm.swap(idx2);
+  }
+}
+
+}  // namespace fvs2d

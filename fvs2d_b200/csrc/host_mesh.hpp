@@ -1,0 +1,63 @@
+// host_mesh.hpp -- host-side mesh products of the reference's grid_data (src/grid_procs.f90:170-794),
+// rebuilt with the reference's entity numbering by O(n), OpenMP-parallel algorithms.
+// All ids are 0-based; "boundary / none" is -1 where the Fortran stores 0.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace fvs2d {
+
+struct HostMesh {
+  // raw input (what grid_read / grid_bc_read deliver)
+  int nnodes = 0, ntri = 0, nquad = 0, ncells = 0;
+  std::vector<double> xn, yn;
+  std::vector<int> cptr, cnode;  // CSR cell -> node, triangles first
+  int nb = 0;
+  std::vector<int> b_ncells, b_type, b_cell_ptr, b_cell;
+  // derived
+  std::vector<double> xc, yc, vol;
+  std::vector<int> n2c_ptr, n2c;      // node -> cells, ascending cell id (src/grid_procs.f90:275-300)
+  std::vector<int> nghbre;            // per cell-slot: neighbour across local edge k (v_k -> v_k+1), -1 boundary
+  std::vector<int> cedge;             // per cell-slot: global edge id of local edge k
+  int nedges = 0, nedges_intr = 0, nedges_bndr = 0;
+  std::vector<int> en1, en2, ec1, ec2;  // c1 < c2, c2 == -1 on the boundary, normal points c1 -> c2
+  std::vector<double> ex, ey, ea, enx, eny;
+  int ncells_intr = 0, ncells_bndr = 0;
+  std::vector<int> cell_intr;
+  std::vector<int> b_edge_ptr, b_edge;  // boundary edge lists in .bc order then local-edge order
+  std::vector<int> edge_bc;             // per edge: -1 interior, else boundary index ib
+  double heff1 = 0, heff2 = 0, vol_sum = 0, vol_green = 0;
+
+  int nvrt(int ic) const { return cptr[ic + 1] - cptr[ic]; }
+  // nghbr(slot) of the reference: slot k holds the neighbour across local edge (k-2) (src/grid_procs.f90:330-366)
+  int nghbr(int ic, int k) const {
+    int nv = nvrt(ic);
+    return nghbre[cptr[ic] + (k + nv - 2) % nv];
+  }
+};
+
+// Builds everything in `m` from the raw fields.  Returns "" or the reference's stop message.
+std::string build_mesh(HostMesh &m);
+
+// Gradient operators in one generic sparse form (original numbering):
+//   grad_i = c0_i * p_i + sum_k coef_k * p_{idx_k}            (form == 0, Green-Gauss; 1/vol folded in)
+//   grad_i =              sum_k coef_k * (p_{idx_k} - p_i)    (form == 1, least squares; w folded in)
+struct GradOp {
+  int form = 0;
+  std::vector<int64_t> ptr;  // ncells+1
+  std::vector<int> idx;
+  std::vector<double> cx, cy;
+  std::vector<double> c0x, c0y;  // form 0 only
+  double verify_err = 0;         // LSQ: max |grad(2x+y) - (2,1)| (src/gradient_lsq.f90:490-529)
+  // the LSQ stencil itself (the limiter's min/max set, src/gradient_limiter.f90:54-58) is (ptr, idx)
+};
+
+// grad_method 1 GGCB (src/gradient_ggcb.f90:48-110), 2 GGNB (src/gradient_ggnb.f90:49-177),
+// 3 LSQ fn/nn (src/gradient_lsq.f90:70-365).  Returns "" or an error message.
+std::string build_gradient(const HostMesh &m, int grad_method, int lsq_stencil, double lsq_pow, GradOp &g);
+
+// Hilbert-curve ordering of the cell centroids: perm[new] = old.
+void hilbert_order(const HostMesh &m, std::vector<int> &perm);
+
+}  // namespace fvs2d

@@ -1,0 +1,575 @@
+// kernels.cuh -- sm_100a kernels of the fvs2d hot path (fp64, HBM-bound, no tensor cores).
+//
+//   k_gradient   pass A: cell-parallel gradient (+ limiter) from primitive state   [reference K2,K3]
+//   k_flux_rk    pass B: cell-parallel face-flux gather, residual, RK stage update   [reference K4-K9]
+//   k_bc_state   Dirichlet / freestream ghost states of the boundary faces for one stage time
+//   k_prim       conserved -> primitive                                             [reference K1]
+//   k_vortex_err isentropic-vortex error norms                                      [reference K10]
+//   k_finish_*   fixed-order final reductions of the per-CTA partials (no fp atomics anywhere)
+//
+// Data layout: struct-of-arrays with pitch `np` (cells padded to a multiple of 32): var v of cell i is
+// a[v*np + i].  One thread per cell; per-cell lists are sliced ELL (see layout.hpp) so list reads of a
+// warp are coalesced.  Face fluxes are evaluated in the edge's own orientation (c1 -> c2) by both
+// cells, so the two evaluations are bit-identical and the scheme stays discretely conservative.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fvs2d {
+
+constexpr int kBlock = 128;         // threads per CTA for the cell-parallel kernels
+constexpr int kPadNbr = INT32_MIN;  // == kFacePad
+
+enum UpdateMode { UM_RESID = 0, UM_RK = 1, UM_SSPRK = 2 };
+// reconstruction variants: 0 first order (phi=0, no gradients); 1 kappa=0 and phi==1;
+// 2 kappa=0 with a limiter array; 3 general kappa with a phi array
+enum ReconMode { RC_FIRST = 0, RC_K0 = 1, RC_K0_PHI = 2, RC_GENERAL = 3 };
+
+struct DevMesh {
+  int n_own, n_loc, np;  // np: SoA pitch
+  const int *f_off, *f_nbr, *f_edge;
+  const double *ex, *ey, *ea, *enx, *eny;
+  const double *xc, *yc, *vol;
+  const int *g_off, *g_idx;
+  const double *g_cx, *g_cy, *c0x, *c0y;
+  const int *bf_type, *bf_edge;
+  const unsigned char *is_intr;
+  const int *orig_id;
+  int nbf;
+};
+
+struct Phys {
+  double gamma, kappa, cfl;
+  double pinf[4];
+  double vpos[2], vkap, vinf[4];
+  double mms[4][4];
+  int lvortex, limiter;
+};
+
+struct StageParams {
+  int stage;        // 0..3
+  int last;         // stage == nstages-1
+  double h;         // h_rk(stage)   (unsteady)  |  cst (steady: multiplies dt_local)
+  double c;         // rk_coef(stage)
+  double dt;        // global dt
+};
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void vortex_exact(const Phys &P, double t, double x, double y, double pv[4]) {
+  // src/mms.f90:219-265
+  const double pi = 3.141592653589793238462643383279502884;
+  const double rho_inf = P.vinf[0], u_inf = P.vinf[1], v_inf = P.vinf[2], p_inf = P.vinf[3];
+  const double T_inf = p_inf / rho_inf;
+  const double xc = P.vpos[0] + u_inf * t, yc = P.vpos[1] + v_inf * t;
+  const double dx = x - xc, dy = y - yc;
+  const double r = sqrt(dx * dx + dy * dy);
+  const double kk = P.vkap / (2.0 * pi);
+  const double e1 = exp(0.5 * (1.0 - r * r));
+  pv[1] = u_inf - kk * dy * e1;
+  pv[2] = v_inf + kk * dx * e1;
+  const double temp = T_inf - kk * kk * (P.gamma - 1.0) / (2.0 * P.gamma) * exp(1.0 - r * r);
+  const double rho = pow(temp, 1.0 / (P.gamma - 1.0));
+  pv[0] = rho;
+  pv[3] = pow(rho, P.gamma);
+}
+
+__device__ __forceinline__ void mms_exact(const Phys &P, double x, double y, double pv[4]) {
+  // src/mms.f90:137-146 (solution only; nx+ny==0 branch of manufactured_sol :203)
+#pragma unroll
+  for (int v = 0; v < 4; v++) pv[v] = P.mms[v][0] + P.mms[v][1] * sin(P.mms[v][2] * x + P.mms[v][3] * y);
+}
+
+// Roe flux with Harten's entropy fix, primitive inputs (src/flux_invscid.f90:37-136).
+// aL, aR only ever appear squared in the reference (HL = aL*aL/(gamma-1)+kL), so c2 = gamma*p/rho is
+// used directly; divisions by a shared denominator are one reciprocal.
+__device__ __forceinline__ void roe_flux(const double gamma, const double L[4], const double R[4], const double nx,
+                                         const double ny, double flux[4], double &ws_max) {
+  const double gm1 = gamma - 1.0, igm1 = 1.0 / gm1;
+  const double tx = -ny, ty = nx;
+  const double rhoL = L[0], uL = L[1], vL = L[2], pL = L[3];
+  const double rhoR = R[0], uR = R[1], vR = R[2], pR = R[3];
+  const double irL = 1.0 / rhoL;
+  const double unL = uL * nx + vL * ny, unR = uR * nx + vR * ny;
+  const double utL = uL * tx + vL * ty, utR = uR * tx + vR * ty;
+  const double kL = 0.5 * (uL * uL + vL * vL), kR = 0.5 * (uR * uR + vR * vR);
+  const double HL = gamma * pL * irL * igm1 + kL;
+  const double HR = gamma * pR / rhoR * igm1 + kR;
+  const double RT = sqrt(rhoR * irL);
+  const double rho = RT * rhoL;
+  const double iw = 1.0 / (1.0 + RT);
+  const double u = (uL + RT * uR) * iw;
+  const double v = (vL + RT * vR) * iw;
+  const double H = (HL + RT * HR) * iw;
+  const double tke = 0.5 * (u * u + v * v);
+  const double a2 = gm1 * (H - tke);
+  const double a = sqrt(a2);
+  const double ia2 = 1.0 / (a * a);
+  const double un = u * nx + v * ny, ut = u * tx + v * ty;
+  const double drho = rhoR - rhoL, dp = pR - pL, dun = unR - unL, dut = utR - utL;
+  const double l1 = (dp - rho * a * dun) * (0.5 * ia2);
+  const double l2 = rho * dut;
+  const double l3 = drho - dp * ia2;
+  const double l4 = (dp + rho * a * dun) * (0.5 * ia2);
+  double w1 = fabs(un - a), w2 = fabs(un), w4 = fabs(un + a);
+  const double dws = 1.0 / 5.0;
+  if (w1 < dws) w1 = 0.5 * (w1 * w1 / dws + dws);
+  if (w4 < dws) w4 = 0.5 * (w4 * w4 / dws + dws);
+  const double s1 = w1 * l1, s2 = w2 * l2, s3 = w2 * l3, s4 = w4 * l4;
+  // diss_i = sum_j ws_j LdU_j R_ij, j = 1..4 in order (src/flux_invscid.f90:111-116)
+  const double d0 = s1 + s3 + s4;
+  const double d1 = s1 * (u - a * nx) + s2 * tx + s3 * u + s4 * (u + a * nx);
+  const double d2 = s1 * (v - a * ny) + s2 * ty + s3 * v + s4 * (v + a * ny);
+  const double d3 = s1 * (H - un * a) + s2 * ut + s3 * tke + s4 * (H + un * a);
+  const double mL = rhoL * unL, mR = rhoR * unR;
+  flux[0] = 0.5 * (mL + mR - d0);
+  flux[1] = 0.5 * (mL * uL + pL * nx + (mR * uR + pR * nx) - d1);
+  flux[2] = 0.5 * (mL * vL + pL * ny + (mR * vR + pR * ny) - d2);
+  flux[3] = 0.5 * (mL * HL + mR * HR - d3);
+  ws_max = 0.5 * (fabs(un) + a);
+}
+
+// limiter function (src/gradient_limiter.f90:103-134); eps2 is precomputed per cell
+__device__ __forceinline__ double limiter_fn(int type, double a, double b, double eps2) {
+  if (type == 1) return ((a * a + eps2) + 2.0 * b * a) / (a * a + 2.0 * (b * b) + a * b + eps2);
+  if (type == 2) return fmin(1.0, a / b);
+  const double l = ((b * b + eps2) * a + (a * a + eps2) * b) / (a * a + b * b + 2.0 * eps2);
+  return l / (b + eps2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: conserved -> primitive (src/data_solution.f90:72-86)
+__global__ void __launch_bounds__(256) k_prim(int n, int np, double gamma, const double *__restrict__ q, double *__restrict__ p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double r = q[i], ru = q[np + i], rv = q[2 * np + i], re = q[3 * np + i];
+  const double u = ru / r, v = rv / r;
+  p[i] = r;
+  p[np + i] = u;
+  p[2 * np + i] = v;
+  p[3 * np + i] = (gamma - 1.0) * (re - 0.5 * r * (u * u + v * v));
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass A: gradient of the primitive variables (+ limiter) for the owned cells
+//   FORM 0: grad = c0*p_i + sum c_k p_k   (GGCB src/gradient_ggcb.f90:116-138, GGNB src/gradient_ggnb.f90:183-210)
+//   FORM 1: grad = sum c_k (p_k - p_i)    (LSQ src/gradient_lsq.f90:393-401)
+//   LIM: phi_i = min over vars and faces (src/gradient_limiter.f90:47-91); min/max over the stencil
+template <int FORM, bool LIM>
+__global__ void __launch_bounds__(kBlock) k_gradient(const DevMesh m, const int limiter_type, const double *__restrict__ p,
+                                                     double *__restrict__ gx, double *__restrict__ gy,
+                                                     double *__restrict__ phi) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= m.n_own) return;
+  const int np = m.np, lane = threadIdx.x & 31, sl = i >> 5;
+  const int off = __ldg(&m.g_off[sl]);
+  const int w = (__ldg(&m.g_off[sl + 1]) - off) >> 5;
+  double p0[4], ax[4], ay[4], pmin[4], pmax[4];
+#pragma unroll
+  for (int v = 0; v < 4; v++) p0[v] = p[v * np + i];
+  if (FORM == 0) {
+    const double c0x = m.c0x[i], c0y = m.c0y[i];
+#pragma unroll
+    for (int v = 0; v < 4; v++) { ax[v] = c0x * p0[v]; ay[v] = c0y * p0[v]; }
+  } else {
+#pragma unroll
+    for (int v = 0; v < 4; v++) { ax[v] = 0.0; ay[v] = 0.0; }
+  }
+  if (LIM) {
+#pragma unroll
+    for (int v = 0; v < 4; v++) { pmin[v] = p0[v]; pmax[v] = p0[v]; }
+  }
+  for (int k = 0; k < w; k++) {
+    const int e = off + 32 * k + lane;
+    const int j = __ldg(&m.g_idx[e]);
+    const double cx = __ldg(&m.g_cx[e]), cy = __ldg(&m.g_cy[e]);
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      const double pj = p[v * np + j];
+      const double d = FORM == 0 ? pj : pj - p0[v];
+      ax[v] += cx * d;
+      ay[v] += cy * d;
+      if (LIM) { pmin[v] = fmin(pmin[v], pj); pmax[v] = fmax(pmax[v], pj); }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < 4; v++) { gx[v * np + i] = ax[v]; gy[v * np + i] = ay[v]; }
+  if (LIM) {
+    const double pi = 3.141592653589793238462643383279502884;
+    const double xc = m.xc[i], yc = m.yc[i];
+    const double h = 2.0 * sqrt(m.vol[i] / pi);
+    const double kh = (limiter_type == 1 ? 5.0 : 0.3) * h;
+    const double eps2 = kh * kh * kh;
+    const int foff = __ldg(&m.f_off[sl]);
+    const int fw = (__ldg(&m.f_off[sl + 1]) - foff) >> 5;
+    double ph = 1.0;  // min(1, ...) over faces and variables
+    for (int k = 0; k < fw; k++) {
+      const int e = foff + 32 * k + lane;
+      if (__ldg(&m.f_nbr[e]) == kPadNbr) continue;
+      const int ed = __ldg(&m.f_edge[e]) >> 1;
+      const double dx = __ldg(&m.ex[ed]) - xc, dy = __ldg(&m.ey[ed]) - yc;
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        const double pf = p0[v] + dx * ax[v] + dy * ay[v];
+        const double diff = pf - p0[v];
+        double f = 1.0;
+        if (diff > 0.0) f = limiter_fn(limiter_type, pmax[v] - p0[v], diff, eps2);
+        else if (diff < 0.0) f = limiter_fn(limiter_type, pmin[v] - p0[v], diff, eps2);
+        ph = fmin(ph, f);
+      }
+    }
+    phi[i] = ph;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ghost states of the boundary faces that do not depend on the interior state
+// (src/residual.f90:195-217: freestream -> pvar_inf, dirichlet -> vortex(t) or MMS at the face centre)
+__global__ void __launch_bounds__(128) k_bc_state(const DevMesh m, const Phys P, const double time, double *__restrict__ bc /* [4][nbf] */) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= m.nbf) return;
+  const int type = m.bf_type[b];
+  double pv[4] = {0, 0, 0, 0};
+  if (type == 1) {
+#pragma unroll
+    for (int v = 0; v < 4; v++) pv[v] = P.pinf[v];
+  } else if (type == 4) {
+    const int ed = m.bf_edge[b];
+    if (P.lvortex) vortex_exact(P, time, m.ex[ed], m.ey[ed], pv);
+    else mms_exact(P, m.ex[ed], m.ey[ed], pv);
+  }
+#pragma unroll
+  for (int v = 0; v < 4; v++) bc[v * m.nbf + b] = pv[v];
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-wide sum of NV values per thread -> out[blockIdx.x*NV + v] (fixed order, deterministic)
+template <int NV>
+__device__ __forceinline__ void block_sum_store(double val[NV], double *__restrict__ out) {
+  __shared__ double sm[NV][kBlock / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    double x = val[v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) sm[v][wid] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; w++) s += sm[threadIdx.x][w];
+    out[blockIdx.x * NV + threadIdx.x] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass B: face-flux gather + residual + Runge-Kutta stage update for the owned cells.
+//   interior faces  src/residual.f90:66-103     boundary faces  src/residual.f90:111-157
+//   -R/vol          src/residual.f90:164-166    local dt        src/runge_kutta.f90:424-437
+//   RK update       src/runge_kutta.f90:156-162 (RK), :225-226 (SSPRK), :299-313, :383-387 (steady)
+//   norms           src/runge_kutta.f90:169-184 (sum of (q-q0)^2 per CTA -> partial)
+template <int UM, bool STEADY, int RC>
+__global__ void __launch_bounds__(kBlock) k_flux_rk(const DevMesh m, const Phys P, const StageParams S,
+                                                    const double *__restrict__ p, const double *__restrict__ gx,
+                                                    const double *__restrict__ gy, const double *__restrict__ phi,
+                                                    const double *__restrict__ bc, double *__restrict__ q,
+                                                    double *__restrict__ f, double *__restrict__ pout,
+                                                    double *__restrict__ dtl, double *__restrict__ resid_out,
+                                                    double *__restrict__ ws_out, double *__restrict__ partial) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  const bool live = i < m.n_own;
+  const int np = m.np, lane = threadIdx.x & 31;
+  double dq2[4] = {0.0, 0.0, 0.0, 0.0};
+  if (live) {
+    const int sl = i >> 5;
+    const int off = __ldg(&m.f_off[sl]);
+    const int w = (__ldg(&m.f_off[sl + 1]) - off) >> 5;
+    double p0[4], g0x[4], g0y[4];
+#pragma unroll
+    for (int v = 0; v < 4; v++) p0[v] = p[v * np + i];
+    if (RC != RC_FIRST) {
+#pragma unroll
+      for (int v = 0; v < 4; v++) { g0x[v] = gx[v * np + i]; g0y[v] = gy[v * np + i]; }
+    }
+    const double x0 = m.xc[i], y0 = m.yc[i];
+    const double phi0 = (RC >= RC_K0_PHI) ? phi[i] : 1.0;
+    const double kap = P.kappa;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0}, wsacc = 0.0;
+    for (int k = 0; k < w; k++) {
+      const int e = off + 32 * k + lane;
+      const int nb = __ldg(&m.f_nbr[e]);
+      if (nb == kPadNbr) continue;
+      const int fe = __ldg(&m.f_edge[e]);
+      const int ed = fe >> 1;
+      const bool self_c1 = (fe & 1) == 0;
+      const double xf = __ldg(&m.ex[ed]), yf = __ldg(&m.ey[ed]), af = __ldg(&m.ea[ed]);
+      const double nx = __ldg(&m.enx[ed]), ny = __ldg(&m.eny[ed]);
+      double me[4];  // this cell's reconstruction increment (x_f - x_c) . grad p
+      if (RC != RC_FIRST) {
+        const double dx = xf - x0, dy = yf - y0;
+#pragma unroll
+        for (int v = 0; v < 4; v++) me[v] = dx * g0x[v] + dy * g0y[v];
+      }
+      double flux[4], ws;
+      if (nb >= 0) {
+        double pj[4], ot[4];
+#pragma unroll
+        for (int v = 0; v < 4; v++) pj[v] = p[v * np + nb];
+        double phij = 1.0;
+        if (RC != RC_FIRST) {
+          const double dx = xf - m.xc[nb], dy = yf - m.yc[nb];
+#pragma unroll
+          for (int v = 0; v < 4; v++) ot[v] = dx * gx[v * np + nb] + dy * gy[v * np + nb];
+          if (RC >= RC_K0_PHI) phij = phi[nb];
+        }
+        double sL[4], sR[4];
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+          // edge orientation: L = c1, R = c2
+          const double pL = self_c1 ? p0[v] : pj[v], pR = self_c1 ? pj[v] : p0[v];
+          if (RC == RC_FIRST) { sL[v] = pL; sR[v] = pR; }
+          else {
+            const double gL = self_c1 ? me[v] : ot[v], gR = self_c1 ? ot[v] : me[v];
+            const double fL = self_c1 ? phi0 : phij, fR = self_c1 ? phij : phi0;
+            if (RC == RC_K0) { sL[v] = pL + gL; sR[v] = pR + gR; }
+            else if (RC == RC_K0_PHI) { sL[v] = pL + fL * gL; sR[v] = pR + fR * gR; }
+            else {
+              const double gC = pR - pL;
+              sL[v] = pL + fL * (kap / 2.0 * gC + (1.0 - kap) * gL);
+              sR[v] = pR + fR * (-kap / 2.0 * gC + (1.0 - kap) * gR);
+            }
+          }
+        }
+        roe_flux(P.gamma, sL, sR, nx, ny, flux, ws);
+        const double sa = self_c1 ? af : -af;
+#pragma unroll
+        for (int v = 0; v < 4; v++) acc[v] += flux[v] * sa;
+        wsacc += ws * af;
+      } else {
+        // boundary face: this cell is c1 (src/residual.f90:125-155)
+        const int b = -1 - nb;
+        const int type = __ldg(&m.bf_type[b]);
+        double sL[4], sR[4];
+#pragma unroll
+        for (int v = 0; v < 4; v++) sL[v] = (RC == RC_FIRST) ? p0[v] : p0[v] + phi0 * me[v];
+        if (type == 2) {  // slip wall: mirror the normal velocity
+          const double un = sL[1] * nx + sL[2] * ny;
+          sR[0] = sL[0]; sR[3] = sL[3];
+          sR[1] = sL[1] - 2.0 * un * nx;
+          sR[2] = sL[2] - 2.0 * un * ny;
+        } else {
+#pragma unroll
+          for (int v = 0; v < 4; v++) sR[v] = __ldg(&bc[v * m.nbf + b]);
+        }
+        roe_flux(P.gamma, sL, sR, nx, ny, flux, ws);
+#pragma unroll
+        for (int v = 0; v < 4; v++) acc[v] += flux[v] * af;
+        wsacc += ws * af;
+      }
+    }
+    const double vol = m.vol[i];
+    double R[4];
+#pragma unroll
+    for (int v = 0; v < 4; v++) R[v] = -acc[v] / vol;
+
+    if (UM == UM_RESID) {
+#pragma unroll
+      for (int v = 0; v < 4; v++) resid_out[v * np + i] = R[v];
+      if (ws_out) ws_out[i] = wsacc;
+    } else {
+      double h = S.h;
+      if (STEADY) {
+        double dl;
+        if (S.stage == 0) { dl = P.cfl * vol / (0.5 * wsacc); dtl[i] = dl; }
+        else dl = dtl[i];
+        h = dl * S.h;
+      }
+      double q0[4], fo[4], qn[4];
+#pragma unroll
+      for (int v = 0; v < 4; v++) q0[v] = q[v * np + i];
+#pragma unroll
+      for (int v = 0; v < 4; v++) fo[v] = (S.stage == 0) ? 0.0 : f[v * np + i];
+      if (UM == UM_RK) {
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+          const double fn = fo[v] + S.c * R[v];
+          qn[v] = S.last ? q0[v] + h * fn : q0[v] + h * R[v];
+          if (!S.last) f[v * np + i] = fn;
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+          qn[v] = q0[v] + h * (S.c * R[v] + fo[v]);
+          if (!S.last) f[v * np + i] = fo[v] + R[v];
+        }
+      }
+      // primitive state for the next stage (cvar2pvar of the next compute_residual)
+      const double u = qn[1] / qn[0], vv = qn[2] / qn[0];
+      pout[i] = qn[0];
+      pout[np + i] = u;
+      pout[2 * np + i] = vv;
+      pout[3 * np + i] = (P.gamma - 1.0) * (qn[3] - 0.5 * qn[0] * (u * u + vv * vv));
+      if (S.last) {
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+          q[v * np + i] = qn[v];
+          const double d = fabs(qn[v] - q0[v]);
+          dq2[v] = d * d;
+        }
+      }
+    }
+  }
+  if (UM != UM_RESID && S.last) block_sum_store<4>(dq2, partial);
+}
+
+// ------------------------------------------------------------------------------------------------
+// final reduction of per-CTA partial sums: out[v] = sum_b partial[b*NV+v], one CTA, fixed order
+template <int NV>
+__global__ void __launch_bounds__(256) k_finish_sum(const double *__restrict__ partial, int nblocks, double *__restrict__ out) {
+  __shared__ double sm[256];
+  for (int v = 0; v < NV; v++) {
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) s += partial[(size_t)b * NV + v];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[v] = sm[0];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K10: vortex error norms over the interior cells (src/mms.f90:315-361).  Per CTA:
+// partial[b*13 + 0..3] = max |dq_v|, [4..7] = sum |dq_v|, [8..11] = sum dq_v^2, [12] = best rho error;
+// best_id[b] = original id of the first cell attaining it.
+__global__ void __launch_bounds__(kBlock) k_vortex_err(const DevMesh m, const Phys P, const double time,
+                                                       const double *__restrict__ q, double *__restrict__ partial,
+                                                       int *__restrict__ best_id) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  const int np = m.np;
+  double d[4] = {0, 0, 0, 0};
+  int oid = 0x7fffffff;
+  bool use = false;
+  if (i < m.n_own && m.is_intr[i]) {
+    use = true;
+    double pv[4];
+    vortex_exact(P, time, m.xc[i], m.yc[i], pv);
+    const double ex0 = pv[0], ex1 = pv[0] * pv[1], ex2 = pv[0] * pv[2];
+    const double ex3 = pv[3] / (P.gamma - 1.0) + 0.5 * pv[0] * (pv[1] * pv[1] + pv[2] * pv[2]);
+    d[0] = fabs(q[i] - ex0);
+    d[1] = fabs(q[np + i] - ex1);
+    d[2] = fabs(q[2 * np + i] - ex2);
+    d[3] = fabs(q[3 * np + i] - ex3);
+    oid = m.orig_id[i];
+  }
+  __shared__ double smx[4][kBlock / 32], s1[4][kBlock / 32], s2[4][kBlock / 32], sb[kBlock / 32];
+  __shared__ int sid[kBlock / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double bv = use ? d[0] : -1.0;
+  int bi = oid;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+#pragma unroll
+  for (int v = 0; v < 4; v++) {
+    double mx = d[v], a = d[v], b = d[v] * d[v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+      a += __shfl_down_sync(0xffffffffu, a, o);
+      b += __shfl_down_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) { smx[v][wid] = mx; s1[v][wid] = a; s2[v][wid] = b; }
+  }
+  if (lane == 0) { sb[wid] = bv; sid[wid] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    const int v = threadIdx.x;
+    double mx = 0, a = 0, b = 0;
+    for (int w = 0; w < kBlock / 32; w++) { mx = fmax(mx, smx[v][w]); a += s1[v][w]; b += s2[v][w]; }
+    partial[(size_t)blockIdx.x * 13 + v] = mx;
+    partial[(size_t)blockIdx.x * 13 + 4 + v] = a;
+    partial[(size_t)blockIdx.x * 13 + 8 + v] = b;
+  }
+  if (threadIdx.x == 0) {
+    double bb = sb[0]; int ii = sid[0];
+    for (int w = 1; w < kBlock / 32; w++)
+      if (sb[w] > bb || (sb[w] == bb && sid[w] < ii)) { bb = sb[w]; ii = sid[w]; }
+    partial[(size_t)blockIdx.x * 13 + 12] = bb;
+    best_id[blockIdx.x] = ii;
+  }
+}
+
+// out[0..3] max, [4..7] sum, [8..11] sum of squares, [12] best value; out_id[0] = original id of the best cell
+__global__ void __launch_bounds__(256) k_finish_vortex(const double *__restrict__ partial, const int *__restrict__ best_id,
+                                                        int nblocks, double *__restrict__ out, int *__restrict__ out_id) {
+  __shared__ double sm[256];
+  __shared__ int si[256];
+  for (int v = 0; v < 12; v++) {
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) {
+      const double x = partial[(size_t)b * 13 + v];
+      s = v < 4 ? fmax(s, x) : s + x;
+    }
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) sm[threadIdx.x] = v < 4 ? fmax(sm[threadIdx.x], sm[threadIdx.x + o]) : sm[threadIdx.x] + sm[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[v] = sm[0];
+    __syncthreads();
+  }
+  double bv = -1.0; int bi = 0x7fffffff;
+  for (int b = threadIdx.x; b < nblocks; b += 256) {
+    const double x = partial[(size_t)b * 13 + 12];
+    const int id = best_id[b];
+    if (x > bv || (x == bv && id < bi)) { bv = x; bi = id; }
+  }
+  sm[threadIdx.x] = bv; si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const double x = sm[threadIdx.x + o]; const int id = si[threadIdx.x + o];
+      if (x > sm[threadIdx.x] || (x == sm[threadIdx.x] && id < si[threadIdx.x])) { sm[threadIdx.x] = x; si[threadIdx.x] = id; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[12] = sm[0]; out_id[0] = si[0]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// halo pack: buf[v*n + k] = a[v*np + idx[k]] for nv variables
+__global__ void __launch_bounds__(256) k_pack(int n, int nv, int np, const int *__restrict__ idx, const double *__restrict__ a,
+                                               double *__restrict__ buf) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int i = idx[k];
+  for (int v = 0; v < nv; v++) buf[(size_t)v * n + k] = a[(size_t)v * np + i];
+}
+
+// permuting copies between the caller's (4,ncells) AoS arrays (original numbering, staged on the device)
+// and the device SoA (local numbering)
+__global__ void __launch_bounds__(256) k_scatter_in(int n, int np, int nvar, const int *__restrict__ orig_id,
+                                                     const double *__restrict__ aos, double *__restrict__ soa) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t o = orig_id[i];
+  for (int v = 0; v < nvar; v++) soa[(size_t)v * np + i] = aos[o * nvar + v];
+}
+__global__ void __launch_bounds__(256) k_gather_out(int n, int np, int nvar, const int *__restrict__ orig_id,
+                                                     const double *__restrict__ soa, double *__restrict__ aos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t o = orig_id[i];
+  for (int v = 0; v < nvar; v++) aos[o * nvar + v] = soa[(size_t)v * np + i];
+}
+
+}  // namespace fvs2d

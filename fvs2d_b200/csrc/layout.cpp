@@ -1,0 +1,225 @@
+// layout.cpp -- see layout.hpp.
+#include "layout.hpp"
+
+#include <algorithm>
+#include <cstdio>
+
+namespace fvs2d {
+
+namespace {
+struct FaceTmp {
+  int key_b;   // 0 interior, 1+ib boundary: the reference sums interior edges first, then the boundaries in .bc order
+  int edge;    // original global edge id (ascending = the reference's accumulation order, src/residual.f90:66,111)
+  int nbr;     // original neighbour id or -1
+};
+}  // namespace
+
+std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<int> &perm, int rank, int nranks, Layout &L) {
+  const int nc = m.ncells;
+  L = Layout();
+  L.rank = rank; L.nranks = nranks; L.nc_global = nc;
+  L.perm = perm;
+  std::vector<int> iperm(nc);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < nc; i++) iperm[perm[i]] = i;
+  auto range_begin = [&](int r) { return (int)((int64_t)nc * r / nranks); };
+  const int b0 = range_begin(rank), b1 = range_begin(rank + 1);
+  L.own_begin = b0;
+  L.n_own = b1 - b0;
+  L.g_form = g.form;
+
+  // ---- ghosts: everything an owned cell reads that it does not own
+  std::vector<int> new2loc;
+  std::vector<int> ghosts;
+  if (nranks > 1) {
+    std::vector<unsigned char> mark(nc, 0);
+#pragma omp parallel for schedule(static)
+    for (int i = b0; i < b1; i++) {
+      const int o = perm[i];
+      for (int s = m.cptr[o]; s < m.cptr[o + 1]; s++) {
+        const int j = m.nghbre[s];
+        if (j >= 0) { const int jn = iperm[j]; if (jn < b0 || jn >= b1) mark[jn] = 1; }
+      }
+      for (int64_t t = g.ptr[o]; t < g.ptr[o + 1]; t++) {
+        const int jn = iperm[g.idx[t]];
+        if (jn < b0 || jn >= b1) mark[jn] = 1;
+      }
+    }
+    for (int i = 0; i < nc; i++) if (mark[i]) ghosts.push_back(i);
+  }
+  L.n_loc = L.n_own + (int)ghosts.size();
+  L.loc2new.resize(L.n_loc);
+  for (int i = 0; i < L.n_own; i++) L.loc2new[i] = b0 + i;
+  for (size_t k = 0; k < ghosts.size(); k++) L.loc2new[L.n_own + k] = ghosts[k];
+  auto to_local = [&](int newid) -> int {
+    if (newid >= b0 && newid < b1) return newid - b0;
+    return new2loc[newid];
+  };
+  if (nranks > 1) {
+    new2loc.assign(nc, -1);
+    for (size_t k = 0; k < ghosts.size(); k++) new2loc[ghosts[k]] = L.n_own + (int)k;
+  }
+
+  // ---- per-cell data
+  L.orig_id.resize(L.n_loc); L.xc.resize(L.n_loc); L.yc.resize(L.n_loc);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < L.n_loc; i++) {
+    const int o = perm[L.loc2new[i]];
+    L.orig_id[i] = o; L.xc[i] = m.xc[o]; L.yc[i] = m.yc[o];
+  }
+  L.vol.resize(L.n_own); L.is_intr.resize(L.n_own);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < L.n_own; i++) {
+    const int o = L.orig_id[i];
+    L.vol[i] = m.vol[o];
+    bool intr = true;
+    for (int s = m.cptr[o]; s < m.cptr[o + 1]; s++) intr = intr && m.nghbre[s] >= 0;
+    L.is_intr[i] = intr;
+  }
+
+  // ---- local edge numbering by first touch (sequential: order matters)
+  std::vector<int> edge_loc(m.nedges, -1);
+  int ne_loc = 0, nbf = 0;
+  for (int i = 0; i < L.n_own; i++) {
+    const int o = L.orig_id[i];
+    for (int s = m.cptr[o]; s < m.cptr[o + 1]; s++) {
+      const int je = m.cedge[s];
+      if (edge_loc[je] < 0) edge_loc[je] = ne_loc++;
+      nbf += m.nghbre[s] < 0;
+    }
+  }
+  L.nedges = ne_loc;
+  L.ex.resize(ne_loc); L.ey.resize(ne_loc); L.ea.resize(ne_loc); L.enx.resize(ne_loc); L.eny.resize(ne_loc);
+#pragma omp parallel for schedule(static)
+  for (int je = 0; je < m.nedges; je++) {
+    const int l = edge_loc[je];
+    if (l >= 0) { L.ex[l] = m.ex[je]; L.ey[l] = m.ey[je]; L.ea[l] = m.ea[je]; L.enx[l] = m.enx[je]; L.eny[l] = m.eny[je]; }
+  }
+
+  // ---- faces as sliced ELL
+  const int nsl = L.nslices = (L.n_own + 31) / 32;
+  L.f_off.assign(nsl + 1, 0);
+  L.g_off.assign(nsl + 1, 0);
+  for (int s = 0; s < nsl; s++) {
+    int wf = 0, wg = 0;
+    for (int i = 32 * s; i < std::min(L.n_own, 32 * s + 32); i++) {
+      const int o = L.orig_id[i];
+      wf = std::max(wf, m.cptr[o + 1] - m.cptr[o]);
+      wg = std::max(wg, (int)(g.ptr[o + 1] - g.ptr[o]));
+    }
+    const int64_t nf = (int64_t)L.f_off[s] + 32 * wf, ng = (int64_t)L.g_off[s] + 32 * wg;
+    if (nf > INT32_MAX || ng > INT32_MAX) return "build_layout: per-GPU list exceeds 2^31 entries; use more GPUs";
+    L.f_off[s + 1] = (int)nf;
+    L.g_off[s + 1] = (int)ng;
+  }
+  L.f_nbr.assign(L.f_off[nsl], kFacePad);
+  L.f_edge.assign(L.f_off[nsl], 0);
+  L.nbf = nbf;
+  L.bf_type.resize(nbf); L.bf_edge.resize(nbf);
+  // boundary-face ids: sequential in cell order
+  std::vector<int> bf_start(L.n_own + 1, 0);
+  for (int i = 0; i < L.n_own; i++) {
+    const int o = L.orig_id[i];
+    int c = 0;
+    for (int s = m.cptr[o]; s < m.cptr[o + 1]; s++) c += m.nghbre[s] < 0;
+    bf_start[i + 1] = bf_start[i] + c;
+  }
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < L.n_own; i++) {
+    const int o = L.orig_id[i];
+    const int nv = m.cptr[o + 1] - m.cptr[o];
+    FaceTmp f[4];
+    for (int k = 0; k < nv; k++) {
+      const int s = m.cptr[o] + k, je = m.cedge[s];
+      f[k].edge = je; f[k].nbr = m.nghbre[s];
+      f[k].key_b = m.nghbre[s] >= 0 ? 0 : 1 + m.edge_bc[je];
+    }
+    std::sort(f, f + nv, [](const FaceTmp &a, const FaceTmp &b) { return a.key_b != b.key_b ? a.key_b < b.key_b : a.edge < b.edge; });
+    const int sl = i >> 5, lane = i & 31;
+    int bf = bf_start[i];
+    for (int k = 0; k < nv; k++) {
+      const int e = L.f_off[sl] + 32 * k + lane;
+      const int le = edge_loc[f[k].edge];
+      L.f_edge[e] = 2 * le + (m.ec1[f[k].edge] == o ? 0 : 1);
+      if (f[k].nbr >= 0) {
+        L.f_nbr[e] = to_local(iperm[f[k].nbr]);
+      } else {
+        L.f_nbr[e] = -1 - bf;
+        L.bf_type[bf] = m.b_type[m.edge_bc[f[k].edge]];
+        L.bf_edge[bf] = le;
+        bf++;
+      }
+    }
+  }
+
+  // ---- gradient stencil as sliced ELL (padding: the cell itself with zero weight)
+  L.g_idx.resize(L.g_off[nsl]);
+  L.g_cx.assign(L.g_off[nsl], 0.0);
+  L.g_cy.assign(L.g_off[nsl], 0.0);
+  if (g.form == 0) { L.c0x.resize(L.n_own); L.c0y.resize(L.n_own); }
+#pragma omp parallel for schedule(static)
+  for (int s = 0; s < nsl; s++) {
+    const int w = (L.g_off[s + 1] - L.g_off[s]) >> 5;
+    for (int lane = 0; lane < 32; lane++) {
+      const int i = 32 * s + lane;
+      const bool live = i < L.n_own;
+      const int o = live ? L.orig_id[i] : 0;
+      const int n = live ? (int)(g.ptr[o + 1] - g.ptr[o]) : 0;
+      for (int k = 0; k < w; k++) {
+        const int e = L.g_off[s] + 32 * k + lane;
+        if (k < n) {
+          L.g_idx[e] = to_local(iperm[g.idx[g.ptr[o] + k]]);
+          L.g_cx[e] = g.cx[g.ptr[o] + k];
+          L.g_cy[e] = g.cy[g.ptr[o] + k];
+        } else {
+          L.g_idx[e] = live ? i : 0;
+        }
+      }
+      if (live && g.form == 0) { L.c0x[i] = g.c0x[o]; L.c0y[i] = g.c0y[o]; }
+    }
+  }
+
+  // ---- halo plan
+  if (nranks > 1) {
+    std::vector<std::vector<unsigned char>> need(nranks);
+    for (int p = 0; p < nranks; p++) {
+      if (p == rank) continue;
+      const int p0 = range_begin(p), p1 = range_begin(p + 1);
+      std::vector<unsigned char> &mask = need[p];
+      mask.assign(L.n_own, 0);
+      bool any = false;
+#pragma omp parallel for schedule(static) reduction(|| : any)
+      for (int i = p0; i < p1; i++) {
+        const int o = perm[i];
+        for (int s = m.cptr[o]; s < m.cptr[o + 1]; s++) {
+          const int j = m.nghbre[s];
+          if (j >= 0) { const int jn = iperm[j]; if (jn >= b0 && jn < b1) { mask[jn - b0] = 1; any = true; } }
+        }
+        for (int64_t t = g.ptr[o]; t < g.ptr[o + 1]; t++) {
+          const int jn = iperm[g.idx[t]];
+          if (jn >= b0 && jn < b1) { mask[jn - b0] = 1; any = true; }
+        }
+      }
+      if (!any) mask.clear();
+    }
+    L.send_ptr.push_back(0);
+    for (int p = 0; p < nranks; p++) {
+      if (p == rank) continue;
+      const int p0 = range_begin(p), p1 = range_begin(p + 1);
+      // ghosts owned by p: contiguous run of the sorted ghost list
+      const int gb = (int)(std::lower_bound(ghosts.begin(), ghosts.end(), p0) - ghosts.begin());
+      const int ge = (int)(std::lower_bound(ghosts.begin(), ghosts.end(), p1) - ghosts.begin());
+      const bool sends = !need[p].empty();
+      if (ge == gb && !sends) continue;
+      L.peers.push_back(p);
+      L.recv_begin.push_back(L.n_own + gb);
+      L.recv_count.push_back(ge - gb);
+      if (sends)
+        for (int i = 0; i < L.n_own; i++) if (need[p][i]) L.send_idx.push_back(i);
+      L.send_ptr.push_back((int)L.send_idx.size());
+    }
+  }
+  return "";
+}
+
+}  // namespace fvs2d

@@ -1,0 +1,57 @@
+// layout.hpp -- the device-side data layout, built on the host from HostMesh + GradOp.
+//
+// Cells are renumbered along a Hilbert curve ("new" ids).  A rank owns a contiguous range of new ids
+// (the whole mesh on one GPU) and additionally stores ghost copies of every cell its owned cells read
+// (face neighbours and gradient-stencil members).  Local ids: owned cells first in new-id order, then
+// ghosts sorted by new id -- so the ghosts received from one peer are one contiguous run.
+//
+// Per-cell lists (faces, gradient stencil) are stored as sliced ELL with slices of 32 cells (one warp):
+// entry (k, lane) of slice s sits at off[s] + 32*k + lane, so every list access of a warp is coalesced.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "host_mesh.hpp"
+
+namespace fvs2d {
+
+constexpr int kFacePad = INT32_MIN;  // f_nbr value of a padding entry (triangle in a width-4 slice)
+
+struct Layout {
+  int rank = 0, nranks = 1;
+  int nc_global = 0;
+  int n_own = 0, n_loc = 0;        // owned cells, owned + ghost cells
+  int own_begin = 0;               // first owned new id
+  std::vector<int> perm;           // global: new id -> original id
+  std::vector<int> loc2new;        // local id -> new id (owned: own_begin + i)
+  std::vector<int> orig_id;        // local id -> original id
+  // per local cell
+  std::vector<double> xc, yc;
+  // per owned cell
+  std::vector<double> vol;
+  std::vector<unsigned char> is_intr;  // cell_intr membership (no boundary face), src/grid_procs.f90:704-720
+  // faces, sliced ELL over owned cells
+  int nslices = 0;
+  std::vector<int> f_off;    // nslices+1 entry offsets
+  std::vector<int> f_nbr;    // local id of the neighbour | -1-bf (bf = local boundary-face id) | kFacePad
+  std::vector<int> f_edge;   // 2*local_edge + (0 if this cell is the edge's c1, else 1)
+  // local edges (those touched by owned cells), numbered by first touch
+  int nedges = 0;
+  std::vector<double> ex, ey, ea, enx, eny;
+  // local boundary faces
+  int nbf = 0;
+  std::vector<int> bf_type, bf_edge;
+  // gradient stencil, sliced ELL over owned cells
+  int g_form = 0;
+  std::vector<int> g_off, g_idx;
+  std::vector<double> g_cx, g_cy, c0x, c0y;
+  // halo plan: peers in ascending rank; send_idx = owned local ids the peer needs (ascending new id),
+  // recv = contiguous run [recv_begin, recv_begin+recv_count) of local ghost ids
+  std::vector<int> peers, send_ptr, send_idx, recv_begin, recv_count;
+};
+
+// Builds the layout of `rank` out of `nranks` (equal contiguous chunks of the Hilbert order).
+std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<int> &perm, int rank, int nranks, Layout &L);
+
+}  // namespace fvs2d
