@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="mesh refinement factor relative to the named workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library tuning option key=value (fvs2d_gpu_set_option)")
     args = ap.parse_args()
     K, W = args.steps, max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
@@ -196,6 +197,9 @@ def main():
     mesh, run, desc, (bA, bB) = make_workload(args.workload, ngpus, args.scale)
     cfg = run.to_config(ngpus)
     gpu = solver.Fvs2dGpu(cfg, device=local_rank, comm=comm)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        gpu.set_option(k, int(v))
     gpu.set_mesh(mesh)
     gpu.initialize_solution()
     sizes, scal = gpu.sizes(), gpu.scalars()

@@ -73,6 +73,11 @@ struct Ctx {
   size_t stage_aos_len = 0;
   double *logbuf = nullptr; int *logid = nullptr; size_t log_cap = 0;
   int *send_idx = nullptr; double *sendbuf = nullptr;
+  TileMeta tm{};
+  PipeMeta pm{};
+  int opt_tile = 2;      // pass-B kernel: 2 persistent smem pipeline (default), 1 one-tile-per-CTA smem kernel, 0 direct gather
+  bool tile_ok = false;
+  int nsm = 148, nparts = 0;
   bool bc_static_done = false;
   double rk_coef[4], h_rk[4], dts[4], dte[4];
   // timing
@@ -254,18 +259,49 @@ int launch_gradient(const double *p) {
   return 0;
 }
 
-template <int UM, bool STEADY>
-void launch_flux_rc(const StageParams &S, const double *pin, double *pout) {
+template <int UM, bool STEADY, int RC>
+void launch_flux_one(const StageParams &S, const double *pin, double *pout) {
   const double *gx = C->g, *gy = C->g + 4 * (size_t)C->np;
   const int nb = C->nblocks;
-#define GO(RC) k_flux_rk<UM, STEADY, RC><<<nb, kBlock, 0, C->st>>>(C->dm, C->phys, S, pin, gx, gy, C->phi, C->bc, C->q, C->f, pout, C->dtl, C->resid, C->ws, C->partial)
-  switch (C->recon) {
-    case RC_FIRST: GO(RC_FIRST); break;
-    case RC_K0: GO(RC_K0); break;
-    case RC_K0_PHI: GO(RC_K0_PHI); break;
-    default: GO(RC_GENERAL); break;
+  constexpr int NCA = RC == RC_FIRST ? 4 : (RC == RC_K0 ? 14 : 15);
+  if (C->tile_ok && C->opt_tile == 2) {
+    const size_t stage = ((size_t)NCA * C->pm.S + 5 * (size_t)C->pm.E) * 8 + 4 * kBlock * 4 + 16;
+    const size_t smem = kStages * stage + 4 * sizeof(uint64_t);
+    static size_t configured = 0;
+    if (configured < smem) {
+      cudaFuncSetAttribute(k_flux_pipe<UM, STEADY, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured = smem;
+    }
+    const int per_sm = std::max(1, std::min(3, (int)((227 * 1024) / (smem + 1024))));
+    const int grid = std::min(C->pm.ntiles, C->nsm * per_sm);
+    k_flux_pipe<UM, STEADY, RC><<<grid, kPipeThreads, smem, C->st>>>(C->dm, C->pm, C->phys, S, pin, gx, gy, C->phi, C->bc, C->q, C->f,
+                                                                     pout, C->dtl, C->resid, C->ws, C->partial);
+    C->nparts = grid;
+  } else if (C->tile_ok && C->opt_tile == 1) {
+    const size_t smem = ((size_t)NCA * C->tm.S + 5 * (size_t)C->tm.E) * 8 + 16;
+    static size_t configured = 0;
+    if (configured < smem) {
+      cudaFuncSetAttribute(k_flux_tile<UM, STEADY, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured = smem;
+    }
+    k_flux_tile<UM, STEADY, RC><<<nb, kBlock, smem, C->st>>>(C->dm, C->tm, C->phys, S, pin, gx, gy, C->phi, C->bc, C->q, C->f, pout,
+                                                             C->dtl, C->resid, C->ws, C->partial);
+    C->nparts = nb;
+  } else {
+    k_flux_rk<UM, STEADY, RC><<<nb, kBlock, 0, C->st>>>(C->dm, C->phys, S, pin, gx, gy, C->phi, C->bc, C->q, C->f, pout, C->dtl,
+                                                        C->resid, C->ws, C->partial);
+    C->nparts = nb;
   }
-#undef GO
+}
+
+template <int UM, bool STEADY>
+void launch_flux_rc(const StageParams &S, const double *pin, double *pout) {
+  switch (C->recon) {
+    case RC_FIRST: launch_flux_one<UM, STEADY, RC_FIRST>(S, pin, pout); break;
+    case RC_K0: launch_flux_one<UM, STEADY, RC_K0>(S, pin, pout); break;
+    case RC_K0_PHI: launch_flux_one<UM, STEADY, RC_K0_PHI>(S, pin, pout); break;
+    default: launch_flux_one<UM, STEADY, RC_GENERAL>(S, pin, pout); break;
+  }
 }
 
 int launch_flux(int um, const StageParams &S, const double *pin, double *pout) {
@@ -323,6 +359,7 @@ int fvs2d_gpu_init(const fvs2d_config *cfg, int device) {
   C->device = device;
   CUDA_OK(cudaSetDevice(device));
   CUDA_OK(cudaStreamCreateWithFlags(&C->st, cudaStreamNonBlocking));
+  CUDA_OK(cudaDeviceGetAttribute(&C->nsm, cudaDevAttrMultiProcessorCount, device));
   CUDA_OK(cudaEventCreate(&C->ev0));
   CUDA_OK(cudaEventCreate(&C->ev1));
   // scheme validation: the stop conditions of src/input.f90:181-277 and the limiter/LSQ coupling
@@ -440,7 +477,31 @@ int fvs2d_gpu_set_mesh(int nnodes, int ntri, int nquad, const double *node_xy, c
   C->nblocks = cdiv(L.n_own, kBlock);
   if (dev_upload(d.f_off, L.f_off) || dev_upload(d.f_nbr, L.f_nbr) || dev_upload(d.f_edge, L.f_edge)) return 1;
   if (dev_upload(d.ex, L.ex) || dev_upload(d.ey, L.ey) || dev_upload(d.ea, L.ea) || dev_upload(d.enx, L.enx) || dev_upload(d.eny, L.eny)) return 1;
-  if (dev_upload(d.xc, L.xc) || dev_upload(d.yc, L.yc) || dev_upload(d.vol, L.vol)) return 1;
+  {  // per-cell geometry padded to the SoA pitch (tile bulk copies read whole even-sized runs)
+    std::vector<double> xc(L.xc), yc(L.yc), vol(L.vol);
+    xc.resize(C->np, 0.0); yc.resize(C->np, 0.0); vol.resize(C->np, 1.0);
+    if (dev_upload(d.xc, xc) || dev_upload(d.yc, yc) || dev_upload(d.vol, vol)) return 1;
+  }
+  C->tile_ok = L.tile_hc_max >= 0;
+  if (C->tile_ok) {
+    TileMeta &t = C->tm;
+    const uint32_t *fp;
+    if (dev_upload(t.es, L.tile_es) || dev_upload(t.ne, L.tile_ne) || dev_upload(t.hc_ptr, L.tile_hc_ptr) ||
+        dev_upload(t.he_ptr, L.tile_he_ptr) || dev_upload(t.hc_idx, L.tile_hc_idx) || dev_upload(t.he_idx, L.tile_he_idx) ||
+        dev_upload(fp, L.f_pack) || dev_upload(t.f_bf, L.f_bf)) return 1;
+    t.f_pack = fp;
+    t.S = (kBlock + L.tile_hc_max + 1) & ~1;
+    t.E = (L.tile_e_max + 1) & ~1;
+    PipeMeta &pmeta = C->pm;
+    const int *hdr; const uint32_t *tp;
+    if (dev_upload(hdr, L.tile_hdr) || dev_upload(tp, L.t_pack) || dev_upload(pmeta.t_bf, L.t_bf)) return 1;
+    pmeta.hdr = reinterpret_cast<const int4 *>(hdr);
+    pmeta.t_pack = tp;
+    pmeta.hc_idx = t.hc_idx; pmeta.he_idx = t.he_idx;
+    pmeta.S = t.S; pmeta.E = t.E; pmeta.ntiles = L.ntiles;
+    const size_t smem_max = ((size_t)15 * t.S + 5 * (size_t)t.E) * 8 + 16;
+    if (smem_max > 200 * 1024) C->tile_ok = false;  // pathological numbering: fall back to the direct-gather kernel
+  }
   if (dev_upload(d.g_off, L.g_off) || dev_upload(d.g_idx, L.g_idx) || dev_upload(d.g_cx, L.g_cx) || dev_upload(d.g_cy, L.g_cy)) return 1;
   if (dev_upload(d.c0x, L.c0x) || dev_upload(d.c0y, L.c0y)) return 1;
   if (dev_upload(d.bf_type, L.bf_type) || dev_upload(d.bf_edge, L.bf_edge)) return 1;
@@ -597,7 +658,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
     {
       Span sp(0);
       double *lg = C->logbuf + per * (size_t)(istep - 1);
-      k_finish_sum<4><<<1, 256, 0, C->st>>>(C->partial, C->nblocks, lg);
+      k_finish_sum<4><<<1, 256, 0, C->st>>>(C->partial, C->nparts, lg);
       C->last_launches++;
       if (vort) {
         k_vortex_err<<<C->nblocks, kBlock, 0, C->st>>>(C->dm, C->phys, tend, C->q, C->vpartial, C->vbest);
@@ -739,6 +800,8 @@ long fvs2d_gpu_mesh_array(const char *name, void *out) {
   RET("f_off", C->L.f_off) RET("f_nbr", C->L.f_nbr) RET("f_edge", C->L.f_edge) RET("g_off", C->L.g_off) RET("g_idx", C->L.g_idx)
   RET("g_cx", C->L.g_cx) RET("g_cy", C->L.g_cy) RET("orig_id", C->L.orig_id) RET("bf_type", C->L.bf_type) RET("bf_edge", C->L.bf_edge)
   RET("lex", C->L.ex) RET("ley", C->L.ey) RET("is_intr", C->L.is_intr)
+  RET("tile_es", C->L.tile_es) RET("tile_ne", C->L.tile_ne) RET("tile_hc_ptr", C->L.tile_hc_ptr) RET("tile_he_ptr", C->L.tile_he_ptr)
+  RET("tile_hc_idx", C->L.tile_hc_idx) RET("tile_he_idx", C->L.tile_he_idx) RET("f_pack", C->L.f_pack) RET("f_bf", C->L.f_bf)
   RET("grad_idx", C->grad.idx) RET("grad_cx", C->grad.cx) RET("grad_cy", C->grad.cy) RET("grad_c0x", C->grad.c0x) RET("grad_c0y", C->grad.c0y)
 #undef RET
   if (n == "grad_ptr") {
@@ -760,6 +823,7 @@ int fvs2d_gpu_set_option(const char *key, int value) {
   NEED(C != nullptr, "fvs2d_gpu_set_option: not initialised");
   const std::string k = key ? key : "";
   if (k == "timing") { C->opt_timing = value; return 0; }
+  if (k == "tile") { C->opt_tile = value; return 0; }
   return fail("fvs2d_gpu_set_option: unknown option '%s'", key);
 }
 

@@ -264,11 +264,154 @@ __device__ __forceinline__ void block_sum_store(double val[NV], double *__restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// pass B: face-flux gather + residual + Runge-Kutta stage update for the owned cells.
+// pass B building blocks, shared by the direct-gather kernel (k_flux_rk) and the shared-memory tile
+// kernel (k_flux_tile).
 //   interior faces  src/residual.f90:66-103     boundary faces  src/residual.f90:111-157
 //   -R/vol          src/residual.f90:164-166    local dt        src/runge_kutta.f90:424-437
 //   RK update       src/runge_kutta.f90:156-162 (RK), :225-226 (SSPRK), :299-313, :383-387 (steady)
 //   norms           src/runge_kutta.f90:169-184 (sum of (q-q0)^2 per CTA -> partial)
+
+// interior face: p0/me/phi0 = this cell's state, reconstruction increment and limiter; pj/ot/phij the
+// neighbour's.  The flux is evaluated in the edge's own orientation (L = c1, R = c2).
+template <int RC>
+__device__ __forceinline__ void interior_face(const Phys &P, const bool self_c1, const double p0[4], const double me[4],
+                                              const double phi0, const double pj[4], const double ot[4], const double phij,
+                                              const double nx, const double ny, const double af, double acc[4], double &wsacc) {
+  double sL[4], sR[4];
+  const double kap = P.kappa;
+#pragma unroll
+  for (int v = 0; v < 4; v++) {
+    const double pL = self_c1 ? p0[v] : pj[v], pR = self_c1 ? pj[v] : p0[v];
+    if (RC == RC_FIRST) { sL[v] = pL; sR[v] = pR; }
+    else {
+      const double gL = self_c1 ? me[v] : ot[v], gR = self_c1 ? ot[v] : me[v];
+      const double fL = self_c1 ? phi0 : phij, fR = self_c1 ? phij : phi0;
+      if (RC == RC_K0) { sL[v] = pL + gL; sR[v] = pR + gR; }
+      else if (RC == RC_K0_PHI) { sL[v] = pL + fL * gL; sR[v] = pR + fR * gR; }
+      else {
+        const double gC = pR - pL;
+        sL[v] = pL + fL * (kap / 2.0 * gC + (1.0 - kap) * gL);
+        sR[v] = pR + fR * (-kap / 2.0 * gC + (1.0 - kap) * gR);
+      }
+    }
+  }
+  double flux[4], ws;
+  roe_flux(P.gamma, sL, sR, nx, ny, flux, ws);
+  const double sa = self_c1 ? af : -af;
+#pragma unroll
+  for (int v = 0; v < 4; v++) acc[v] += flux[v] * sa;
+  wsacc += ws * af;
+}
+
+// boundary face: this cell is c1 (src/residual.f90:125-155); bcv = ghost state for freestream/dirichlet
+template <int RC>
+__device__ __forceinline__ void boundary_face(const Phys &P, const int type, const double p0[4], const double me[4],
+                                              const double phi0, const double bcv[4], const double nx, const double ny,
+                                              const double af, double acc[4], double &wsacc) {
+  double sL[4], sR[4];
+#pragma unroll
+  for (int v = 0; v < 4; v++) sL[v] = (RC == RC_FIRST) ? p0[v] : p0[v] + phi0 * me[v];
+  if (type == 2) {  // slip wall: mirror the normal velocity
+    const double un = sL[1] * nx + sL[2] * ny;
+    sR[0] = sL[0]; sR[3] = sL[3];
+    sR[1] = sL[1] - 2.0 * un * nx;
+    sR[2] = sL[2] - 2.0 * un * ny;
+  } else {
+#pragma unroll
+    for (int v = 0; v < 4; v++) sR[v] = bcv[v];
+  }
+  double flux[4], ws;
+  roe_flux(P.gamma, sL, sR, nx, ny, flux, ws);
+#pragma unroll
+  for (int v = 0; v < 4; v++) acc[v] += flux[v] * af;
+  wsacc += ws * af;
+}
+
+// residual -> stage update of cell i with the cell's RK data already in registers (q0 = state at the
+// start of the step, fo = accumulated stage residuals, dl = dt_local of stages > 0);
+// returns (q_new - q0)^2 in dq2 on the last stage
+template <int UM, bool STEADY>
+__device__ __forceinline__ void stage_update_pre(const Phys &P, const StageParams &S, const int i, const int np, const double vol,
+                                                 const double q0[4], const double fo[4], const double dl_in, const double acc[4],
+                                                 const double wsacc, double *__restrict__ q, double *__restrict__ f,
+                                                 double *__restrict__ pout, double *__restrict__ dtl, double *__restrict__ resid_out,
+                                                 double *__restrict__ ws_out, double dq2[4]) {
+  double R[4];
+#pragma unroll
+  for (int v = 0; v < 4; v++) R[v] = -acc[v] / vol;
+  if (UM == UM_RESID) {
+#pragma unroll
+    for (int v = 0; v < 4; v++) resid_out[v * np + i] = R[v];
+    if (ws_out) ws_out[i] = wsacc;
+    return;
+  }
+  double h = S.h;
+  if (STEADY) {
+    double dl = dl_in;
+    if (S.stage == 0) { dl = P.cfl * vol / (0.5 * wsacc); dtl[i] = dl; }
+    h = dl * S.h;
+  }
+  double qn[4];
+  if (UM == UM_RK) {
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      const double fn = fo[v] + S.c * R[v];
+      qn[v] = S.last ? q0[v] + h * fn : q0[v] + h * R[v];
+      if (!S.last) f[v * np + i] = fn;
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      qn[v] = q0[v] + h * (S.c * R[v] + fo[v]);
+      if (!S.last) f[v * np + i] = fo[v] + R[v];
+    }
+  }
+  // primitive state for the next stage (cvar2pvar of the next compute_residual)
+  const double u = qn[1] / qn[0], vv = qn[2] / qn[0];
+  pout[i] = qn[0];
+  pout[np + i] = u;
+  pout[2 * np + i] = vv;
+  pout[3 * np + i] = (P.gamma - 1.0) * (qn[3] - 0.5 * qn[0] * (u * u + vv * vv));
+  if (S.last) {
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      q[v * np + i] = qn[v];
+      const double d = fabs(qn[v] - q0[v]);
+      dq2[v] += d * d;
+    }
+  }
+}
+
+template <int UM, bool STEADY>
+__device__ __forceinline__ void stage_load(const StageParams &S, const int i, const int np, const double *__restrict__ q,
+                                           const double *__restrict__ f, const double *__restrict__ dtl, double q0[4],
+                                           double fo[4], double &dl) {
+  dl = 0.0;
+#pragma unroll
+  for (int v = 0; v < 4; v++) { q0[v] = 0.0; fo[v] = 0.0; }
+  if (UM == UM_RESID) return;
+#pragma unroll
+  for (int v = 0; v < 4; v++) q0[v] = q[v * np + i];
+  if (S.stage != 0) {
+#pragma unroll
+    for (int v = 0; v < 4; v++) fo[v] = f[v * np + i];
+    if (STEADY) dl = dtl[i];
+  }
+}
+
+template <int UM, bool STEADY>
+__device__ __forceinline__ void stage_update(const Phys &P, const StageParams &S, const int i, const int np, const double vol,
+                                             const double acc[4], const double wsacc, double *__restrict__ q,
+                                             double *__restrict__ f, double *__restrict__ pout, double *__restrict__ dtl,
+                                             double *__restrict__ resid_out, double *__restrict__ ws_out, double dq2[4]) {
+  double q0[4], fo[4], dl;
+  stage_load<UM, STEADY>(S, i, np, q, f, dtl, q0, fo, dl);
+  stage_update_pre<UM, STEADY>(P, S, i, np, vol, q0, fo, dl, acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass B, direct-gather variant: neighbour data straight from global memory (works for any mesh
+// numbering; also the fallback when a tile's halo does not fit the packed 16-bit slots).
 template <int UM, bool STEADY, int RC>
 __global__ void __launch_bounds__(kBlock) k_flux_rk(const DevMesh m, const Phys P, const StageParams S,
                                                     const double *__restrict__ p, const double *__restrict__ gx,
@@ -294,7 +437,6 @@ __global__ void __launch_bounds__(kBlock) k_flux_rk(const DevMesh m, const Phys 
     }
     const double x0 = m.xc[i], y0 = m.yc[i];
     const double phi0 = (RC >= RC_K0_PHI) ? phi[i] : 1.0;
-    const double kap = P.kappa;
     double acc[4] = {0.0, 0.0, 0.0, 0.0}, wsacc = 0.0;
     for (int k = 0; k < w; k++) {
       const int e = off + 32 * k + lane;
@@ -305,15 +447,14 @@ __global__ void __launch_bounds__(kBlock) k_flux_rk(const DevMesh m, const Phys 
       const bool self_c1 = (fe & 1) == 0;
       const double xf = __ldg(&m.ex[ed]), yf = __ldg(&m.ey[ed]), af = __ldg(&m.ea[ed]);
       const double nx = __ldg(&m.enx[ed]), ny = __ldg(&m.eny[ed]);
-      double me[4];  // this cell's reconstruction increment (x_f - x_c) . grad p
+      double me[4] = {0.0, 0.0, 0.0, 0.0};  // this cell's reconstruction increment (x_f - x_c) . grad p
       if (RC != RC_FIRST) {
         const double dx = xf - x0, dy = yf - y0;
 #pragma unroll
         for (int v = 0; v < 4; v++) me[v] = dx * g0x[v] + dy * g0y[v];
       }
-      double flux[4], ws;
       if (nb >= 0) {
-        double pj[4], ot[4];
+        double pj[4], ot[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int v = 0; v < 4; v++) pj[v] = p[v * np + nb];
         double phij = 1.0;
@@ -323,104 +464,402 @@ __global__ void __launch_bounds__(kBlock) k_flux_rk(const DevMesh m, const Phys 
           for (int v = 0; v < 4; v++) ot[v] = dx * gx[v * np + nb] + dy * gy[v * np + nb];
           if (RC >= RC_K0_PHI) phij = phi[nb];
         }
-        double sL[4], sR[4];
-#pragma unroll
-        for (int v = 0; v < 4; v++) {
-          // edge orientation: L = c1, R = c2
-          const double pL = self_c1 ? p0[v] : pj[v], pR = self_c1 ? pj[v] : p0[v];
-          if (RC == RC_FIRST) { sL[v] = pL; sR[v] = pR; }
-          else {
-            const double gL = self_c1 ? me[v] : ot[v], gR = self_c1 ? ot[v] : me[v];
-            const double fL = self_c1 ? phi0 : phij, fR = self_c1 ? phij : phi0;
-            if (RC == RC_K0) { sL[v] = pL + gL; sR[v] = pR + gR; }
-            else if (RC == RC_K0_PHI) { sL[v] = pL + fL * gL; sR[v] = pR + fR * gR; }
-            else {
-              const double gC = pR - pL;
-              sL[v] = pL + fL * (kap / 2.0 * gC + (1.0 - kap) * gL);
-              sR[v] = pR + fR * (-kap / 2.0 * gC + (1.0 - kap) * gR);
-            }
-          }
-        }
-        roe_flux(P.gamma, sL, sR, nx, ny, flux, ws);
-        const double sa = self_c1 ? af : -af;
-#pragma unroll
-        for (int v = 0; v < 4; v++) acc[v] += flux[v] * sa;
-        wsacc += ws * af;
+        interior_face<RC>(P, self_c1, p0, me, phi0, pj, ot, phij, nx, ny, af, acc, wsacc);
       } else {
-        // boundary face: this cell is c1 (src/residual.f90:125-155)
         const int b = -1 - nb;
         const int type = __ldg(&m.bf_type[b]);
-        double sL[4], sR[4];
+        double bcv[4];
 #pragma unroll
-        for (int v = 0; v < 4; v++) sL[v] = (RC == RC_FIRST) ? p0[v] : p0[v] + phi0 * me[v];
-        if (type == 2) {  // slip wall: mirror the normal velocity
-          const double un = sL[1] * nx + sL[2] * ny;
-          sR[0] = sL[0]; sR[3] = sL[3];
-          sR[1] = sL[1] - 2.0 * un * nx;
-          sR[2] = sL[2] - 2.0 * un * ny;
-        } else {
-#pragma unroll
-          for (int v = 0; v < 4; v++) sR[v] = __ldg(&bc[v * m.nbf + b]);
-        }
-        roe_flux(P.gamma, sL, sR, nx, ny, flux, ws);
-#pragma unroll
-        for (int v = 0; v < 4; v++) acc[v] += flux[v] * af;
-        wsacc += ws * af;
+        for (int v = 0; v < 4; v++) bcv[v] = __ldg(&bc[v * m.nbf + b]);
+        boundary_face<RC>(P, type, p0, me, phi0, bcv, nx, ny, af, acc, wsacc);
       }
     }
-    const double vol = m.vol[i];
-    double R[4];
-#pragma unroll
-    for (int v = 0; v < 4; v++) R[v] = -acc[v] / vol;
-
-    if (UM == UM_RESID) {
-#pragma unroll
-      for (int v = 0; v < 4; v++) resid_out[v * np + i] = R[v];
-      if (ws_out) ws_out[i] = wsacc;
-    } else {
-      double h = S.h;
-      if (STEADY) {
-        double dl;
-        if (S.stage == 0) { dl = P.cfl * vol / (0.5 * wsacc); dtl[i] = dl; }
-        else dl = dtl[i];
-        h = dl * S.h;
-      }
-      double q0[4], fo[4], qn[4];
-#pragma unroll
-      for (int v = 0; v < 4; v++) q0[v] = q[v * np + i];
-#pragma unroll
-      for (int v = 0; v < 4; v++) fo[v] = (S.stage == 0) ? 0.0 : f[v * np + i];
-      if (UM == UM_RK) {
-#pragma unroll
-        for (int v = 0; v < 4; v++) {
-          const double fn = fo[v] + S.c * R[v];
-          qn[v] = S.last ? q0[v] + h * fn : q0[v] + h * R[v];
-          if (!S.last) f[v * np + i] = fn;
-        }
-      } else {
-#pragma unroll
-        for (int v = 0; v < 4; v++) {
-          qn[v] = q0[v] + h * (S.c * R[v] + fo[v]);
-          if (!S.last) f[v * np + i] = fo[v] + R[v];
-        }
-      }
-      // primitive state for the next stage (cvar2pvar of the next compute_residual)
-      const double u = qn[1] / qn[0], vv = qn[2] / qn[0];
-      pout[i] = qn[0];
-      pout[np + i] = u;
-      pout[2 * np + i] = vv;
-      pout[3 * np + i] = (P.gamma - 1.0) * (qn[3] - 0.5 * qn[0] * (u * u + vv * vv));
-      if (S.last) {
-#pragma unroll
-        for (int v = 0; v < 4; v++) {
-          q[v * np + i] = qn[v];
-          const double d = fabs(qn[v] - q0[v]);
-          dq2[v] = d * d;
-        }
-      }
-    }
+    stage_update<UM, STEADY>(P, S, i, np, m.vol[i], acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
   }
   if (UM != UM_RESID && S.last) block_sum_store<4>(dq2, partial);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass B, shared-memory tile variant (the production path).  One CTA = one tile of kBlock consecutive
+// cells of the Hilbert order.  Staging into shared memory:
+//   - the tile's own cells and own edges are contiguous runs of the SoA arrays: one elected thread
+//     issues TMA bulk copies (cp.async.bulk, completion on an mbarrier);
+//   - halo cells / halo edges (listed per tile at upload time) are gathered with 8-byte cp.async;
+// then every thread computes its cell's faces out of shared memory.  Several CTAs are resident per SM,
+// so one tile's loads overlap another tile's fp64 work.
+struct TileMeta {
+  const int *es, *ne, *hc_ptr, *he_ptr, *hc_idx, *he_idx;
+  const uint32_t *f_pack;
+  const int *f_bf;
+  int S, E;  // smem strides (even): cell slots (kBlock + max halo), edge slots
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+template <int UM, bool STEADY, int RC>
+__global__ void __launch_bounds__(kBlock) k_flux_tile(const DevMesh m, const TileMeta tm, const Phys P, const StageParams S,
+                                                      const double *__restrict__ p, const double *__restrict__ gx,
+                                                      const double *__restrict__ gy, const double *__restrict__ phi,
+                                                      const double *__restrict__ bc, double *__restrict__ q,
+                                                      double *__restrict__ f, double *__restrict__ pout,
+                                                      double *__restrict__ dtl, double *__restrict__ resid_out,
+                                                      double *__restrict__ ws_out, double *__restrict__ partial) {
+  // cell arrays staged: p(4) [, gx(4), gy(4), xc, yc [, phi]]
+  constexpr int NCA = RC == RC_FIRST ? 4 : (RC == RC_K0 ? 14 : 15);
+  extern __shared__ __align__(16) double smem[];
+  const int SS = tm.S, EE = tm.E;
+  double *sc = smem;
+  double *se = smem + (size_t)NCA * SS;
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(se + 5 * (size_t)EE);
+  const int t = blockIdx.x, tid = threadIdx.x, np = m.np;
+  const int c0 = t * kBlock;
+  const int ncell = min(kBlock, m.n_own - c0);
+  const int es = __ldg(&tm.es[t]), ne = __ldg(&tm.ne[t]);
+  auto cell_src = [&](int a) -> const double * {
+    return a < 4 ? p + (size_t)a * np : a < 8 ? gx + (size_t)(a - 4) * np : a < 12 ? gy + (size_t)(a - 8) * np : a == 12 ? m.xc : a == 13 ? m.yc : phi;
+  };
+  auto edge_src = [&](int a) -> const double * { return a == 0 ? m.ex : a == 1 ? m.ey : a == 2 ? m.ea : a == 3 ? m.enx : m.eny; };
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    const uint32_t bytes_c = (uint32_t)((ncell + 1) & ~1) * 8u, bytes_e = (uint32_t)ne * 8u;
+    mbar_expect_tx(mbar, NCA * bytes_c + 5u * bytes_e);
+#pragma unroll
+    for (int a = 0; a < NCA; a++) bulk_g2s(sc + (size_t)a * SS, cell_src(a) + c0, bytes_c, mbar);
+    if (ne > 0) {
+#pragma unroll
+      for (int a = 0; a < 5; a++) bulk_g2s(se + (size_t)a * EE, edge_src(a) + es, bytes_e, mbar);
+    }
+  }
+  {  // halo gathers
+    const int hp = __ldg(&tm.hc_ptr[t]), nh = __ldg(&tm.hc_ptr[t + 1]) - hp;
+    for (int h = tid; h < nh; h += kBlock) {
+      const int j = __ldg(&tm.hc_idx[hp + h]);
+#pragma unroll
+      for (int a = 0; a < NCA; a++) cp_async8(sc + (size_t)a * SS + kBlock + h, cell_src(a) + j);
+    }
+    const int ep = __ldg(&tm.he_ptr[t]), nhe = __ldg(&tm.he_ptr[t + 1]) - ep;
+    for (int h = tid; h < nhe; h += kBlock) {
+      const int j = __ldg(&tm.he_idx[ep + h]);
+#pragma unroll
+      for (int a = 0; a < 5; a++) cp_async8(se + (size_t)a * EE + ne + h, edge_src(a) + j);
+    }
+  }
+  // this thread's face entries, while the copies fly
+  const int i = c0 + tid;
+  const bool live = tid < ncell;
+  const int lane = tid & 31, sl = i >> 5;
+  int off = 0, w = 0;
+  uint32_t fp[4] = {0xFFFEu, 0xFFFEu, 0xFFFEu, 0xFFFEu};
+  if (live) {
+    off = __ldg(&m.f_off[sl]);
+    w = (__ldg(&m.f_off[sl + 1]) - off) >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (k < w) fp[k] = __ldg(&tm.f_pack[off + 32 * k + lane]);
+  }
+  cp_async_wait_all();
+  __syncthreads();  // mbarrier init + every thread's cp.async data visible
+  mbar_wait(mbar, 0);
+
+  double dq2[4] = {0.0, 0.0, 0.0, 0.0};
+  if (live) {
+    double p0[4], g0x[4], g0y[4];
+#pragma unroll
+    for (int v = 0; v < 4; v++) p0[v] = sc[(size_t)v * SS + tid];
+    double x0 = 0.0, y0 = 0.0;
+    if (RC != RC_FIRST) {
+#pragma unroll
+      for (int v = 0; v < 4; v++) { g0x[v] = sc[(size_t)(4 + v) * SS + tid]; g0y[v] = sc[(size_t)(8 + v) * SS + tid]; }
+      x0 = sc[12 * (size_t)SS + tid]; y0 = sc[13 * (size_t)SS + tid];
+    }
+    const double phi0 = (RC >= RC_K0_PHI) ? sc[14 * (size_t)SS + tid] : 1.0;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0}, wsacc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (k >= w) break;
+      const uint32_t pk = fp[k];
+      const uint32_t ns = pk & 0xFFFFu;
+      if (ns == 0xFFFEu) continue;
+      const int eslot = (pk >> 16) & 0x7FFF;
+      const bool self_c1 = (pk >> 31) == 0;
+      const double xf = se[eslot], yf = se[EE + eslot], af = se[2 * EE + eslot];
+      const double nx = se[3 * EE + eslot], ny = se[4 * EE + eslot];
+      double me[4] = {0.0, 0.0, 0.0, 0.0};
+      if (RC != RC_FIRST) {
+        const double dx = xf - x0, dy = yf - y0;
+#pragma unroll
+        for (int v = 0; v < 4; v++) me[v] = dx * g0x[v] + dy * g0y[v];
+      }
+      if (ns != 0xFFFFu) {
+        double pj[4], ot[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int v = 0; v < 4; v++) pj[v] = sc[(size_t)v * SS + ns];
+        double phij = 1.0;
+        if (RC != RC_FIRST) {
+          const double dx = xf - sc[12 * (size_t)SS + ns], dy = yf - sc[13 * (size_t)SS + ns];
+#pragma unroll
+          for (int v = 0; v < 4; v++) ot[v] = dx * sc[(size_t)(4 + v) * SS + ns] + dy * sc[(size_t)(8 + v) * SS + ns];
+          if (RC >= RC_K0_PHI) phij = sc[14 * (size_t)SS + ns];
+        }
+        interior_face<RC>(P, self_c1, p0, me, phi0, pj, ot, phij, nx, ny, af, acc, wsacc);
+      } else {
+        const int b = __ldg(&tm.f_bf[off + 32 * k + lane]);
+        const int type = __ldg(&m.bf_type[b]);
+        double bcv[4];
+#pragma unroll
+        for (int v = 0; v < 4; v++) bcv[v] = __ldg(&bc[v * m.nbf + b]);
+        boundary_face<RC>(P, type, p0, me, phi0, bcv, nx, ny, af, acc, wsacc);
+      }
+    }
+    stage_update<UM, STEADY>(P, S, i, np, m.vol[i], acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
+  }
+  if (UM != UM_RESID && S.last) block_sum_store<4>(dq2, partial);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass B, persistent warp-specialised pipeline (the production path).
+// CTA = 4 consumer warps (one thread per cell of a tile) + 1 producer warp, looping over tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...  A 2-stage shared-memory ring decouples them:
+//   producer: waits empty[s]; reads the tile header; one lane issues the TMA bulk copies (own cells,
+//             own edges, face table -> complete_tx on full[s]); all lanes gather the halo cells / edges
+//             with 8-byte cp.async and hand their completion to full[s] (cp.async.mbarrier.arrive.noinc);
+//   consumer: prefetches its cell's RK data (registers), waits full[s], computes its faces out of shared
+//             memory (left/right states are addressed by slot, so no operand swapping), arrives on
+//             empty[s], applies the stage update.
+// Global-memory latency is thus only ever seen by the producer warp.
+constexpr int kPipeThreads = kBlock + 32;
+constexpr int kStages = 2;
+
+struct PipeMeta {
+  const int4 *hdr;  // 2 x int4 per tile: {es, ne, hc_ptr, n_hc}, {he_ptr, n_he, fbase, fw}
+  const int *hc_idx, *he_idx;
+  const uint32_t *t_pack;
+  const int *t_bf;
+  int S, E, ntiles;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int UM, bool STEADY, int RC>
+__global__ void __launch_bounds__(kPipeThreads, 3) k_flux_pipe(const DevMesh m, const PipeMeta pm, const Phys P, const StageParams S,
+                                                               const double *__restrict__ p, const double *__restrict__ gx,
+                                                               const double *__restrict__ gy, const double *__restrict__ phi,
+                                                               const double *__restrict__ bc, double *__restrict__ q,
+                                                               double *__restrict__ f, double *__restrict__ pout,
+                                                               double *__restrict__ dtl, double *__restrict__ resid_out,
+                                                               double *__restrict__ ws_out, double *__restrict__ partial) {
+  constexpr int NCA = RC == RC_FIRST ? 4 : (RC == RC_K0 ? 14 : 15);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int SS = pm.S, EE = pm.E, np = m.np;
+  const size_t stage_bytes = ((size_t)NCA * SS + 5 * (size_t)EE) * 8 + 4 * kBlock * sizeof(uint32_t) + 16;  // + {fw, fbase}
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kStages * stage_bytes);
+  uint64_t *empty = full + kStages;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 33); mbar_init(&empty[s], kBlock); }
+  }
+  __syncthreads();
+
+  if (warp == kBlock / 32) {
+    // ================================ producer warp ================================
+    auto cell_src = [&](int a) -> const double * {
+      return a < 4 ? p + (size_t)a * np : a < 8 ? gx + (size_t)(a - 4) * np : a < 12 ? gy + (size_t)(a - 8) * np : a == 12 ? m.xc : a == 13 ? m.yc : phi;
+    };
+    auto edge_src = [&](int a) -> const double * { return a == 0 ? m.ex : a == 1 ? m.ey : a == 2 ? m.ea : a == 3 ? m.enx : m.eny; };
+    int it = 0;
+    for (int t = blockIdx.x; t < pm.ntiles; t += gridDim.x, it++) {
+      const int s = it & (kStages - 1);
+      const uint32_t ph = (it / kStages) & 1;
+      const int4 h0 = __ldg(&pm.hdr[2 * t]), h1 = __ldg(&pm.hdr[2 * t + 1]);
+      const int es = h0.x, ne = h0.y, hp = h0.z, nh = h0.w, ep = h1.x, nhe = h1.y, fbase = h1.z, fw = h1.w;
+      // halo indices first: their latency overlaps the wait for a free stage
+      int jc[3], je[3];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        jc[r] = (lane + 32 * r < nh) ? __ldg(&pm.hc_idx[hp + lane + 32 * r]) : 0;
+        je[r] = (lane + 32 * r < nhe) ? __ldg(&pm.he_idx[ep + lane + 32 * r]) : 0;
+      }
+      mbar_wait(&empty[s], ph ^ 1);
+      double *sc = reinterpret_cast<double *>(smem_raw + s * stage_bytes);
+      double *se = sc + (size_t)NCA * SS;
+      uint32_t *sf = reinterpret_cast<uint32_t *>(se + 5 * (size_t)EE);
+      const int c0 = t * kBlock;
+      const int ncell = min(kBlock, m.n_own - c0);
+      if (lane == 0) {
+        const uint32_t bytes_c = (uint32_t)((ncell + 1) & ~1) * 8u, bytes_e = (uint32_t)ne * 8u;
+        const uint32_t bytes_f = (uint32_t)fw * kBlock * 4u;
+        int *sh = reinterpret_cast<int *>(sf + 4 * kBlock);
+        sh[0] = fw; sh[1] = fbase;  // published to the consumers by the arrive below (release)
+        mbar_expect_tx(&full[s], NCA * bytes_c + 5u * bytes_e + bytes_f);
+#pragma unroll
+        for (int a = 0; a < NCA; a++) bulk_g2s(sc + (size_t)a * SS, cell_src(a) + c0, bytes_c, &full[s]);
+        if (ne > 0) {
+#pragma unroll
+          for (int a = 0; a < 5; a++) bulk_g2s(se + (size_t)a * EE, edge_src(a) + es, bytes_e, &full[s]);
+        }
+        if (fw > 0) bulk_g2s(sf, pm.t_pack + fbase, bytes_f, &full[s]);
+      }
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const int h = lane + 32 * r;
+        if (h < nh) {
+#pragma unroll
+          for (int a = 0; a < NCA; a++) cp_async8(sc + (size_t)a * SS + kBlock + h, cell_src(a) + jc[r]);
+        }
+        if (h < nhe) {
+#pragma unroll
+          for (int a = 0; a < 5; a++) cp_async8(se + (size_t)a * EE + ne + h, edge_src(a) + je[r]);
+        }
+      }
+      for (int h = lane + 96; h < nh; h += 32) {  // rare: more than 96 halo cells
+        const int j = __ldg(&pm.hc_idx[hp + h]);
+#pragma unroll
+        for (int a = 0; a < NCA; a++) cp_async8(sc + (size_t)a * SS + kBlock + h, cell_src(a) + j);
+      }
+      for (int h = lane + 96; h < nhe; h += 32) {
+        const int j = __ldg(&pm.he_idx[ep + h]);
+#pragma unroll
+        for (int a = 0; a < 5; a++) cp_async8(se + (size_t)a * EE + ne + h, edge_src(a) + j);
+      }
+      cp_async_mbar_arrive_noinc(&full[s]);
+    }
+    return;
+  }
+
+  // ================================== consumer warps ==================================
+  double dq2[4] = {0.0, 0.0, 0.0, 0.0};
+  int it = 0;
+  for (int t = blockIdx.x; t < pm.ntiles; t += gridDim.x, it++) {
+    const int s = it & (kStages - 1);
+    const uint32_t ph = (it / kStages) & 1;
+    const int c0 = t * kBlock;
+    const int ncell = min(kBlock, m.n_own - c0);
+    const int i = c0 + tid;
+    const bool live = tid < ncell;
+    double q0[4], fo[4], dl = 0.0, vol = 1.0;
+    if (live) {  // RK data of this cell: in flight while the faces are computed
+      stage_load<UM, STEADY>(S, i, np, q, f, dtl, q0, fo, dl);
+      vol = m.vol[i];
+    }
+    const double *sc = reinterpret_cast<const double *>(smem_raw + s * stage_bytes);
+    const double *se = sc + (size_t)NCA * SS;
+    const uint32_t *sf = reinterpret_cast<const uint32_t *>(se + 5 * (size_t)EE);
+    mbar_wait(&full[s], ph);
+    const int fw = reinterpret_cast<const int *>(sf + 4 * kBlock)[0], fbase = reinterpret_cast<const int *>(sf + 4 * kBlock)[1];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0}, wsacc = 0.0;
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (k >= fw) break;
+        const uint32_t pk = sf[k * kBlock + tid];
+        const uint32_t ns = pk & 0xFFFFu;
+        if (ns == 0xFFFEu) continue;
+        const int eslot = (pk >> 16) & 0x7FFF;
+        const bool self_c1 = (pk >> 31) == 0;
+        const double xf = se[eslot], yf = se[EE + eslot], af = se[2 * EE + eslot];
+        const double nx = se[3 * EE + eslot], ny = se[4 * EE + eslot];
+        double sL[4], sR[4], flux[4], ws;
+        if (ns != 0xFFFFu) {
+          // edge orientation: L = c1, R = c2 -- address both sides by slot
+          const int a_ = self_c1 ? tid : (int)ns, b_ = self_c1 ? (int)ns : tid;
+          if (RC == RC_FIRST) {
+#pragma unroll
+            for (int v = 0; v < 4; v++) { sL[v] = sc[(size_t)v * SS + a_]; sR[v] = sc[(size_t)v * SS + b_]; }
+          } else {
+            const double dxL = xf - sc[12 * (size_t)SS + a_], dyL = yf - sc[13 * (size_t)SS + a_];
+            const double dxR = xf - sc[12 * (size_t)SS + b_], dyR = yf - sc[13 * (size_t)SS + b_];
+            const double fL = (RC >= RC_K0_PHI) ? sc[14 * (size_t)SS + a_] : 1.0;
+            const double fR = (RC >= RC_K0_PHI) ? sc[14 * (size_t)SS + b_] : 1.0;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+              const double pL = sc[(size_t)v * SS + a_], pR = sc[(size_t)v * SS + b_];
+              const double gL = dxL * sc[(size_t)(4 + v) * SS + a_] + dyL * sc[(size_t)(8 + v) * SS + a_];
+              const double gR = dxR * sc[(size_t)(4 + v) * SS + b_] + dyR * sc[(size_t)(8 + v) * SS + b_];
+              if (RC == RC_K0) { sL[v] = pL + gL; sR[v] = pR + gR; }
+              else if (RC == RC_K0_PHI) { sL[v] = pL + fL * gL; sR[v] = pR + fR * gR; }
+              else {
+                const double gC = pR - pL;
+                sL[v] = pL + fL * (P.kappa / 2.0 * gC + (1.0 - P.kappa) * gL);
+                sR[v] = pR + fR * (-P.kappa / 2.0 * gC + (1.0 - P.kappa) * gR);
+              }
+            }
+          }
+          roe_flux(P.gamma, sL, sR, nx, ny, flux, ws);
+          const double sa = self_c1 ? af : -af;
+#pragma unroll
+          for (int v = 0; v < 4; v++) acc[v] += flux[v] * sa;
+          wsacc += ws * af;
+        } else {
+          double p0[4], me[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+          for (int v = 0; v < 4; v++) p0[v] = sc[(size_t)v * SS + tid];
+          if (RC != RC_FIRST) {
+            const double dx = xf - sc[12 * (size_t)SS + tid], dy = yf - sc[13 * (size_t)SS + tid];
+#pragma unroll
+            for (int v = 0; v < 4; v++) me[v] = dx * sc[(size_t)(4 + v) * SS + tid] + dy * sc[(size_t)(8 + v) * SS + tid];
+          }
+          const double phi0 = (RC >= RC_K0_PHI) ? sc[14 * (size_t)SS + tid] : 1.0;
+          const int b = __ldg(&pm.t_bf[fbase + k * kBlock + tid]);
+          const int type = __ldg(&m.bf_type[b]);
+          double bcv[4];
+#pragma unroll
+          for (int v = 0; v < 4; v++) bcv[v] = __ldg(&bc[v * m.nbf + b]);
+          boundary_face<RC>(P, type, p0, me, phi0, bcv, nx, ny, af, acc, wsacc);
+        }
+      }
+    }
+    mbar_arrive(&empty[s]);  // this thread is done reading stage s
+    if (live) stage_update_pre<UM, STEADY>(P, S, i, np, vol, q0, fo, dl, acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
+  }
+  if (UM != UM_RESID && S.last) {
+    // sum of (q - q0)^2 over this CTA's cells: warp shuffles, then the 4 consumer warps through smem
+    __shared__ double red[4][kBlock / 32];
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      double x = dq2[v];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (lane == 0) red[v][warp] = x;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");
+    if (tid < 4) {
+      double ssum = 0.0;
+#pragma unroll
+      for (int w = 0; w < kBlock / 32; w++) ssum += red[tid][w];
+      partial[blockIdx.x * 4 + tid] = ssum;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -80,7 +80,15 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
   // ---- local edge numbering by first touch (sequential: order matters)
   std::vector<int> edge_loc(m.nedges, -1);
   int ne_loc = 0, nbf = 0;
+  L.ntiles = (L.n_own + kTile - 1) / kTile;
+  L.tile_es.assign(L.ntiles, 0);
+  L.tile_ne.assign(L.ntiles, 0);
   for (int i = 0; i < L.n_own; i++) {
+    if (i % kTile == 0) {  // a tile's own-edge range starts 16-byte aligned (bulk-copy requirement)
+      if (i > 0) L.tile_ne[i / kTile - 1] = ((ne_loc + 1) & ~1) - L.tile_es[i / kTile - 1];
+      ne_loc = (ne_loc + 1) & ~1;
+      L.tile_es[i / kTile] = ne_loc;
+    }
     const int o = L.orig_id[i];
     for (int s = m.cptr[o]; s < m.cptr[o + 1]; s++) {
       const int je = m.cedge[s];
@@ -88,8 +96,10 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
       nbf += m.nghbre[s] < 0;
     }
   }
+  ne_loc = (ne_loc + 1) & ~1;
+  if (L.ntiles) L.tile_ne[L.ntiles - 1] = ne_loc - L.tile_es[L.ntiles - 1];
   L.nedges = ne_loc;
-  L.ex.resize(ne_loc); L.ey.resize(ne_loc); L.ea.resize(ne_loc); L.enx.resize(ne_loc); L.eny.resize(ne_loc);
+  L.ex.assign(ne_loc, 0.0); L.ey.assign(ne_loc, 0.0); L.ea.assign(ne_loc, 0.0); L.enx.assign(ne_loc, 0.0); L.eny.assign(ne_loc, 0.0);
 #pragma omp parallel for schedule(static)
   for (int je = 0; je < m.nedges; je++) {
     const int l = edge_loc[je];
@@ -150,6 +160,98 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
         bf++;
       }
     }
+  }
+
+  // ---- tile metadata for the shared-memory pass-B kernel
+  {
+    const int nt = L.ntiles;
+    std::vector<std::vector<int>> hc(nt), he(nt);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int t = 0; t < nt; t++) {
+      const int c0 = t * kTile, c1 = std::min(L.n_own, c0 + kTile);
+      std::vector<int> &vc = hc[t], &ve = he[t];
+      for (int i = c0; i < c1; i++) {
+        const int sl = i >> 5, lane = i & 31;
+        const int w = (L.f_off[sl + 1] - L.f_off[sl]) >> 5;
+        for (int k = 0; k < w; k++) {
+          const int e = L.f_off[sl] + 32 * k + lane;
+          const int nb = L.f_nbr[e];
+          if (nb == kFacePad) continue;
+          if (nb >= 0 && (nb < c0 || nb >= c1)) vc.push_back(nb);
+          const int le = L.f_edge[e] >> 1;
+          if (le < L.tile_es[t]) ve.push_back(le);
+        }
+      }
+      std::sort(vc.begin(), vc.end()); vc.erase(std::unique(vc.begin(), vc.end()), vc.end());
+      std::sort(ve.begin(), ve.end()); ve.erase(std::unique(ve.begin(), ve.end()), ve.end());
+    }
+    L.tile_hc_ptr.assign(nt + 1, 0);
+    L.tile_he_ptr.assign(nt + 1, 0);
+    for (int t = 0; t < nt; t++) {
+      L.tile_hc_ptr[t + 1] = L.tile_hc_ptr[t] + (int)hc[t].size();
+      L.tile_he_ptr[t + 1] = L.tile_he_ptr[t] + (int)he[t].size();
+      L.tile_hc_max = std::max(L.tile_hc_max, (int)hc[t].size());
+      L.tile_e_max = std::max(L.tile_e_max, L.tile_ne[t] + (int)he[t].size());
+    }
+    L.tile_hc_idx.resize(L.tile_hc_ptr[nt]);
+    L.tile_he_idx.resize(L.tile_he_ptr[nt]);
+    L.f_pack.assign(L.f_nbr.size(), 0xFFFEu);
+    L.f_bf.assign(L.f_nbr.size(), -1);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int t = 0; t < nt; t++) {
+      std::copy(hc[t].begin(), hc[t].end(), L.tile_hc_idx.begin() + L.tile_hc_ptr[t]);
+      std::copy(he[t].begin(), he[t].end(), L.tile_he_idx.begin() + L.tile_he_ptr[t]);
+      const int c0 = t * kTile, c1 = std::min(L.n_own, c0 + kTile);
+      for (int i = c0; i < c1; i++) {
+        const int sl = i >> 5, lane = i & 31;
+        const int w = (L.f_off[sl + 1] - L.f_off[sl]) >> 5;
+        for (int k = 0; k < w; k++) {
+          const int e = L.f_off[sl] + 32 * k + lane;
+          const int nb = L.f_nbr[e];
+          if (nb == kFacePad) continue;
+          uint32_t ns;
+          if (nb < 0) { ns = 0xFFFFu; L.f_bf[e] = -1 - nb; }
+          else if (nb >= c0 && nb < c1) ns = (uint32_t)(nb - c0);
+          else ns = (uint32_t)(kTile + (std::lower_bound(hc[t].begin(), hc[t].end(), nb) - hc[t].begin()));
+          const int le = L.f_edge[e] >> 1;
+          uint32_t es;
+          if (le >= L.tile_es[t]) es = (uint32_t)(le - L.tile_es[t]);
+          else es = (uint32_t)(L.tile_ne[t] + (std::lower_bound(he[t].begin(), he[t].end(), le) - he[t].begin()));
+          L.f_pack[e] = ns | (es << 16) | ((uint32_t)(L.f_edge[e] & 1) << 31);
+        }
+      }
+    }
+    // tile headers + tile-sliced face table
+    L.tile_hdr.assign(8 * (size_t)nt, 0);
+    int64_t fbase = 0;
+    for (int t = 0; t < nt; t++) {
+      int fw = 0;
+      for (int sl = 4 * t; sl < std::min(L.nslices, 4 * t + 4); sl++) fw = std::max(fw, (L.f_off[sl + 1] - L.f_off[sl]) >> 5);
+      int *h = &L.tile_hdr[8 * (size_t)t];
+      h[0] = L.tile_es[t]; h[1] = L.tile_ne[t];
+      h[2] = L.tile_hc_ptr[t]; h[3] = L.tile_hc_ptr[t + 1] - L.tile_hc_ptr[t];
+      h[4] = L.tile_he_ptr[t]; h[5] = L.tile_he_ptr[t + 1] - L.tile_he_ptr[t];
+      h[6] = (int)fbase; h[7] = fw;
+      fbase += (int64_t)fw * kTile;
+      if (fbase > INT32_MAX) return "build_layout: face table exceeds 2^31 entries; use more GPUs";
+    }
+    L.t_pack.assign(fbase, 0xFFFEu);
+    L.t_bf.assign(fbase, -1);
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < nt; t++) {
+      const int *h = &L.tile_hdr[8 * (size_t)t];
+      const int c0 = t * kTile, c1 = std::min(L.n_own, c0 + kTile);
+      for (int i = c0; i < c1; i++) {
+        const int sl = i >> 5, lane = i & 31;
+        const int w = (L.f_off[sl + 1] - L.f_off[sl]) >> 5;
+        for (int k = 0; k < w; k++) {
+          const int e = L.f_off[sl] + 32 * k + lane;
+          L.t_pack[h[6] + kTile * k + (i - c0)] = L.f_pack[e];
+          L.t_bf[h[6] + kTile * k + (i - c0)] = L.f_bf[e];
+        }
+      }
+    }
+    if (L.tile_hc_max + kTile >= 0xFFFE || L.tile_e_max >= 0x7FFF) L.tile_hc_max = -1;  // no tile kernel for this mesh
   }
 
   // ---- gradient stencil as sliced ELL (padding: the cell itself with zero weight)

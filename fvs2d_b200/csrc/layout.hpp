@@ -17,6 +17,7 @@
 namespace fvs2d {
 
 constexpr int kFacePad = INT32_MIN;  // f_nbr value of a padding entry (triangle in a width-4 slice)
+constexpr int kTile = 128;           // cells per tile (== threads per CTA of the cell-parallel kernels)
 
 struct Layout {
   int rank = 0, nranks = 1;
@@ -46,6 +47,23 @@ struct Layout {
   int g_form = 0;
   std::vector<int> g_off, g_idx;
   std::vector<double> g_cx, g_cy, c0x, c0y;
+  // ---- tiles: kTile consecutive owned cells = one CTA of the shared-memory pass-B kernel.
+  // A tile stages in smem: its own cells [t*kTile, ...), its halo cells (face neighbours outside the
+  // tile, tile_hc_idx), its own edges (first touched by this tile: the contiguous, even-aligned range
+  // [tile_es, tile_es+tile_ne)) and its halo edges (first touched by an earlier tile, tile_he_idx).
+  // f_pack = per face entry: bits 0-15 neighbour slot (own: id - tile start; halo: kTile + pos;
+  // 0xFFFF boundary; 0xFFFE padding), bits 16-30 edge slot (own: id - tile_es; halo: tile_ne + pos),
+  // bit 31 set when this cell is the edge's c2.  f_bf = boundary-face id of a boundary entry.
+  int ntiles = 0, tile_hc_max = 0, tile_e_max = 0;
+  std::vector<int> tile_es, tile_ne, tile_hc_ptr, tile_he_ptr, tile_hc_idx, tile_he_idx;
+  std::vector<uint32_t> f_pack;
+  std::vector<int> f_bf;
+  // the same per tile in the form the persistent pipeline kernel consumes: one 32-byte header per tile
+  // {es, ne, hc_ptr, n_hc, he_ptr, n_he, fbase, fw} and the face table sliced per TILE: entry (k, j) of
+  // tile t at fbase + kTile*k + j, k < fw (so a tile's face table is one contiguous, 512-byte aligned run)
+  std::vector<int> tile_hdr;       // 8 ints per tile
+  std::vector<uint32_t> t_pack;
+  std::vector<int> t_bf;
   // halo plan: peers in ascending rank; send_idx = owned local ids the peer needs (ascending new id),
   // recv = contiguous run [recv_begin, recv_begin+recv_count) of local ghost ids
   std::vector<int> peers, send_ptr, send_idx, recv_begin, recv_count;
