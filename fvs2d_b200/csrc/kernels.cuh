@@ -79,47 +79,82 @@ __device__ __forceinline__ void mms_exact(const Phys &P, double x, double y, dou
   for (int v = 0; v < 4; v++) pv[v] = P.mms[v][0] + P.mms[v][1] * sin(P.mms[v][2] * x + P.mms[v][3] * y);
 }
 
+// Branch-free fp64 reciprocal and reciprocal square root for normal, positive arguments (densities,
+// 1+RT, a^2): hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~20 bits) + two Newton steps -> <= 1 ulp-level
+// error, no slow path (the IEEE division / sqrt sequences cost twice the instructions plus a branch).
+__device__ __forceinline__ double fast_rcp(const double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+__device__ __forceinline__ double fast_rsqrt(const double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x * y, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  e = fma(-x * y, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  return y;
+}
+// sqrt(x) and 1/x from one rsqrt: s = x*r corrected by one Newton step, 1/x = r*r
+__device__ __forceinline__ void fast_sqrt_rcp(const double x, double &s, double &inv) {
+  const double r = fast_rsqrt(x);
+  double t = x * r;
+  t = fma(fma(-t, t, x), 0.5 * r, t);
+  s = t;
+  inv = r * r;
+}
+
 // Roe flux with Harten's entropy fix, primitive inputs (src/flux_invscid.f90:37-136).
 // aL, aR only ever appear squared in the reference (HL = aL*aL/(gamma-1)+kL), so c2 = gamma*p/rho is
-// used directly; divisions by a shared denominator are one reciprocal.
+// used directly; divisions are reciprocals shared between quotients; gog = gamma/(gamma-1).
 __device__ __forceinline__ void roe_flux(const double gamma, const double L[4], const double R[4], const double nx,
                                          const double ny, double flux[4], double &ws_max) {
-  const double gm1 = gamma - 1.0, igm1 = 1.0 / gm1;
+  const double gm1 = gamma - 1.0;
+  const double gog = gamma / gm1;  // uniform: hoisted out of the face loop by the compiler
   const double tx = -ny, ty = nx;
   const double rhoL = L[0], uL = L[1], vL = L[2], pL = L[3];
   const double rhoR = R[0], uR = R[1], vR = R[2], pR = R[3];
-  const double irL = 1.0 / rhoL;
+  const double irL = fast_rcp(rhoL), irR = fast_rcp(rhoR);
   const double unL = uL * nx + vL * ny, unR = uR * nx + vR * ny;
   const double utL = uL * tx + vL * ty, utR = uR * tx + vR * ty;
   const double kL = 0.5 * (uL * uL + vL * vL), kR = 0.5 * (uR * uR + vR * vR);
-  const double HL = gamma * pL * irL * igm1 + kL;
-  const double HR = gamma * pR / rhoR * igm1 + kR;
-  const double RT = sqrt(rhoR * irL);
+  const double HL = gog * pL * irL + kL;
+  const double HR = gog * pR * irR + kR;
+  double RT, dum;
+  fast_sqrt_rcp(rhoR * irL, RT, dum);
   const double rho = RT * rhoL;
-  const double iw = 1.0 / (1.0 + RT);
+  const double iw = fast_rcp(1.0 + RT);
   const double u = (uL + RT * uR) * iw;
   const double v = (vL + RT * vR) * iw;
   const double H = (HL + RT * HR) * iw;
   const double tke = 0.5 * (u * u + v * v);
   const double a2 = gm1 * (H - tke);
-  const double a = sqrt(a2);
-  const double ia2 = 1.0 / (a * a);
+  double a, ia2;
+  fast_sqrt_rcp(a2, a, ia2);
   const double un = u * nx + v * ny, ut = u * tx + v * ty;
   const double drho = rhoR - rhoL, dp = pR - pL, dun = unR - unL, dut = utR - utL;
-  const double l1 = (dp - rho * a * dun) * (0.5 * ia2);
+  const double rad = rho * a * dun, hia2 = 0.5 * ia2;
+  const double l1 = (dp - rad) * hia2;
   const double l2 = rho * dut;
   const double l3 = drho - dp * ia2;
-  const double l4 = (dp + rho * a * dun) * (0.5 * ia2);
+  const double l4 = (dp + rad) * hia2;
   double w1 = fabs(un - a), w2 = fabs(un), w4 = fabs(un + a);
   const double dws = 1.0 / 5.0;
-  if (w1 < dws) w1 = 0.5 * (w1 * w1 / dws + dws);
-  if (w4 < dws) w4 = 0.5 * (w4 * w4 / dws + dws);
+  // Harten's entropy fix (src/flux_invscid.f90:97-101); 1/dws == 5 exactly
+  w1 = w1 < dws ? 0.5 * (w1 * w1 * 5.0 + dws) : w1;
+  w4 = w4 < dws ? 0.5 * (w4 * w4 * 5.0 + dws) : w4;
   const double s1 = w1 * l1, s2 = w2 * l2, s3 = w2 * l3, s4 = w4 * l4;
   // diss_i = sum_j ws_j LdU_j R_ij, j = 1..4 in order (src/flux_invscid.f90:111-116)
+  const double anx = a * nx, any = a * ny, una = un * a;
   const double d0 = s1 + s3 + s4;
-  const double d1 = s1 * (u - a * nx) + s2 * tx + s3 * u + s4 * (u + a * nx);
-  const double d2 = s1 * (v - a * ny) + s2 * ty + s3 * v + s4 * (v + a * ny);
-  const double d3 = s1 * (H - un * a) + s2 * ut + s3 * tke + s4 * (H + un * a);
+  const double d1 = s1 * (u - anx) + s2 * tx + s3 * u + s4 * (u + anx);
+  const double d2 = s1 * (v - any) + s2 * ty + s3 * v + s4 * (v + any);
+  const double d3 = s1 * (H - una) + s2 * ut + s3 * tke + s4 * (H + una);
   const double mL = rhoL * unL, mR = rhoR * unR;
   flux[0] = 0.5 * (mL + mR - d0);
   flux[1] = 0.5 * (mL * uL + pL * nx + (mR * uR + pR * nx) - d1);
@@ -697,23 +732,30 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_flux_pipe(const DevMesh m, 
       return a < 4 ? p + (size_t)a * np : a < 8 ? gx + (size_t)(a - 4) * np : a < 12 ? gy + (size_t)(a - 8) * np : a == 12 ? m.xc : a == 13 ? m.yc : phi;
     };
     auto edge_src = [&](int a) -> const double * { return a == 0 ? m.ex : a == 1 ? m.ey : a == 2 ? m.ea : a == 3 ? m.enx : m.eny; };
+    // the header and the halo index lists of the NEXT tile are fetched while the current one is in
+    // flight, so only one memory latency (the data itself) sits between "stage free" and "stage full"
+    int4 h0 = make_int4(0, 0, 0, 0), h1 = make_int4(0, 0, 0, 0);
+    int jc[3] = {0, 0, 0}, je[3] = {0, 0, 0};
+    auto fetch_meta = [&](int t) {
+      h0 = __ldg(&pm.hdr[2 * t]);
+      h1 = __ldg(&pm.hdr[2 * t + 1]);
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        jc[r] = (lane + 32 * r < h0.w) ? __ldg(&pm.hc_idx[h0.z + lane + 32 * r]) : 0;
+        je[r] = (lane + 32 * r < h1.y) ? __ldg(&pm.he_idx[h1.x + lane + 32 * r]) : 0;
+      }
+    };
+    if ((int)blockIdx.x < pm.ntiles) fetch_meta(blockIdx.x);
     int it = 0;
     for (int t = blockIdx.x; t < pm.ntiles; t += gridDim.x, it++) {
       const int s = it & (kStages - 1);
       const uint32_t ph = (it / kStages) & 1;
-      const int4 h0 = __ldg(&pm.hdr[2 * t]), h1 = __ldg(&pm.hdr[2 * t + 1]);
       const int es = h0.x, ne = h0.y, hp = h0.z, nh = h0.w, ep = h1.x, nhe = h1.y, fbase = h1.z, fw = h1.w;
-      // halo indices first: their latency overlaps the wait for a free stage
-      int jc[3], je[3];
-#pragma unroll
-      for (int r = 0; r < 3; r++) {
-        jc[r] = (lane + 32 * r < nh) ? __ldg(&pm.hc_idx[hp + lane + 32 * r]) : 0;
-        je[r] = (lane + 32 * r < nhe) ? __ldg(&pm.he_idx[ep + lane + 32 * r]) : 0;
-      }
+      const int jcc[3] = {jc[0], jc[1], jc[2]}, jee[3] = {je[0], je[1], je[2]};
       mbar_wait(&empty[s], ph ^ 1);
       double *sc = reinterpret_cast<double *>(smem_raw + s * stage_bytes);
-      double *se = sc + (size_t)NCA * SS;
-      uint32_t *sf = reinterpret_cast<uint32_t *>(se + 5 * (size_t)EE);
+      double *se = sc + NCA * SS;
+      uint32_t *sf = reinterpret_cast<uint32_t *>(se + 5 * EE);
       const int c0 = t * kBlock;
       const int ncell = min(kBlock, m.n_own - c0);
       if (lane == 0) {
@@ -723,10 +765,10 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_flux_pipe(const DevMesh m, 
         sh[0] = fw; sh[1] = fbase;  // published to the consumers by the arrive below (release)
         mbar_expect_tx(&full[s], NCA * bytes_c + 5u * bytes_e + bytes_f);
 #pragma unroll
-        for (int a = 0; a < NCA; a++) bulk_g2s(sc + (size_t)a * SS, cell_src(a) + c0, bytes_c, &full[s]);
+        for (int a = 0; a < NCA; a++) bulk_g2s(sc + a * SS, cell_src(a) + c0, bytes_c, &full[s]);
         if (ne > 0) {
 #pragma unroll
-          for (int a = 0; a < 5; a++) bulk_g2s(se + (size_t)a * EE, edge_src(a) + es, bytes_e, &full[s]);
+          for (int a = 0; a < 5; a++) bulk_g2s(se + a * EE, edge_src(a) + es, bytes_e, &full[s]);
         }
         if (fw > 0) bulk_g2s(sf, pm.t_pack + fbase, bytes_f, &full[s]);
       }
@@ -735,24 +777,25 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_flux_pipe(const DevMesh m, 
         const int h = lane + 32 * r;
         if (h < nh) {
 #pragma unroll
-          for (int a = 0; a < NCA; a++) cp_async8(sc + (size_t)a * SS + kBlock + h, cell_src(a) + jc[r]);
+          for (int a = 0; a < NCA; a++) cp_async8(sc + a * SS + kBlock + h, cell_src(a) + jcc[r]);
         }
         if (h < nhe) {
 #pragma unroll
-          for (int a = 0; a < 5; a++) cp_async8(se + (size_t)a * EE + ne + h, edge_src(a) + je[r]);
+          for (int a = 0; a < 5; a++) cp_async8(se + a * EE + ne + h, edge_src(a) + jee[r]);
         }
       }
       for (int h = lane + 96; h < nh; h += 32) {  // rare: more than 96 halo cells
         const int j = __ldg(&pm.hc_idx[hp + h]);
 #pragma unroll
-        for (int a = 0; a < NCA; a++) cp_async8(sc + (size_t)a * SS + kBlock + h, cell_src(a) + j);
+        for (int a = 0; a < NCA; a++) cp_async8(sc + a * SS + kBlock + h, cell_src(a) + j);
       }
       for (int h = lane + 96; h < nhe; h += 32) {
         const int j = __ldg(&pm.he_idx[ep + h]);
 #pragma unroll
-        for (int a = 0; a < 5; a++) cp_async8(se + (size_t)a * EE + ne + h, edge_src(a) + j);
+        for (int a = 0; a < 5; a++) cp_async8(se + a * EE + ne + h, edge_src(a) + j);
       }
       cp_async_mbar_arrive_noinc(&full[s]);
+      if (t + (int)gridDim.x < pm.ntiles) fetch_meta(t + gridDim.x);
     }
     return;
   }
@@ -773,70 +816,69 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_flux_pipe(const DevMesh m, 
       vol = m.vol[i];
     }
     const double *sc = reinterpret_cast<const double *>(smem_raw + s * stage_bytes);
-    const double *se = sc + (size_t)NCA * SS;
-    const uint32_t *sf = reinterpret_cast<const uint32_t *>(se + 5 * (size_t)EE);
+    const double *se = sc + NCA * SS;
+    const uint32_t *sf = reinterpret_cast<const uint32_t *>(se + 5 * EE);
     mbar_wait(&full[s], ph);
     const int fw = reinterpret_cast<const int *>(sf + 4 * kBlock)[0], fbase = reinterpret_cast<const int *>(sf + 4 * kBlock)[1];
     double acc[4] = {0.0, 0.0, 0.0, 0.0}, wsacc = 0.0;
     if (live) {
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        if (k >= fw) break;
+#pragma unroll 1
+      for (int k = 0; k < fw; k++) {
         const uint32_t pk = sf[k * kBlock + tid];
         const uint32_t ns = pk & 0xFFFFu;
         if (ns == 0xFFFEu) continue;
         const int eslot = (pk >> 16) & 0x7FFF;
         const bool self_c1 = (pk >> 31) == 0;
-        const double xf = se[eslot], yf = se[EE + eslot], af = se[2 * EE + eslot];
-        const double nx = se[3 * EE + eslot], ny = se[4 * EE + eslot];
-        double sL[4], sR[4], flux[4], ws;
-        if (ns != 0xFFFFu) {
-          // edge orientation: L = c1, R = c2 -- address both sides by slot
-          const int a_ = self_c1 ? tid : (int)ns, b_ = self_c1 ? (int)ns : tid;
-          if (RC == RC_FIRST) {
+        const bool bnd = ns == 0xFFFFu;
+        const double *eg = se + eslot;
+        const double xf = eg[0], yf = eg[EE], af = eg[2 * EE], nx = eg[3 * EE], ny = eg[4 * EE];
+        // edge orientation: L = c1, R = c2 -- both sides are addressed by slot (no operand swapping);
+        // on a boundary face this cell is c1 and the right state comes from the boundary condition
+        const double *cl = sc + ((self_c1 || bnd) ? tid : (int)ns);
+        const double *cr = sc + ((self_c1 && !bnd) ? (int)ns : tid);
+        double sL[4], sR[4];
+        if (RC == RC_FIRST) {
 #pragma unroll
-            for (int v = 0; v < 4; v++) { sL[v] = sc[(size_t)v * SS + a_]; sR[v] = sc[(size_t)v * SS + b_]; }
-          } else {
-            const double dxL = xf - sc[12 * (size_t)SS + a_], dyL = yf - sc[13 * (size_t)SS + a_];
-            const double dxR = xf - sc[12 * (size_t)SS + b_], dyR = yf - sc[13 * (size_t)SS + b_];
-            const double fL = (RC >= RC_K0_PHI) ? sc[14 * (size_t)SS + a_] : 1.0;
-            const double fR = (RC >= RC_K0_PHI) ? sc[14 * (size_t)SS + b_] : 1.0;
+          for (int v = 0; v < 4; v++) { sL[v] = cl[v * SS]; sR[v] = cr[v * SS]; }
+        } else {
+          const double dxL = xf - cl[12 * SS], dyL = yf - cl[13 * SS];
+          const double dxR = xf - cr[12 * SS], dyR = yf - cr[13 * SS];
+          const double fL = (RC >= RC_K0_PHI) ? cl[14 * SS] : 1.0;
+          const double fR = (RC >= RC_K0_PHI) ? cr[14 * SS] : 1.0;
 #pragma unroll
-            for (int v = 0; v < 4; v++) {
-              const double pL = sc[(size_t)v * SS + a_], pR = sc[(size_t)v * SS + b_];
-              const double gL = dxL * sc[(size_t)(4 + v) * SS + a_] + dyL * sc[(size_t)(8 + v) * SS + a_];
-              const double gR = dxR * sc[(size_t)(4 + v) * SS + b_] + dyR * sc[(size_t)(8 + v) * SS + b_];
-              if (RC == RC_K0) { sL[v] = pL + gL; sR[v] = pR + gR; }
-              else if (RC == RC_K0_PHI) { sL[v] = pL + fL * gL; sR[v] = pR + fR * gR; }
-              else {
-                const double gC = pR - pL;
-                sL[v] = pL + fL * (P.kappa / 2.0 * gC + (1.0 - P.kappa) * gL);
-                sR[v] = pR + fR * (-P.kappa / 2.0 * gC + (1.0 - P.kappa) * gR);
-              }
+          for (int v = 0; v < 4; v++) {
+            const double pL = cl[v * SS], pR = cr[v * SS];
+            const double gL = dxL * cl[(4 + v) * SS] + dyL * cl[(8 + v) * SS];
+            const double gR = dxR * cr[(4 + v) * SS] + dyR * cr[(8 + v) * SS];
+            if (RC == RC_K0) { sL[v] = pL + gL; sR[v] = pR + gR; }
+            else if (RC == RC_K0_PHI) { sL[v] = pL + fL * gL; sR[v] = pR + fR * gR; }
+            else {
+              // boundary faces carry no kappa term (src/residual.f90:128)
+              const double gC = bnd ? 0.0 : pR - pL, k1 = bnd ? 1.0 : 1.0 - P.kappa;
+              sL[v] = pL + fL * (P.kappa / 2.0 * gC + k1 * gL);
+              sR[v] = pR + fR * (-P.kappa / 2.0 * gC + k1 * gR);
             }
           }
-          roe_flux(P.gamma, sL, sR, nx, ny, flux, ws);
-          const double sa = self_c1 ? af : -af;
-#pragma unroll
-          for (int v = 0; v < 4; v++) acc[v] += flux[v] * sa;
-          wsacc += ws * af;
-        } else {
-          double p0[4], me[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-          for (int v = 0; v < 4; v++) p0[v] = sc[(size_t)v * SS + tid];
-          if (RC != RC_FIRST) {
-            const double dx = xf - sc[12 * (size_t)SS + tid], dy = yf - sc[13 * (size_t)SS + tid];
-#pragma unroll
-            for (int v = 0; v < 4; v++) me[v] = dx * sc[(size_t)(4 + v) * SS + tid] + dy * sc[(size_t)(8 + v) * SS + tid];
-          }
-          const double phi0 = (RC >= RC_K0_PHI) ? sc[14 * (size_t)SS + tid] : 1.0;
+        }
+        if (bnd) {
           const int b = __ldg(&pm.t_bf[fbase + k * kBlock + tid]);
           const int type = __ldg(&m.bf_type[b]);
-          double bcv[4];
+          if (type == 2) {  // slip wall: mirror the normal velocity (src/residual.f90:200-204)
+            const double un = sL[1] * nx + sL[2] * ny;
+            sR[0] = sL[0]; sR[3] = sL[3];
+            sR[1] = sL[1] - 2.0 * un * nx;
+            sR[2] = sL[2] - 2.0 * un * ny;
+          } else {
 #pragma unroll
-          for (int v = 0; v < 4; v++) bcv[v] = __ldg(&bc[v * m.nbf + b]);
-          boundary_face<RC>(P, type, p0, me, phi0, bcv, nx, ny, af, acc, wsacc);
+            for (int v = 0; v < 4; v++) sR[v] = __ldg(&bc[v * m.nbf + b]);
+          }
         }
+        double flux[4], ws;
+        roe_flux(P.gamma, sL, sR, nx, ny, flux, ws);
+        const double sa = self_c1 ? af : -af;
+#pragma unroll
+        for (int v = 0; v < 4; v++) acc[v] += flux[v] * sa;
+        wsacc += ws * af;
       }
     }
     mbar_arrive(&empty[s]);  // this thread is done reading stage s
