@@ -19,7 +19,8 @@ _LIB = None
 # every symbol include/fvs2d_gpu.h declares (tests check that the .so exports them all)
 SYMBOLS = [
     "fvs2d_gpu_init", "fvs2d_gpu_comm_unique_id", "fvs2d_gpu_comm_init", "fvs2d_gpu_set_mesh",
-    "fvs2d_gpu_initialize_solution", "fvs2d_gpu_set_state", "fvs2d_gpu_get_state",
+    "fvs2d_gpu_initialize_solution", "fvs2d_gpu_set_state", "fvs2d_gpu_get_state", "fvs2d_gpu_set_state_local",
+    "fvs2d_gpu_get_state_local",
     "fvs2d_gpu_time_integration", "fvs2d_gpu_compute_residual", "fvs2d_gpu_get_aux", "fvs2d_gpu_test_resid",
     "fvs2d_gpu_sizes", "fvs2d_gpu_scalars", "fvs2d_gpu_mesh_array", "fvs2d_host_build", "fvs2d_gpu_last_timing",
     "fvs2d_gpu_set_option", "fvs2d_gpu_last_error", "fvs2d_gpu_finalize",
@@ -49,6 +50,8 @@ def lib():
     L.fvs2d_gpu_initialize_solution.argtypes = []
     L.fvs2d_gpu_set_state.argtypes = [vp]
     L.fvs2d_gpu_get_state.argtypes = [vp]
+    L.fvs2d_gpu_set_state_local.argtypes = [vp]
+    L.fvs2d_gpu_get_state_local.argtypes = [vp]
     L.fvs2d_gpu_time_integration.argtypes = [cd, ci, vp, vp, vp]
     L.fvs2d_gpu_compute_residual.argtypes = [cd, vp, vp]
     L.fvs2d_gpu_get_aux.argtypes = [vp, vp, vp]
@@ -82,7 +85,7 @@ def ptr(a):
 _INT_ARRAYS = {"en1", "en2", "ec1", "ec2", "cedge", "nghbre", "cell_intr", "b_edge", "b_edge_ptr", "grad_ptr", "grad_idx",
                "perm", "f_off", "f_nbr", "f_edge", "g_off", "g_idx", "orig_id", "loc2new", "bf_type", "bf_edge", "peers",
                "send_ptr", "send_idx", "recv_begin", "recv_count", "tile_es", "tile_ne", "tile_hc_ptr", "tile_he_ptr",
-               "tile_hc_idx", "tile_he_idx", "f_bf"}
+               "tile_hc_idx", "tile_he_idx", "f_bf", "tile_hdr", "t_bf"}
 _U32_ARRAYS = {"f_pack"}
 _BYTE_ARRAYS = {"is_intr"}
 

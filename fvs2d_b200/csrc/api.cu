@@ -3,9 +3,12 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <omp.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -417,6 +420,10 @@ int host_build(int nnodes, int ntri, int nquad, const double *node_xy, const int
   NEED(nb == 0 || (b_ncells && b_type && b_cell), "fvs2d_gpu_set_mesh: null boundary array");
   C->has_mesh = C->has_state = false;
   C->bc_static_done = false;
+  {  // launchers such as torchrun export OMP_NUM_THREADS=1; the one-off pre-processing takes its share of the cores
+    const int hw = (int)std::thread::hardware_concurrency();
+    omp_set_num_threads(std::max(1, std::min(32, hw / std::max(1, C->nranks))));
+  }
   HostMesh &m = C->mesh;
   m = HostMesh();
   const int nc = ntri + nquad;
@@ -548,6 +555,36 @@ int fvs2d_gpu_set_state(const double *cvar) {
   return 0;
 }
 
+int fvs2d_gpu_set_state_local(const double *cvar_own) {
+  NEED(C && C->has_mesh, "fvs2d_gpu_set_state_local: no mesh");
+  NEED(cvar_own != nullptr, "fvs2d_gpu_set_state_local: null cvar");
+  const size_t n = (size_t)C->L.n_own * 4;
+  if (ensure_stage(n)) return 1;
+  CUDA_OK(cudaMemcpyAsync(C->stage_aos, cvar_own, n * 8, cudaMemcpyHostToDevice, C->st));
+  k_scatter_in<<<cdiv(C->L.n_own, 256), 256, 0, C->st>>>(C->L.n_own, C->np, 4, nullptr, C->stage_aos, C->q);
+  k_prim<<<cdiv(C->L.n_own, 256), 256, 0, C->st>>>(C->L.n_own, C->np, C->cfg.gamma, C->q, C->pa);
+  CUDA_OK(cudaGetLastError());
+  if (C->nranks > 1) {  // ghost copies of the primitive state come from their owners
+    HaloItem it{C->pa, 4};
+    if (halo_exchange(&it, 1)) return 1;
+  }
+  CUDA_OK(cudaStreamSynchronize(C->st));
+  C->has_state = true;
+  return 0;
+}
+
+int fvs2d_gpu_get_state_local(double *cvar_own) {
+  NEED(C && C->has_state, "fvs2d_gpu_get_state_local: no state");
+  NEED(cvar_own != nullptr, "fvs2d_gpu_get_state_local: null cvar");
+  const size_t n = (size_t)C->L.n_own * 4;
+  if (ensure_stage(n)) return 1;
+  k_gather_out<<<cdiv(C->L.n_own, 256), 256, 0, C->st>>>(C->L.n_own, C->np, 4, nullptr, C->q, C->stage_aos);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(cvar_own, C->stage_aos, n * 8, cudaMemcpyDeviceToHost, C->st));
+  CUDA_OK(cudaStreamSynchronize(C->st));
+  return 0;
+}
+
 int fvs2d_gpu_get_state(double *cvar) {
   NEED(C && C->has_state, "fvs2d_gpu_get_state: no state");
   NEED(cvar != nullptr, "fvs2d_gpu_get_state: null cvar");
@@ -661,8 +698,9 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
       k_finish_sum<4><<<1, 256, 0, C->st>>>(C->partial, C->nparts, lg);
       C->last_launches++;
       if (vort) {
-        k_vortex_err<<<C->nblocks, kBlock, 0, C->st>>>(C->dm, C->phys, tend, C->q, C->vpartial, C->vbest);
-        k_finish_vortex<<<1, 256, 0, C->st>>>(C->vpartial, C->vbest, C->nblocks, lg + 4, C->logid + (istep - 1));
+        const int vgrid = std::min(C->nblocks, C->nsm * 8);
+        k_vortex_err<<<vgrid, kBlock, 0, C->st>>>(C->dm, C->phys, tend, C->q, C->vpartial, C->vbest);
+        k_finish_vortex<<<1, 256, 0, C->st>>>(C->vpartial, C->vbest, vgrid, lg + 4, C->logid + (istep - 1));
         C->last_launches += 2;
       }
     }
@@ -801,6 +839,7 @@ long fvs2d_gpu_mesh_array(const char *name, void *out) {
   RET("g_cx", C->L.g_cx) RET("g_cy", C->L.g_cy) RET("orig_id", C->L.orig_id) RET("bf_type", C->L.bf_type) RET("bf_edge", C->L.bf_edge)
   RET("lex", C->L.ex) RET("ley", C->L.ey) RET("is_intr", C->L.is_intr)
   RET("tile_es", C->L.tile_es) RET("tile_ne", C->L.tile_ne) RET("tile_hc_ptr", C->L.tile_hc_ptr) RET("tile_he_ptr", C->L.tile_he_ptr)
+  RET("tile_hdr", C->L.tile_hdr) RET("t_pack", C->L.t_pack) RET("t_bf", C->L.t_bf)
   RET("tile_hc_idx", C->L.tile_hc_idx) RET("tile_he_idx", C->L.tile_he_idx) RET("f_pack", C->L.f_pack) RET("f_bf", C->L.f_bf)
   RET("grad_idx", C->grad.idx) RET("grad_cx", C->grad.cx) RET("grad_cy", C->grad.cy) RET("grad_c0x", C->grad.c0x) RET("grad_c0y", C->grad.c0y)
 #undef RET

@@ -930,28 +930,31 @@ __global__ void __launch_bounds__(256) k_finish_sum(const double *__restrict__ p
 __global__ void __launch_bounds__(kBlock) k_vortex_err(const DevMesh m, const Phys P, const double time,
                                                        const double *__restrict__ q, double *__restrict__ partial,
                                                        int *__restrict__ best_id) {
-  const int i = blockIdx.x * kBlock + threadIdx.x;
+  // grid-stride over the owned cells with a fixed grid: the partial count is small and the summation
+  // order is a function of the launch configuration only (deterministic)
   const int np = m.np;
-  double d[4] = {0, 0, 0, 0};
-  int oid = 0x7fffffff;
-  bool use = false;
-  if (i < m.n_own && m.is_intr[i]) {
-    use = true;
+  double dmx[4] = {0, 0, 0, 0}, ds1[4] = {0, 0, 0, 0}, ds2[4] = {0, 0, 0, 0};
+  double bv = -1.0;
+  int bi = 0x7fffffff;
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < m.n_own; i += gridDim.x * kBlock) {
+    if (!m.is_intr[i]) continue;
     double pv[4];
     vortex_exact(P, time, m.xc[i], m.yc[i], pv);
     const double ex0 = pv[0], ex1 = pv[0] * pv[1], ex2 = pv[0] * pv[2];
     const double ex3 = pv[3] / (P.gamma - 1.0) + 0.5 * pv[0] * (pv[1] * pv[1] + pv[2] * pv[2]);
+    double d[4];
     d[0] = fabs(q[i] - ex0);
     d[1] = fabs(q[np + i] - ex1);
     d[2] = fabs(q[2 * np + i] - ex2);
     d[3] = fabs(q[3 * np + i] - ex3);
-    oid = m.orig_id[i];
+#pragma unroll
+    for (int v = 0; v < 4; v++) { dmx[v] = fmax(dmx[v], d[v]); ds1[v] += d[v]; ds2[v] += d[v] * d[v]; }
+    const int oid = m.orig_id[i];
+    if (d[0] > bv || (d[0] == bv && oid < bi)) { bv = d[0]; bi = oid; }
   }
   __shared__ double smx[4][kBlock / 32], s1[4][kBlock / 32], s2[4][kBlock / 32], sb[kBlock / 32];
   __shared__ int sid[kBlock / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double bv = use ? d[0] : -1.0;
-  int bi = oid;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const double ov = __shfl_down_sync(0xffffffffu, bv, o);
@@ -960,7 +963,7 @@ __global__ void __launch_bounds__(kBlock) k_vortex_err(const DevMesh m, const Ph
   }
 #pragma unroll
   for (int v = 0; v < 4; v++) {
-    double mx = d[v], a = d[v], b = d[v] * d[v];
+    double mx = dmx[v], a = ds1[v], b = ds2[v];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
@@ -1042,14 +1045,14 @@ __global__ void __launch_bounds__(256) k_scatter_in(int n, int np, int nvar, con
                                                      const double *__restrict__ aos, double *__restrict__ soa) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const size_t o = orig_id[i];
+  const size_t o = orig_id ? orig_id[i] : i;  // null: the caller's array is already in local order
   for (int v = 0; v < nvar; v++) soa[(size_t)v * np + i] = aos[o * nvar + v];
 }
 __global__ void __launch_bounds__(256) k_gather_out(int n, int np, int nvar, const int *__restrict__ orig_id,
                                                      const double *__restrict__ soa, double *__restrict__ aos) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const size_t o = orig_id[i];
+  const size_t o = orig_id ? orig_id[i] : i;
   for (int v = 0; v < nvar; v++) aos[o * nvar + v] = soa[(size_t)v * np + i];
 }
 

@@ -77,6 +77,14 @@ class Fvs2dGpu:
         capi.check(self.L.fvs2d_gpu_get_state(capi.ptr(out)))
         return out
 
+    def set_state_local(self, cvar_own):
+        """owned cells only, library cell order (see ``capi.mesh_array("orig_id")``)."""
+        capi.check(self.L.fvs2d_gpu_set_state_local(capi.ptr(cvar_own)))
+
+    def get_state_local(self, out):
+        capi.check(self.L.fvs2d_gpu_get_state_local(capi.ptr(out)))
+        return out
+
     # -- the hot path ------------------------------------------------------------------------
     def time_integration(self, t1: float, nsub: int, logs: bool = True):
         """-> (res_l2[nsub,4], vortex_err[nsub,14] | None, vortex_xy[nsub,2] | None); logs=False skips

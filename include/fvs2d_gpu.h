@@ -77,6 +77,13 @@ int fvs2d_gpu_initialize_solution(void);
 int fvs2d_gpu_set_state(const double *cvar);
 int fvs2d_gpu_get_state(double *cvar);
 
+/* Distributed hosts: the same for the owned cells only, cvar_own(4, ncells_own) in the library's local
+ * cell order (fvs2d_gpu_mesh_array("orig_id") lists the original id of every local cell, owned first).
+ * No permutation, no global array: a plain contiguous copy per rank; ghost copies are refreshed by a
+ * halo exchange inside set_state_local. */
+int fvs2d_gpu_set_state_local(const double *cvar_own);
+int fvs2d_gpu_get_state_local(double *cvar_own);
+
 /* ---- the hot path ------------------------------------------------------------------------ */
 
 /* Replaces: time_integration(t1, ntimes_sub) (src/runge_kutta.f90:94-418), incl. the per-step
