@@ -285,7 +285,7 @@ def main():
 
     peak, peak_src = load_peaks()
     n_own = sizes["ncells_own"]
-    roof = {"bound": "hbm", "kernel": "k_flux_rk (pass B: face-flux gather + residual + RK update)",
+    roof = {"bound": "hbm", "kernel": "k_flux_pipe (pass B: face-flux gather + residual + RK update; persistent TMA/cp.async smem pipeline)",
             "achieved": bB * n_own / (flux_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
             "alg_bytes_per_cell": bB, "avg_launch_ms": flux_ms, "traffic": None}
     roof["frac"] = roof["achieved"] / peak

@@ -524,14 +524,29 @@ void hilbert_order(const HostMesh &m, std::vector<int> &perm) {
   const int bits = 20;
   double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
   for (int i = 0; i < nc; i++) { x0 = std::min(x0, m.xc[i]); x1 = std::max(x1, m.xc[i]); y0 = std::min(y0, m.yc[i]); y1 = std::max(y1, m.yc[i]); }
-  const double span = std::max(std::max(x1 - x0, y1 - y0), 1e-300);
+  // Anisotropy: the curve should be compact in CELL COUNTS, not in physical distance (a 128-cell tile of a
+  // mesh with 8:1 cells would otherwise be a 2-row strip with a huge halo).  Each axis is measured in units of
+  // the mean cell extent along it.
+  double ex = 0, ey = 0;
+#pragma omp parallel for schedule(static) reduction(+ : ex, ey)
+  for (int i = 0; i < nc; i++) {
+    double xa = 1e300, xb = -1e300, ya = 1e300, yb = -1e300;
+    for (int s = m.cptr[i]; s < m.cptr[i + 1]; s++) {
+      const int v = m.cnode[s];
+      xa = std::min(xa, m.xn[v]); xb = std::max(xb, m.xn[v]); ya = std::min(ya, m.yn[v]); yb = std::max(yb, m.yn[v]);
+    }
+    ex += xb - xa; ey += yb - ya;
+  }
+  ex = std::max(ex / nc, 1e-300); ey = std::max(ey / nc, 1e-300);
+  const double span = std::max(std::max((x1 - x0) / ex, (y1 - y0) / ey), 1e-300);
   const double scale = ((double)(1u << bits) - 1.0) / span;
+  const double scale_x = scale / ex, scale_y = scale / ey;
   std::vector<uint64_t> key(nc), key2(nc);
   std::vector<int> idx2(nc);
   perm.resize(nc);
 #pragma omp parallel for schedule(static)
   for (int i = 0; i < nc; i++) {
-    const uint32_t ix = (uint32_t)((m.xc[i] - x0) * scale), iy = (uint32_t)((m.yc[i] - y0) * scale);
+    const uint32_t ix = (uint32_t)((m.xc[i] - x0) * scale_x), iy = (uint32_t)((m.yc[i] - y0) * scale_y);
     key[i] = hilbert_d(ix, iy, bits);
     perm[i] = i;
   }
