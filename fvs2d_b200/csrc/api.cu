@@ -379,6 +379,7 @@ int fvs2d_gpu_init(const fvs2d_config *cfg, int device) {
   else C->recon = RC_GENERAL;
   Phys &P = C->phys;
   P.gamma = cfg->gamma; P.kappa = kap; P.cfl = cfg->cfl_user;
+  P.gm1 = cfg->gamma - 1.0; P.gog = cfg->gamma / (cfg->gamma - 1.0);
   for (int i = 0; i < 4; i++) { P.pinf[i] = cfg->pvar_inf[i]; P.vinf[i] = cfg->vortex_inf[i]; }
   P.vpos[0] = cfg->vortex_pos[0]; P.vpos[1] = cfg->vortex_pos[1]; P.vkap = cfg->vortex_kappa;
   for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) P.mms[i][j] = cfg->mms_c[i][j];

@@ -40,6 +40,7 @@ struct DevMesh {
 
 struct Phys {
   double gamma, kappa, cfl;
+  double gm1, gog;  // gamma-1, gamma/(gamma-1)
   double pinf[4];
   double vpos[2], vkap, vinf[4];
   double mms[4][4];
@@ -56,21 +57,23 @@ struct StageParams {
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void vortex_exact(const Phys &P, double t, double x, double y, double pv[4]) {
-  // src/mms.f90:219-265
+  // src/mms.f90:219-265.  exp(1-r^2) = exp((1-r^2)/2)^2; rho = temp^(1/(gamma-1)) and p = rho^gamma =
+  // temp^(gamma/(gamma-1)) through one log and two exp (two pow calls cost twice as much; |log(temp)| is
+  // small, so the composition stays at the 1-2 ulp level of the library pow)
   const double pi = 3.141592653589793238462643383279502884;
   const double rho_inf = P.vinf[0], u_inf = P.vinf[1], v_inf = P.vinf[2], p_inf = P.vinf[3];
   const double T_inf = p_inf / rho_inf;
   const double xc = P.vpos[0] + u_inf * t, yc = P.vpos[1] + v_inf * t;
   const double dx = x - xc, dy = y - yc;
-  const double r = sqrt(dx * dx + dy * dy);
+  const double r2 = dx * dx + dy * dy;
   const double kk = P.vkap / (2.0 * pi);
-  const double e1 = exp(0.5 * (1.0 - r * r));
+  const double e1 = exp(0.5 * (1.0 - r2));
   pv[1] = u_inf - kk * dy * e1;
   pv[2] = v_inf + kk * dx * e1;
-  const double temp = T_inf - kk * kk * (P.gamma - 1.0) / (2.0 * P.gamma) * exp(1.0 - r * r);
-  const double rho = pow(temp, 1.0 / (P.gamma - 1.0));
-  pv[0] = rho;
-  pv[3] = pow(rho, P.gamma);
+  const double temp = T_inf - kk * kk * (P.gamma - 1.0) / (2.0 * P.gamma) * (e1 * e1);
+  const double lt = log(temp);
+  pv[0] = exp(lt / P.gm1);
+  pv[3] = exp(P.gog * lt);  // rho^gamma = temp^(gamma/(gamma-1))
 }
 
 __device__ __forceinline__ void mms_exact(const Phys &P, double x, double y, double pv[4]) {
@@ -112,10 +115,9 @@ __device__ __forceinline__ void fast_sqrt_rcp(const double x, double &s, double 
 // Roe flux with Harten's entropy fix, primitive inputs (src/flux_invscid.f90:37-136).
 // aL, aR only ever appear squared in the reference (HL = aL*aL/(gamma-1)+kL), so c2 = gamma*p/rho is
 // used directly; divisions are reciprocals shared between quotients; gog = gamma/(gamma-1).
-__device__ __forceinline__ void roe_flux(const double gamma, const double L[4], const double R[4], const double nx,
+__device__ __forceinline__ void roe_flux(const Phys &P, const double L[4], const double R[4], const double nx,
                                          const double ny, double flux[4], double &ws_max) {
-  const double gm1 = gamma - 1.0;
-  const double gog = gamma / gm1;  // uniform: hoisted out of the face loop by the compiler
+  const double gm1 = P.gm1, gog = P.gog;
   const double tx = -ny, ty = nx;
   const double rhoL = L[0], uL = L[1], vL = L[2], pL = L[3];
   const double rhoR = R[0], uR = R[1], vR = R[2], pR = R[3];
@@ -331,7 +333,7 @@ __device__ __forceinline__ void interior_face(const Phys &P, const bool self_c1,
     }
   }
   double flux[4], ws;
-  roe_flux(P.gamma, sL, sR, nx, ny, flux, ws);
+  roe_flux(P, sL, sR, nx, ny, flux, ws);
   const double sa = self_c1 ? af : -af;
 #pragma unroll
   for (int v = 0; v < 4; v++) acc[v] += flux[v] * sa;
@@ -356,7 +358,7 @@ __device__ __forceinline__ void boundary_face(const Phys &P, const int type, con
     for (int v = 0; v < 4; v++) sR[v] = bcv[v];
   }
   double flux[4], ws;
-  roe_flux(P.gamma, sL, sR, nx, ny, flux, ws);
+  roe_flux(P, sL, sR, nx, ny, flux, ws);
 #pragma unroll
   for (int v = 0; v < 4; v++) acc[v] += flux[v] * af;
   wsacc += ws * af;
@@ -874,7 +876,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_flux_pipe(const DevMesh m, 
           }
         }
         double flux[4], ws;
-        roe_flux(P.gamma, sL, sR, nx, ny, flux, ws);
+        roe_flux(P, sL, sR, nx, ny, flux, ws);
         const double sa = self_c1 ? af : -af;
 #pragma unroll
         for (int v = 0; v < 4; v++) acc[v] += flux[v] * sa;
