@@ -81,6 +81,7 @@ struct Ctx {
   int opt_tile = 2;      // pass-B kernel: 2 persistent smem pipeline (default), 1 one-tile-per-CTA smem kernel, 0 direct gather
   bool tile_ok = false;
   int nsm = 148, nparts = 0;
+  int opt_ctas = 0;      // persistent pass-B CTAs per SM: 0 = as many as shared memory allows (max 3)
   bool bc_static_done = false;
   double rk_coef[4], h_rk[4], dts[4], dte[4];
   // timing
@@ -275,7 +276,8 @@ void launch_flux_one(const StageParams &S, const double *pin, double *pout) {
       cudaFuncSetAttribute(k_flux_pipe<UM, STEADY, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       configured = smem;
     }
-    const int per_sm = std::max(1, std::min(3, (int)((227 * 1024) / (smem + 1024))));
+    int per_sm = std::max(1, std::min(3, (int)((227 * 1024) / (smem + 1024))));
+    if (C->opt_ctas > 0) per_sm = std::min(per_sm, C->opt_ctas);
     const int grid = std::min(C->pm.ntiles, C->nsm * per_sm);
     k_flux_pipe<UM, STEADY, RC><<<grid, kPipeThreads, smem, C->st>>>(C->dm, C->pm, C->phys, S, pin, gx, gy, C->phi, C->bc, C->q, C->f,
                                                                      pout, C->dtl, C->resid, C->ws, C->partial);
@@ -864,6 +866,7 @@ int fvs2d_gpu_set_option(const char *key, int value) {
   const std::string k = key ? key : "";
   if (k == "timing") { C->opt_timing = value; return 0; }
   if (k == "tile") { C->opt_tile = value; return 0; }
+  if (k == "ctas") { C->opt_ctas = value; return 0; }
   return fail("fvs2d_gpu_set_option: unknown option '%s'", key);
 }
 

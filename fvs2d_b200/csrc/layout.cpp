@@ -22,7 +22,8 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
   std::vector<int> iperm(nc);
 #pragma omp parallel for schedule(static)
   for (int i = 0; i < nc; i++) iperm[perm[i]] = i;
-  auto range_begin = [&](int r) { return (int)((int64_t)nc * r / nranks); };
+  // rank boundaries on tile boundaries of the global order (tiles are sorted internally by hilbert_order)
+  auto range_begin = [&](int r) { return r >= nranks ? nc : (int)((int64_t)nc * r / nranks / kTile * kTile); };
   const int b0 = range_begin(rank), b1 = range_begin(rank + 1);
   L.own_begin = b0;
   L.n_own = b1 - b0;
