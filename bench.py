@@ -201,9 +201,10 @@ def main():
         k, v = kv.split("=")
         gpu.set_option(k, int(v))
     gpu.set_mesh(mesh)
+    ncells = mesh.ncells
+    del mesh                                          # the library holds its own copy
     gpu.initialize_solution()
     sizes, scal = gpu.sizes(), gpu.scalars()
-    ncells = mesh.ncells
     t_setup = time.perf_counter() - t_setup
 
     def barrier():

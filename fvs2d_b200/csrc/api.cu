@@ -824,7 +824,7 @@ int fvs2d_gpu_sizes(int s[10]) {
 int fvs2d_gpu_scalars(double s[6]) {
   NEED(C && C->has_mesh, "fvs2d_gpu_scalars: no mesh");
   const HostMesh &m = C->mesh;
-  s[0] = m.heff1; s[1] = m.heff2; s[2] = m.vol_sum; s[3] = m.vol_green; s[4] = C->grad.verify_err; s[5] = (double)C->bytes;
+  s[0] = m.heff1; s[1] = m.heff2; s[2] = m.vol_sum; s[3] = m.vol_green; s[4] = C->L.lsq_verify_err; s[5] = (double)C->bytes;
   return 0;
 }
 
@@ -833,7 +833,26 @@ long fvs2d_gpu_mesh_array(const char *name, void *out) {
   const HostMesh &m = C->mesh;
   const std::string n = name;
 #define RET(nm, vec) if (n == nm) { if (out) memcpy(out, (vec).data(), (vec).size() * sizeof((vec)[0])); return (long)(vec).size(); }
-  RET("xc", m.xc) RET("yc", m.yc) RET("vol", m.vol) RET("ex", m.ex) RET("ey", m.ey) RET("ea", m.ea) RET("enx", m.enx) RET("eny", m.eny)
+  RET("xc", m.xc) RET("yc", m.yc) RET("vol", m.vol)
+  if (n == "ex" || n == "ey" || n == "ea" || n == "enx" || n == "eny") {  // materialised on demand (verification only)
+    if (out) for (int je = 0; je < m.nedges; je++) {
+      const EdgeGeom eg = edge_geom(m, je);
+      ((double *)out)[je] = n == "ex" ? eg.x : n == "ey" ? eg.y : n == "ea" ? eg.a : n == "enx" ? eg.nx : eg.ny;
+    }
+    return m.nedges;
+  }
+  if (n == "grad_cx" || n == "grad_cy" || n == "grad_c0x" || n == "grad_c0y") {  // the same for the gradient coefficients
+    const GradOp &g = C->grad;
+    const bool c0 = n == "grad_c0x" || n == "grad_c0y";
+    if (c0 && g.form != 0) return 0;
+    if (out) for (int ic = 0; ic < m.ncells; ic++) {
+      double cx[kMaxStencil], cy[kMaxStencil], c0x, c0y;
+      grad_cell_coeffs(m, g, ic, cx, cy, c0x, c0y);
+      if (c0) ((double *)out)[ic] = n == "grad_c0x" ? c0x : c0y;
+      else for (int64_t k = g.ptr[ic]; k < g.ptr[ic + 1]; k++) ((double *)out)[k] = n == "grad_cx" ? cx[k - g.ptr[ic]] : cy[k - g.ptr[ic]];
+    }
+    return c0 ? m.ncells : (long)g.ptr[m.ncells];
+  }
   RET("en1", m.en1) RET("en2", m.en2) RET("ec1", m.ec1) RET("ec2", m.ec2) RET("cedge", m.cedge) RET("nghbre", m.nghbre)
   RET("cell_intr", m.cell_intr) RET("b_edge", m.b_edge) RET("b_edge_ptr", m.b_edge_ptr) RET("perm", C->L.perm)
   RET("loc2new", C->L.loc2new) RET("peers", C->L.peers) RET("send_ptr", C->L.send_ptr) RET("send_idx", C->L.send_idx)
@@ -844,7 +863,7 @@ long fvs2d_gpu_mesh_array(const char *name, void *out) {
   RET("tile_es", C->L.tile_es) RET("tile_ne", C->L.tile_ne) RET("tile_hc_ptr", C->L.tile_hc_ptr) RET("tile_he_ptr", C->L.tile_he_ptr)
   RET("tile_hdr", C->L.tile_hdr) RET("t_pack", C->L.t_pack) RET("t_bf", C->L.t_bf)
   RET("tile_hc_idx", C->L.tile_hc_idx) RET("tile_he_idx", C->L.tile_he_idx) RET("f_pack", C->L.f_pack) RET("f_bf", C->L.f_bf)
-  RET("grad_idx", C->grad.idx) RET("grad_cx", C->grad.cx) RET("grad_cy", C->grad.cy) RET("grad_c0x", C->grad.c0x) RET("grad_c0y", C->grad.c0y)
+  RET("grad_idx", C->grad.idx)
 #undef RET
   if (n == "grad_ptr") {
     if (out) for (size_t i = 0; i < C->grad.ptr.size(); i++) ((int *)out)[i] = (int)C->grad.ptr[i];

@@ -130,20 +130,6 @@ std::string build_mesh(HostMesh &m) {
   }
   if (bad) return "build_mesh: inconsistent face neighbours (non-conforming mesh?)";
 
-  // -- edge geometry (src/grid_procs.f90:630-647)
-  m.ex.resize(ne); m.ey.resize(ne); m.ea.resize(ne); m.enx.resize(ne); m.eny.resize(ne);
-#pragma omp parallel for schedule(static)
-  for (int i = 0; i < ne; i++) {
-    const int v1 = m.en1[i], v2 = m.en2[i];
-    const double dx = m.xn[v2] - m.xn[v1], dy = m.yn[v2] - m.yn[v1];
-    const double a = std::sqrt(dx * dx + dy * dy);
-    m.ea[i] = a;
-    m.ex[i] = 0.5 * (m.xn[v1] + m.xn[v2]);
-    m.ey[i] = 0.5 * (m.yn[v1] + m.yn[v2]);
-    m.enx[i] = dy / a;
-    m.eny[i] = -dx / a;
-  }
-
   // -- interior / boundary cells and edges (src/grid_procs.f90:697-763)
   m.cell_intr.clear();
   m.cell_intr.reserve(nc);
@@ -199,7 +185,8 @@ std::string build_mesh(HostMesh &m) {
     for (int s = m.cptr[ic]; s < m.cptr[ic + 1]; s++) {
       const int je = m.cedge[s];
       const double sgn = m.ec1[je] == ic ? 1.0 : -1.0;
-      v += m.enx[je] * sgn * m.ex[je] * m.ea[je];
+      const EdgeGeom eg = edge_geom(m, je);
+      v += eg.nx * sgn * eg.x * eg.a;
     }
     vg += v;
   }
@@ -273,43 +260,23 @@ void knn(const BucketGrid &g, const std::vector<double> &x, const std::vector<do
 std::string build_gradient(const HostMesh &m, int grad_method, int lsq_stencil, double lsq_pow, GradOp &g) {
   const int nc = m.ncells;
   g = GradOp();
+  g.method = grad_method; g.lsq_pow = lsq_pow;
+  g.form = grad_method == 3 ? 1 : 0;
   g.ptr.assign(nc + 1, 0);
   if (grad_method == 1) {
     // ---- Green-Gauss cell-based: one entry per face; a boundary face points back at the cell itself
-    g.form = 0;
     for (int ic = 0; ic < nc; ic++) g.ptr[ic + 1] = m.cptr[ic + 1];
-    const int64_t tot = g.ptr[nc];
-    g.idx.resize(tot); g.cx.resize(tot); g.cy.resize(tot); g.c0x.resize(nc); g.c0y.resize(nc);
+    g.idx.resize(g.ptr[nc]);
 #pragma omp parallel for schedule(static)
-    for (int ic = 0; ic < nc; ic++) {
-      const double xc = m.xc[ic], yc = m.yc[ic], vol = m.vol[ic];
-      double c0x = 0, c0y = 0;
-      for (int s = m.cptr[ic]; s < m.cptr[ic + 1]; s++) {
-        const int je = m.cedge[s];
-        const double sgn = m.ec1[je] == ic ? 1.0 : -1.0;
-        const double af = m.ea[je], nxf = m.enx[je] * sgn, nyf = m.eny[je] * sgn, xf = m.ex[je], yf = m.ey[je];
-        double dx = xf - xc, dy = yf - yc;
-        const double d0 = std::sqrt(dx * dx + dy * dy);
-        const int jc = m.nghbre[s] >= 0 ? m.nghbre[s] : ic;
-        dx = xf - m.xc[jc]; dy = yf - m.yc[jc];
-        const double d1 = std::sqrt(dx * dx + dy * dy);
-        c0x = c0x + d1 / (d0 + d1) * nxf * af;
-        c0y = c0y + d1 / (d0 + d1) * nyf * af;
-        g.idx[s] = jc;
-        g.cx[s] = d0 / (d0 + d1) * nxf * af / vol;
-        g.cy[s] = d0 / (d0 + d1) * nyf * af / vol;
-      }
-      g.c0x[ic] = c0x / vol;
-      g.c0y[ic] = c0y / vol;
-    }
+    for (int ic = 0; ic < nc; ic++)
+      for (int s = m.cptr[ic]; s < m.cptr[ic + 1]; s++) g.idx[s] = m.nghbre[s] >= 0 ? m.nghbre[s] : ic;
     return "";
   }
   if (grad_method == 2) {
-    // ---- Green-Gauss node-based: inverse-distance cell->node interpolation folded into per-cell
-    // coefficients; entries of the same neighbour (shared through two vertices) are merged.
-    g.form = 0;
+    // ---- Green-Gauss node-based: stencil = sorted unique cells sharing a vertex (the cell itself is
+    // dropped: coefnb = 0, src/gradient_ggnb.f90:145; a neighbour reached through two vertices is merged)
     const int nn = m.nnodes;
-    std::vector<double> idw(nn);
+    g.idw.resize(nn);
 #pragma omp parallel for schedule(static)
     for (int in = 0; in < nn; in++) {
       double idt = 0;
@@ -318,89 +285,16 @@ std::string build_gradient(const HostMesh &m, int grad_method, int lsq_stencil, 
         const double dx = m.xc[ic] - m.xn[in], dy = m.yc[ic] - m.yn[in];
         idt = idt + 1.0 / std::sqrt(dx * dx + dy * dy);
       }
-      idw[in] = 1.0 / idt;
+      g.idw[in] = 1.0 / idt;
     }
-    // pass 1: unique neighbour count per cell; pass 2: fill
-    std::vector<int> cnt(nc);
-    auto gather = [&](int ic, int *ids, double *wx, double *wy, double &c0x, double &c0y) {
-      const int nv = m.nvrt(ic), b = m.cptr[ic];
-      const double xc = m.xc[ic], yc = m.yc[ic];
-      double ex[4] = {0, 0, 0, 0}, ey[4] = {0, 0, 0, 0};  // coefedg per vertex: sum over the two touching edges of n*a/2
-      c0x = c0y = 0;
-      for (int e = 0; e < nv; e++) {
-        const int je = m.cedge[b + e];
-        const double sgn = m.ec1[je] == ic ? 1.0 : -1.0;
-        const double af = m.ea[je], nxf = m.enx[je] * sgn, nyf = m.eny[je] * sgn;
-        const int iv1 = m.en1[je], iv2 = m.en2[je];
-        double dx = xc - m.xn[iv1], dy = yc - m.yn[iv1];
-        const double w1 = 1.0 / std::sqrt(dx * dx + dy * dy);
-        dx = xc - m.xn[iv2]; dy = yc - m.yn[iv2];
-        const double w2 = 1.0 / std::sqrt(dx * dx + dy * dy);
-        c0x = c0x + af * nxf / 2.0 * (w1 * idw[iv1] + w2 * idw[iv2]);
-        c0y = c0y + af * nyf / 2.0 * (w1 * idw[iv1] + w2 * idw[iv2]);
-        for (int v = 0; v < nv; v++) {
-          const int iv = m.cnode[b + v];
-          if (iv == iv1) { ex[v] += af * nxf / 2.0; ey[v] += af * nyf / 2.0; }
-          if (iv == iv2) { ex[v] += af * nxf / 2.0; ey[v] += af * nyf / 2.0; }
-        }
-      }
-      int n = 0;
-      for (int v = 0; v < nv; v++) {
-        const int iv = m.cnode[b + v];
-        for (int j = m.n2c_ptr[iv]; j < m.n2c_ptr[iv + 1]; j++) {
-          const int jc = m.n2c[j];
-          if (jc == ic) continue;  // coefnb = 0 for the cell itself (src/gradient_ggnb.f90:145)
-          const double dx = m.xc[jc] - m.xn[iv], dy = m.yc[jc] - m.yn[iv];
-          const double cnb = idw[iv] / std::sqrt(dx * dx + dy * dy);
-          int p = 0;
-          while (p < n && ids[p] != jc) p++;
-          if (p == n) { ids[n] = jc; wx[n] = 0; wy[n] = 0; n++; }
-          wx[p] += ex[v] * cnb;
-          wy[p] += ey[v] * cnb;
-        }
-      }
-      return n;
-    };
-    int overflow = 0;
-#pragma omp parallel for schedule(static) reduction(+ : overflow)
-    for (int ic = 0; ic < nc; ic++) {
-      int tot = 0;
-      for (int s = m.cptr[ic]; s < m.cptr[ic + 1]; s++) tot += m.n2c_ptr[m.cnode[s] + 1] - m.n2c_ptr[m.cnode[s]];
-      if (tot > 256) { overflow++; cnt[ic] = 0; continue; }
-      int ids[256]; double wx[256], wy[256], a, b2;
-      cnt[ic] = gather(ic, ids, wx, wy, a, b2);
-    }
-    if (overflow) return "build_gradient: node valence too high for the GGNB stencil buffer";
-    for (int ic = 0; ic < nc; ic++) g.ptr[ic + 1] = g.ptr[ic] + cnt[ic];
-    const int64_t tot = g.ptr[nc];
-    g.idx.resize(tot); g.cx.resize(tot); g.cy.resize(tot); g.c0x.resize(nc); g.c0y.resize(nc);
-#pragma omp parallel for schedule(static)
-    for (int ic = 0; ic < nc; ic++) {
-      int ids[256]; double wx[256], wy[256], c0x, c0y;
-      const int n = gather(ic, ids, wx, wy, c0x, c0y);
-      const double vol = m.vol[ic];
-      g.c0x[ic] = c0x / vol; g.c0y[ic] = c0y / vol;
-      // ascending neighbour id: deterministic and memory-friendly
-      int ord[256];
-      for (int i = 0; i < n; i++) ord[i] = i;
-      std::sort(ord, ord + n, [&](int a, int b) { return ids[a] < ids[b]; });
-      for (int i = 0; i < n; i++) {
-        g.idx[g.ptr[ic] + i] = ids[ord[i]];
-        g.cx[g.ptr[ic] + i] = wx[ord[i]] / vol;
-        g.cy[g.ptr[ic] + i] = wy[ord[i]] / vol;
-      }
-    }
-    return "";
+  } else if (grad_method != 3) {
+    return "check cell-center gradient scheme in input file";
   }
-  if (grad_method != 3) return "check cell-center gradient scheme in input file";
-
-  // ---- least squares: stencil first
-  g.form = 1;
-  std::vector<int> sten;
-  if (lsq_stencil == 0) {
-    // fn: face neighbours; each boundary slot (in nghbr slot order) takes the next nearest centroid
+  if (grad_method == 3 && lsq_stencil == 0) {
+    // ---- LSQ fn: face neighbours; each boundary slot (in nghbr slot order) takes the next nearest centroid
     // that is neither the cell nor a face neighbour (src/gradient_lsq.f90:88-131)
     for (int ic = 0; ic < nc; ic++) g.ptr[ic + 1] = m.cptr[ic + 1];
+    std::vector<int> &sten = g.idx;
     sten.assign(g.ptr[nc], -1);
     std::vector<int> bcells;
     int too_many = 0;
@@ -439,67 +333,128 @@ std::string build_gradient(const HostMesh &m, int grad_method, int lsq_stencil, 
       }
       if (fail) return "gradient_lsq setup_fn: could not complete a boundary-cell stencil from the 8 nearest cells";
     }
-  } else {
-    // nn: sorted unique cells sharing a vertex (src/gradient_lsq.f90:227-271)
-    std::vector<int> cnt(nc);
-    auto collect = [&](int ic, int *tmp) {
-      int nt = 0;
-      for (int s = m.cptr[ic]; s < m.cptr[ic + 1]; s++) {
-        const int iv = m.cnode[s];
-        for (int j = m.n2c_ptr[iv]; j < m.n2c_ptr[iv + 1]; j++)
-          if (m.n2c[j] != ic && nt < 256) tmp[nt++] = m.n2c[j];
-      }
-      std::sort(tmp, tmp + nt);
-      return (int)(std::unique(tmp, tmp + nt) - tmp);
-    };
-#pragma omp parallel for schedule(static)
-    for (int ic = 0; ic < nc; ic++) { int tmp[256]; cnt[ic] = collect(ic, tmp); }
-    for (int ic = 0; ic < nc; ic++) g.ptr[ic + 1] = g.ptr[ic] + cnt[ic];
-    sten.resize(g.ptr[nc]);
-#pragma omp parallel for schedule(static)
-    for (int ic = 0; ic < nc; ic++) { int tmp[256]; int n = collect(ic, tmp); std::copy(tmp, tmp + n, sten.begin() + g.ptr[ic]); }
+    return "";
   }
-  // ---- normal equations per cell (src/gradient_lsq.f90:137-203 / 281-347)
-  const int64_t tot = g.ptr[nc];
-  g.idx = sten;
-  g.cx.resize(tot); g.cy.resize(tot);
-  double verr = 0;
-  int singular = 0;
-#pragma omp parallel for schedule(static) reduction(max : verr) reduction(+ : singular)
+  // ---- vertex-neighbour stencils (LSQ nn: src/gradient_lsq.f90:227-271; GGNB)
+  std::vector<int> cnt(nc);
+  auto collect = [&](int ic, int *tmp) {
+    int nt = 0;
+    for (int s = m.cptr[ic]; s < m.cptr[ic + 1]; s++) {
+      const int iv = m.cnode[s];
+      for (int j = m.n2c_ptr[iv]; j < m.n2c_ptr[iv + 1]; j++)
+        if (m.n2c[j] != ic && nt < kMaxStencil) tmp[nt++] = m.n2c[j];
+    }
+    std::sort(tmp, tmp + nt);
+    return (int)(std::unique(tmp, tmp + nt) - tmp);
+  };
+  int overflow = 0;
+#pragma omp parallel for schedule(static) reduction(+ : overflow)
   for (int ic = 0; ic < nc; ic++) {
-    const double xc = m.xc[ic], yc = m.yc[ic];
-    const int64_t b = g.ptr[ic];
-    const int n = (int)(g.ptr[ic + 1] - b);
-    double g11 = 0, g12 = 0, g21 = 0, g22 = 0;
-    double dxw[256], dyw[256], w[256];
-    for (int i = 0; i < n && i < 256; i++) {
-      const int jc = sten[b + i];
-      const double ddx = m.xc[jc] - xc, ddy = m.yc[jc] - yc;
-      const double dis = std::sqrt(ddx * ddx + ddy * ddy);
-      w[i] = dis > 0.0 ? 1.0 / std::pow(dis, lsq_pow) : 0.0;
-      dxw[i] = w[i] * ddx; dyw[i] = w[i] * ddy;
-    }
-    for (int i = 0; i < n; i++) { g11 += dxw[i] * dxw[i]; g12 += dxw[i] * dyw[i]; g21 += dyw[i] * dxw[i]; g22 += dyw[i] * dyw[i]; }
-    const double det = g11 * g22 - g12 * g21;
-    if (!(std::fabs(det) > 0)) singular++;
-    const double i11 = 1.0 / det * g22, i22 = 1.0 / det * g11, i12 = -1.0 / det * g12, i21 = -1.0 / det * g21;
-    double dfx = 0, dfy = 0;
-    for (int i = 0; i < n; i++) {
-      const double c1 = i11 * dxw[i] + i12 * dyw[i], c2 = i21 * dxw[i] + i22 * dyw[i];
-      g.cx[b + i] = c1 * w[i];  // w folded in: grad = sum coef*w*(p_j - p_i)
-      g.cy[b + i] = c2 * w[i];
-      // linear-exactness self check with f = 2x + y (src/gradient_lsq.f90:490-529)
-      const int jc = sten[b + i];
-      const double diff = 1.0 * m.yc[jc] + 2.0 * m.xc[jc] - (1.0 * yc + 2.0 * xc);
-      dfx += c1 * diff * w[i];
-      dfy += c2 * diff * w[i];
-    }
-    verr = std::max(verr, std::max(std::fabs(dfx - 2.0), std::fabs(dfy - 1.0)));
+    int tot = 0;
+    for (int s = m.cptr[ic]; s < m.cptr[ic + 1]; s++) tot += m.n2c_ptr[m.cnode[s] + 1] - m.n2c_ptr[m.cnode[s]];
+    if (tot > kMaxStencil) { overflow++; cnt[ic] = 0; continue; }
+    int tmp[kMaxStencil];
+    cnt[ic] = collect(ic, tmp);
   }
-  g.verify_err = verr;
-  if (singular) return "gradient_lsq: singular least-squares system";
-  if (!(verr <= 1.0e-10)) return " LSQ coefficients are not correct";
+  if (overflow) return "build_gradient: node valence too high for the stencil buffer";
+  for (int ic = 0; ic < nc; ic++) g.ptr[ic + 1] = g.ptr[ic] + cnt[ic];
+  g.idx.resize(g.ptr[nc]);
+#pragma omp parallel for schedule(static)
+  for (int ic = 0; ic < nc; ic++) { int tmp[kMaxStencil]; const int n = collect(ic, tmp); std::copy(tmp, tmp + n, g.idx.begin() + g.ptr[ic]); }
   return "";
+}
+
+// Coefficients of one cell for its stencil g.idx[g.ptr[ic] ...): cx/cy (n entries) and, for the Green-Gauss
+// forms, c0x/c0y.  Returns the LSQ linear-exactness error of the cell (0 for Green-Gauss), or -1 when the
+// least-squares system is singular.
+double grad_cell_coeffs(const HostMesh &m, const GradOp &g, int ic, double *cx, double *cy, double &c0x, double &c0y) {
+  const int64_t b = g.ptr[ic];
+  const int n = (int)(g.ptr[ic + 1] - b);
+  const double xc = m.xc[ic], yc = m.yc[ic], vol = m.vol[ic];
+  c0x = c0y = 0;
+  if (g.method == 1) {  // src/gradient_ggcb.f90:55-107, 1/vol folded in
+    for (int k = 0; k < n; k++) {
+      const int s = m.cptr[ic] + k, je = m.cedge[s];
+      const double sgn = m.ec1[je] == ic ? 1.0 : -1.0;
+      const EdgeGeom eg = edge_geom(m, je);
+      const double af = eg.a, nxf = eg.nx * sgn, nyf = eg.ny * sgn;
+      double dx = eg.x - xc, dy = eg.y - yc;
+      const double d0 = std::sqrt(dx * dx + dy * dy);
+      const int jc = g.idx[b + k];
+      dx = eg.x - m.xc[jc]; dy = eg.y - m.yc[jc];
+      const double d1 = std::sqrt(dx * dx + dy * dy);
+      c0x = c0x + d1 / (d0 + d1) * nxf * af;
+      c0y = c0y + d1 / (d0 + d1) * nyf * af;
+      cx[k] = d0 / (d0 + d1) * nxf * af / vol;
+      cy[k] = d0 / (d0 + d1) * nyf * af / vol;
+    }
+    c0x /= vol; c0y /= vol;
+    return 0.0;
+  }
+  if (g.method == 2) {  // src/gradient_ggnb.f90:85-174: coefedg(v) * coefnb(v, j) summed per neighbour j, 1/vol folded in
+    const int nv = m.nvrt(ic), cb = m.cptr[ic];
+    double ex[4] = {0, 0, 0, 0}, ey[4] = {0, 0, 0, 0};
+    for (int e = 0; e < nv; e++) {
+      const int je = m.cedge[cb + e];
+      const double sgn = m.ec1[je] == ic ? 1.0 : -1.0;
+      const EdgeGeom eg = edge_geom(m, je);
+      const double af = eg.a, nxf = eg.nx * sgn, nyf = eg.ny * sgn;
+      const int iv1 = m.en1[je], iv2 = m.en2[je];
+      double dx = xc - m.xn[iv1], dy = yc - m.yn[iv1];
+      const double w1 = 1.0 / std::sqrt(dx * dx + dy * dy);
+      dx = xc - m.xn[iv2]; dy = yc - m.yn[iv2];
+      const double w2 = 1.0 / std::sqrt(dx * dx + dy * dy);
+      c0x = c0x + af * nxf / 2.0 * (w1 * g.idw[iv1] + w2 * g.idw[iv2]);
+      c0y = c0y + af * nyf / 2.0 * (w1 * g.idw[iv1] + w2 * g.idw[iv2]);
+      for (int v = 0; v < nv; v++) {
+        const int iv = m.cnode[cb + v];
+        if (iv == iv1) { ex[v] += af * nxf / 2.0; ey[v] += af * nyf / 2.0; }
+        if (iv == iv2) { ex[v] += af * nxf / 2.0; ey[v] += af * nyf / 2.0; }
+      }
+    }
+    for (int k = 0; k < n; k++) { cx[k] = 0; cy[k] = 0; }
+    for (int v = 0; v < nv; v++) {
+      const int iv = m.cnode[cb + v];
+      for (int j = m.n2c_ptr[iv]; j < m.n2c_ptr[iv + 1]; j++) {
+        const int jc = m.n2c[j];
+        if (jc == ic) continue;
+        const double dx = m.xc[jc] - m.xn[iv], dy = m.yc[jc] - m.yn[iv];
+        const double cnb = g.idw[iv] / std::sqrt(dx * dx + dy * dy);
+        const int k = (int)(std::lower_bound(g.idx.begin() + b, g.idx.begin() + b + n, jc) - (g.idx.begin() + b));
+        cx[k] += ex[v] * cnb;
+        cy[k] += ey[v] * cnb;
+      }
+    }
+    for (int k = 0; k < n; k++) { cx[k] /= vol; cy[k] /= vol; }
+    c0x /= vol; c0y /= vol;
+    return 0.0;
+  }
+  // least squares: normal equations per cell (src/gradient_lsq.f90:137-203 / 281-347), w folded in
+  double g11 = 0, g12 = 0, g21 = 0, g22 = 0;
+  double dxw[kMaxStencil], dyw[kMaxStencil], w[kMaxStencil];
+  for (int i = 0; i < n; i++) {
+    const int jc = g.idx[b + i];
+    const double ddx = m.xc[jc] - xc, ddy = m.yc[jc] - yc;
+    const double dis = std::sqrt(ddx * ddx + ddy * ddy);
+    w[i] = dis > 0.0 ? 1.0 / std::pow(dis, g.lsq_pow) : 0.0;
+    dxw[i] = w[i] * ddx; dyw[i] = w[i] * ddy;
+  }
+  for (int i = 0; i < n; i++) { g11 += dxw[i] * dxw[i]; g12 += dxw[i] * dyw[i]; g21 += dyw[i] * dxw[i]; g22 += dyw[i] * dyw[i]; }
+  const double det = g11 * g22 - g12 * g21;
+  if (!(std::fabs(det) > 0)) return -1.0;
+  const double i11 = 1.0 / det * g22, i22 = 1.0 / det * g11, i12 = -1.0 / det * g12, i21 = -1.0 / det * g21;
+  double dfx = 0, dfy = 0;
+  for (int i = 0; i < n; i++) {
+    const double c1 = i11 * dxw[i] + i12 * dyw[i], c2 = i21 * dxw[i] + i22 * dyw[i];
+    cx[i] = c1 * w[i];  // grad = sum coef*w*(p_j - p_i)
+    cy[i] = c2 * w[i];
+    // linear-exactness self check with f = 2x + y (src/gradient_lsq.f90:490-529)
+    const int jc = g.idx[b + i];
+    const double diff = 1.0 * m.yc[jc] + 2.0 * m.xc[jc] - (1.0 * yc + 2.0 * xc);
+    dfx += c1 * diff * w[i];
+    dfy += c2 * diff * w[i];
+  }
+  return std::max(std::fabs(dfx - 2.0), std::fabs(dfy - 1.0));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -2,6 +2,7 @@
 // rebuilt with the reference's entity numbering by O(n), OpenMP-parallel algorithms.
 // All ids are 0-based; "boundary / none" is -1 where the Fortran stores 0.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -22,7 +23,7 @@ struct HostMesh {
   std::vector<int> cedge;             // per cell-slot: global edge id of local edge k
   int nedges = 0, nedges_intr = 0, nedges_bndr = 0;
   std::vector<int> en1, en2, ec1, ec2;  // c1 < c2, c2 == -1 on the boundary, normal points c1 -> c2
-  std::vector<double> ex, ey, ea, enx, eny;
+  // edge geometry is not stored (4.6 GB at 69 M cells): edge_geom() recomputes it from the end nodes
   int ncells_intr = 0, ncells_bndr = 0;
   std::vector<int> cell_intr;
   std::vector<int> b_edge_ptr, b_edge;  // boundary edge lists in .bc order then local-edge order
@@ -40,22 +41,33 @@ struct HostMesh {
 // Builds everything in `m` from the raw fields.  Returns "" or the reference's stop message.
 std::string build_mesh(HostMesh &m);
 
+// Edge centre, length and unit normal (c1 -> c2), src/grid_procs.f90:630-647.
+struct EdgeGeom { double x, y, a, nx, ny; };
+inline EdgeGeom edge_geom(const HostMesh &m, int je) {
+  const int v1 = m.en1[je], v2 = m.en2[je];
+  const double dx = m.xn[v2] - m.xn[v1], dy = m.yn[v2] - m.yn[v1];
+  const double a = std::sqrt(dx * dx + dy * dy);
+  return {0.5 * (m.xn[v1] + m.xn[v2]), 0.5 * (m.yn[v1] + m.yn[v2]), a, dy / a, -dx / a};
+}
+
 // Gradient operators in one generic sparse form (original numbering):
 //   grad_i = c0_i * p_i + sum_k coef_k * p_{idx_k}            (form == 0, Green-Gauss; 1/vol folded in)
 //   grad_i =              sum_k coef_k * (p_{idx_k} - p_i)    (form == 1, least squares; w folded in)
+// Only the stencil STRUCTURE is kept for all cells (the partitioner needs it); coefficients are produced
+// per cell on demand (grad_cell_coeffs), so a rank only ever computes and stores those of its own cells.
+constexpr int kMaxStencil = 256;
 struct GradOp {
-  int form = 0;
+  int form = 0, method = 1;
+  double lsq_pow = 0;
   std::vector<int64_t> ptr;  // ncells+1
-  std::vector<int> idx;
-  std::vector<double> cx, cy;
-  std::vector<double> c0x, c0y;  // form 0 only
-  double verify_err = 0;         // LSQ: max |grad(2x+y) - (2,1)| (src/gradient_lsq.f90:490-529)
-  // the LSQ stencil itself (the limiter's min/max set, src/gradient_limiter.f90:54-58) is (ptr, idx)
+  std::vector<int> idx;      // the LSQ stencil is also the limiter's min/max set (src/gradient_limiter.f90:54-58)
+  std::vector<double> idw;   // GGNB: node weights 1 / sum_c 1/|x_c - x_v| (src/gradient_ggnb.f90:59-80)
 };
 
 // grad_method 1 GGCB (src/gradient_ggcb.f90:48-110), 2 GGNB (src/gradient_ggnb.f90:49-177),
 // 3 LSQ fn/nn (src/gradient_lsq.f90:70-365).  Returns "" or an error message.
 std::string build_gradient(const HostMesh &m, int grad_method, int lsq_stencil, double lsq_pow, GradOp &g);
+double grad_cell_coeffs(const HostMesh &m, const GradOp &g, int ic, double *cx, double *cy, double &c0x, double &c0y);
 
 // Hilbert-curve ordering of the cell centroids (perm[new] = old), measured in cell counts per axis so that
 // anisotropic meshes still give compact tiles.  (Tried and rejected on B200: scanline order inside each

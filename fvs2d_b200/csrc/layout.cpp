@@ -104,7 +104,7 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
 #pragma omp parallel for schedule(static)
   for (int je = 0; je < m.nedges; je++) {
     const int l = edge_loc[je];
-    if (l >= 0) { L.ex[l] = m.ex[je]; L.ey[l] = m.ey[je]; L.ea[l] = m.ea[je]; L.enx[l] = m.enx[je]; L.eny[l] = m.eny[je]; }
+    if (l >= 0) { const EdgeGeom eg = edge_geom(m, je); L.ex[l] = eg.x; L.ey[l] = eg.y; L.ea[l] = eg.a; L.enx[l] = eg.nx; L.eny[l] = eg.ny; }
   }
 
   // ---- faces as sliced ELL
@@ -260,27 +260,38 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
   L.g_cx.assign(L.g_off[nsl], 0.0);
   L.g_cy.assign(L.g_off[nsl], 0.0);
   if (g.form == 0) { L.c0x.resize(L.n_own); L.c0y.resize(L.n_own); }
-#pragma omp parallel for schedule(static)
+  double verr = 0;
+  int singular = 0;
+#pragma omp parallel for schedule(static) reduction(max : verr) reduction(+ : singular)
   for (int s = 0; s < nsl; s++) {
     const int w = (L.g_off[s + 1] - L.g_off[s]) >> 5;
+    double cx[kMaxStencil], cy[kMaxStencil];
     for (int lane = 0; lane < 32; lane++) {
       const int i = 32 * s + lane;
       const bool live = i < L.n_own;
       const int o = live ? L.orig_id[i] : 0;
       const int n = live ? (int)(g.ptr[o + 1] - g.ptr[o]) : 0;
+      double c0x = 0, c0y = 0;
+      if (live) {
+        const double e = grad_cell_coeffs(m, g, o, cx, cy, c0x, c0y);
+        if (e < 0) singular++; else verr = std::max(verr, e);
+      }
       for (int k = 0; k < w; k++) {
         const int e = L.g_off[s] + 32 * k + lane;
         if (k < n) {
           L.g_idx[e] = to_local(iperm[g.idx[g.ptr[o] + k]]);
-          L.g_cx[e] = g.cx[g.ptr[o] + k];
-          L.g_cy[e] = g.cy[g.ptr[o] + k];
+          L.g_cx[e] = cx[k];
+          L.g_cy[e] = cy[k];
         } else {
           L.g_idx[e] = live ? i : 0;
         }
       }
-      if (live && g.form == 0) { L.c0x[i] = g.c0x[o]; L.c0y[i] = g.c0y[o]; }
+      if (live && g.form == 0) { L.c0x[i] = c0x; L.c0y[i] = c0y; }
     }
   }
+  L.lsq_verify_err = verr;
+  if (singular) return "gradient_lsq: singular least-squares system";
+  if (g.form == 1 && !(verr <= 1.0e-10)) return " LSQ coefficients are not correct";
 
   // ---- halo plan
   if (nranks > 1) {

@@ -67,6 +67,7 @@ struct Layout {
   // halo plan: peers in ascending rank; send_idx = owned local ids the peer needs (ascending new id),
   // recv = contiguous run [recv_begin, recv_begin+recv_count) of local ghost ids
   std::vector<int> peers, send_ptr, send_idx, recv_begin, recv_count;
+  double lsq_verify_err = 0;  // max linear-exactness error over the owned cells (src/gradient_lsq.f90:490-529)
 };
 
 // Builds the layout of `rank` out of `nranks` (equal contiguous chunks of the Hilbert order).

@@ -27,7 +27,7 @@ def make_mesh(nx: int, ny: int, lx: float = 20.0, ly: float = 10.0, quad_band=No
     if nx < 2 or ny < 2:
         raise ValueError("need at least 2x2 background quads")
     hx, hy = lx / nx, ly / ny
-    ii, jj = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="xy")  # (ny+1, nx+1)
+    ii, jj = np.meshgrid(np.arange(nx + 1, dtype=np.int32), np.arange(ny + 1, dtype=np.int32), indexing="xy")  # (ny+1, nx+1)
     xy = np.stack([ii * hx, jj * hy], axis=-1).astype(np.float64).reshape(-1, 2)
     if jitter > 0:
         rng = np.random.default_rng(seed)
@@ -36,8 +36,12 @@ def make_mesh(nx: int, ny: int, lx: float = 20.0, ly: float = 10.0, quad_band=No
         d[:, 1] *= hy
         interior = ((ii > 0) & (ii < nx) & (jj > 0) & (jj < ny)).reshape(-1)
         xy[interior] += d[interior]
-    node = lambda i, j: j * (nx + 1) + i
-    qi, qj = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+        del d, interior
+    if (nx + 1) * (ny + 1) >= 2**31:
+        raise ValueError("mesh too large for 32-bit node ids")
+    node = lambda i, j: (j * np.int32(nx + 1) + i).astype(np.int32)
+    del ii, jj
+    qi, qj = np.meshgrid(np.arange(nx, dtype=np.int32), np.arange(ny, dtype=np.int32), indexing="xy")
     qi, qj = qi.reshape(-1), qj.reshape(-1)
     n00, n10, n11, n01 = node(qi, qj), node(qi + 1, qj), node(qi + 1, qj + 1), node(qi, qj + 1)
     is_quad = (qi >= b0) & (qi < b1)
@@ -49,11 +53,13 @@ def make_mesh(nx: int, ny: int, lx: float = 20.0, ly: float = 10.0, quad_band=No
     tri = np.empty((2 * int(is_tri.sum()), 3), dtype=np.int32)
     tri[0::2] = t_lo[is_tri]
     tri[1::2] = t_hi[is_tri]
-    quad = np.stack([n00, n10, n11, n01], 1)[is_quad].astype(np.int32)
+    del t_lo, t_hi
+    quad = np.stack([n00[is_quad], n10[is_quad], n11[is_quad], n01[is_quad]], 1).astype(np.int32)
+    del n00, n10, n11, n01
     ntri = tri.shape[0]
     # cell id of a background quad's pieces
-    tri_rank = np.cumsum(is_tri) - 1
-    quad_rank = np.cumsum(is_quad) - 1
+    tri_rank = np.cumsum(is_tri, dtype=np.int32) - 1
+    quad_rank = np.cumsum(is_quad, dtype=np.int32) - 1
     lo_id = np.where(is_tri, 2 * tri_rank, ntri + quad_rank)      # piece holding the bottom edge (and, unflipped, the right edge)
     hi_id = np.where(is_tri, 2 * tri_rank + 1, ntri + quad_rank)  # piece holding the top edge (and, unflipped, the left edge)
     Q = lambda i, j: j * nx + i
