@@ -292,6 +292,13 @@ def main():
     roof = {"bound": "hbm", "kernel": "k_flux_pipe (pass B: face-flux gather + residual + RK update; persistent TMA/cp.async smem pipeline)",
             "achieved": bB * n_own / (flux_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
             "alg_bytes_per_cell": bB, "avg_launch_ms": flux_ms, "traffic": None}
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if world == 1 and args.scale == 1.0 and os.path.exists(tpath):
+        tr = json.load(open(tpath)).get(args.workload)
+        if tr:
+            roof["traffic"] = tr / 1e9  # GB per launch, from the committed ncu capture
+            roof["traffic_unit"] = "GB per launch (ncu dram__bytes_read+write, profiles/r1_ncu_summary.md)"
+            roof["alg_GB_per_launch"] = bB * n_own / 1e9
     roof["frac"] = roof["achieved"] / peak
     stage = {"alg_bytes_per_cell_stage": bA + bB, "achieved_GBs": (bA + bB) * ncells * 4 * K / (dev_ms * 1e-3) / 1e9}
     stage["frac"] = stage["achieved_GBs"] / (peak * world)

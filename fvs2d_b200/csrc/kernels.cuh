@@ -717,7 +717,9 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_flux_pipe(const DevMesh m, 
                                                                double *__restrict__ ws_out, double *__restrict__ partial) {
   constexpr int NCA = RC == RC_FIRST ? 4 : (RC == RC_K0 ? 14 : 15);
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int SS = pm.S, EE = pm.E, np = m.np;
+  int SS = pm.S, EE = pm.E;
+  asm volatile("" : "+r"(SS), "+r"(EE));  // keep the strides in registers: no constant-bank reloads in the face loop
+  const int np = m.np;
   const size_t stage_bytes = ((size_t)NCA * SS + 5 * (size_t)EE) * 8 + 4 * kBlock * sizeof(uint32_t) + 16;  // + {fw, fbase}
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kStages * stage_bytes);
   uint64_t *empty = full + kStages;
@@ -824,9 +826,11 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_flux_pipe(const DevMesh m, 
     const int fw = reinterpret_cast<const int *>(sf + 4 * kBlock)[0], fbase = reinterpret_cast<const int *>(sf + 4 * kBlock)[1];
     double acc[4] = {0.0, 0.0, 0.0, 0.0}, wsacc = 0.0;
     if (live) {
+      uint32_t pk_next = fw > 0 ? sf[tid] : 0xFFFEu;
 #pragma unroll 1
       for (int k = 0; k < fw; k++) {
-        const uint32_t pk = sf[k * kBlock + tid];
+        const uint32_t pk = pk_next;
+        if (k + 1 < fw) pk_next = sf[(k + 1) * kBlock + tid];  // next face's table word: its latency hides behind this face
         const uint32_t ns = pk & 0xFFFFu;
         if (ns == 0xFFFEu) continue;
         const int eslot = (pk >> 16) & 0x7FFF;
