@@ -82,6 +82,11 @@ struct Ctx {
   bool tile_ok = false;
   int nsm = 148, nparts = 0;
   int opt_ctas = 0;      // persistent pass-B CTAs per SM: 0 = as many as shared memory allows (max 3)
+  int opt_overlap = 1;   // multi-GPU: overlap the halo exchanges with interior-tile work (second stream)
+  cudaStream_t sx = nullptr;  // exchange stream
+  cudaEvent_t e_a = nullptr, e_g = nullptr, e_b = nullptr, e_p = nullptr;
+  const int *d_tile_int = nullptr, *d_tile_bnd = nullptr;
+  int n_int = 0, n_bnd = 0;
   bool bc_static_done = false;
   double rk_coef[4], h_rk[4], dts[4], dte[4];
   // timing
@@ -184,14 +189,15 @@ int rk_setup() {  // src/runge_kutta.f90:25-88
 
 // ---- halo exchange: owned send-cells -> the peers' ghost runs, nv variables of SoA array a ---------
 struct HaloItem { double *a; int nv; };
-int halo_exchange(const HaloItem *items, int nitems) {
+int halo_exchange(const HaloItem *items, int nitems, cudaStream_t st = nullptr) {
   if (C->nranks == 1) return 0;
+  if (!st) st = C->st;
   const Layout &L = C->L;
   const int nsend = L.send_ptr.empty() ? 0 : L.send_ptr.back();
   // pack: sendbuf layout [item][var][all send cells]
   size_t boff = 0;
   for (int it = 0; it < nitems; it++) {
-    if (nsend) k_pack<<<cdiv(nsend, 256), 256, 0, C->st>>>(nsend, items[it].nv, C->np, C->send_idx, items[it].a, C->sendbuf + boff);
+    if (nsend) k_pack<<<cdiv(nsend, 256), 256, 0, st>>>(nsend, items[it].nv, C->np, C->send_idx, items[it].a, C->sendbuf + boff);
     C->last_launches++;
     boff += (size_t)items[it].nv * nsend;
   }
@@ -202,8 +208,8 @@ int halo_exchange(const HaloItem *items, int nitems) {
       const int peer = L.peers[pi];
       const int s0 = L.send_ptr[pi], sn = L.send_ptr[pi + 1] - s0;
       for (int v = 0; v < items[it].nv; v++) {
-        if (sn) NCCL_OK(g_nccl.Send(C->sendbuf + boff + (size_t)v * nsend + s0, sn, ncclDouble, peer, C->comm, C->st));
-        if (L.recv_count[pi]) NCCL_OK(g_nccl.Recv(items[it].a + (size_t)v * C->np + L.recv_begin[pi], L.recv_count[pi], ncclDouble, peer, C->comm, C->st));
+        if (sn) NCCL_OK(g_nccl.Send(C->sendbuf + boff + (size_t)v * nsend + s0, sn, ncclDouble, peer, C->comm, st));
+        if (L.recv_count[pi]) NCCL_OK(g_nccl.Recv(items[it].a + (size_t)v * C->np + L.recv_begin[pi], L.recv_count[pi], ncclDouble, peer, C->comm, st));
       }
     }
     boff += (size_t)items[it].nv * nsend;
@@ -246,22 +252,26 @@ int download_aos(const double *soa, int nvar, double *host_out) {
   return 0;
 }
 
-int launch_gradient(const double *p) {
+int launch_gradient(const double *p, const int *list = nullptr, int nlist = 0) {
   if (C->recon == RC_FIRST) return 0;
+  const int nb = list ? nlist : C->nblocks;
+  if (nb == 0) return 0;
   Span sp(1);
   const bool lim = C->cfg.limiter > 0;
   double *gx = C->g, *gy = C->g + 4 * (size_t)C->np;
-  const int nb = C->nblocks;
   if (C->L.g_form == 0) {
-    if (lim) k_gradient<0, true><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, gx, gy, C->phi);
-    else k_gradient<0, false><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, gx, gy, C->phi);
+    if (lim) k_gradient<0, true><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, gx, gy, C->phi, list);
+    else k_gradient<0, false><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, gx, gy, C->phi, list);
   } else {
-    if (lim) k_gradient<1, true><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, gx, gy, C->phi);
-    else k_gradient<1, false><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, gx, gy, C->phi);
+    if (lim) k_gradient<1, true><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, gx, gy, C->phi, list);
+    else k_gradient<1, false><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, gx, gy, C->phi, list);
   }
   C->last_launches++;
   return 0;
 }
+
+struct TileSel { const int *list = nullptr; int n = 0, part_off = 0; };  // subset of tiles for the pipeline kernel
+TileSel g_sel;
 
 template <int UM, bool STEADY, int RC>
 void launch_flux_one(const StageParams &S, const double *pin, double *pout) {
@@ -278,10 +288,13 @@ void launch_flux_one(const StageParams &S, const double *pin, double *pout) {
     }
     int per_sm = std::max(1, std::min(3, (int)((227 * 1024) / (smem + 1024))));
     if (C->opt_ctas > 0) per_sm = std::min(per_sm, C->opt_ctas);
-    const int grid = std::min(C->pm.ntiles, C->nsm * per_sm);
-    k_flux_pipe<UM, STEADY, RC><<<grid, kPipeThreads, smem, C->st>>>(C->dm, C->pm, C->phys, S, pin, gx, gy, C->phi, C->bc, C->q, C->f,
-                                                                     pout, C->dtl, C->resid, C->ws, C->partial);
-    C->nparts = grid;
+    PipeMeta pm = C->pm;
+    if (g_sel.list) { pm.tile_list = g_sel.list; pm.ntiles = g_sel.n; }
+    const int grid = std::min(pm.ntiles, C->nsm * per_sm);
+    if (grid > 0)
+      k_flux_pipe<UM, STEADY, RC><<<grid, kPipeThreads, smem, C->st>>>(C->dm, pm, C->phys, S, pin, gx, gy, C->phi, C->bc, C->q, C->f, pout,
+                                                                       C->dtl, C->resid, C->ws, C->partial + 4 * (size_t)g_sel.part_off);
+    C->nparts = g_sel.part_off + grid;
   } else if (C->tile_ok && C->opt_tile == 1) {
     const size_t smem = ((size_t)NCA * C->tm.S + 5 * (size_t)C->tm.E) * 8 + 16;
     static size_t configured = 0;
@@ -309,7 +322,9 @@ void launch_flux_rc(const StageParams &S, const double *pin, double *pout) {
   }
 }
 
-int launch_flux(int um, const StageParams &S, const double *pin, double *pout) {
+int launch_flux(int um, const StageParams &S, const double *pin, double *pout, const int *list = nullptr, int nlist = 0, int part_off = 0) {
+  g_sel.list = list; g_sel.n = nlist; g_sel.part_off = part_off;
+  if (list && nlist == 0) { C->nparts = part_off; return 0; }
   Span sp(2);
   const bool steady = C->cfg.steady != 0;
   if (um == UM_RESID) launch_flux_rc<UM_RESID, false>(S, pin, pout);
@@ -532,6 +547,12 @@ int fvs2d_gpu_set_mesh(int nnodes, int ntri, int nquad, const double *node_xy, c
     CUDA_OK(cudaMemcpy(C->phi, ones.data(), np * 8, cudaMemcpyHostToDevice));
   }
   if (C->nranks > 1) {
+    if (dev_upload(C->d_tile_int, L.tile_int) || dev_upload(C->d_tile_bnd, L.tile_bnd)) return 1;
+    C->n_int = (int)L.tile_int.size(); C->n_bnd = (int)L.tile_bnd.size();
+    if (!C->sx) {
+      CUDA_OK(cudaStreamCreateWithFlags(&C->sx, cudaStreamNonBlocking));
+      for (cudaEvent_t *e : {&C->e_a, &C->e_g, &C->e_b, &C->e_p}) CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
     const int nsend = L.send_ptr.empty() ? 0 : L.send_ptr.back();
     const int *si;
     if (dev_upload(si, L.send_idx)) return 1;
@@ -672,6 +693,8 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   C->last_launches = 0;
   C->ev_used = 0;
   for (auto &s : C->ev_spans) s.clear();
+  const bool overlap = C->nranks > 1 && C->opt_overlap && C->tile_ok && C->opt_tile == 2;
+  bool p_pending = false;
   CUDA_OK(cudaEventRecord(C->ev0, C->st));
   for (int istep = 1; istep <= nsub; istep++) {
     const double told = t1 + (double)(istep - 1) * dt;  // src/runge_kutta.f90:135-139
@@ -686,12 +709,38 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
       if (c.steady) S.h = c.ssprk ? (rk == 3 ? 1.0 / 4.0 : 1.0 / 3.0) : (rk == 2 ? 1.0 : rk == 3 ? 1.0 / 6.0 : 1.0 / 2.0);
       else S.h = C->h_rk[rk];
       if (launch_bc(ts)) return 1;
-      if (pass_a(C->pa)) return 1;
-      if (launch_flux(um, S, C->pa, C->pb)) return 1;
-      if (C->nranks > 1) {
-        Span sp(0);
-        HaloItem it{C->pb, 4};
-        if (halo_exchange(&it, 1)) return 1;
+      if (overlap) {
+        // interior tiles never read a ghost: they run while the exchanges are in flight on the second stream
+        const bool grad = C->recon != RC_FIRST;
+        if (grad) {
+          if (launch_gradient(C->pa, C->d_tile_int, C->n_int)) return 1;
+          if (p_pending) CUDA_OK(cudaStreamWaitEvent(C->st, C->e_p, 0));   // ghost state of this stage has landed
+          if (launch_gradient(C->pa, C->d_tile_bnd, C->n_bnd)) return 1;
+          CUDA_OK(cudaEventRecord(C->e_a, C->st));
+          CUDA_OK(cudaStreamWaitEvent(C->sx, C->e_a, 0));
+          HaloItem it[2] = {{C->g, 8}, {C->phi, 1}};
+          if (halo_exchange(it, c.limiter > 0 ? 2 : 1, C->sx)) return 1;
+          CUDA_OK(cudaEventRecord(C->e_g, C->sx));
+        }
+        if (launch_flux(um, S, C->pa, C->pb, C->d_tile_int, C->n_int, 0)) return 1;
+        const int parts_int = C->nparts;
+        if (grad) CUDA_OK(cudaStreamWaitEvent(C->st, C->e_g, 0));          // ghost gradients have landed
+        else if (p_pending) CUDA_OK(cudaStreamWaitEvent(C->st, C->e_p, 0));
+        if (launch_flux(um, S, C->pa, C->pb, C->d_tile_bnd, C->n_bnd, parts_int)) return 1;
+        CUDA_OK(cudaEventRecord(C->e_b, C->st));
+        CUDA_OK(cudaStreamWaitEvent(C->sx, C->e_b, 0));
+        HaloItem itp{C->pb, 4};
+        if (halo_exchange(&itp, 1, C->sx)) return 1;                       // overlaps the next stage's interior gradient
+        CUDA_OK(cudaEventRecord(C->e_p, C->sx));
+        p_pending = true;
+      } else {
+        if (pass_a(C->pa)) return 1;
+        if (launch_flux(um, S, C->pa, C->pb)) return 1;
+        if (C->nranks > 1) {
+          Span sp(0);
+          HaloItem it{C->pb, 4};
+          if (halo_exchange(&it, 1)) return 1;
+        }
       }
       std::swap(C->pa, C->pb);
     }
@@ -708,6 +757,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
       }
     }
   }
+  if (p_pending) CUDA_OK(cudaStreamWaitEvent(C->st, C->e_p, 0));  // the last exchange belongs to this call
   CUDA_OK(cudaEventRecord(C->ev1, C->st));
   CUDA_OK(cudaGetLastError());
   // ---- logs back to the host (the only device->host traffic of the call)
@@ -886,6 +936,7 @@ int fvs2d_gpu_set_option(const char *key, int value) {
   if (k == "timing") { C->opt_timing = value; return 0; }
   if (k == "tile") { C->opt_tile = value; return 0; }
   if (k == "ctas") { C->opt_ctas = value; return 0; }
+  if (k == "overlap") { C->opt_overlap = value; return 0; }
   return fail("fvs2d_gpu_set_option: unknown option '%s'", key);
 }
 
@@ -893,6 +944,7 @@ int fvs2d_gpu_finalize(void) {
   if (!C) return 0;
   if (C->inited) {
     cudaSetDevice(C->device);
+    if (C->sx) cudaStreamSynchronize(C->sx);
     if (C->st) cudaStreamSynchronize(C->st);
     free_device();
   }
@@ -900,6 +952,7 @@ int fvs2d_gpu_finalize(void) {
   if (C->ev0) cudaEventDestroy(C->ev0);
   if (C->ev1) cudaEventDestroy(C->ev1);
   if (C->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(C->comm);
+  if (C->sx) { cudaStreamDestroy(C->sx); for (cudaEvent_t e : {C->e_a, C->e_g, C->e_b, C->e_p}) if (e) cudaEventDestroy(e); }
   if (C->st) cudaStreamDestroy(C->st);
   delete C;
   C = nullptr;

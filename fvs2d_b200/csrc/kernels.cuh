@@ -194,8 +194,9 @@ __global__ void __launch_bounds__(256) k_prim(int n, int np, double gamma, const
 template <int FORM, bool LIM>
 __global__ void __launch_bounds__(kBlock) k_gradient(const DevMesh m, const int limiter_type, const double *__restrict__ p,
                                                      double *__restrict__ gx, double *__restrict__ gy,
-                                                     double *__restrict__ phi) {
-  const int i = blockIdx.x * kBlock + threadIdx.x;
+                                                     double *__restrict__ phi, const int *__restrict__ tile_list) {
+  // one CTA = one 128-cell tile; tile_list (or null = all tiles in order) selects the interior / boundary subset
+  const int i = (tile_list ? __ldg(&tile_list[blockIdx.x]) : (int)blockIdx.x) * kBlock + threadIdx.x;
   if (i >= m.n_own) return;
   const int np = m.np, lane = threadIdx.x & 31, sl = i >> 5;
   const int off = __ldg(&m.g_off[sl]);
@@ -698,6 +699,7 @@ struct PipeMeta {
   const uint32_t *t_pack;
   const int *t_bf;
   int S, E, ntiles;
+  const int *tile_list;  // null: tiles 0..ntiles-1; else the ntiles tile ids to process (interior / boundary subset)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -749,9 +751,11 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_flux_pipe(const DevMesh m, 
         je[r] = (lane + 32 * r < h1.y) ? __ldg(&pm.he_idx[h1.x + lane + 32 * r]) : 0;
       }
     };
-    if ((int)blockIdx.x < pm.ntiles) fetch_meta(blockIdx.x);
+    auto tile_id = [&](int j) { return pm.tile_list ? __ldg(&pm.tile_list[j]) : j; };
+    if ((int)blockIdx.x < pm.ntiles) fetch_meta(tile_id(blockIdx.x));
     int it = 0;
-    for (int t = blockIdx.x; t < pm.ntiles; t += gridDim.x, it++) {
+    for (int j = blockIdx.x; j < pm.ntiles; j += gridDim.x, it++) {
+      const int t = tile_id(j);
       const int s = it & (kStages - 1);
       const uint32_t ph = (it / kStages) & 1;
       const int es = h0.x, ne = h0.y, hp = h0.z, nh = h0.w, ep = h1.x, nhe = h1.y, fbase = h1.z, fw = h1.w;
@@ -799,7 +803,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_flux_pipe(const DevMesh m, 
         for (int a = 0; a < 5; a++) cp_async8(se + a * EE + ne + h, edge_src(a) + j);
       }
       cp_async_mbar_arrive_noinc(&full[s]);
-      if (t + (int)gridDim.x < pm.ntiles) fetch_meta(t + gridDim.x);
+      if (j + (int)gridDim.x < pm.ntiles) fetch_meta(tile_id(j + gridDim.x));
     }
     return;
   }
@@ -807,7 +811,8 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_flux_pipe(const DevMesh m, 
   // ================================== consumer warps ==================================
   double dq2[4] = {0.0, 0.0, 0.0, 0.0};
   int it = 0;
-  for (int t = blockIdx.x; t < pm.ntiles; t += gridDim.x, it++) {
+  for (int j = blockIdx.x; j < pm.ntiles; j += gridDim.x, it++) {
+    const int t = pm.tile_list ? __ldg(&pm.tile_list[j]) : j;
     const int s = it & (kStages - 1);
     const uint32_t ph = (it / kStages) & 1;
     const int c0 = t * kBlock;

@@ -332,6 +332,20 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
         for (int i = 0; i < L.n_own; i++) if (need[p][i]) L.send_idx.push_back(i);
       L.send_ptr.push_back((int)L.send_idx.size());
     }
+    // interior / boundary tiles
+    std::vector<unsigned char> bnd(L.ntiles, 0);
+    for (int i : L.send_idx) bnd[i / kTile] = 1;
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < L.ntiles; t++) {
+      bool b = bnd[t];
+      for (int i = t * kTile; i < std::min(L.n_own, (t + 1) * kTile) && !b; i++) {
+        const int sl = i >> 5, lane = i & 31;
+        for (int k = 0; k < ((L.f_off[sl + 1] - L.f_off[sl]) >> 5) && !b; k++) b = L.f_nbr[L.f_off[sl] + 32 * k + lane] >= L.n_own;
+        for (int k = 0; k < ((L.g_off[sl + 1] - L.g_off[sl]) >> 5) && !b; k++) b = L.g_idx[L.g_off[sl] + 32 * k + lane] >= L.n_own;
+      }
+      bnd[t] = b;
+    }
+    for (int t = 0; t < L.ntiles; t++) (bnd[t] ? L.tile_bnd : L.tile_int).push_back(t);
   }
   return "";
 }

@@ -67,6 +67,9 @@ struct Layout {
   // halo plan: peers in ascending rank; send_idx = owned local ids the peer needs (ascending new id),
   // recv = contiguous run [recv_begin, recv_begin+recv_count) of local ghost ids
   std::vector<int> peers, send_ptr, send_idx, recv_begin, recv_count;
+  // overlap of the halo exchange with interior work: a tile is "boundary" when one of its cells is sent to a
+  // peer or reads a ghost (through a face or the gradient stencil); all other tiles are "interior"
+  std::vector<int> tile_int, tile_bnd;
   double lsq_verify_err = 0;  // max linear-exactness error over the owned cells (src/gradient_lsq.f90:490-529)
 };
 
