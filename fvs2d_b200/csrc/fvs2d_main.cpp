@@ -7,7 +7,7 @@
 // 169-184), log_vortex_err.plt / log_vortex_err_xy.plt (src/mms.f90:283-294,357-363), inst.cd + inst.s4|.s8
 // (node-interpolated primitive variables, src/io.f90:60-144, src/interpolation.f90:62-123), save.cd + save.s8
 // (src/io.f90:95-113,156-178; ios format of src/ios_unstrc.f90:141-290: text header + big-endian
-// direct-access records), log.grid, and in MMS mode (ntstart=0) the error_resid.plt row of test_resid
+// direct-access records), log_cp.plt / log_un.plt / log_clcd.plt when a wall boundary exists (src/io.f90:340-449), log.grid, and in MMS mode (ntstart=0) the error_resid.plt row of test_resid
 // (src/test.f90:481-519).  All numerics of the hot path happen in libfvs2d_gpu.so; this file is I/O only.
 #include <algorithm>
 #include <cmath>
@@ -347,6 +347,57 @@ int main(int argc, char **argv) {
     vxy.open("log_vortex_err_xy.plt");
     vxy << "variables = \"t\", \"x\" \"y\"\n";
   }
+  // ---- wall post-processing set-up (src/io.f90:340-362): only when a slip_wall / solid_wall boundary exists
+  bool lcp = false;
+  for (int t : g.bt) lcp = lcp || t == FVS2D_BC_SLIP_WALL || t == FVS2D_BC_SOLID_WALL;
+  std::ofstream fcp, fun, fclcd;
+  std::vector<int> b_edge, b_edge_ptr, ec1;
+  std::vector<double> ex, ey, ea, enx, eny, xcc, ycc;
+  if (lcp) {
+    fcp.open("log_cp.plt"); fun.open("log_un.plt"); fclcd.open("log_clcd.plt");
+    fun << "VARIABLES = \"time\" \"|V<sub>n</sub>|<sub><math>%</math></sub>\",   \"|V<sub>n</sub>|<sub>2</sub>\" , \"|V<sub>n</sub>|<sub>1</sub>\"\n";
+    fclcd << "VARIABLES = \"time\" \"c<sub>l</sub>\",   \"c<sub>d</sub>\", \"c<sub>l1</sub>\",   \"c<sub>d1</sub>\"\n";
+    auto geti = [&](const char *n, std::vector<int> &v) { v.resize(fvs2d_gpu_mesh_array(n, nullptr)); fvs2d_gpu_mesh_array(n, v.data()); };
+    auto getd = [&](const char *n, std::vector<double> &v) { v.resize(fvs2d_gpu_mesh_array(n, nullptr)); fvs2d_gpu_mesh_array(n, v.data()); };
+    geti("b_edge", b_edge); geti("b_edge_ptr", b_edge_ptr); geti("ec1", ec1);
+    getd("ex", ex); getd("ey", ey); getd("ea", ea); getd("enx", enx); getd("eny", eny); getd("xc", xcc); getd("yc", ycc);
+  }
+  // write_inst_cp_un (src/io.f90:340-449): wall pressure coefficient, normal-velocity norms and force coefficients from
+  // the cell values extrapolated to the wall faces with the (unlimited) cell gradients of p, u, v
+  auto write_inst_cp_un = [&](double sol_time) {
+    if (!lcp) return;
+    std::vector<double> pv(4 * (size_t)nc), gr(8 * (size_t)nc);
+    check(fvs2d_gpu_compute_residual(sol_time, nullptr, nullptr));   // refreshes pvar and grad of the current state
+    check(fvs2d_gpu_get_aux(pv.data(), gr.data(), nullptr));
+    const double *gx = gr.data(), *gy = gr.data() + 4 * (size_t)nc;
+    const double p_inf = 1.0 / in.gamma, q2 = 2.0 / (in.mach * in.mach);
+    const double ca_ = in.aoa == 0.0 ? 1.0 : std::cos(in.aoa * pi / 180.0), sa_ = in.aoa == 0.0 ? 0.0 : std::sin(in.aoa * pi / 180.0);
+    for (size_t ib = 0; ib < g.bt.size(); ib++) {
+      if (g.bt[ib] != FVS2D_BC_SLIP_WALL && g.bt[ib] != FVS2D_BC_SOLID_WALL) continue;
+      const int e0 = b_edge_ptr[ib], e1 = b_edge_ptr[ib + 1];
+      fcp << "TITLE     = \"cp\"\nVARIABLES = \"x\" \"cp_w\" \"cp_cell\"\nZONE I=" << (e1 - e0) << " J=1\n"
+          << "STRANDID=1, SOLUTIONTIME=" << fortran_e(sol_time, 16, 8) << "\n";
+      double un_max = 0, un_l2 = 0, un_l1 = 0, cn = 0, ca = 0, cn1 = 0, ca1 = 0;
+      for (int i = e0; i < e1; i++) {
+        const int ie = b_edge[i], ic = ec1[ie];  // the reference indexes bndry%cell by the edge counter
+        const double dx = ex[ie] - xcc[ic], dy = ey[ie] - ycc[ic];
+        const double pw = pv[4 * (size_t)ic + 3] + dx * gx[4 * (size_t)ic + 3] + dy * gy[4 * (size_t)ic + 3];
+        const double cp = q2 * (pw - p_inf), cp1 = q2 * (pv[4 * (size_t)ic + 3] - p_inf);
+        fcp << fortran_e(ex[ie], 16, 8) << " " << fortran_e(cp, 16, 8) << " " << fortran_e(cp1, 16, 8) << " \n";
+        cn = cn + cp * eny[ie] * ea[ie];   ca = ca + cp * enx[ie] * ea[ie];
+        cn1 = cn1 + cp1 * eny[ie] * ea[ie]; ca1 = ca1 + cp1 * enx[ie] * ea[ie];
+        const double uw = pv[4 * (size_t)ic + 1] + dx * gx[4 * (size_t)ic + 1] + dy * gy[4 * (size_t)ic + 1];
+        const double vw = pv[4 * (size_t)ic + 2] + dx * gx[4 * (size_t)ic + 2] + dy * gy[4 * (size_t)ic + 2];
+        const double un = uw * enx[ie] + vw * eny[ie];
+        un_l2 += un * un; un_l1 += std::fabs(un); un_max = std::max(un_max, std::fabs(un));
+      }
+      const double n = (double)(e1 - e0);
+      fun << fortran_e(sol_time, 16, 8) << " " << fortran_e(un_max, 16, 8) << " " << fortran_e(std::sqrt(un_l2 / n), 16, 8) << " "
+          << fortran_e(un_l1 / n, 16, 8) << " \n";
+      fclcd << fortran_e(sol_time, 16, 8) << " " << fortran_e(cn * ca_ - ca * sa_, 16, 8) << " " << fortran_e(cn * sa_ + ca * ca_, 16, 8) << " "
+            << fortran_e(cn1 * ca_ - ca1 * sa_, 16, 8) << " " << fortran_e(cn1 * sa_ + ca1 * ca_, 16, 8) << " \n";
+    }
+  };
   double t0 = (double)(in.ntstart - 1) * in.dt, ms_tot = 0, ms_grad = 0, ms_flux = 0;
   int it_tot = 0, icont = 0;
   fvs2d_gpu_set_option("timing", 1);
@@ -391,6 +442,7 @@ int main(int argc, char **argv) {
         write_be(inst, fv.data(), fv.size(), !in.s8);
       }
     }
+    write_inst_cp_un(t0);  // src/fvs2d.f90:157
   }
   // ---- write_save_ios (src/io.f90:156-178): 4 records of cvar at the cell centres, real*8, big-endian
   check(fvs2d_gpu_get_state(cvar.data()));
