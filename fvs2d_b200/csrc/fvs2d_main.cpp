@@ -7,7 +7,8 @@
 // 169-184), log_vortex_err.plt / log_vortex_err_xy.plt (src/mms.f90:283-294,357-363), inst.cd + inst.s4|.s8
 // (node-interpolated primitive variables, src/io.f90:60-144, src/interpolation.f90:62-123), save.cd + save.s8
 // (src/io.f90:95-113,156-178; ios format of src/ios_unstrc.f90:141-290: text header + big-endian
-// direct-access records), log_cp.plt / log_un.plt / log_clcd.plt when a wall boundary exists (src/io.f90:340-449), log.grid, and in MMS mode (ntstart=0) the error_resid.plt row of test_resid
+// direct-access records), log_cp.plt / log_un.plt / log_clcd.plt when a wall boundary exists
+// (src/io.f90:340-449), log.grid, and in MMS mode (ntstart=0) the error_resid.plt row of test_resid
 // (src/test.f90:481-519).  All numerics of the hot path happen in libfvs2d_gpu.so; this file is I/O only.
 #include <algorithm>
 #include <cmath>

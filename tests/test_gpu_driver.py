@@ -112,3 +112,45 @@ def test_mms_mode_appends_error_resid(tmp_path):
     assert len(lines) == 3 and lines[0].startswith("variables")
     got = np.array([[float(x) for x in ln.split()] for ln in lines[1:]])
     np.testing.assert_allclose(got, np.array(rows), rtol=6e-9)
+
+
+def test_naca_wall_postprocessing(tmp_path, naca_mesh):
+    """C2 (limiter 0 as shipped): log_cp.plt / log_un.plt / log_clcd.plt (src/io.f90:340-449) against the same
+    formulas evaluated on the oracle's pvar / grad at the oracle's state; log_res against the oracle."""
+    from fvs2d_b200 import config, meshio
+    from oracle.oracle import Oracle
+    r = run_input("naca")
+    r.ntimes, r.nsaves = 10, 1
+    d = str(tmp_path)
+    meshio.write_mesh(os.path.join(d, "naca0012_omesh"), naca_mesh)
+    config.write_input(os.path.join(d, "fvs2d.input"), r)
+    _run(d)
+    orc = Oracle(naca_mesh, r.to_config())
+    orc.initialize_solution()
+    res_o, _, _ = orc.time_integration(0.0, 10)
+    lines = open(os.path.join(d, "log_res.plt")).read().splitlines()[1:]
+    got = np.array([[float(x) for x in ln.split()[1:]] for ln in lines])
+    np.testing.assert_allclose(got, res_o, rtol=6e-8)
+    # wall quantities from the oracle
+    orc.compute_residual(10 * r.dt)
+    pv, gr = orc.array("pvar").reshape(-1, 4), orc.array("grad").reshape(2, -1, 4)
+    bptr, bedge, ec1 = orc.array("b_edge_ptr"), orc.array("b_edge"), orc.array("ec1")
+    ex, ey, ea, enx, eny, xc, yc = (orc.array(n) for n in ("ex", "ey", "ea", "enx", "eny", "xc", "yc"))
+    ib = naca_mesh.bndry_type.index("slip_wall")
+    ie = bedge[bptr[ib]:bptr[ib + 1]]
+    ic = ec1[ie]
+    dx, dy = ex[ie] - xc[ic], ey[ie] - yc[ic]
+    wall = lambda v: pv[ic, v] + dx * gr[0, ic, v] + dy * gr[1, ic, v]
+    cp = 2.0 / r.mach_inf**2 * (wall(3) - 1.0 / r.gamma)
+    cp1 = 2.0 / r.mach_inf**2 * (pv[ic, 3] - 1.0 / r.gamma)
+    un = wall(1) * enx[ie] + wall(2) * eny[ie]
+    cpl = open(os.path.join(d, "log_cp.plt")).read().splitlines()
+    assert cpl[0] == 'TITLE     = "cp"' and cpl[2] == f"ZONE I={len(ie)} J=1" and cpl[3].startswith("STRANDID=1, SOLUTIONTIME=")
+    tab = np.array([[float(x) for x in ln.split()] for ln in cpl[4:4 + len(ie)]])
+    np.testing.assert_allclose(tab[:, 0], ex[ie], rtol=6e-8, atol=1e-12)
+    np.testing.assert_allclose(tab[:, 1], cp, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(tab[:, 2], cp1, rtol=1e-6, atol=1e-7)
+    unl = [float(x) for x in open(os.path.join(d, "log_un.plt")).read().splitlines()[1].split()]
+    np.testing.assert_allclose(unl[1:], [np.abs(un).max(), np.sqrt((un**2).mean()), np.abs(un).mean()], rtol=1e-6)
+    cl = [float(x) for x in open(os.path.join(d, "log_clcd.plt")).read().splitlines()[1].split()]
+    np.testing.assert_allclose(cl[1:3], [(cp * eny[ie] * ea[ie]).sum(), (cp * enx[ie] * ea[ie]).sum()], rtol=1e-6, atol=1e-7)
