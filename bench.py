@@ -43,6 +43,17 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def workload_desc(name: str, ngpus: int, scale: float = 1.0) -> str:
+    if name == "c4":
+        nx, ny = int(round(9600 * scale)), int(round(600 * scale)) * ngpus
+        return f"C4 synthetic mixed tri/quad vortex mesh {nx}x{ny} background quads, GGCB, upwind-2nd, Roe, RK4"
+    if name == "c3":
+        nx = int(round(2000 * scale))
+        return f"C3 synthetic triangle vortex mesh {nx}x{nx // 2} split quads, GGCB, upwind-2nd, Roe, RK4"
+    return {"naca": "C2 naca0012_ogrid, LSQ-nn + Venkatakrishnan, SSPRK(4,2) steady CFL 1.25",
+            "vortex": "C1 isentropic_vortex example as shipped, LSQ-fn, RK4"}[name]
+
+
 def make_workload(name: str, ngpus: int, scale: float = 1.0):
     """-> (mesh, RunInput, description, (bytes_passA, bytes_passB) per cell-stage)"""
     golden = os.path.join(ROOT, "tests", "golden")
@@ -54,50 +65,67 @@ def make_workload(name: str, ngpus: int, scale: float = 1.0):
         ft = mesh.ntri / mesh.ncells
         ba = ft * B_ALG["tri_ggcb"][0] + (1 - ft) * B_ALG["quad_ggcb"][0]
         bb = ft * B_ALG["tri_ggcb"][1] + (1 - ft) * B_ALG["quad_ggcb"][1]
-        desc = f"C4 synthetic mixed tri/quad vortex mesh {nx}x{ny} background quads, GGCB, upwind-2nd, Roe, RK4"
-        return mesh, run, desc, (ba, bb)
+        return mesh, run, workload_desc(name, ngpus, scale), (ba, bb)
     if name == "c3":
         nx = int(round(2000 * scale))
         mesh = meshgen.vortex_tri_mesh(nx)
         run = fcfg.RunInput(grad_cellcntr_imethd=1, lvortex=True, dt=0.002 / scale)
-        return mesh, run, f"C3 synthetic triangle vortex mesh {nx}x{nx // 2} split quads, GGCB, upwind-2nd, Roe, RK4", B_ALG["tri_ggcb"]
+        return mesh, run, workload_desc(name, ngpus, scale), B_ALG["tri_ggcb"]
     inp = json.load(open(os.path.join(golden, "inputs.json")))
     if name == "naca":
         mesh = meshio.load_npz(os.path.join(golden, "naca_mesh.npz"))
         d = inp["naca"]
         run = fcfg.RunInput(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in d.items()})
         run.grad_limiter_imethd = 1
-        return mesh, run, "C2 naca0012_ogrid, LSQ-nn + Venkatakrishnan, SSPRK(4,2) steady CFL 1.25", B_ALG["quad_lsqnn_venk_steady"]
+        return mesh, run, workload_desc(name, ngpus, scale), B_ALG["quad_lsqnn_venk_steady"]
     if name == "vortex":
         mesh = meshio.load_npz(os.path.join(golden, "vortex_mesh.npz"))
         d = inp["vortex"]
         run = fcfg.RunInput(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in d.items()})
-        return mesh, run, "C1 isentropic_vortex example as shipped, LSQ-fn, RK4", B_ALG["tri_lsqfn"]
+        return mesh, run, workload_desc(name, ngpus, scale), B_ALG["tri_lsqfn"]
     raise SystemExit(f"unknown workload {name}")
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md recipe), polled through NVML
+    every few ms (an nvidia-smi subprocess would return one sample per ~100 ms region); nvidia-smi is the fallback."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
-        self.rows, self.stop, self.index = [], False, index
+        self.rows, self.stop, self.index, self.max_mhz = [], False, index, None
         self.th = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop:
+                self.rows.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), pynvml.nvmlDeviceGetPowerUsage(h) / 1e3,
+                                  int(get_reasons(h))))
+                time.sleep(0.004)
+            return
+        except Exception:
+            pass
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        bits = [0x8, 0x40, 0x20, 0x4]
         while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([t.strip() for t in out.split(",")])
+                t = [x.strip() for x in out.split(",")]
+                self.max_mhz = float(t[1])
+                self.rows.append((float(t[0]), float(t[2]), sum(b for b, x in zip(bits, t[3:7]) if x.lower().startswith("active"))))
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def __enter__(self):
         self.th.start()
+        time.sleep(0.02)
         return self
 
     def __exit__(self, *a):
@@ -106,12 +134,13 @@ class ClockSampler:
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows if len(r) > 3 + k)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "samples": len(self.rows),
-                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"]}
+        sm = sorted(r[0] for r in self.rows)
+        mask = 0
+        for r in self.rows:
+            mask |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz, "samples": len(self.rows),
+                "power_w_max": max(r[1] for r in self.rows), "reasons": [n for b, n in self.REASONS.items() if mask & b]}
 
 
 def cpu_baseline(name: str, run, steps: int, warmup: int = 0):
@@ -149,6 +178,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="mesh refinement factor relative to the named workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the additional C3 measurement at N=1")
     ap.add_argument("--opt", action="append", default=[], help="library tuning option key=value (fvs2d_gpu_set_option)")
     args = ap.parse_args()
     K, W = args.steps, max(args.warmup, 0)
@@ -161,14 +191,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        desc = {"c4": "C4 synthetic mixed tri/quad vortex mesh, GGCB, upwind-2nd, Roe, RK4", "c3": "C3 synthetic triangle vortex mesh, GGCB, upwind-2nd, Roe, RK4",
-                "naca": "C2 naca0012_ogrid, LSQ-nn + Venkatakrishnan, SSPRK(4,2) steady CFL 1.25", "vortex": "C1 isentropic_vortex example as shipped"}[args.workload]
+        desc = workload_desc(args.workload, max(args.gpus, 1), args.scale)
         cb, ms_step = cpu_baseline(args.workload, None, max(K, 1), W)
         line = {"metric": metric, "value": cb["value"], "unit": "cell-stage updates/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "impl": "reference",
-                "config": {"workload": desc, "note": "reference algorithm on host cores (C restatement, oracle/; the Fortran "
-                           "reference cannot be compiled in this image); each step is a bounded sample: " + cb["sample"]},
+                "config": {"workload": desc, "parallelism": "1 host thread (the reference's OpenMP flux loop races, src/residual.f90:65)",
+                           "note": "reference algorithm on the host (C restatement in oracle/, -Ofast; the Fortran reference cannot be "
+                                   "compiled in this image); each step is a bounded sample of the workload: " + cb["sample"]},
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "cell-stage updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -282,6 +312,26 @@ def main():
                "amortized_note": f"one seam call as the reference makes it: set_state + time_integration({K} steps) + get_state"}
 
     gpu.close()
+    other = {}
+    if world == 1 and args.workload == "c4" and args.scale == 1.0 and not args.no_extra:
+        # BASELINE configs[2] (C3, the single-GPU triangle case) measured in the same run, same rules
+        mesh3, run3, desc3, (a3, b3) = make_workload("c3", 1)
+        g3 = solver.Fvs2dGpu(run3.to_config(1), device=local_rank)
+        g3.set_mesh(mesh3)
+        nc3 = mesh3.ncells
+        del mesh3
+        g3.initialize_solution()
+        g3.set_option("timing", 1)
+        g3.time_integration(0.0, W, logs=False)
+        torch.cuda.synchronize()
+        g3.time_integration(W * run3.dt, K, logs=False)
+        t3 = g3.last_timing()
+        g3.close()
+        pk, _ = load_peaks()
+        other["c3"] = {"workload": desc3, "value": nc3 * 4 * K / (t3["total_ms"] * 1e-3), "ms_per_step": t3["total_ms"] / K,
+                       "pass_b_avg_launch_ms": t3["flux_ms"] / (4 * K), "pass_a_avg_launch_ms": t3["grad_ms"] / (4 * K),
+                       "pass_b_roofline_frac": b3 * nc3 / (t3["flux_ms"] / (4 * K) * 1e-3) / 1e9 / pk,
+                       "stage_roofline_frac": (a3 + b3) * nc3 * 4 * K / (t3["total_ms"] * 1e-3) / 1e9 / pk}
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -312,6 +362,8 @@ def main():
                        "setup_s": round(t_setup, 1)},
             "roofline": roof, "stage_roofline": stage, "gradient_kernel": gradk,
             "wall_ms_per_step": wall * 1e3 / K, "gpu_launches": launches, "clocks": clk.summary(), "e2e": e2e}
+    if other:
+        line["other_configs"] = other
     if not args.no_cpu_baseline:
         cb, _ = cpu_baseline(args.workload, run, 4 if args.workload in ("c3", "c4") else 50)
         line["cpu_baseline"] = cb
