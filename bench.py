@@ -71,6 +71,12 @@ def make_workload(name: str, ngpus: int, scale: float = 1.0):
         mesh = meshgen.vortex_tri_mesh(nx)
         run = fcfg.RunInput(grad_cellcntr_imethd=1, lvortex=True, dt=0.002 / scale)
         return mesh, run, workload_desc(name, ngpus, scale), B_ALG["tri_ggcb"]
+    if name.startswith("x:"):  # experiment: x:nx,ny,b0,b1 (b0==b1==0: all triangles)
+        nx, ny, b0, b1 = (int(t) for t in name[2:].split(","))
+        mesh = meshgen.make_mesh(nx, ny, 20.0, 10.0, (b0, b1) if b1 > b0 else None)
+        run = fcfg.RunInput(grad_cellcntr_imethd=1, lvortex=True, dt=0.1 * min(20.0 / nx, 10.0 / ny))
+        ft = mesh.ntri / mesh.ncells
+        return mesh, run, f"experiment {name}", (ft * 180 + (1 - ft) * 200, ft * 332 + (1 - ft) * 360)
     inp = json.load(open(os.path.join(golden, "inputs.json")))
     if name == "naca":
         mesh = meshio.load_npz(os.path.join(golden, "naca_mesh.npz"))

@@ -13,7 +13,8 @@ import numpy as np
 from .config import Fvs2dConfig
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libfvs2d_gpu.so")
+# FVS2D_GPU_LIB selects an alternative build of the same library (tuning experiments: other tile sizes)
+LIB_PATH = os.environ.get("FVS2D_GPU_LIB") or os.path.join(_HERE, "csrc", "libfvs2d_gpu.so")
 _LIB = None
 
 # every symbol include/fvs2d_gpu.h declares (tests check that the .so exports them all)

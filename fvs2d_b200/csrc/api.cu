@@ -83,6 +83,8 @@ struct Ctx {
   int nsm = 148, nparts = 0;
   int opt_ctas = 0;      // persistent pass-B CTAs per SM: 0 = as many as shared memory allows (max 3)
   int opt_overlap = 1;   // multi-GPU: overlap the halo exchanges with interior-tile work (second stream)
+  int opt_smem_pad = 0;  // experiment: extra dynamic shared memory (KB) per pass-B CTA (shrinks the L1 carve-out)
+  int opt_carveout = -1; // experiment: preferred shared-memory carve-out of the pass-B kernel in KB (-1: driver default)
   cudaStream_t sx = nullptr;  // exchange stream
   cudaEvent_t e_a = nullptr, e_g = nullptr, e_b = nullptr, e_p = nullptr;
   const int *d_tile_int = nullptr, *d_tile_bnd = nullptr;
@@ -280,14 +282,19 @@ void launch_flux_one(const StageParams &S, const double *pin, double *pout) {
   constexpr int NCA = RC == RC_FIRST ? 4 : (RC == RC_K0 ? 14 : 15);
   if (C->tile_ok && C->opt_tile == 2) {
     const size_t stage = ((size_t)NCA * C->pm.S + 5 * (size_t)C->pm.E) * 8 + 4 * kBlock * 4 + 16;
-    const size_t smem = kStages * stage + 4 * sizeof(uint64_t);
+    const size_t smem = kStages * stage + 4 * sizeof(uint64_t) + (size_t)C->opt_smem_pad * 1024;
     static size_t configured = 0;
     if (configured < smem) {
       cudaFuncSetAttribute(k_flux_pipe<UM, STEADY, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       configured = smem;
     }
-    int per_sm = std::max(1, std::min(3, (int)((227 * 1024) / (smem + 1024))));
+    if (C->opt_carveout >= 0)
+      cudaFuncSetAttribute(k_flux_pipe<UM, STEADY, RC>, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(100, C->opt_carveout * 100 / 228 + 1));
+    int per_sm = 0;  // persistent kernel: exactly as many CTAs as are co-resident
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flux_pipe<UM, STEADY, RC>, kPipeThreads, smem);
+    per_sm = std::max(1, per_sm);
     if (C->opt_ctas > 0) per_sm = std::min(per_sm, C->opt_ctas);
+    if (getenv("FVS2D_DEBUG")) { static int once = 0; if (!once++) fprintf(stderr, "[fvs2d] k_flux_pipe: %zu B smem/CTA, %d CTAs/SM\n", smem, per_sm); }
     PipeMeta pm = C->pm;
     if (g_sel.list) { pm.tile_list = g_sel.list; pm.ntiles = g_sel.n; }
     const int grid = std::min(pm.ntiles, C->nsm * per_sm);
@@ -937,6 +944,8 @@ int fvs2d_gpu_set_option(const char *key, int value) {
   if (k == "tile") { C->opt_tile = value; return 0; }
   if (k == "ctas") { C->opt_ctas = value; return 0; }
   if (k == "overlap") { C->opt_overlap = value; return 0; }
+  if (k == "smem_pad") { C->opt_smem_pad = value; return 0; }
+  if (k == "carveout") { C->opt_carveout = value; return 0; }
   return fail("fvs2d_gpu_set_option: unknown option '%s'", key);
 }
 

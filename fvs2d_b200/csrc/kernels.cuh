@@ -17,7 +17,13 @@
 
 namespace fvs2d {
 
-constexpr int kBlock = 128;         // threads per CTA for the cell-parallel kernels
+#ifndef FVS2D_TILE
+#define FVS2D_TILE 128
+#endif
+#ifndef FVS2D_PIPE_CTAS
+#define FVS2D_PIPE_CTAS 3
+#endif
+constexpr int kBlock = FVS2D_TILE;  // threads per CTA for the cell-parallel kernels = cells per tile
 constexpr int kPadNbr = INT32_MIN;  // == kFacePad
 
 enum UpdateMode { UM_RESID = 0, UM_RK = 1, UM_SSPRK = 2 };
@@ -710,7 +716,7 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
 }
 
 template <int UM, bool STEADY, int RC>
-__global__ void __launch_bounds__(kPipeThreads, 3) k_flux_pipe(const DevMesh m, const PipeMeta pm, const Phys P, const StageParams S,
+__global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(const DevMesh m, const PipeMeta pm, const Phys P, const StageParams S,
                                                                const double *__restrict__ p, const double *__restrict__ gx,
                                                                const double *__restrict__ gy, const double *__restrict__ phi,
                                                                const double *__restrict__ bc, double *__restrict__ q,

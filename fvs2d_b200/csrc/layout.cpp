@@ -227,7 +227,7 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
     int64_t fbase = 0;
     for (int t = 0; t < nt; t++) {
       int fw = 0;
-      for (int sl = 4 * t; sl < std::min(L.nslices, 4 * t + 4); sl++) fw = std::max(fw, (L.f_off[sl + 1] - L.f_off[sl]) >> 5);
+      for (int sl = (kTile / 32) * t; sl < std::min(L.nslices, (kTile / 32) * (t + 1)); sl++) fw = std::max(fw, (L.f_off[sl + 1] - L.f_off[sl]) >> 5);
       int *h = &L.tile_hdr[8 * (size_t)t];
       h[0] = L.tile_es[t]; h[1] = L.tile_ne[t];
       h[2] = L.tile_hc_ptr[t]; h[3] = L.tile_hc_ptr[t + 1] - L.tile_hc_ptr[t];

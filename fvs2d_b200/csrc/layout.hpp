@@ -14,10 +14,14 @@
 
 #include "host_mesh.hpp"
 
+#ifndef FVS2D_TILE
+#define FVS2D_TILE 128
+#endif
+
 namespace fvs2d {
 
 constexpr int kFacePad = INT32_MIN;  // f_nbr value of a padding entry (triangle in a width-4 slice)
-constexpr int kTile = 128;           // cells per tile (== threads per CTA of the cell-parallel kernels)
+constexpr int kTile = FVS2D_TILE;           // cells per tile (== threads per CTA of the cell-parallel kernels)
 
 struct Layout {
   int rank = 0, nranks = 1;
