@@ -76,9 +76,8 @@ struct Ctx {
   size_t stage_aos_len = 0;
   double *logbuf = nullptr; int *logid = nullptr; size_t log_cap = 0;
   int *send_idx = nullptr; double *sendbuf = nullptr;
-  TileMeta tm{};
   PipeMeta pm{};
-  int opt_tile = 2;      // pass-B kernel: 2 persistent smem pipeline (default), 1 one-tile-per-CTA smem kernel, 0 direct gather
+  int opt_tile = 2;      // pass-B kernel: 2 persistent smem pipeline (default), 0 direct gather
   bool tile_ok = false;
   int nsm = 148, nparts = 0;
   int opt_ctas = 0;      // persistent pass-B CTAs per SM: 0 = as many as shared memory allows (max 3)
@@ -190,28 +189,37 @@ int rk_setup() {  // src/runge_kutta.f90:25-88
 }
 
 // ---- halo exchange: owned send-cells -> the peers' ghost runs, nv variables of SoA array a ---------
-struct HaloItem { double *a; int nv; };
+// nv = number of double variables; pair != 0: the array is pair-interleaved (nv/2 double2 variables)
+struct HaloItem { double *a; int nv; int pair; };
 int halo_exchange(const HaloItem *items, int nitems, cudaStream_t st = nullptr) {
   if (C->nranks == 1) return 0;
   if (!st) st = C->st;
   const Layout &L = C->L;
   const int nsend = L.send_ptr.empty() ? 0 : L.send_ptr.back();
-  // pack: sendbuf layout [item][var][all send cells]
+  // pack: sendbuf layout [item][element variable][all send cells]
   size_t boff = 0;
   for (int it = 0; it < nitems; it++) {
-    if (nsend) k_pack<<<cdiv(nsend, 256), 256, 0, st>>>(nsend, items[it].nv, C->np, C->send_idx, items[it].a, C->sendbuf + boff);
+    if (nsend) {
+      if (items[it].pair)
+        k_pack<double2><<<cdiv(nsend, 256), 256, 0, st>>>(nsend, items[it].nv / 2, C->np, C->send_idx, reinterpret_cast<const double2 *>(items[it].a),
+                                                        reinterpret_cast<double2 *>(C->sendbuf + boff));
+      else
+        k_pack<double><<<cdiv(nsend, 256), 256, 0, st>>>(nsend, items[it].nv, C->np, C->send_idx, items[it].a, C->sendbuf + boff);
+    }
     C->last_launches++;
     boff += (size_t)items[it].nv * nsend;
   }
   NCCL_OK(g_nccl.GroupStart());
   boff = 0;
   for (int it = 0; it < nitems; it++) {
+    const int w = items[it].pair ? 2 : 1, nvar = items[it].nv / w;  // element width in doubles, element variables
     for (size_t pi = 0; pi < L.peers.size(); pi++) {
       const int peer = L.peers[pi];
       const int s0 = L.send_ptr[pi], sn = L.send_ptr[pi + 1] - s0;
-      for (int v = 0; v < items[it].nv; v++) {
-        if (sn) NCCL_OK(g_nccl.Send(C->sendbuf + boff + (size_t)v * nsend + s0, sn, ncclDouble, peer, C->comm, st));
-        if (L.recv_count[pi]) NCCL_OK(g_nccl.Recv(items[it].a + (size_t)v * C->np + L.recv_begin[pi], L.recv_count[pi], ncclDouble, peer, C->comm, st));
+      for (int v = 0; v < nvar; v++) {
+        if (sn) NCCL_OK(g_nccl.Send(C->sendbuf + boff + ((size_t)v * nsend + s0) * w, (size_t)sn * w, ncclDouble, peer, C->comm, st));
+        if (L.recv_count[pi])
+          NCCL_OK(g_nccl.Recv(items[it].a + ((size_t)v * C->np + L.recv_begin[pi]) * w, (size_t)L.recv_count[pi] * w, ncclDouble, peer, C->comm, st));
       }
     }
     boff += (size_t)items[it].nv * nsend;
@@ -234,10 +242,10 @@ int ensure_stage(size_t ndoubles) {
 }
 
 // device SoA (local numbering, owned cells) -> caller AoS (original numbering)
-int download_aos(const double *soa, int nvar, double *host_out) {
+int download_aos(const double *soa, int nvar, double *host_out, int pair = 0, int v0 = 0) {
   const size_t ng = (size_t)C->L.nc_global * nvar;
   if (ensure_stage(ng)) return 1;
-  k_gather_out<<<cdiv(C->L.n_own, 256), 256, 0, C->st>>>(C->L.n_own, C->np, nvar, C->dm.orig_id, soa, C->stage_aos);
+  k_gather_out<<<cdiv(C->L.n_own, 256), 256, 0, C->st>>>(C->L.n_own, C->np, nvar, C->dm.orig_id, soa, C->stage_aos, pair, v0);
   CUDA_OK(cudaGetLastError());
   if (C->nranks == 1) {
     CUDA_OK(cudaMemcpyAsync(host_out, C->stage_aos, ng * 8, cudaMemcpyDeviceToHost, C->st));
@@ -260,13 +268,12 @@ int launch_gradient(const double *p, const int *list = nullptr, int nlist = 0) {
   if (nb == 0) return 0;
   Span sp(1);
   const bool lim = C->cfg.limiter > 0;
-  double *gx = C->g, *gy = C->g + 4 * (size_t)C->np;
   if (C->L.g_form == 0) {
-    if (lim) k_gradient<0, true><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, gx, gy, C->phi, list);
-    else k_gradient<0, false><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, gx, gy, C->phi, list);
+    if (lim) k_gradient<0, true><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi, list);
+    else k_gradient<0, false><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi, list);
   } else {
-    if (lim) k_gradient<1, true><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, gx, gy, C->phi, list);
-    else k_gradient<1, false><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, gx, gy, C->phi, list);
+    if (lim) k_gradient<1, true><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi, list);
+    else k_gradient<1, false><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi, list);
   }
   C->last_launches++;
   return 0;
@@ -277,12 +284,9 @@ TileSel g_sel;
 
 template <int UM, bool STEADY, int RC>
 void launch_flux_one(const StageParams &S, const double *pin, double *pout) {
-  const double *gx = C->g, *gy = C->g + 4 * (size_t)C->np;
   const int nb = C->nblocks;
-  constexpr int NCA = RC == RC_FIRST ? 4 : (RC == RC_K0 ? 14 : 15);
   if (C->tile_ok && C->opt_tile == 2) {
-    const size_t stage = ((size_t)NCA * C->pm.S + 5 * (size_t)C->pm.E) * 8 + 4 * kBlock * 4 + 16;
-    const size_t smem = kStages * stage + 4 * sizeof(uint64_t) + (size_t)C->opt_smem_pad * 1024;
+    const size_t smem = kStages * pipe_stage_bytes<RC>(C->pm.S, C->pm.E) + 4 * sizeof(uint64_t) + (size_t)C->opt_smem_pad * 1024;
     static size_t configured = 0;
     if (configured < smem) {
       cudaFuncSetAttribute(k_flux_pipe<UM, STEADY, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -299,22 +303,12 @@ void launch_flux_one(const StageParams &S, const double *pin, double *pout) {
     if (g_sel.list) { pm.tile_list = g_sel.list; pm.ntiles = g_sel.n; }
     const int grid = std::min(pm.ntiles, C->nsm * per_sm);
     if (grid > 0)
-      k_flux_pipe<UM, STEADY, RC><<<grid, kPipeThreads, smem, C->st>>>(C->dm, pm, C->phys, S, pin, gx, gy, C->phi, C->bc, C->q, C->f, pout,
+      k_flux_pipe<UM, STEADY, RC><<<grid, kPipeThreads, smem, C->st>>>(C->dm, pm, C->phys, S, pin, C->g, C->phi, C->bc, C->q, C->f, pout,
                                                                        C->dtl, C->resid, C->ws, C->partial + 4 * (size_t)g_sel.part_off);
     C->nparts = g_sel.part_off + grid;
-  } else if (C->tile_ok && C->opt_tile == 1) {
-    const size_t smem = ((size_t)NCA * C->tm.S + 5 * (size_t)C->tm.E) * 8 + 16;
-    static size_t configured = 0;
-    if (configured < smem) {
-      cudaFuncSetAttribute(k_flux_tile<UM, STEADY, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      configured = smem;
-    }
-    k_flux_tile<UM, STEADY, RC><<<nb, kBlock, smem, C->st>>>(C->dm, C->tm, C->phys, S, pin, gx, gy, C->phi, C->bc, C->q, C->f, pout,
-                                                             C->dtl, C->resid, C->ws, C->partial);
-    C->nparts = nb;
   } else {
-    k_flux_rk<UM, STEADY, RC><<<nb, kBlock, 0, C->st>>>(C->dm, C->phys, S, pin, gx, gy, C->phi, C->bc, C->q, C->f, pout, C->dtl,
-                                                        C->resid, C->ws, C->partial);
+    k_flux_rk<UM, STEADY, RC><<<nb, kBlock, 0, C->st>>>(C->dm, C->phys, S, pin, C->g, C->phi, C->bc, C->q, C->f, pout, C->dtl, C->resid,
+                                                        C->ws, C->partial);
     C->nparts = nb;
   }
 }
@@ -357,7 +351,7 @@ int pass_a(const double *p) {
   if (launch_gradient(p)) return 1;
   if (C->nranks > 1 && C->recon != RC_FIRST) {
     Span sp(0);
-    HaloItem it[2] = {{C->g, 8}, {C->phi, 1}};
+    HaloItem it[2] = {{C->g, 8, 1}, {C->phi, 1, 0}};
     if (halo_exchange(it, C->cfg.limiter > 0 ? 2 : 1)) return 1;
   }
   return 0;
@@ -508,31 +502,26 @@ int fvs2d_gpu_set_mesh(int nnodes, int ntri, int nquad, const double *node_xy, c
   C->np = d.np = (L.n_loc + 31) / 32 * 32;
   C->nblocks = cdiv(L.n_own, kBlock);
   if (dev_upload(d.f_off, L.f_off) || dev_upload(d.f_nbr, L.f_nbr) || dev_upload(d.f_edge, L.f_edge)) return 1;
-  if (dev_upload(d.ex, L.ex) || dev_upload(d.ey, L.ey) || dev_upload(d.ea, L.ea) || dev_upload(d.enx, L.enx) || dev_upload(d.eny, L.eny)) return 1;
-  {  // per-cell geometry padded to the SoA pitch (tile bulk copies read whole even-sized runs)
-    std::vector<double> xc(L.xc), yc(L.yc), vol(L.vol);
-    xc.resize(C->np, 0.0); yc.resize(C->np, 0.0); vol.resize(C->np, 1.0);
-    if (dev_upload(d.xc, xc) || dev_upload(d.yc, yc) || dev_upload(d.vol, vol)) return 1;
+  {  // pair-interleaved geometry (16-byte gathers); per-cell arrays padded to the SoA pitch
+    std::vector<double2> exy(L.nedges), enxy(L.nedges), xy(C->np, make_double2(0.0, 0.0));
+    for (int e = 0; e < L.nedges; e++) { exy[e] = make_double2(L.ex[e], L.ey[e]); enxy[e] = make_double2(L.enx[e], L.eny[e]); }
+    for (int i = 0; i < L.n_loc; i++) xy[i] = make_double2(L.xc[i], L.yc[i]);
+    std::vector<double> vol(L.vol);
+    vol.resize(C->np, 1.0);
+    if (dev_upload(d.exy, exy) || dev_upload(d.enxy, enxy) || dev_upload(d.ea, L.ea) || dev_upload(d.xy, xy) || dev_upload(d.vol, vol)) return 1;
   }
   C->tile_ok = L.tile_hc_max >= 0;
   if (C->tile_ok) {
-    TileMeta &t = C->tm;
-    const uint32_t *fp;
-    if (dev_upload(t.es, L.tile_es) || dev_upload(t.ne, L.tile_ne) || dev_upload(t.hc_ptr, L.tile_hc_ptr) ||
-        dev_upload(t.he_ptr, L.tile_he_ptr) || dev_upload(t.hc_idx, L.tile_hc_idx) || dev_upload(t.he_idx, L.tile_he_idx) ||
-        dev_upload(fp, L.f_pack) || dev_upload(t.f_bf, L.f_bf)) return 1;
-    t.f_pack = fp;
-    t.S = (kBlock + L.tile_hc_max + 1) & ~1;
-    t.E = (L.tile_e_max + 1) & ~1;
     PipeMeta &pmeta = C->pm;
     const int *hdr; const uint32_t *tp;
-    if (dev_upload(hdr, L.tile_hdr) || dev_upload(tp, L.t_pack) || dev_upload(pmeta.t_bf, L.t_bf)) return 1;
+    if (dev_upload(pmeta.hc_idx, L.tile_hc_idx) || dev_upload(pmeta.he_idx, L.tile_he_idx) || dev_upload(hdr, L.tile_hdr) ||
+        dev_upload(tp, L.t_pack) || dev_upload(pmeta.t_bf, L.t_bf)) return 1;
     pmeta.hdr = reinterpret_cast<const int4 *>(hdr);
     pmeta.t_pack = tp;
-    pmeta.hc_idx = t.hc_idx; pmeta.he_idx = t.he_idx;
-    pmeta.S = t.S; pmeta.E = t.E; pmeta.ntiles = L.ntiles;
-    const size_t smem_max = ((size_t)15 * t.S + 5 * (size_t)t.E) * 8 + 16;
-    if (smem_max > 200 * 1024) C->tile_ok = false;  // pathological numbering: fall back to the direct-gather kernel
+    pmeta.S = (kBlock + L.tile_hc_max + 1) & ~1;
+    pmeta.E = (L.tile_e_max + 1) & ~1;
+    pmeta.ntiles = L.ntiles;
+    if (kStages * pipe_stage_bytes<RC_GENERAL>(pmeta.S, pmeta.E) + 64 > 220 * 1024) C->tile_ok = false;  // pathological numbering: direct-gather kernel
   }
   if (dev_upload(d.g_off, L.g_off) || dev_upload(d.g_idx, L.g_idx) || dev_upload(d.g_cx, L.g_cx) || dev_upload(d.g_cy, L.g_cy)) return 1;
   if (dev_upload(d.c0x, L.c0x) || dev_upload(d.c0y, L.c0y)) return 1;
@@ -578,7 +567,7 @@ int fvs2d_gpu_set_state(const double *cvar) {
   const size_t ng = (size_t)C->L.nc_global * 4;
   if (ensure_stage(ng)) return 1;
   CUDA_OK(cudaMemcpyAsync(C->stage_aos, cvar, ng * 8, cudaMemcpyHostToDevice, C->st));
-  k_scatter_in<<<cdiv(C->L.n_loc, 256), 256, 0, C->st>>>(C->L.n_loc, C->np, 4, C->dm.orig_id, C->stage_aos, C->q);
+  k_scatter_in<<<cdiv(C->L.n_loc, 256), 256, 0, C->st>>>(C->L.n_loc, C->np, 4, C->dm.orig_id, C->stage_aos, C->q, 0);
   k_prim<<<cdiv(C->L.n_loc, 256), 256, 0, C->st>>>(C->L.n_loc, C->np, C->cfg.gamma, C->q, C->pa);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(C->st));
@@ -592,11 +581,11 @@ int fvs2d_gpu_set_state_local(const double *cvar_own) {
   const size_t n = (size_t)C->L.n_own * 4;
   if (ensure_stage(n)) return 1;
   CUDA_OK(cudaMemcpyAsync(C->stage_aos, cvar_own, n * 8, cudaMemcpyHostToDevice, C->st));
-  k_scatter_in<<<cdiv(C->L.n_own, 256), 256, 0, C->st>>>(C->L.n_own, C->np, 4, nullptr, C->stage_aos, C->q);
+  k_scatter_in<<<cdiv(C->L.n_own, 256), 256, 0, C->st>>>(C->L.n_own, C->np, 4, nullptr, C->stage_aos, C->q, 0);
   k_prim<<<cdiv(C->L.n_own, 256), 256, 0, C->st>>>(C->L.n_own, C->np, C->cfg.gamma, C->q, C->pa);
   CUDA_OK(cudaGetLastError());
   if (C->nranks > 1) {  // ghost copies of the primitive state come from their owners
-    HaloItem it{C->pa, 4};
+    HaloItem it{C->pa, 4, 1};
     if (halo_exchange(&it, 1)) return 1;
   }
   CUDA_OK(cudaStreamSynchronize(C->st));
@@ -609,7 +598,7 @@ int fvs2d_gpu_get_state_local(double *cvar_own) {
   NEED(cvar_own != nullptr, "fvs2d_gpu_get_state_local: null cvar");
   const size_t n = (size_t)C->L.n_own * 4;
   if (ensure_stage(n)) return 1;
-  k_gather_out<<<cdiv(C->L.n_own, 256), 256, 0, C->st>>>(C->L.n_own, C->np, 4, nullptr, C->q, C->stage_aos);
+  k_gather_out<<<cdiv(C->L.n_own, 256), 256, 0, C->st>>>(C->L.n_own, C->np, 4, nullptr, C->q, C->stage_aos, 0, 0);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpyAsync(cvar_own, C->stage_aos, n * 8, cudaMemcpyDeviceToHost, C->st));
   CUDA_OK(cudaStreamSynchronize(C->st));
@@ -674,12 +663,12 @@ int fvs2d_gpu_compute_residual(double time, double *resid, double *ws_nrml) {
 
 int fvs2d_gpu_get_aux(double *pvar, double *grad, double *phi_lim) {
   NEED(C && C->has_state, "fvs2d_gpu_get_aux: no state");
-  if (pvar && download_aos(C->pa, 4, pvar)) return 1;
+  if (pvar && download_aos(C->pa, 4, pvar, 1, 0)) return 1;
   if (phi_lim && download_aos(C->phi, 1, phi_lim)) return 1;
-  if (grad) {  // Fortran grad(ivar,ic,idim): two planes of (4,ncells)
+  if (grad) {  // Fortran grad(ivar,ic,idim): two planes of (4,ncells); device g holds gx0-3, gy0-3 pair-interleaved
     const size_t plane = 4 * (size_t)C->L.nc_global;
-    if (download_aos(C->g, 4, grad)) return 1;
-    if (download_aos(C->g + 4 * (size_t)C->np, 4, grad + plane)) return 1;
+    if (download_aos(C->g, 4, grad, 1, 0)) return 1;
+    if (download_aos(C->g, 4, grad + plane, 1, 4)) return 1;
   }
   return 0;
 }
@@ -725,7 +714,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
           if (launch_gradient(C->pa, C->d_tile_bnd, C->n_bnd)) return 1;
           CUDA_OK(cudaEventRecord(C->e_a, C->st));
           CUDA_OK(cudaStreamWaitEvent(C->sx, C->e_a, 0));
-          HaloItem it[2] = {{C->g, 8}, {C->phi, 1}};
+          HaloItem it[2] = {{C->g, 8, 1}, {C->phi, 1, 0}};
           if (halo_exchange(it, c.limiter > 0 ? 2 : 1, C->sx)) return 1;
           CUDA_OK(cudaEventRecord(C->e_g, C->sx));
         }
@@ -736,7 +725,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
         if (launch_flux(um, S, C->pa, C->pb, C->d_tile_bnd, C->n_bnd, parts_int)) return 1;
         CUDA_OK(cudaEventRecord(C->e_b, C->st));
         CUDA_OK(cudaStreamWaitEvent(C->sx, C->e_b, 0));
-        HaloItem itp{C->pb, 4};
+        HaloItem itp{C->pb, 4, 1};
         if (halo_exchange(&itp, 1, C->sx)) return 1;                       // overlaps the next stage's interior gradient
         CUDA_OK(cudaEventRecord(C->e_p, C->sx));
         p_pending = true;
@@ -745,7 +734,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
         if (launch_flux(um, S, C->pa, C->pb)) return 1;
         if (C->nranks > 1) {
           Span sp(0);
-          HaloItem it{C->pb, 4};
+          HaloItem it{C->pb, 4, 1};
           if (halo_exchange(&it, 1)) return 1;
         }
       }

@@ -7,9 +7,13 @@
 //   k_vortex_err isentropic-vortex error norms                                      [reference K10]
 //   k_finish_*   fixed-order final reductions of the per-CTA partials (no fp atomics anywhere)
 //
-// Data layout: struct-of-arrays with pitch `np` (cells padded to a multiple of 32): var v of cell i is
-// a[v*np + i].  One thread per cell; per-cell lists are sliced ELL (see layout.hpp) so list reads of a
-// warp are coalesced.  Face fluxes are evaluated in the edge's own orientation (c1 -> c2) by both
+// Data layout: struct-of-arrays with pitch `np` (cells padded to a multiple of 32).  The arrays that other
+// cells gather -- primitive state p (4 vars), gradients g (8 vars: gx0-3, gy0-3), centroids xy, edge centres
+// exy and normals enxy -- are PAIR-interleaved: variables 2k and 2k+1 of cell i form the double2
+// a2[k*np + i], so every gather is a 16-byte access (LDG.128 / LDS.128 / L1-bypassing cp.async.cg) and
+// own-cell runs stay contiguous for the TMA bulk copies.  q, f (touched only by the owning thread) are
+// plain SoA a[v*np + i].  One thread per cell; per-cell lists are sliced ELL (see layout.hpp) so list
+// reads of a warp are coalesced.  Face fluxes are evaluated in the edge's own orientation (c1 -> c2) by both
 // cells, so the two evaluations are bit-identical and the scheme stays discretely conservative.
 #pragma once
 #include <cuda_runtime.h>
@@ -34,8 +38,10 @@ enum ReconMode { RC_FIRST = 0, RC_K0 = 1, RC_K0_PHI = 2, RC_GENERAL = 3 };
 struct DevMesh {
   int n_own, n_loc, np;  // np: SoA pitch
   const int *f_off, *f_nbr, *f_edge;
-  const double *ex, *ey, *ea, *enx, *eny;
-  const double *xc, *yc, *vol;
+  const double2 *exy, *enxy;  // edge centre (x,y), unit normal (nx,ny) c1 -> c2
+  const double *ea;           // edge length
+  const double2 *xy;          // cell centroid
+  const double *vol;
   const int *g_off, *g_idx;
   const double *g_cx, *g_cy, *c0x, *c0y;
   const int *bf_type, *bf_edge;
@@ -60,6 +66,13 @@ struct StageParams {
   double c;         // rk_coef(stage)
   double dt;        // global dt
 };
+
+// variable v of cell i in a pair-interleaved array (as doubles)
+__host__ __device__ __forceinline__ size_t pidx(int v, int np, int i) { return ((size_t)(v >> 1) * np + i) * 2 + (v & 1); }
+__device__ __forceinline__ void load4(const double2 *__restrict__ a2, int np, int i, double out[4]) {
+  const double2 a = a2[i], b = a2[np + i];
+  out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+}
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void vortex_exact(const Phys &P, double t, double x, double y, double pv[4]) {
@@ -186,10 +199,9 @@ __global__ void __launch_bounds__(256) k_prim(int n, int np, double gamma, const
   if (i >= n) return;
   const double r = q[i], ru = q[np + i], rv = q[2 * np + i], re = q[3 * np + i];
   const double u = ru / r, v = rv / r;
-  p[i] = r;
-  p[np + i] = u;
-  p[2 * np + i] = v;
-  p[3 * np + i] = (gamma - 1.0) * (re - 0.5 * r * (u * u + v * v));
+  double2 *p2 = reinterpret_cast<double2 *>(p);
+  p2[i] = make_double2(r, u);
+  p2[np + i] = make_double2(v, (gamma - 1.0) * (re - 0.5 * r * (u * u + v * v)));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -199,17 +211,17 @@ __global__ void __launch_bounds__(256) k_prim(int n, int np, double gamma, const
 //   LIM: phi_i = min over vars and faces (src/gradient_limiter.f90:47-91); min/max over the stencil
 template <int FORM, bool LIM>
 __global__ void __launch_bounds__(kBlock) k_gradient(const DevMesh m, const int limiter_type, const double *__restrict__ p,
-                                                     double *__restrict__ gx, double *__restrict__ gy,
-                                                     double *__restrict__ phi, const int *__restrict__ tile_list) {
+                                                     double *__restrict__ g, double *__restrict__ phi,
+                                                     const int *__restrict__ tile_list) {
   // one CTA = one 128-cell tile; tile_list (or null = all tiles in order) selects the interior / boundary subset
   const int i = (tile_list ? __ldg(&tile_list[blockIdx.x]) : (int)blockIdx.x) * kBlock + threadIdx.x;
   if (i >= m.n_own) return;
   const int np = m.np, lane = threadIdx.x & 31, sl = i >> 5;
   const int off = __ldg(&m.g_off[sl]);
   const int w = (__ldg(&m.g_off[sl + 1]) - off) >> 5;
+  const double2 *p2 = reinterpret_cast<const double2 *>(p);
   double p0[4], ax[4], ay[4], pmin[4], pmax[4];
-#pragma unroll
-  for (int v = 0; v < 4; v++) p0[v] = p[v * np + i];
+  load4(p2, np, i, p0);
   if (FORM == 0) {
     const double c0x = m.c0x[i], c0y = m.c0y[i];
 #pragma unroll
@@ -226,20 +238,25 @@ __global__ void __launch_bounds__(kBlock) k_gradient(const DevMesh m, const int 
     const int e = off + 32 * k + lane;
     const int j = __ldg(&m.g_idx[e]);
     const double cx = __ldg(&m.g_cx[e]), cy = __ldg(&m.g_cy[e]);
+    double pjv[4];
+    load4(p2, np, j, pjv);  // two 16-byte gathers per stencil member
 #pragma unroll
     for (int v = 0; v < 4; v++) {
-      const double pj = p[v * np + j];
+      const double pj = pjv[v];
       const double d = FORM == 0 ? pj : pj - p0[v];
       ax[v] += cx * d;
       ay[v] += cy * d;
       if (LIM) { pmin[v] = fmin(pmin[v], pj); pmax[v] = fmax(pmax[v], pj); }
     }
   }
-#pragma unroll
-  for (int v = 0; v < 4; v++) { gx[v * np + i] = ax[v]; gy[v * np + i] = ay[v]; }
+  double2 *g2 = reinterpret_cast<double2 *>(g);
+  g2[i] = make_double2(ax[0], ax[1]);
+  g2[np + i] = make_double2(ax[2], ax[3]);
+  g2[2 * np + i] = make_double2(ay[0], ay[1]);
+  g2[3 * np + i] = make_double2(ay[2], ay[3]);
   if (LIM) {
     const double pi = 3.141592653589793238462643383279502884;
-    const double xc = m.xc[i], yc = m.yc[i];
+    const double xc = m.xy[i].x, yc = m.xy[i].y;
     const double h = 2.0 * sqrt(m.vol[i] / pi);
     const double kh = (limiter_type == 1 ? 5.0 : 0.3) * h;
     const double eps2 = kh * kh * kh;
@@ -250,7 +267,8 @@ __global__ void __launch_bounds__(kBlock) k_gradient(const DevMesh m, const int 
       const int e = foff + 32 * k + lane;
       if (__ldg(&m.f_nbr[e]) == kPadNbr) continue;
       const int ed = __ldg(&m.f_edge[e]) >> 1;
-      const double dx = __ldg(&m.ex[ed]) - xc, dy = __ldg(&m.ey[ed]) - yc;
+      const double2 ec = __ldg(&m.exy[ed]);
+      const double dx = ec.x - xc, dy = ec.y - yc;
 #pragma unroll
       for (int v = 0; v < 4; v++) {
         const double pf = p0[v] + dx * ax[v] + dy * ay[v];
@@ -278,8 +296,9 @@ __global__ void __launch_bounds__(128) k_bc_state(const DevMesh m, const Phys P,
     for (int v = 0; v < 4; v++) pv[v] = P.pinf[v];
   } else if (type == 4) {
     const int ed = m.bf_edge[b];
-    if (P.lvortex) vortex_exact(P, time, m.ex[ed], m.ey[ed], pv);
-    else mms_exact(P, m.ex[ed], m.ey[ed], pv);
+    const double2 ec = m.exy[ed];
+    if (P.lvortex) vortex_exact(P, time, ec.x, ec.y, pv);
+    else mms_exact(P, ec.x, ec.y, pv);
   }
 #pragma unroll
   for (int v = 0; v < 4; v++) bc[v * m.nbf + b] = pv[v];
@@ -309,7 +328,7 @@ __device__ __forceinline__ void block_sum_store(double val[NV], double *__restri
 
 // ------------------------------------------------------------------------------------------------
 // pass B building blocks, shared by the direct-gather kernel (k_flux_rk) and the shared-memory tile
-// kernel (k_flux_tile).
+// kernel (k_flux_pipe).
 //   interior faces  src/residual.f90:66-103     boundary faces  src/residual.f90:111-157
 //   -R/vol          src/residual.f90:164-166    local dt        src/runge_kutta.f90:424-437
 //   RK update       src/runge_kutta.f90:156-162 (RK), :225-226 (SSPRK), :299-313, :383-387 (steady)
@@ -412,10 +431,9 @@ __device__ __forceinline__ void stage_update_pre(const Phys &P, const StageParam
   }
   // primitive state for the next stage (cvar2pvar of the next compute_residual)
   const double u = qn[1] / qn[0], vv = qn[2] / qn[0];
-  pout[i] = qn[0];
-  pout[np + i] = u;
-  pout[2 * np + i] = vv;
-  pout[3 * np + i] = (P.gamma - 1.0) * (qn[3] - 0.5 * qn[0] * (u * u + vv * vv));
+  double2 *po = reinterpret_cast<double2 *>(pout);
+  po[i] = make_double2(qn[0], u);
+  po[np + i] = make_double2(vv, (P.gamma - 1.0) * (qn[3] - 0.5 * qn[0] * (u * u + vv * vv)));
   if (S.last) {
 #pragma unroll
     for (int v = 0; v < 4; v++) {
@@ -458,28 +476,24 @@ __device__ __forceinline__ void stage_update(const Phys &P, const StageParams &S
 // numbering; also the fallback when a tile's halo does not fit the packed 16-bit slots).
 template <int UM, bool STEADY, int RC>
 __global__ void __launch_bounds__(kBlock) k_flux_rk(const DevMesh m, const Phys P, const StageParams S,
-                                                    const double *__restrict__ p, const double *__restrict__ gx,
-                                                    const double *__restrict__ gy, const double *__restrict__ phi,
-                                                    const double *__restrict__ bc, double *__restrict__ q,
-                                                    double *__restrict__ f, double *__restrict__ pout,
+                                                    const double *__restrict__ p, const double *__restrict__ g,
+                                                    const double *__restrict__ phi, const double *__restrict__ bc,
+                                                    double *__restrict__ q, double *__restrict__ f, double *__restrict__ pout,
                                                     double *__restrict__ dtl, double *__restrict__ resid_out,
                                                     double *__restrict__ ws_out, double *__restrict__ partial) {
   const int i = blockIdx.x * kBlock + threadIdx.x;
   const bool live = i < m.n_own;
   const int np = m.np, lane = threadIdx.x & 31;
+  const double2 *p2 = reinterpret_cast<const double2 *>(p), *g2 = reinterpret_cast<const double2 *>(g);
   double dq2[4] = {0.0, 0.0, 0.0, 0.0};
   if (live) {
     const int sl = i >> 5;
     const int off = __ldg(&m.f_off[sl]);
     const int w = (__ldg(&m.f_off[sl + 1]) - off) >> 5;
     double p0[4], g0x[4], g0y[4];
-#pragma unroll
-    for (int v = 0; v < 4; v++) p0[v] = p[v * np + i];
-    if (RC != RC_FIRST) {
-#pragma unroll
-      for (int v = 0; v < 4; v++) { g0x[v] = gx[v * np + i]; g0y[v] = gy[v * np + i]; }
-    }
-    const double x0 = m.xc[i], y0 = m.yc[i];
+    load4(p2, np, i, p0);
+    if (RC != RC_FIRST) { load4(g2, np, i, g0x); load4(g2 + 2 * (size_t)np, np, i, g0y); }
+    const double2 c0 = m.xy[i];
     const double phi0 = (RC >= RC_K0_PHI) ? phi[i] : 1.0;
     double acc[4] = {0.0, 0.0, 0.0, 0.0}, wsacc = 0.0;
     for (int k = 0; k < w; k++) {
@@ -489,33 +503,36 @@ __global__ void __launch_bounds__(kBlock) k_flux_rk(const DevMesh m, const Phys 
       const int fe = __ldg(&m.f_edge[e]);
       const int ed = fe >> 1;
       const bool self_c1 = (fe & 1) == 0;
-      const double xf = __ldg(&m.ex[ed]), yf = __ldg(&m.ey[ed]), af = __ldg(&m.ea[ed]);
-      const double nx = __ldg(&m.enx[ed]), ny = __ldg(&m.eny[ed]);
+      const double2 fc = __ldg(&m.exy[ed]), fn = __ldg(&m.enxy[ed]);
+      const double af = __ldg(&m.ea[ed]);
       double me[4] = {0.0, 0.0, 0.0, 0.0};  // this cell's reconstruction increment (x_f - x_c) . grad p
       if (RC != RC_FIRST) {
-        const double dx = xf - x0, dy = yf - y0;
+        const double dx = fc.x - c0.x, dy = fc.y - c0.y;
 #pragma unroll
         for (int v = 0; v < 4; v++) me[v] = dx * g0x[v] + dy * g0y[v];
       }
       if (nb >= 0) {
         double pj[4], ot[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int v = 0; v < 4; v++) pj[v] = p[v * np + nb];
+        load4(p2, np, nb, pj);
         double phij = 1.0;
         if (RC != RC_FIRST) {
-          const double dx = xf - m.xc[nb], dy = yf - m.yc[nb];
+          double gjx[4], gjy[4];
+          load4(g2, np, nb, gjx);
+          load4(g2 + 2 * (size_t)np, np, nb, gjy);
+          const double2 cj = m.xy[nb];
+          const double dx = fc.x - cj.x, dy = fc.y - cj.y;
 #pragma unroll
-          for (int v = 0; v < 4; v++) ot[v] = dx * gx[v * np + nb] + dy * gy[v * np + nb];
+          for (int v = 0; v < 4; v++) ot[v] = dx * gjx[v] + dy * gjy[v];
           if (RC >= RC_K0_PHI) phij = phi[nb];
         }
-        interior_face<RC>(P, self_c1, p0, me, phi0, pj, ot, phij, nx, ny, af, acc, wsacc);
+        interior_face<RC>(P, self_c1, p0, me, phi0, pj, ot, phij, fn.x, fn.y, af, acc, wsacc);
       } else {
         const int b = -1 - nb;
         const int type = __ldg(&m.bf_type[b]);
         double bcv[4];
 #pragma unroll
         for (int v = 0; v < 4; v++) bcv[v] = __ldg(&bc[v * m.nbf + b]);
-        boundary_face<RC>(P, type, p0, me, phi0, bcv, nx, ny, af, acc, wsacc);
+        boundary_face<RC>(P, type, p0, me, phi0, bcv, fn.x, fn.y, af, acc, wsacc);
       }
     }
     stage_update<UM, STEADY>(P, S, i, np, m.vol[i], acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
@@ -524,20 +541,7 @@ __global__ void __launch_bounds__(kBlock) k_flux_rk(const DevMesh m, const Phys 
 }
 
 // ------------------------------------------------------------------------------------------------
-// pass B, shared-memory tile variant (the production path).  One CTA = one tile of kBlock consecutive
-// cells of the Hilbert order.  Staging into shared memory:
-//   - the tile's own cells and own edges are contiguous runs of the SoA arrays: one elected thread
-//     issues TMA bulk copies (cp.async.bulk, completion on an mbarrier);
-//   - halo cells / halo edges (listed per tile at upload time) are gathered with 8-byte cp.async;
-// then every thread computes its cell's faces out of shared memory.  Several CTAs are resident per SM,
-// so one tile's loads overlap another tile's fp64 work.
-struct TileMeta {
-  const int *es, *ne, *hc_ptr, *he_ptr, *hc_idx, *he_idx;
-  const uint32_t *f_pack;
-  const int *f_bf;
-  int S, E;  // smem strides (even): cell slots (kBlock + max halo), edge slots
-};
-
+// PTX helpers of the shared-memory pipeline: mbarrier, TMA bulk copy (cp.async.bulk), cp.async
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -561,141 +565,26 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ void cp_async8(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-
-template <int UM, bool STEADY, int RC>
-__global__ void __launch_bounds__(kBlock) k_flux_tile(const DevMesh m, const TileMeta tm, const Phys P, const StageParams S,
-                                                      const double *__restrict__ p, const double *__restrict__ gx,
-                                                      const double *__restrict__ gy, const double *__restrict__ phi,
-                                                      const double *__restrict__ bc, double *__restrict__ q,
-                                                      double *__restrict__ f, double *__restrict__ pout,
-                                                      double *__restrict__ dtl, double *__restrict__ resid_out,
-                                                      double *__restrict__ ws_out, double *__restrict__ partial) {
-  // cell arrays staged: p(4) [, gx(4), gy(4), xc, yc [, phi]]
-  constexpr int NCA = RC == RC_FIRST ? 4 : (RC == RC_K0 ? 14 : 15);
-  extern __shared__ __align__(16) double smem[];
-  const int SS = tm.S, EE = tm.E;
-  double *sc = smem;
-  double *se = smem + (size_t)NCA * SS;
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(se + 5 * (size_t)EE);
-  const int t = blockIdx.x, tid = threadIdx.x, np = m.np;
-  const int c0 = t * kBlock;
-  const int ncell = min(kBlock, m.n_own - c0);
-  const int es = __ldg(&tm.es[t]), ne = __ldg(&tm.ne[t]);
-  auto cell_src = [&](int a) -> const double * {
-    return a < 4 ? p + (size_t)a * np : a < 8 ? gx + (size_t)(a - 4) * np : a < 12 ? gy + (size_t)(a - 8) * np : a == 12 ? m.xc : a == 13 ? m.yc : phi;
-  };
-  auto edge_src = [&](int a) -> const double * { return a == 0 ? m.ex : a == 1 ? m.ey : a == 2 ? m.ea : a == 3 ? m.enx : m.eny; };
-  if (tid == 0) {
-    mbar_init(mbar, 1);
-    const uint32_t bytes_c = (uint32_t)((ncell + 1) & ~1) * 8u, bytes_e = (uint32_t)ne * 8u;
-    mbar_expect_tx(mbar, NCA * bytes_c + 5u * bytes_e);
-#pragma unroll
-    for (int a = 0; a < NCA; a++) bulk_g2s(sc + (size_t)a * SS, cell_src(a) + c0, bytes_c, mbar);
-    if (ne > 0) {
-#pragma unroll
-      for (int a = 0; a < 5; a++) bulk_g2s(se + (size_t)a * EE, edge_src(a) + es, bytes_e, mbar);
-    }
-  }
-  {  // halo gathers
-    const int hp = __ldg(&tm.hc_ptr[t]), nh = __ldg(&tm.hc_ptr[t + 1]) - hp;
-    for (int h = tid; h < nh; h += kBlock) {
-      const int j = __ldg(&tm.hc_idx[hp + h]);
-#pragma unroll
-      for (int a = 0; a < NCA; a++) cp_async8(sc + (size_t)a * SS + kBlock + h, cell_src(a) + j);
-    }
-    const int ep = __ldg(&tm.he_ptr[t]), nhe = __ldg(&tm.he_ptr[t + 1]) - ep;
-    for (int h = tid; h < nhe; h += kBlock) {
-      const int j = __ldg(&tm.he_idx[ep + h]);
-#pragma unroll
-      for (int a = 0; a < 5; a++) cp_async8(se + (size_t)a * EE + ne + h, edge_src(a) + j);
-    }
-  }
-  // this thread's face entries, while the copies fly
-  const int i = c0 + tid;
-  const bool live = tid < ncell;
-  const int lane = tid & 31, sl = i >> 5;
-  int off = 0, w = 0;
-  uint32_t fp[4] = {0xFFFEu, 0xFFFEu, 0xFFFEu, 0xFFFEu};
-  if (live) {
-    off = __ldg(&m.f_off[sl]);
-    w = (__ldg(&m.f_off[sl + 1]) - off) >> 5;
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      if (k < w) fp[k] = __ldg(&tm.f_pack[off + 32 * k + lane]);
-  }
-  cp_async_wait_all();
-  __syncthreads();  // mbarrier init + every thread's cp.async data visible
-  mbar_wait(mbar, 0);
-
-  double dq2[4] = {0.0, 0.0, 0.0, 0.0};
-  if (live) {
-    double p0[4], g0x[4], g0y[4];
-#pragma unroll
-    for (int v = 0; v < 4; v++) p0[v] = sc[(size_t)v * SS + tid];
-    double x0 = 0.0, y0 = 0.0;
-    if (RC != RC_FIRST) {
-#pragma unroll
-      for (int v = 0; v < 4; v++) { g0x[v] = sc[(size_t)(4 + v) * SS + tid]; g0y[v] = sc[(size_t)(8 + v) * SS + tid]; }
-      x0 = sc[12 * (size_t)SS + tid]; y0 = sc[13 * (size_t)SS + tid];
-    }
-    const double phi0 = (RC >= RC_K0_PHI) ? sc[14 * (size_t)SS + tid] : 1.0;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0}, wsacc = 0.0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      if (k >= w) break;
-      const uint32_t pk = fp[k];
-      const uint32_t ns = pk & 0xFFFFu;
-      if (ns == 0xFFFEu) continue;
-      const int eslot = (pk >> 16) & 0x7FFF;
-      const bool self_c1 = (pk >> 31) == 0;
-      const double xf = se[eslot], yf = se[EE + eslot], af = se[2 * EE + eslot];
-      const double nx = se[3 * EE + eslot], ny = se[4 * EE + eslot];
-      double me[4] = {0.0, 0.0, 0.0, 0.0};
-      if (RC != RC_FIRST) {
-        const double dx = xf - x0, dy = yf - y0;
-#pragma unroll
-        for (int v = 0; v < 4; v++) me[v] = dx * g0x[v] + dy * g0y[v];
-      }
-      if (ns != 0xFFFFu) {
-        double pj[4], ot[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int v = 0; v < 4; v++) pj[v] = sc[(size_t)v * SS + ns];
-        double phij = 1.0;
-        if (RC != RC_FIRST) {
-          const double dx = xf - sc[12 * (size_t)SS + ns], dy = yf - sc[13 * (size_t)SS + ns];
-#pragma unroll
-          for (int v = 0; v < 4; v++) ot[v] = dx * sc[(size_t)(4 + v) * SS + ns] + dy * sc[(size_t)(8 + v) * SS + ns];
-          if (RC >= RC_K0_PHI) phij = sc[14 * (size_t)SS + ns];
-        }
-        interior_face<RC>(P, self_c1, p0, me, phi0, pj, ot, phij, nx, ny, af, acc, wsacc);
-      } else {
-        const int b = __ldg(&tm.f_bf[off + 32 * k + lane]);
-        const int type = __ldg(&m.bf_type[b]);
-        double bcv[4];
-#pragma unroll
-        for (int v = 0; v < 4; v++) bcv[v] = __ldg(&bc[v * m.nbf + b]);
-        boundary_face<RC>(P, type, p0, me, phi0, bcv, nx, ny, af, acc, wsacc);
-      }
-    }
-    stage_update<UM, STEADY>(P, S, i, np, m.vol[i], acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
-  }
-  if (UM != UM_RESID && S.last) block_sum_store<4>(dq2, partial);
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {  // L1-bypassing (LDGSTS.BYPASS)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
 // pass B, persistent warp-specialised pipeline (the production path).
-// CTA = 4 consumer warps (one thread per cell of a tile) + 1 producer warp, looping over tiles
+// CTA = kBlock/32 consumer warps (one thread per cell of a tile) + 1 producer warp, looping over tiles
 // blockIdx.x, blockIdx.x + gridDim.x, ...  A 2-stage shared-memory ring decouples them:
-//   producer: waits empty[s]; reads the tile header; one lane issues the TMA bulk copies (own cells,
-//             own edges, face table -> complete_tx on full[s]); all lanes gather the halo cells / edges
-//             with 8-byte cp.async and hand their completion to full[s] (cp.async.mbarrier.arrive.noinc);
+//   producer: waits empty[s]; one lane issues the TMA bulk copies (cp.async.bulk, complete_tx on full[s]) for
+//             the tile's contiguous runs -- own cells of p (2 x double2), g (4), xy (1) [, phi], own edges
+//             exy / enxy / ea, and the face table; all lanes gather the halo cells / edges listed for the
+//             tile with 16-byte L1-bypassing cp.async.cg (8 bytes for phi / ea) and hand their completion to
+//             full[s] (cp.async.mbarrier.arrive.noinc); the next tile's header and index lists are prefetched;
 //   consumer: prefetches its cell's RK data (registers), waits full[s], computes its faces out of shared
-//             memory (left/right states are addressed by slot, so no operand swapping), arrives on
-//             empty[s], applies the stage update.
-// Global-memory latency is thus only ever seen by the producer warp.
+//             memory with 16-byte LDS (left/right states are addressed by slot, so no operand swapping),
+//             arrives on empty[s], applies the stage update.
+// Global-memory latency is only ever seen by the producer warp.
+// (Measured on B200: with 8-byte cp.async, which can only go THROUGH L1, the gathers were throttled by L1
+// line allocation -- pass B ran 25 % slower whenever 3 CTAs' shared memory pushed the carve-out from 196 to
+// 228 KB; the pair-interleaved layout exists to make every gather a 16-byte bypass copy.)
 constexpr int kPipeThreads = kBlock + 32;
 constexpr int kStages = 2;
 
@@ -704,9 +593,18 @@ struct PipeMeta {
   const int *hc_idx, *he_idx;
   const uint32_t *t_pack;
   const int *t_bf;
-  int S, E, ntiles;
+  int S, E, ntiles;      // smem strides in elements (even): cell slots (kBlock + max halo), edge slots
   const int *tile_list;  // null: tiles 0..ntiles-1; else the ntiles tile ids to process (interior / boundary subset)
 };
+
+// bytes of one stage: double2 cell arrays [NC2][S] | phi [S] (limited variants) | exy, enxy [2][E] | ea [E] |
+// face table [4][kBlock] | {fw, fbase}
+template <int RC>
+__host__ __device__ constexpr int pipe_nc2() { return RC == RC_FIRST ? 2 : 7; }
+template <int RC>
+__host__ __device__ inline size_t pipe_stage_bytes(int S, int E) {
+  return (size_t)pipe_nc2<RC>() * S * 16 + (RC >= RC_K0_PHI ? (size_t)S * 8 : 0) + (size_t)E * 40 + 4 * kBlock * sizeof(uint32_t) + 16;
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -717,21 +615,26 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
 
 template <int UM, bool STEADY, int RC>
 __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(const DevMesh m, const PipeMeta pm, const Phys P, const StageParams S,
-                                                               const double *__restrict__ p, const double *__restrict__ gx,
-                                                               const double *__restrict__ gy, const double *__restrict__ phi,
-                                                               const double *__restrict__ bc, double *__restrict__ q,
-                                                               double *__restrict__ f, double *__restrict__ pout,
-                                                               double *__restrict__ dtl, double *__restrict__ resid_out,
-                                                               double *__restrict__ ws_out, double *__restrict__ partial) {
-  constexpr int NCA = RC == RC_FIRST ? 4 : (RC == RC_K0 ? 14 : 15);
+                                                               const double *__restrict__ p, const double *__restrict__ g,
+                                                               const double *__restrict__ phi, const double *__restrict__ bc,
+                                                               double *__restrict__ q, double *__restrict__ f,
+                                                               double *__restrict__ pout, double *__restrict__ dtl,
+                                                               double *__restrict__ resid_out, double *__restrict__ ws_out,
+                                                               double *__restrict__ partial) {
+  constexpr int NC2 = pipe_nc2<RC>();
+  constexpr bool PHI = RC >= RC_K0_PHI;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  int SS = pm.S, EE = pm.E;
-  asm volatile("" : "+r"(SS), "+r"(EE));  // keep the strides in registers: no constant-bank reloads in the face loop
-  const int np = m.np;
-  const size_t stage_bytes = ((size_t)NCA * SS + 5 * (size_t)EE) * 8 + 4 * kBlock * sizeof(uint32_t) + 16;  // + {fw, fbase}
+  const int SS = pm.S, EE = pm.E, np = m.np;
+  const size_t stage_bytes = pipe_stage_bytes<RC>(SS, EE);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kStages * stage_bytes);
   uint64_t *empty = full + kStages;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // stage layout helpers
+  auto st_c2 = [&](int s) { return reinterpret_cast<double2 *>(smem_raw + s * stage_bytes); };
+  auto st_phi = [&](int s) { return reinterpret_cast<double *>(st_c2(s) + NC2 * SS); };
+  auto st_e2 = [&](int s) { return reinterpret_cast<double2 *>(st_phi(s) + (PHI ? SS : 0)); };
+  auto st_ea = [&](int s) { return reinterpret_cast<double *>(st_e2(s) + 2 * EE); };
+  auto st_f = [&](int s) { return reinterpret_cast<uint32_t *>(st_ea(s) + EE); };
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 33); mbar_init(&empty[s], kBlock); }
@@ -740,10 +643,8 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
 
   if (warp == kBlock / 32) {
     // ================================ producer warp ================================
-    auto cell_src = [&](int a) -> const double * {
-      return a < 4 ? p + (size_t)a * np : a < 8 ? gx + (size_t)(a - 4) * np : a < 12 ? gy + (size_t)(a - 8) * np : a == 12 ? m.xc : a == 13 ? m.yc : phi;
-    };
-    auto edge_src = [&](int a) -> const double * { return a == 0 ? m.ex : a == 1 ? m.ey : a == 2 ? m.ea : a == 3 ? m.enx : m.eny; };
+    const double2 *p2 = reinterpret_cast<const double2 *>(p), *g2 = reinterpret_cast<const double2 *>(g);
+    auto cell_src = [&](int a) -> const double2 * { return a < 2 ? p2 + (size_t)a * np : a < 6 ? g2 + (size_t)(a - 2) * np : m.xy; };
     // the header and the halo index lists of the NEXT tile are fetched while the current one is in
     // flight, so only one memory latency (the data itself) sits between "stage free" and "stage full"
     int4 h0 = make_int4(0, 0, 0, 0), h1 = make_int4(0, 0, 0, 0);
@@ -758,6 +659,18 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
       }
     };
     auto tile_id = [&](int j) { return pm.tile_list ? __ldg(&pm.tile_list[j]) : j; };
+    auto gather_cell = [&](int s, int h, int j) {
+      double2 *c2 = st_c2(s);
+#pragma unroll
+      for (int a = 0; a < NC2; a++) cp_async16(c2 + a * SS + kBlock + h, cell_src(a) + j);
+      if (PHI) cp_async8(st_phi(s) + kBlock + h, phi + j);
+    };
+    auto gather_edge = [&](int s, int ne, int h, int j) {
+      double2 *e2 = st_e2(s);
+      cp_async16(e2 + ne + h, m.exy + j);
+      cp_async16(e2 + EE + ne + h, m.enxy + j);
+      cp_async8(st_ea(s) + ne + h, m.ea + j);
+    };
     if ((int)blockIdx.x < pm.ntiles) fetch_meta(tile_id(blockIdx.x));
     int it = 0;
     for (int j = blockIdx.x; j < pm.ntiles; j += gridDim.x, it++) {
@@ -767,47 +680,34 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
       const int es = h0.x, ne = h0.y, hp = h0.z, nh = h0.w, ep = h1.x, nhe = h1.y, fbase = h1.z, fw = h1.w;
       const int jcc[3] = {jc[0], jc[1], jc[2]}, jee[3] = {je[0], je[1], je[2]};
       mbar_wait(&empty[s], ph ^ 1);
-      double *sc = reinterpret_cast<double *>(smem_raw + s * stage_bytes);
-      double *se = sc + NCA * SS;
-      uint32_t *sf = reinterpret_cast<uint32_t *>(se + 5 * EE);
       const int c0 = t * kBlock;
       const int ncell = min(kBlock, m.n_own - c0);
       if (lane == 0) {
-        const uint32_t bytes_c = (uint32_t)((ncell + 1) & ~1) * 8u, bytes_e = (uint32_t)ne * 8u;
-        const uint32_t bytes_f = (uint32_t)fw * kBlock * 4u;
+        double2 *c2 = st_c2(s), *e2 = st_e2(s);
+        uint32_t *sf = st_f(s);
+        const uint32_t bytes_c = (uint32_t)ncell * 16u, bytes_phi = PHI ? (uint32_t)((ncell + 1) & ~1) * 8u : 0u;
+        const uint32_t bytes_e = (uint32_t)ne * 16u, bytes_ea = (uint32_t)ne * 8u, bytes_f = (uint32_t)fw * kBlock * 4u;
         int *sh = reinterpret_cast<int *>(sf + 4 * kBlock);
         sh[0] = fw; sh[1] = fbase;  // published to the consumers by the arrive below (release)
-        mbar_expect_tx(&full[s], NCA * bytes_c + 5u * bytes_e + bytes_f);
+        mbar_expect_tx(&full[s], NC2 * bytes_c + bytes_phi + 2u * bytes_e + bytes_ea + bytes_f);
 #pragma unroll
-        for (int a = 0; a < NCA; a++) bulk_g2s(sc + a * SS, cell_src(a) + c0, bytes_c, &full[s]);
+        for (int a = 0; a < NC2; a++) bulk_g2s(c2 + a * SS, cell_src(a) + c0, bytes_c, &full[s]);
+        if (PHI) bulk_g2s(st_phi(s), phi + c0, bytes_phi, &full[s]);
         if (ne > 0) {
-#pragma unroll
-          for (int a = 0; a < 5; a++) bulk_g2s(se + a * EE, edge_src(a) + es, bytes_e, &full[s]);
+          bulk_g2s(e2, m.exy + es, bytes_e, &full[s]);
+          bulk_g2s(e2 + EE, m.enxy + es, bytes_e, &full[s]);
+          bulk_g2s(st_ea(s), m.ea + es, bytes_ea, &full[s]);
         }
         if (fw > 0) bulk_g2s(sf, pm.t_pack + fbase, bytes_f, &full[s]);
       }
 #pragma unroll
       for (int r = 0; r < 3; r++) {
         const int h = lane + 32 * r;
-        if (h < nh) {
-#pragma unroll
-          for (int a = 0; a < NCA; a++) cp_async8(sc + a * SS + kBlock + h, cell_src(a) + jcc[r]);
-        }
-        if (h < nhe) {
-#pragma unroll
-          for (int a = 0; a < 5; a++) cp_async8(se + a * EE + ne + h, edge_src(a) + jee[r]);
-        }
+        if (h < nh) gather_cell(s, h, jcc[r]);
+        if (h < nhe) gather_edge(s, ne, h, jee[r]);
       }
-      for (int h = lane + 96; h < nh; h += 32) {  // rare: more than 96 halo cells
-        const int j = __ldg(&pm.hc_idx[hp + h]);
-#pragma unroll
-        for (int a = 0; a < NCA; a++) cp_async8(sc + a * SS + kBlock + h, cell_src(a) + j);
-      }
-      for (int h = lane + 96; h < nhe; h += 32) {
-        const int j = __ldg(&pm.he_idx[ep + h]);
-#pragma unroll
-        for (int a = 0; a < 5; a++) cp_async8(se + a * EE + ne + h, edge_src(a) + j);
-      }
+      for (int h = lane + 96; h < nh; h += 32) gather_cell(s, h, __ldg(&pm.hc_idx[hp + h]));  // rare: more than 96 halo cells
+      for (int h = lane + 96; h < nhe; h += 32) gather_edge(s, ne, h, __ldg(&pm.he_idx[ep + h]));
       cp_async_mbar_arrive_noinc(&full[s]);
       if (j + (int)gridDim.x < pm.ntiles) fetch_meta(tile_id(j + gridDim.x));
     }
@@ -830,9 +730,9 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
       stage_load<UM, STEADY>(S, i, np, q, f, dtl, q0, fo, dl);
       vol = m.vol[i];
     }
-    const double *sc = reinterpret_cast<const double *>(smem_raw + s * stage_bytes);
-    const double *se = sc + NCA * SS;
-    const uint32_t *sf = reinterpret_cast<const uint32_t *>(se + 5 * EE);
+    const double2 *c2 = st_c2(s), *e2 = st_e2(s);
+    const double *sphi = st_phi(s), *sea = st_ea(s);
+    const uint32_t *sf = st_f(s);
     mbar_wait(&full[s], ph);
     const int fw = reinterpret_cast<const int *>(sf + 4 * kBlock)[0], fbase = reinterpret_cast<const int *>(sf + 4 * kBlock)[1];
     double acc[4] = {0.0, 0.0, 0.0, 0.0}, wsacc = 0.0;
@@ -847,33 +747,43 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
         const int eslot = (pk >> 16) & 0x7FFF;
         const bool self_c1 = (pk >> 31) == 0;
         const bool bnd = ns == 0xFFFFu;
-        const double *eg = se + eslot;
-        const double xf = eg[0], yf = eg[EE], af = eg[2 * EE], nx = eg[3 * EE], ny = eg[4 * EE];
+        const double2 fc = e2[eslot], fn = e2[EE + eslot];
+        const double af = sea[eslot], nx = fn.x, ny = fn.y;
         // edge orientation: L = c1, R = c2 -- both sides are addressed by slot (no operand swapping);
         // on a boundary face this cell is c1 and the right state comes from the boundary condition
-        const double *cl = sc + ((self_c1 || bnd) ? tid : (int)ns);
-        const double *cr = sc + ((self_c1 && !bnd) ? (int)ns : tid);
+        const int sl_ = (self_c1 || bnd) ? tid : (int)ns, sr_ = (self_c1 && !bnd) ? (int)ns : tid;
+        const double2 *cl = c2 + sl_, *cr = c2 + sr_;
         double sL[4], sR[4];
-        if (RC == RC_FIRST) {
-#pragma unroll
-          for (int v = 0; v < 4; v++) { sL[v] = cl[v * SS]; sR[v] = cr[v * SS]; }
-        } else {
-          const double dxL = xf - cl[12 * SS], dyL = yf - cl[13 * SS];
-          const double dxR = xf - cr[12 * SS], dyR = yf - cr[13 * SS];
-          const double fL = (RC >= RC_K0_PHI) ? cl[14 * SS] : 1.0;
-          const double fR = (RC >= RC_K0_PHI) ? cr[14 * SS] : 1.0;
+        {
+          const double2 a = cl[0], b = cl[SS], c = cr[0], d = cr[SS];
+          sL[0] = a.x; sL[1] = a.y; sL[2] = b.x; sL[3] = b.y;
+          sR[0] = c.x; sR[1] = c.y; sR[2] = d.x; sR[3] = d.y;
+        }
+        if (RC != RC_FIRST) {
+          const double2 xl = cl[6 * SS], xr = cr[6 * SS];
+          const double dxL = fc.x - xl.x, dyL = fc.y - xl.y, dxR = fc.x - xr.x, dyR = fc.y - xr.y;
+          const double fL = PHI ? sphi[sl_] : 1.0, fR = PHI ? sphi[sr_] : 1.0;
+          double gL[4], gR[4];
+          {
+            const double2 a = cl[2 * SS], b = cl[3 * SS], c = cl[4 * SS], d = cl[5 * SS];
+            gL[0] = dxL * a.x + dyL * c.x; gL[1] = dxL * a.y + dyL * c.y;
+            gL[2] = dxL * b.x + dyL * d.x; gL[3] = dxL * b.y + dyL * d.y;
+          }
+          {
+            const double2 a = cr[2 * SS], b = cr[3 * SS], c = cr[4 * SS], d = cr[5 * SS];
+            gR[0] = dxR * a.x + dyR * c.x; gR[1] = dxR * a.y + dyR * c.y;
+            gR[2] = dxR * b.x + dyR * d.x; gR[3] = dxR * b.y + dyR * d.y;
+          }
 #pragma unroll
           for (int v = 0; v < 4; v++) {
-            const double pL = cl[v * SS], pR = cr[v * SS];
-            const double gL = dxL * cl[(4 + v) * SS] + dyL * cl[(8 + v) * SS];
-            const double gR = dxR * cr[(4 + v) * SS] + dyR * cr[(8 + v) * SS];
-            if (RC == RC_K0) { sL[v] = pL + gL; sR[v] = pR + gR; }
-            else if (RC == RC_K0_PHI) { sL[v] = pL + fL * gL; sR[v] = pR + fR * gR; }
+            const double pL = sL[v], pR = sR[v];
+            if (RC == RC_K0) { sL[v] = pL + gL[v]; sR[v] = pR + gR[v]; }
+            else if (RC == RC_K0_PHI) { sL[v] = pL + fL * gL[v]; sR[v] = pR + fR * gR[v]; }
             else {
               // boundary faces carry no kappa term (src/residual.f90:128)
               const double gC = bnd ? 0.0 : pR - pL, k1 = bnd ? 1.0 : 1.0 - P.kappa;
-              sL[v] = pL + fL * (P.kappa / 2.0 * gC + k1 * gL);
-              sR[v] = pR + fR * (-P.kappa / 2.0 * gC + k1 * gR);
+              sL[v] = pL + fL * (P.kappa / 2.0 * gC + k1 * gL[v]);
+              sR[v] = pR + fR * (-P.kappa / 2.0 * gC + k1 * gR[v]);
             }
           }
         }
@@ -902,7 +812,7 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
     if (live) stage_update_pre<UM, STEADY>(P, S, i, np, vol, q0, fo, dl, acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
   }
   if (UM != UM_RESID && S.last) {
-    // sum of (q - q0)^2 over this CTA's cells: warp shuffles, then the 4 consumer warps through smem
+    // sum of (q - q0)^2 over this CTA's cells: warp shuffles, then the consumer warps through smem
     __shared__ double red[4][kBlock / 32];
 #pragma unroll
     for (int v = 0; v < 4; v++) {
@@ -956,7 +866,8 @@ __global__ void __launch_bounds__(kBlock) k_vortex_err(const DevMesh m, const Ph
   for (int i = blockIdx.x * kBlock + threadIdx.x; i < m.n_own; i += gridDim.x * kBlock) {
     if (!m.is_intr[i]) continue;
     double pv[4];
-    vortex_exact(P, time, m.xc[i], m.yc[i], pv);
+    const double2 cc = m.xy[i];
+    vortex_exact(P, time, cc.x, cc.y, pv);
     const double ex0 = pv[0], ex1 = pv[0] * pv[1], ex2 = pv[0] * pv[2];
     const double ex3 = pv[3] / (P.gamma - 1.0) + 0.5 * pv[0] * (pv[1] * pv[1] + pv[2] * pv[2]);
     double d[4];
@@ -1047,30 +958,33 @@ __global__ void __launch_bounds__(256) k_finish_vortex(const double *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// halo pack: buf[v*n + k] = a[v*np + idx[k]] for nv variables
-__global__ void __launch_bounds__(256) k_pack(int n, int nv, int np, const int *__restrict__ idx, const double *__restrict__ a,
-                                               double *__restrict__ buf) {
+// halo pack: buf[v*n + k] = a[v*np + idx[k]] for nv arrays of elements T (double2 for the pair-interleaved
+// arrays p and g, double for phi)
+template <class T>
+__global__ void __launch_bounds__(256) k_pack(int n, int nv, int np, const int *__restrict__ idx, const T *__restrict__ a,
+                                               T *__restrict__ buf) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int i = idx[k];
   for (int v = 0; v < nv; v++) buf[(size_t)v * n + k] = a[(size_t)v * np + i];
 }
 
-// permuting copies between the caller's (4,ncells) AoS arrays (original numbering, staged on the device)
-// and the device SoA (local numbering)
+// permuting copies between the caller's (nvar,ncells) AoS arrays (original numbering, staged on the device)
+// and the device arrays (local numbering): pair != 0 selects the pair-interleaved layout (variables v0..),
+// orig_id == null means the caller's array is already in local order
 __global__ void __launch_bounds__(256) k_scatter_in(int n, int np, int nvar, const int *__restrict__ orig_id,
-                                                     const double *__restrict__ aos, double *__restrict__ soa) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const size_t o = orig_id ? orig_id[i] : i;  // null: the caller's array is already in local order
-  for (int v = 0; v < nvar; v++) soa[(size_t)v * np + i] = aos[o * nvar + v];
-}
-__global__ void __launch_bounds__(256) k_gather_out(int n, int np, int nvar, const int *__restrict__ orig_id,
-                                                     const double *__restrict__ soa, double *__restrict__ aos) {
+                                                     const double *__restrict__ aos, double *__restrict__ soa, int pair) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const size_t o = orig_id ? orig_id[i] : i;
-  for (int v = 0; v < nvar; v++) aos[o * nvar + v] = soa[(size_t)v * np + i];
+  for (int v = 0; v < nvar; v++) soa[pair ? pidx(v, np, i) : (size_t)v * np + i] = aos[o * nvar + v];
+}
+__global__ void __launch_bounds__(256) k_gather_out(int n, int np, int nvar, const int *__restrict__ orig_id,
+                                                     const double *__restrict__ soa, double *__restrict__ aos, int pair, int v0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t o = orig_id ? orig_id[i] : i;
+  for (int v = 0; v < nvar; v++) aos[o * nvar + v] = soa[pair ? pidx(v0 + v, np, i) : (size_t)(v0 + v) * np + i];
 }
 
 }  // namespace fvs2d
