@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace fvs2d {
 
 #ifndef FVS2D_TILE
@@ -737,21 +739,18 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
     const int fw = reinterpret_cast<const int *>(sf + 4 * kBlock)[0], fbase = reinterpret_cast<const int *>(sf + 4 * kBlock)[1];
     double acc[4] = {0.0, 0.0, 0.0, 0.0}, wsacc = 0.0;
     if (live) {
-      uint32_t pk_next = fw > 0 ? sf[tid] : 0xFFFEu;
-#pragma unroll 1
-      for (int k = 0; k < fw; k++) {
-        const uint32_t pk = pk_next;
-        if (k + 1 < fw) pk_next = sf[(k + 1) * kBlock + tid];  // next face's table word: its latency hides behind this face
-        const uint32_t ns = pk & 0xFFFFu;
-        if (ns == 0xFFFEu) continue;
-        const int eslot = (pk >> 16) & 0x7FFF;
-        const bool self_c1 = (pk >> 31) == 0;
-        const bool bnd = ns == 0xFFFFu;
+      // one face: reconstruct both sides from shared memory (addressed by slot -- no operand swapping), Roe flux
+      // in the edge's own orientation (L = c1, R = c2), accumulate.  BND selects the boundary variant (this cell
+      // is c1, right state from the boundary condition); boundary faces come last in a cell's list, so handling
+      // them in a second, rarely taken loop keeps the reference's accumulation order and keeps the
+      // boundary-condition loads out of the common path.
+      auto face = [&](const uint32_t pk, const int k, const auto bnd_tag) {
+        constexpr bool BND = decltype(bnd_tag)::value;
+        const int ns = pk & 0xFFFFu, eslot = (pk >> 16) & 0x7FFF;
+        const bool self_c1 = BND || (pk >> 31) == 0;
         const double2 fc = e2[eslot], fn = e2[EE + eslot];
         const double af = sea[eslot], nx = fn.x, ny = fn.y;
-        // edge orientation: L = c1, R = c2 -- both sides are addressed by slot (no operand swapping);
-        // on a boundary face this cell is c1 and the right state comes from the boundary condition
-        const int sl_ = (self_c1 || bnd) ? tid : (int)ns, sr_ = (self_c1 && !bnd) ? (int)ns : tid;
+        const int sl_ = self_c1 ? tid : ns, sr_ = (self_c1 && !BND) ? ns : tid;
         const double2 *cl = c2 + sl_, *cr = c2 + sr_;
         double sL[4], sR[4];
         {
@@ -781,13 +780,13 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
             else if (RC == RC_K0_PHI) { sL[v] = pL + fL * gL[v]; sR[v] = pR + fR * gR[v]; }
             else {
               // boundary faces carry no kappa term (src/residual.f90:128)
-              const double gC = bnd ? 0.0 : pR - pL, k1 = bnd ? 1.0 : 1.0 - P.kappa;
+              const double gC = BND ? 0.0 : pR - pL, k1 = BND ? 1.0 : 1.0 - P.kappa;
               sL[v] = pL + fL * (P.kappa / 2.0 * gC + k1 * gL[v]);
               sR[v] = pR + fR * (-P.kappa / 2.0 * gC + k1 * gR[v]);
             }
           }
         }
-        if (bnd) {
+        if (BND) {
           const int b = __ldg(&pm.t_bf[fbase + k * kBlock + tid]);
           const int type = __ldg(&m.bf_type[b]);
           if (type == 2) {  // slip wall: mirror the normal velocity (src/residual.f90:200-204)
@@ -806,6 +805,24 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
 #pragma unroll
         for (int v = 0; v < 4; v++) acc[v] += flux[v] * sa;
         wsacc += ws * af;
+      };
+      bool has_bnd = false;
+      uint32_t pk_next = fw > 0 ? sf[tid] : 0xFFFEu;
+#pragma unroll 1
+      for (int k = 0; k < fw; k++) {
+        const uint32_t pk = pk_next;
+        if (k + 1 < fw) pk_next = sf[(k + 1) * kBlock + tid];  // next face's table word: its latency hides behind this face
+        const uint32_t ns = pk & 0xFFFFu;
+        if (ns == 0xFFFEu) continue;
+        if (ns == 0xFFFFu) { has_bnd = true; continue; }
+        face(pk, k, std::false_type{});
+      }
+      if (has_bnd) {
+#pragma unroll 1
+        for (int k = 0; k < fw; k++) {
+          const uint32_t pk = sf[k * kBlock + tid];
+          if ((pk & 0xFFFFu) == 0xFFFFu) face(pk, k, std::true_type{});
+        }
       }
     }
     mbar_arrive(&empty[s]);  // this thread is done reading stage s
