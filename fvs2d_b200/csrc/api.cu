@@ -80,6 +80,11 @@ struct Ctx {
   int opt_tile = 2;      // pass-B kernel: 2 persistent smem pipeline (default), 0 direct gather
   bool tile_ok = false;
   int nsm = 148, nparts = 0;
+  StepClock *clk = nullptr;            // device step clock
+  int opt_graph = 1;                   // replay time steps as a CUDA graph (single GPU, timing off)
+  cudaGraphExec_t graph_exec = nullptr;
+  const void *graph_logbuf = nullptr;  // the graph is tied to these
+  int graph_um = -1;
   int opt_ctas = 0;      // persistent pass-B CTAs per SM: 0 = as many as shared memory allows (max 3)
   int opt_overlap = 1;   // multi-GPU: overlap the halo exchanges with interior-tile work (second stream)
   int opt_smem_pad = 0;  // experiment: extra dynamic shared memory (KB) per pass-B CTA (shrinks the L1 carve-out)
@@ -335,12 +340,12 @@ int launch_flux(int um, const StageParams &S, const double *pin, double *pout, c
   return 0;
 }
 
-int launch_bc(double time) {
+int launch_bc(int stage) {
   if (C->L.nbf == 0) return 0;
   const bool time_dep = C->cfg.lvortex != 0;
   if (!time_dep && C->bc_static_done) return 0;
   Span sp(0);
-  k_bc_state<<<cdiv(C->L.nbf, 128), 128, 0, C->st>>>(C->dm, C->phys, time, C->bc);
+  k_bc_state<<<cdiv(C->L.nbf, 128), 128, 0, C->st>>>(C->dm, C->phys, C->clk, stage, C->bc);
   C->last_launches++;
   C->bc_static_done = true;
   return 0;
@@ -532,6 +537,8 @@ int fvs2d_gpu_set_mesh(int nnodes, int ntri, int nquad, const double *node_xy, c
   if (dev_alloc(C->g, 8 * np) || dev_alloc(C->phi, np)) return 1;
   if (C->cfg.steady && dev_alloc(C->dtl, np)) return 1;
   if (dev_alloc(C->bc, 4 * (size_t)std::max(1, L.nbf))) return 1;
+  if (dev_alloc(C->clk, 1)) return 1;
+  if (C->graph_exec) { cudaGraphExecDestroy(C->graph_exec); C->graph_exec = nullptr; }
   if (dev_alloc(C->partial, (size_t)C->nblocks * 4) || dev_alloc(C->vpartial, (size_t)C->nblocks * 13) || dev_alloc(C->vbest, (size_t)C->nblocks)) return 1;
   CUDA_OK(cudaMemset(C->q, 0, 4 * np * 8));
   CUDA_OK(cudaMemset(C->f, 0, 4 * np * 8));
@@ -650,7 +657,13 @@ int fvs2d_gpu_compute_residual(double time, double *resid, double *ws_nrml) {
   const size_t np = C->np;
   if (!C->resid && (dev_alloc(C->resid, 4 * np) || dev_alloc(C->ws, np))) return 1;
   C->last_launches = 0;
-  if (launch_bc(time)) return 1;
+  {
+    StepClock hc{};
+    hc.t1 = time;
+    CUDA_OK(cudaMemcpyAsync(C->clk, &hc, sizeof hc, cudaMemcpyHostToDevice, C->st));
+    CUDA_OK(cudaStreamSynchronize(C->st));  // hc is a stack variable
+  }
+  if (launch_bc(0)) return 1;
   if (pass_a(C->pa)) return 1;
   StageParams S{0, 0, 0.0, 0.0, C->cfg.dt};
   if (launch_flux(UM_RESID, S, C->pa, C->pb)) return 1;
@@ -691,20 +704,23 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   for (auto &s : C->ev_spans) s.clear();
   const bool overlap = C->nranks > 1 && C->opt_overlap && C->tile_ok && C->opt_tile == 2;
   bool p_pending = false;
+  {  // device step clock (src/runge_kutta.f90:135-145, 218-221): stage times are told + off[stage]
+    StepClock hc{};
+    hc.t1 = t1; hc.dt = dt; hc.istep = 0;
+    for (int rk = 0; rk < 4; rk++) hc.off[rk] = c.ssprk ? C->dts[rk] : (rk == 0 ? 0.0 : rk == 3 ? dt : 0.5 * dt);
+    hc.off_end = c.ssprk ? C->dte[3] : dt;
+    CUDA_OK(cudaMemcpyAsync(C->clk, &hc, sizeof hc, cudaMemcpyHostToDevice, C->st));
+    CUDA_OK(cudaStreamSynchronize(C->st));  // hc is a stack variable
+  }
   CUDA_OK(cudaEventRecord(C->ev0, C->st));
-  for (int istep = 1; istep <= nsub; istep++) {
-    const double told = t1 + (double)(istep - 1) * dt;  // src/runge_kutta.f90:135-139
-    const double t12 = told + 0.5 * dt, tnew = told + dt;
-    const double tstart[4] = {told, t12, t12, tnew};
-    double tend = tnew;
+  // one time step = a fixed kernel sequence; nothing in it depends on the host-side step counter
+  auto run_step = [&]() -> int {
     for (int rk = 0; rk < 4; rk++) {
-      const double ts = c.ssprk ? told + C->dts[rk] : tstart[rk];
-      if (c.ssprk) tend = told + C->dte[rk];
       StageParams S;
       S.stage = rk; S.last = rk == 3; S.c = C->rk_coef[rk]; S.dt = dt;
       if (c.steady) S.h = c.ssprk ? (rk == 3 ? 1.0 / 4.0 : 1.0 / 3.0) : (rk == 2 ? 1.0 : rk == 3 ? 1.0 / 6.0 : 1.0 / 2.0);
       else S.h = C->h_rk[rk];
-      if (launch_bc(ts)) return 1;
+      if (launch_bc(rk)) return 1;
       if (overlap) {
         // interior tiles never read a ghost: they run while the exchanges are in flight on the second stream
         const bool grad = C->recon != RC_FIRST;
@@ -742,16 +758,47 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
     }
     {
       Span sp(0);
-      double *lg = C->logbuf + per * (size_t)(istep - 1);
-      k_finish_sum<4><<<1, 256, 0, C->st>>>(C->partial, C->nparts, lg);
+      k_finish_sum<4><<<1, 256, 0, C->st>>>(C->partial, C->nparts, C->logbuf, (int)per, C->clk);
       C->last_launches++;
       if (vort) {
         const int vgrid = std::min(C->nblocks, C->nsm * 8);
-        k_vortex_err<<<vgrid, kBlock, 0, C->st>>>(C->dm, C->phys, tend, C->q, C->vpartial, C->vbest);
-        k_finish_vortex<<<1, 256, 0, C->st>>>(C->vpartial, C->vbest, vgrid, lg + 4, C->logid + (istep - 1));
+        k_vortex_err<<<vgrid, kBlock, 0, C->st>>>(C->dm, C->phys, C->clk, C->q, C->vpartial, C->vbest);
+        k_finish_vortex<<<1, 256, 0, C->st>>>(C->vpartial, C->vbest, vgrid, C->logbuf, (int)per, C->logid, C->clk);
         C->last_launches += 2;
       }
+      k_clock_advance<<<1, 1, 0, C->st>>>(C->clk);
+      C->last_launches++;
     }
+    return 0;
+  };
+  // Small meshes are launch-bound (a 65 k-cell step is ~10 kernels of ~10 us): the first step runs eagerly (it also
+  // configures the kernels), the remaining ones replay a CUDA graph captured from the same sequence.
+  const bool use_graph = C->opt_graph && C->nranks == 1 && !C->opt_timing && nsub >= 3;
+  int done = 0;
+  if (nsub > 0) { if (run_step()) return 1; done = 1; }
+  if (use_graph) {
+    if (C->graph_exec && (C->graph_logbuf != C->logbuf || C->graph_um != um * 16 + C->opt_tile * 4 + C->opt_ctas)) {
+      cudaGraphExecDestroy(C->graph_exec);
+      C->graph_exec = nullptr;
+    }
+    if (!C->graph_exec) {
+      const long l0 = C->last_launches;
+      cudaGraph_t graph = nullptr;
+      CUDA_OK(cudaStreamBeginCapture(C->st, cudaStreamCaptureModeThreadLocal));
+      const int rc = run_step();
+      const cudaError_t ce = cudaStreamEndCapture(C->st, &graph);
+      C->last_launches = l0;
+      if (rc || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return rc ? 1 : fail("CUDA graph capture failed: %s", cudaGetErrorString(ce)); }
+      CUDA_OK(cudaGraphInstantiate(&C->graph_exec, graph, 0));
+      cudaGraphDestroy(graph);
+      C->graph_logbuf = C->logbuf;
+      C->graph_um = um * 16 + C->opt_tile * 4 + C->opt_ctas;
+    }
+    const long per_step = C->last_launches;
+    for (; done < nsub; done++) CUDA_OK(cudaGraphLaunch(C->graph_exec, C->st));
+    C->last_launches = per_step * nsub;
+  } else {
+    for (; done < nsub; done++) if (run_step()) return 1;
   }
   if (p_pending) CUDA_OK(cudaStreamWaitEvent(C->st, C->e_p, 0));  // the last exchange belongs to this call
   CUDA_OK(cudaEventRecord(C->ev1, C->st));
@@ -933,6 +980,7 @@ int fvs2d_gpu_set_option(const char *key, int value) {
   if (k == "tile") { C->opt_tile = value; return 0; }
   if (k == "ctas") { C->opt_ctas = value; return 0; }
   if (k == "overlap") { C->opt_overlap = value; return 0; }
+  if (k == "graph") { C->opt_graph = value; return 0; }
   if (k == "smem_pad") { C->opt_smem_pad = value; return 0; }
   if (k == "carveout") { C->opt_carveout = value; return 0; }
   return fail("fvs2d_gpu_set_option: unknown option '%s'", key);
@@ -949,6 +997,7 @@ int fvs2d_gpu_finalize(void) {
   for (auto &e : C->ev_pool) cudaEventDestroy(e);
   if (C->ev0) cudaEventDestroy(C->ev0);
   if (C->ev1) cudaEventDestroy(C->ev1);
+  if (C->graph_exec) cudaGraphExecDestroy(C->graph_exec);
   if (C->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(C->comm);
   if (C->sx) { cudaStreamDestroy(C->sx); for (cudaEvent_t e : {C->e_a, C->e_g, C->e_b, C->e_p}) if (e) cudaEventDestroy(e); }
   if (C->st) cudaStreamDestroy(C->st);

@@ -61,6 +61,15 @@ struct Phys {
   int lvortex, limiter;
 };
 
+// Time of the current step / stage, kept in device memory so that the kernel sequence of one time step has no
+// host-side parameter that changes from step to step (it can be replayed as a CUDA graph):
+// told = t1 + istep*dt (src/runge_kutta.f90:135), stage time = told + off[stage], end-of-step time = told + off_end
+struct StepClock {
+  double t1, dt, off[4], off_end;
+  int istep, pad;
+};
+__device__ __forceinline__ double clock_told(const StepClock *c) { return c->t1 + (double)c->istep * c->dt; }
+
 struct StageParams {
   int stage;        // 0..3
   int last;         // stage == nstages-1
@@ -78,9 +87,9 @@ __device__ __forceinline__ void load4(const double2 *__restrict__ a2, int np, in
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void vortex_exact(const Phys &P, double t, double x, double y, double pv[4]) {
-  // src/mms.f90:219-265.  exp(1-r^2) = exp((1-r^2)/2)^2; rho = temp^(1/(gamma-1)) and p = rho^gamma =
-  // temp^(gamma/(gamma-1)) through one log and two exp (two pow calls cost twice as much; |log(temp)| is
-  // small, so the composition stays at the 1-2 ulp level of the library pow)
+  // src/mms.f90:219-265.  exp(1-r^2) = exp((1-r^2)/2)^2; rho = temp^(1/(gamma-1)) through one log and one exp,
+  // p = rho^gamma = rho * temp (two pow calls cost three times as much; |log(temp)| is small, so the
+  // composition stays at the 1-2 ulp level of the library pow)
   const double pi = 3.141592653589793238462643383279502884;
   const double rho_inf = P.vinf[0], u_inf = P.vinf[1], v_inf = P.vinf[2], p_inf = P.vinf[3];
   const double T_inf = p_inf / rho_inf;
@@ -92,9 +101,9 @@ __device__ __forceinline__ void vortex_exact(const Phys &P, double t, double x, 
   pv[1] = u_inf - kk * dy * e1;
   pv[2] = v_inf + kk * dx * e1;
   const double temp = T_inf - kk * kk * (P.gamma - 1.0) / (2.0 * P.gamma) * (e1 * e1);
-  const double lt = log(temp);
-  pv[0] = exp(lt / P.gm1);
-  pv[3] = exp(P.gog * lt);  // rho^gamma = temp^(gamma/(gamma-1))
+  const double rho = exp(log(temp) / P.gm1);
+  pv[0] = rho;
+  pv[3] = rho * temp;  // rho^gamma = rho * rho^(gamma-1) = rho * temp
 }
 
 __device__ __forceinline__ void mms_exact(const Phys &P, double x, double y, double pv[4]) {
@@ -288,9 +297,11 @@ __global__ void __launch_bounds__(kBlock) k_gradient(const DevMesh m, const int 
 // ------------------------------------------------------------------------------------------------
 // ghost states of the boundary faces that do not depend on the interior state
 // (src/residual.f90:195-217: freestream -> pvar_inf, dirichlet -> vortex(t) or MMS at the face centre)
-__global__ void __launch_bounds__(128) k_bc_state(const DevMesh m, const Phys P, const double time, double *__restrict__ bc /* [4][nbf] */) {
+__global__ void __launch_bounds__(128) k_bc_state(const DevMesh m, const Phys P, const StepClock *__restrict__ clk, const int stage,
+                                                  double *__restrict__ bc /* [4][nbf] */) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= m.nbf) return;
+  const double time = clock_told(clk) + clk->off[stage];
   const int type = m.bf_type[b];
   double pv[4] = {0, 0, 0, 0};
   if (type == 1) {
@@ -851,8 +862,10 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
 // ------------------------------------------------------------------------------------------------
 // final reduction of per-CTA partial sums: out[v] = sum_b partial[b*NV+v], one CTA, fixed order
 template <int NV>
-__global__ void __launch_bounds__(256) k_finish_sum(const double *__restrict__ partial, int nblocks, double *__restrict__ out) {
+__global__ void __launch_bounds__(256) k_finish_sum(const double *__restrict__ partial, int nblocks, double *__restrict__ logbuf,
+                                                    int stride, const StepClock *__restrict__ clk) {
   __shared__ double sm[256];
+  double *out = logbuf + (size_t)stride * clk->istep;  // this step's row of the device log
   for (int v = 0; v < NV; v++) {
     double s = 0.0;
     for (int b = threadIdx.x; b < nblocks; b += 256) s += partial[(size_t)b * NV + v];
@@ -871,9 +884,10 @@ __global__ void __launch_bounds__(256) k_finish_sum(const double *__restrict__ p
 // K10: vortex error norms over the interior cells (src/mms.f90:315-361).  Per CTA:
 // partial[b*13 + 0..3] = max |dq_v|, [4..7] = sum |dq_v|, [8..11] = sum dq_v^2, [12] = best rho error;
 // best_id[b] = original id of the first cell attaining it.
-__global__ void __launch_bounds__(kBlock) k_vortex_err(const DevMesh m, const Phys P, const double time,
+__global__ void __launch_bounds__(kBlock) k_vortex_err(const DevMesh m, const Phys P, const StepClock *__restrict__ clk,
                                                        const double *__restrict__ q, double *__restrict__ partial,
                                                        int *__restrict__ best_id) {
+  const double time = clock_told(clk) + clk->off_end;
   // grid-stride over the owned cells with a fixed grid: the partial count is small and the summation
   // order is a function of the launch configuration only (deterministic)
   const int np = m.np;
@@ -938,9 +952,12 @@ __global__ void __launch_bounds__(kBlock) k_vortex_err(const DevMesh m, const Ph
 
 // out[0..3] max, [4..7] sum, [8..11] sum of squares, [12] best value; out_id[0] = original id of the best cell
 __global__ void __launch_bounds__(256) k_finish_vortex(const double *__restrict__ partial, const int *__restrict__ best_id,
-                                                        int nblocks, double *__restrict__ out, int *__restrict__ out_id) {
+                                                        int nblocks, double *__restrict__ logbuf, int stride, int *__restrict__ logid,
+                                                        const StepClock *__restrict__ clk) {
   __shared__ double sm[256];
   __shared__ int si[256];
+  double *out = logbuf + (size_t)stride * clk->istep + 4;  // after the 4 residual sums of the step's row
+  int *out_id = logid + clk->istep;
   for (int v = 0; v < 12; v++) {
     double s = 0.0;
     for (int b = threadIdx.x; b < nblocks; b += 256) {
@@ -973,6 +990,9 @@ __global__ void __launch_bounds__(256) k_finish_vortex(const double *__restrict_
   }
   if (threadIdx.x == 0) { out[12] = sm[0]; out_id[0] = si[0]; }
 }
+
+// last kernel of a time step
+__global__ void k_clock_advance(StepClock *clk) { clk->istep += 1; }
 
 // ------------------------------------------------------------------------------------------------
 // halo pack: buf[v*n + k] = a[v*np + idx[k]] for nv arrays of elements T (double2 for the pair-interleaved
