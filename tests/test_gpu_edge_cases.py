@@ -1,0 +1,124 @@
+"""GPU: edge cases of the C-ABI -- error behaviour (the reference prints and stops; here: non-zero return +
+fvs2d_gpu_last_error), ragged / tiny inputs (meshes smaller than one 128-cell tile, partial last tiles), zero-length
+calls, and the fallback kernel."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((np.abs(a - b) / np.maximum(np.abs(b).max(axis=0), 1e-300)).max())
+
+
+def test_call_order_and_scheme_errors():
+    from fvs2d_b200 import capi, config, meshgen, solver
+    L = capi.lib()
+    L.fvs2d_gpu_finalize()
+    # no context yet
+    assert L.fvs2d_gpu_time_integration(0.0, 1, None, None, None) != 0
+    assert b"no state" in L.fvs2d_gpu_last_error()
+    # limiter needs the LSQ stencil (src/gradient_limiter.f90:54-58): GGCB + Venkatakrishnan is rejected at init
+    bad = config.RunInput(grad_cellcntr_imethd=1, grad_limiter_imethd=1).to_config()
+    assert L.fvs2d_gpu_init(ctypes.byref(bad), 0) != 0
+    assert b"limiter" in L.fvs2d_gpu_last_error()
+    # SSPRK only for (4 stages, order 2) (src/runge_kutta.f90:56); only 4 stages are coded (:36)
+    for kw in (dict(lSSPRK=True, rk_order=4), dict(rk_nstages=3)):
+        cfg = config.RunInput(**kw).to_config()
+        assert L.fvs2d_gpu_init(ctypes.byref(cfg), 0) != 0
+    # a solid_wall boundary is "not implemented yet" in the reference (src/residual.f90:206-208)
+    gpu = solver.Fvs2dGpu(config.RunInput(grad_cellcntr_imethd=1).to_config(), device=0)
+    mesh = meshgen.make_mesh(8, 8, bc_type="solid_wall")
+    with pytest.raises(capi.Fvs2dError, match="not implemented"):
+        gpu.set_mesh(mesh)
+    # state calls before a mesh / state exist
+    with pytest.raises(capi.Fvs2dError):
+        gpu.get_state(np.zeros((4, 4)))
+    mesh = meshgen.make_mesh(8, 8)
+    gpu.set_mesh(mesh)
+    with pytest.raises(capi.Fvs2dError, match="no state"):
+        gpu.time_integration(0.0, 1)
+    # a cell with two boundary edges breaks the LSQ-fn stencil rule only when > 2 (src/gradient_lsq.f90:128-131); a
+    # .bc file that lists too few cells is caught like in grid_data (src/grid_procs.f90:722-728)
+    import copy
+    m2 = copy.deepcopy(mesh)
+    m2.bndry_cell = [m2.bndry_cell[0][:-2]]
+    with pytest.raises(capi.Fvs2dError, match="boundary cells"):
+        gpu.set_mesh(m2)
+    gpu.close()
+
+
+@pytest.mark.parametrize("nx,ny,band", [(2, 2, None), (3, 2, None), (5, 3, None), (6, 4, (2, 4)), (13, 9, (4, 9)), (17, 11, None)])
+@pytest.mark.parametrize("tile", [2, 0])
+def test_tiny_and_ragged_meshes(nx, ny, band, tile):
+    """meshes of 8 ... 374 cells: less than one tile, exactly-not-a-multiple of 32 / 128, mixed; pipeline and
+    fallback kernels; 6 steps against the oracle."""
+    from fvs2d_b200 import config, meshgen, solver
+    from oracle.oracle import Oracle
+    mesh = meshgen.make_mesh(nx, ny, 20.0, 10.0, band)
+    cfg = config.RunInput(grad_cellcntr_imethd=1, lvortex=True, dt=0.02).to_config()
+    gpu = solver.Fvs2dGpu(cfg, device=0)
+    gpu.set_option("tile", tile)
+    gpu.set_mesh(mesh)
+    gpu.initialize_solution()
+    orc = Oracle(mesh, cfg)
+    orc.initialize_solution()
+    res, ve, vxy = gpu.time_integration(0.0, 6)
+    res_o, ve_o, vxy_o = orc.time_integration(0.0, 6)
+    assert _rel(gpu.get_state(), orc.cvar) <= 1e-10
+    assert float((np.abs(res - res_o) / np.abs(res_o)).max()) <= 1e-10
+    if orc.sizes()["ncells_intr"] > 0:
+        assert float((np.abs(ve - ve_o) / np.maximum(np.abs(ve_o), 1e-300)).max()) <= 1e-8
+        assert np.abs(vxy - vxy_o).max() == 0.0
+    gpu.close()
+
+
+def test_zero_steps_and_repeated_calls():
+    """nsub = 0 is a no-op; 1+2+4 steps in three calls == 7 steps in one (eager first step + graph replay)."""
+    from fvs2d_b200 import config, meshgen, solver
+    mesh = meshgen.vortex_mixed_mesh(24)
+    cfg = config.RunInput(grad_cellcntr_imethd=3, grad_cellcntr_lsq_nghbr="nn", grad_limiter_imethd=1, lvortex=True, dt=0.01).to_config()
+    gpu = solver.Fvs2dGpu(cfg, device=0)
+    gpu.set_mesh(mesh)
+    gpu.initialize_solution()
+    q0 = gpu.get_state().copy()
+    res, ve, _ = gpu.time_integration(0.0, 0)
+    assert res.shape == (0, 4) and np.array_equal(gpu.get_state(), q0)
+    r7, v7, _ = gpu.time_integration(0.0, 7)
+    q7 = gpu.get_state().copy()
+    gpu.set_state(q0)
+    parts = []
+    t = 0.0
+    for n in (1, 2, 4):
+        r, v, _ = gpu.time_integration(t, n)
+        parts.append(r)
+        t += n * 0.01
+    assert np.array_equal(gpu.get_state(), q7)
+    assert np.array_equal(np.concatenate(parts), r7)
+    # graph replay off gives the same bits
+    gpu.set_option("graph", 0)
+    gpu.set_state(q0)
+    r7b, _, _ = gpu.time_integration(0.0, 7)
+    assert np.array_equal(r7b, r7) and np.array_equal(gpu.get_state(), q7)
+    gpu.close()
+
+
+def test_fallback_kernel_matches_pipeline_bitwise():
+    """the direct-gather kernel (any numbering) and the shared-memory pipeline evaluate the same faces in the same
+    order: identical bits."""
+    from fvs2d_b200 import config, meshgen, solver
+    mesh = meshgen.vortex_mixed_mesh(40)
+    cfg = config.RunInput(grad_cellcntr_imethd=2, face_reconst_imethd=3, umuscl_cst=1.0 / 3.0, lvortex=True, dt=0.01).to_config()
+    out = []
+    for tile in (2, 0):
+        gpu = solver.Fvs2dGpu(cfg, device=0)
+        gpu.set_option("tile", tile)
+        gpu.set_mesh(mesh)
+        gpu.initialize_solution()
+        r, v, _ = gpu.time_integration(0.0, 5)
+        out.append((gpu.get_state().copy(), r, v))
+        gpu.close()
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
