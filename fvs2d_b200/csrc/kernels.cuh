@@ -1,11 +1,15 @@
 // kernels.cuh -- sm_100a kernels of the fvs2d hot path (fp64, HBM-bound, no tensor cores).
 //
-//   k_gradient   pass A: cell-parallel gradient (+ limiter) from primitive state   [reference K2,K3]
-//   k_flux_rk    pass B: cell-parallel face-flux gather, residual, RK stage update   [reference K4-K9]
-//   k_bc_state   Dirichlet / freestream ghost states of the boundary faces for one stage time
-//   k_prim       conserved -> primitive                                             [reference K1]
-//   k_vortex_err isentropic-vortex error norms                                      [reference K10]
-//   k_finish_*   fixed-order final reductions of the per-CTA partials (no fp atomics anywhere)
+//   k_gradient      pass A: cell-parallel gradient (+ limiter) from the primitive state        [reference K1-K3]
+//   k_flux_pipe     pass B: face-flux gather + residual + RK stage update; persistent, warp-specialised
+//                   TMA / cp.async shared-memory pipeline (production path)                    [reference K4-K9]
+//   k_flux_rk       pass B, direct global gathers (fallback for meshes whose tiles do not fit the pipeline)
+//   k_bc_state      Dirichlet / freestream ghost states of the boundary faces for one stage time
+//   k_prim          conserved -> primitive
+//   k_vortex_err    isentropic-vortex error norms                                             [reference K10]
+//   k_finish_*      fixed-order final reductions of the per-CTA partials (no fp atomics anywhere)
+//   k_clock_advance device-side step counter (lets a time step be replayed as a CUDA graph)
+//   k_pack, k_scatter_in, k_gather_out   halo packing and AoS <-> device-layout copies
 //
 // Data layout: struct-of-arrays with pitch `np` (cells padded to a multiple of 32).  The arrays that other
 // cells gather -- primitive state p (4 vars), gradients g (8 vars: gx0-3, gy0-3), centroids xy, edge centres
@@ -151,19 +155,21 @@ __device__ __forceinline__ void roe_flux(const Phys &P, const double L[4], const
   const double tx = -ny, ty = nx;
   const double rhoL = L[0], uL = L[1], vL = L[2], pL = L[3];
   const double rhoR = R[0], uR = R[1], vR = R[2], pR = R[3];
-  const double irL = fast_rcp(rhoL), irR = fast_rcp(rhoR);
+  // Roe averages with w = sqrt(rhoL), z = sqrt(rhoR): RT = z/w, 1/(1+RT) = w/(w+z), rho~ = w*z.  The two rsqrt chains
+  // are independent (the reference's sqrt(rhoR/rhoL) -> 1/(1+RT) chain is serial) and give 1/rho = rs^2 for free.
+  const double rsL = fast_rsqrt(rhoL), rsR = fast_rsqrt(rhoR);
+  const double w = rhoL * rsL, z = rhoR * rsR;
+  const double irL = rsL * rsL, irR = rsR * rsR;
   const double unL = uL * nx + vL * ny, unR = uR * nx + vR * ny;
   const double utL = uL * tx + vL * ty, utR = uR * tx + vR * ty;
   const double kL = 0.5 * (uL * uL + vL * vL), kR = 0.5 * (uR * uR + vR * vR);
   const double HL = gog * pL * irL + kL;
   const double HR = gog * pR * irR + kR;
-  double RT, dum;
-  fast_sqrt_rcp(rhoR * irL, RT, dum);
-  const double rho = RT * rhoL;
-  const double iw = fast_rcp(1.0 + RT);
-  const double u = (uL + RT * uR) * iw;
-  const double v = (vL + RT * vR) * iw;
-  const double H = (HL + RT * HR) * iw;
+  const double rho = w * z;
+  const double iw = fast_rcp(w + z);
+  const double u = (w * uL + z * uR) * iw;
+  const double v = (w * vL + z * vR) * iw;
+  const double H = (w * HL + z * HR) * iw;
   const double tke = 0.5 * (u * u + v * v);
   const double a2 = gm1 * (H - tke);
   double a, ia2;
