@@ -22,6 +22,18 @@
 #include <time.h>
 
 #define NVAR 4
+/* -DORC_OMP builds the "all host cores" context variant (liboracle_omp.so): cell loops run under OpenMP and the
+ * interior-edge scatter, which races in the reference (src/residual.f90:65), becomes an edge-parallel flux pass plus
+ * a cell-parallel gather.  Same arithmetic per face, different summation order: NOT the reference algorithm and
+ * never used for parity. */
+#ifdef ORC_OMP
+#include <omp.h>
+#define OMP_FOR _Pragma("omp parallel for schedule(static)")
+#define OMP_FOR_N4 _Pragma("omp parallel for schedule(static)")
+#else
+#define OMP_FOR
+#define OMP_FOR_N4
+#endif
 enum { BC_FREESTREAM = 1, BC_SLIP_WALL = 2, BC_SOLID_WALL = 3, BC_DIRICHLET = 4 };
 
 typedef struct {
@@ -73,6 +85,7 @@ typedef struct {
   double *mms_sol, *mms_source, *mms_source_fixed;
   /* timers: grad, limiter, flux, rk (seconds), src/mainparam.f90:15-16 */
   double cput[4];
+  double *eflux; /* ORC_OMP only: flux*a (4) and ws*a per edge */
   char err[256];
 } orc;
 
@@ -601,6 +614,7 @@ static void mms_compute_euler2d(const orc_config *c, double xc, double yc, doubl
  * ------------------------------------------------------------------------------------------- */
 static void cvar2pvar(orc *m) {
   double g = m->cfg.gamma;
+  OMP_FOR
   for (int ic = 0; ic < m->ncells; ic++) {
     double *p = &m->pvar[4 * ic];
     const double *q = &m->cvar[4 * ic];
@@ -629,6 +643,7 @@ static void pvar2cvar(orc *m) {
 
 static void grad_ggcb(orc *m) { /* src/gradient_ggcb.f90:116-138 */
   for (int ivar = 0; ivar < NVAR; ivar++)
+    OMP_FOR
     for (int ic = 0; ic < m->ncells; ic++) {
       double gx = m->gg_coef0[2 * ic + 0] * m->pvar[4 * ic + ivar];
       double gy = m->gg_coef0[2 * ic + 1] * m->pvar[4 * ic + ivar];
@@ -643,6 +658,7 @@ static void grad_ggcb(orc *m) { /* src/gradient_ggcb.f90:116-138 */
 }
 static void grad_ggnb(orc *m) { /* src/gradient_ggnb.f90:183-210 */
   for (int ivar = 0; ivar < NVAR; ivar++)
+    OMP_FOR
     for (int ic = 0; ic < m->ncells; ic++) {
       double gx = m->gg_coef0[2 * ic + 0] * m->pvar[4 * ic + ivar];
       double gy = m->gg_coef0[2 * ic + 1] * m->pvar[4 * ic + ivar];
@@ -659,7 +675,8 @@ static void grad_ggnb(orc *m) { /* src/gradient_ggnb.f90:183-210 */
       GRAD(m, 1, ic, ivar) = gy / m->vol[ic];
     }
 }
-static void grad_lsq(orc *m) { /* src/gradient_lsq.f90:393-401 */
+static void grad_lsq(orc *m) { /* src/gradient_lsq.f90:393-401 (the one loop the reference runs under OpenMP) */
+  OMP_FOR
   for (int ic = 0; ic < m->ncells; ic++) {
     double gx[4] = {0, 0, 0, 0}, gy[4] = {0, 0, 0, 0};
     for (int i = m->lsq_ptr[ic]; i < m->lsq_ptr[ic + 1]; i++) {
@@ -708,6 +725,7 @@ static int compute_gradient_limiter(orc *m) { /* :19-97 */
   double t1 = wtime();
   for (int ic = 0; ic < nc; ic++) m->phi_lim[ic] = HUGE_VAL;
   for (int ivar = 0; ivar < NVAR; ivar++)
+    OMP_FOR
     for (int ic = 0; ic < nc; ic++) {
       double xc = m->xc[ic], yc = m->yc[ic];
       double pc = m->pvar[4 * ic + ivar];
@@ -818,6 +836,10 @@ static int compute_residual(orc *m, double time) {
   double t1 = wtime();
   double kap = m->cfg.umuscl_cst, gam = m->cfg.gamma;
   /* interior edges: src/residual.f90:66-103 */
+#ifdef ORC_OMP
+  if (!m->eflux) m->eflux = malloc(40 * (size_t)m->nedges);
+  OMP_FOR
+#endif
   for (int i = 0; i < m->nedges_intr; i++) {
     int ie = m->edge_intr[i];
     double xf = m->ex[ie], yf = m->ey[ie], af = m->ea[ie], nxf = m->enx[ie], nyf = m->eny[ie];
@@ -832,13 +854,29 @@ static int compute_residual(orc *m, double time) {
       pfR[v] = m->pvar[4 * icR + v] + m->phi_lim[icR] * (-kap / 2.0 * gradC + (1.0 - kap) * gradR);
     }
     flux_invscid_roe(gam, pfL, pfR, nxf, nyf, flux, &ws_max);
+#ifdef ORC_OMP
+    for (int v = 0; v < 4; v++) m->eflux[5 * (size_t)ie + v] = flux[v] * af;
+    m->eflux[5 * (size_t)ie + 4] = ws_max * af;
+#else
     for (int v = 0; v < 4; v++) {
       m->resid[4 * icL + v] = m->resid[4 * icL + v] + flux[v] * af;
       m->resid[4 * icR + v] = m->resid[4 * icR + v] - flux[v] * af;
     }
     m->ws_nrml[icL] = m->ws_nrml[icL] + ws_max * af;
     m->ws_nrml[icR] = m->ws_nrml[icR] + ws_max * af;
+#endif
   }
+#ifdef ORC_OMP
+  OMP_FOR
+  for (int ic = 0; ic < nc; ic++)
+    for (int s = m->cptr[ic]; s < m->cptr[ic + 1]; s++) {
+      int je = m->cedge[s];
+      if (m->ec2[je] < 0) continue; /* boundary edges are added by the serial loop below */
+      double sg = m->ec1[je] == ic ? 1.0 : -1.0;
+      for (int v = 0; v < 4; v++) m->resid[4 * ic + v] += sg * m->eflux[5 * (size_t)je + v];
+      m->ws_nrml[ic] += m->eflux[5 * (size_t)je + 4];
+    }
+#endif
   /* boundary edges: src/residual.f90:111-157 (left cell = edge%c1) */
   for (int ib = 0; ib < m->nb; ib++)
     for (int i = m->b_edge_ptr[ib]; i < m->b_edge_ptr[ib + 1]; i++) {
@@ -857,6 +895,7 @@ static int compute_residual(orc *m, double time) {
     }
   m->cput[2] += wtime() - t1;
   /* dQ/dt = -R/vol: src/residual.f90:164-166 */
+  OMP_FOR
   for (int ic = 0; ic < nc; ic++)
     for (int v = 0; v < 4; v++) m->resid[4 * ic + v] = -m->resid[4 * ic + v] / m->vol[ic];
   return 0;
@@ -898,6 +937,7 @@ static int runge_kutta_init(orc *m) { /* :25-88 */
 }
 
 static void compute_local_time(orc *m) { /* :424-437 */
+  OMP_FOR
   for (int ic = 0; ic < m->ncells; ic++) m->dt_local[ic] = m->cfg.cfl_user * m->vol[ic] / (0.5 * m->ws_nrml[ic]);
 }
 
@@ -905,6 +945,31 @@ static void error_isentropic_vortex(orc *m, double time, double out[14], double 
   double mx[4] = {0, 0, 0, 0}, l1[4] = {0, 0, 0, 0}, l2[4] = {0, 0, 0, 0}, err_L2 = 0, g = m->cfg.gamma;
   double best = 0.0; int ibest = 0; /* maxloc(erho): first max; erho==0 on boundary cells */
   int first = 1;
+#ifdef ORC_OMP
+#pragma omp parallel
+  {
+    double tmx[4] = {0, 0, 0, 0}, tl1[4] = {0, 0, 0, 0}, tl2[4] = {0, 0, 0, 0}, tbest = 0.0;
+    int tib = -1;
+#pragma omp for schedule(static) nowait
+    for (int i = 0; i < m->ncells_intr; i++) {
+      int ic = m->cell_intr[i];
+      double pv[4], ex[4];
+      isentropic_vortex(&m->cfg, time, m->xc[ic], m->yc[ic], pv);
+      ex[0] = pv[0]; ex[1] = pv[0] * pv[1]; ex[2] = pv[0] * pv[2];
+      ex[3] = pv[3] / (g - 1.0) + 0.5 * pv[0] * (pv[1] * pv[1] + pv[2] * pv[2]);
+      for (int v = 0; v < 4; v++) {
+        double dv = fabs(m->cvar[4 * ic + v] - ex[v]);
+        tmx[v] = fmax(tmx[v], dv); tl1[v] += dv; tl2[v] += dv * dv;
+        if (v == 0 && dv > tbest) { tbest = dv; tib = ic; }
+      }
+    }
+#pragma omp critical
+    {
+      for (int v = 0; v < 4; v++) { mx[v] = fmax(mx[v], tmx[v]); l1[v] += tl1[v]; l2[v] += tl2[v]; err_L2 += tl2[v]; }
+      if (tib >= 0 && (tbest > best || (tbest == best && tib < ibest))) { best = tbest; ibest = tib; }
+    }
+  }
+#else
   for (int i = 0; i < m->ncells_intr; i++) {
     int ic = m->cell_intr[i];
     double pv[4];
@@ -922,6 +987,7 @@ static void error_isentropic_vortex(orc *m, double time, double out[14], double 
     if (d[0] > best) { best = d[0]; ibest = ic; first = 0; }
     err_L2 = err_L2 + d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3];
   }
+#endif
   (void)first;
   double n = (double)m->ncells_intr;
   out[0] = time;
@@ -933,6 +999,9 @@ static void error_isentropic_vortex(orc *m, double time, double out[14], double 
 static void residual_norms(orc *m, const double *cvar0, double out[4]) { /* src/runge_kutta.f90:169-184 */
   for (int v = 0; v < 4; v++) {
     double s = 0;
+#ifdef ORC_OMP
+#pragma omp parallel for reduction(+ : s)
+#endif
     for (int ic = 0; ic < m->ncells; ic++) {
       double d = fabs(m->cvar[4 * ic + v] - cvar0[4 * ic + v]);
       s = s + d * d;
@@ -963,28 +1032,28 @@ int orc_time_integration(orc *m, double t1, int nsub, double *res_l2, double *vo
       double t0 = wtime();
       if (c->steady && rk == 0) compute_local_time(m);
       if (!c->ssprk && !c->steady) {
-        for (size_t i = 0; i < n4; i++) fcvar[i] = fcvar[i] + m->rk_coef[rk] * m->resid[i];
-        if (rk < 3) for (size_t i = 0; i < n4; i++) m->cvar[i] = cvar0[i] + m->h_rk[rk] * m->resid[i];
-        else        for (size_t i = 0; i < n4; i++) m->cvar[i] = cvar0[i] + m->h_rk[rk] * fcvar[i];
+        OMP_FOR_N4 for (size_t i = 0; i < n4; i++) fcvar[i] = fcvar[i] + m->rk_coef[rk] * m->resid[i];
+        if (rk < 3) OMP_FOR_N4 for (size_t i = 0; i < n4; i++) m->cvar[i] = cvar0[i] + m->h_rk[rk] * m->resid[i];
+        else        OMP_FOR_N4 for (size_t i = 0; i < n4; i++) m->cvar[i] = cvar0[i] + m->h_rk[rk] * fcvar[i];
       } else if (c->ssprk && !c->steady) {
-        for (size_t i = 0; i < n4; i++) m->cvar[i] = cvar0[i] + m->h_rk[rk] * (m->rk_coef[rk] * m->resid[i] + fcvar[i]);
-        for (size_t i = 0; i < n4; i++) fcvar[i] = fcvar[i] + m->resid[i];
+        OMP_FOR_N4 for (size_t i = 0; i < n4; i++) m->cvar[i] = cvar0[i] + m->h_rk[rk] * (m->rk_coef[rk] * m->resid[i] + fcvar[i]);
+        OMP_FOR_N4 for (size_t i = 0; i < n4; i++) fcvar[i] = fcvar[i] + m->resid[i];
       } else if (!c->ssprk && c->steady) {
         /* intended algorithm of time_integ_RK_steady (the reference double-allocates diff, Appendix C #4) */
-        for (size_t i = 0; i < n4; i++) fcvar[i] = fcvar[i] + m->rk_coef[rk] * m->resid[i];
+        OMP_FOR_N4 for (size_t i = 0; i < n4; i++) fcvar[i] = fcvar[i] + m->rk_coef[rk] * m->resid[i];
         double cst = 1.0 / 2.0;
         if (rk == 2) cst = 1.0;
         if (rk == 3) cst = 1.0 / 6.0;
-        if (rk < 3) for (int ic = 0; ic < nc; ic++) for (int v = 0; v < 4; v++)
+        if (rk < 3) OMP_FOR for (int ic = 0; ic < nc; ic++) for (int v = 0; v < 4; v++)
             m->cvar[4 * ic + v] = cvar0[4 * ic + v] + m->dt_local[ic] * cst * m->resid[4 * ic + v];
-        else for (int ic = 0; ic < nc; ic++) for (int v = 0; v < 4; v++)
+        else OMP_FOR for (int ic = 0; ic < nc; ic++) for (int v = 0; v < 4; v++)
             m->cvar[4 * ic + v] = cvar0[4 * ic + v] + m->dt_local[ic] * cst * fcvar[4 * ic + v];
       } else {
         double cst = 1.0 / 3.0;
         if (rk == 3) cst = 1.0 / 4.0;
-        for (int ic = 0; ic < nc; ic++) for (int v = 0; v < 4; v++)
+        OMP_FOR for (int ic = 0; ic < nc; ic++) for (int v = 0; v < 4; v++)
             m->cvar[4 * ic + v] = cvar0[4 * ic + v] + m->dt_local[ic] * cst * (m->rk_coef[rk] * m->resid[4 * ic + v] + fcvar[4 * ic + v]);
-        for (size_t i = 0; i < n4; i++) fcvar[i] = fcvar[i] + m->resid[i];
+        OMP_FOR_N4 for (size_t i = 0; i < n4; i++) fcvar[i] = fcvar[i] + m->resid[i];
       }
       m->cput[3] += wtime() - t0;
     }

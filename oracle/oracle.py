@@ -25,8 +25,9 @@ def build(force: bool = False) -> None:
         subprocess.check_call(["make", "-C", _HERE, "-s", "all"])
 
 
-def _lib(fast: bool = False):
-    name = "liboracle_fast.so" if fast else "liboracle.so"
+def _lib(fast=False):
+    """fast: False -> parity build; True -> -Ofast timing build; "omp" -> all-cores context variant (see Makefile)."""
+    name = "liboracle_omp.so" if fast == "omp" else "liboracle_fast.so" if fast else "liboracle.so"
     if name in _LIBS:
         return _LIBS[name]
     path = os.path.join(_HERE, name)
@@ -72,7 +73,7 @@ class OracleError(RuntimeError):
 class Oracle:
     """One mesh + one configuration of the reference algorithm on the CPU."""
 
-    def __init__(self, mesh: Mesh, cfg: Fvs2dConfig | None = None, fast: bool = False):
+    def __init__(self, mesh: Mesh, cfg: Fvs2dConfig | None = None, fast=False):
         self.L = _lib(fast)
         self.mesh = mesh
         xy = np.ascontiguousarray(mesh.node_xy, dtype=np.float64)

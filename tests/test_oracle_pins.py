@@ -162,3 +162,20 @@ def test_oracle_builds_agree_fast_vs_strict(vortex_mesh):
     rb, _, _ = b.time_integration(0.0, 20)
     assert np.abs(a.cvar - b.cvar).max() < 1e-11
     assert (np.abs(ra - rb) / np.abs(ra)).max() < 1e-9
+
+
+@pytest.mark.parametrize("case", ["vortex", "naca"])
+def test_oracle_all_cores_variant_agrees(case, vortex_mesh, naca_mesh):
+    """The OpenMP gather variant (bench context number, not the reference algorithm) differs from the oracle only by
+    the order in which a cell's face fluxes are summed."""
+    from oracle.oracle import Oracle
+    mesh = vortex_mesh if case == "vortex" else naca_mesh
+    cfg = run_input(case).to_config()
+    a, b = Oracle(mesh, cfg, fast=True), Oracle(mesh, cfg, fast="omp")
+    a.initialize_solution(); b.initialize_solution()
+    ra, va, _ = a.time_integration(0.0, 5)
+    rb, vb, _ = b.time_integration(0.0, 5)
+    assert np.abs(a.cvar - b.cvar).max() < 1e-10
+    assert (np.abs(ra - rb) / np.abs(ra).clip(1e-300)).max() < 1e-8
+    if cfg.lvortex:
+        assert np.abs(va - vb).max() < 1e-12
