@@ -403,6 +403,11 @@ int fvs2d_gpu_init(const fvs2d_config *cfg, int device) {
   Phys &P = C->phys;
   P.gamma = cfg->gamma; P.kappa = kap; P.cfl = cfg->cfl_user;
   P.gm1 = cfg->gamma - 1.0; P.gog = cfg->gamma / (cfg->gamma - 1.0);
+  {
+    const double x = 2.0 / P.gm1, n = std::nearbyint(x);
+    P.pow2n = (n >= 1.0 && n <= 64.0 && std::fabs(x - n) < 1e-12) ? (int)n : 0;
+    P.pad = 0;
+  }
   for (int i = 0; i < 4; i++) { P.pinf[i] = cfg->pvar_inf[i]; P.vinf[i] = cfg->vortex_inf[i]; }
   P.vpos[0] = cfg->vortex_pos[0]; P.vpos[1] = cfg->vortex_pos[1]; P.vkap = cfg->vortex_kappa;
   for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) P.mms[i][j] = cfg->mms_c[i][j];
@@ -758,15 +763,14 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
     }
     {
       Span sp(0);
-      k_finish_sum<4><<<1, 256, 0, C->st>>>(C->partial, C->nparts, C->logbuf, (int)per, C->clk);
-      C->last_launches++;
+      int vgrid = 0;
       if (vort) {
-        const int vgrid = std::min(C->nblocks, C->nsm * 8);
+        vgrid = std::min(C->nblocks, C->nsm * kVortexCtas);
         k_vortex_err<<<vgrid, kBlock, 0, C->st>>>(C->dm, C->phys, C->clk, C->q, C->vpartial, C->vbest);
-        k_finish_vortex<<<1, 256, 0, C->st>>>(C->vpartial, C->vbest, vgrid, C->logbuf, (int)per, C->logid, C->clk);
-        C->last_launches += 2;
+        C->last_launches++;
       }
-      k_clock_advance<<<1, 1, 0, C->st>>>(C->clk);
+      k_finish_step<<<1, kFinishThreads, 0, C->st>>>(C->partial, C->nparts, C->vpartial, C->vbest, vgrid, C->logbuf, (int)per,
+                                                      C->logid, C->clk);
       C->last_launches++;
     }
     return 0;

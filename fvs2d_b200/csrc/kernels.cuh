@@ -7,8 +7,8 @@
 //   k_bc_state      Dirichlet / freestream ghost states of the boundary faces for one stage time
 //   k_prim          conserved -> primitive
 //   k_vortex_err    isentropic-vortex error norms                                             [reference K10]
-//   k_finish_*      fixed-order final reductions of the per-CTA partials (no fp atomics anywhere)
-//   k_clock_advance device-side step counter (lets a time step be replayed as a CUDA graph)
+//   k_finish_step   fixed-order final reductions of the per-CTA partials (no fp atomics anywhere) and the
+//                   device-side step counter (lets a time step be replayed as a CUDA graph)
 //   k_pack, k_scatter_in, k_gather_out   halo packing and AoS <-> device-layout copies
 //
 // Data layout: struct-of-arrays with pitch `np` (cells padded to a multiple of 32).  The arrays that other
@@ -63,6 +63,7 @@ struct Phys {
   double vpos[2], vkap, vinf[4];
   double mms[4][4];
   int lvortex, limiter;
+  int pow2n, pad;   // n when 2/(gamma-1) is an integer (gamma = 1.4 -> 5, 5/3 -> 3), else 0
 };
 
 // Time of the current step / stage, kept in device memory so that the kernel sequence of one time step has no
@@ -87,27 +88,6 @@ __host__ __device__ __forceinline__ size_t pidx(int v, int np, int i) { return (
 __device__ __forceinline__ void load4(const double2 *__restrict__ a2, int np, int i, double out[4]) {
   const double2 a = a2[i], b = a2[np + i];
   out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
-}
-
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void vortex_exact(const Phys &P, double t, double x, double y, double pv[4]) {
-  // src/mms.f90:219-265.  exp(1-r^2) = exp((1-r^2)/2)^2; rho = temp^(1/(gamma-1)) through one log and one exp,
-  // p = rho^gamma = rho * temp (two pow calls cost three times as much; |log(temp)| is small, so the
-  // composition stays at the 1-2 ulp level of the library pow)
-  const double pi = 3.141592653589793238462643383279502884;
-  const double rho_inf = P.vinf[0], u_inf = P.vinf[1], v_inf = P.vinf[2], p_inf = P.vinf[3];
-  const double T_inf = p_inf / rho_inf;
-  const double xc = P.vpos[0] + u_inf * t, yc = P.vpos[1] + v_inf * t;
-  const double dx = x - xc, dy = y - yc;
-  const double r2 = dx * dx + dy * dy;
-  const double kk = P.vkap / (2.0 * pi);
-  const double e1 = exp(0.5 * (1.0 - r2));
-  pv[1] = u_inf - kk * dy * e1;
-  pv[2] = v_inf + kk * dx * e1;
-  const double temp = T_inf - kk * kk * (P.gamma - 1.0) / (2.0 * P.gamma) * (e1 * e1);
-  const double rho = exp(log(temp) / P.gm1);
-  pv[0] = rho;
-  pv[3] = rho * temp;  // rho^gamma = rho * rho^(gamma-1) = rho * temp
 }
 
 __device__ __forceinline__ void mms_exact(const Phys &P, double x, double y, double pv[4]) {
@@ -144,6 +124,43 @@ __device__ __forceinline__ void fast_sqrt_rcp(const double x, double &s, double 
   t = fma(fma(-t, t, x), 0.5 * r, t);
   s = t;
   inv = r * r;
+}
+
+// rho = temp^(1/(gamma-1)) (src/mms.f90:251).  For the usual gas constants 2/(gamma-1) is an integer n, so the power
+// is sqrt(temp)^n: one rsqrt chain and a few multiplications instead of log + exp (the exponent the reference
+// forms, 1/(gamma-1) in fp64, differs from n/2 by an ulp: a relative change of 1e-16*|log temp|).
+__device__ __forceinline__ double pow_inv_gm1(const Phys &P, const double temp) {
+  if (P.pow2n > 0) {
+    double s, inv;
+    fast_sqrt_rcp(temp, s, inv);
+    double r = (P.pow2n & 1) ? s : 1.0, b = temp;
+    for (int n = P.pow2n >> 1; n; n >>= 1) {
+      if (n & 1) r *= b;
+      b *= b;
+    }
+    return r;
+  }
+  return exp(log(temp) / P.gm1);
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void vortex_exact(const Phys &P, double t, double x, double y, double pv[4]) {
+  // src/mms.f90:219-265.  exp(1-r^2) = exp((1-r^2)/2)^2; rho = temp^(1/(gamma-1)) once (pow_inv_gm1),
+  // p = rho^gamma = rho * temp (two pow calls cost three times as much)
+  const double pi = 3.141592653589793238462643383279502884;
+  const double rho_inf = P.vinf[0], u_inf = P.vinf[1], v_inf = P.vinf[2], p_inf = P.vinf[3];
+  const double T_inf = p_inf / rho_inf;
+  const double xc = P.vpos[0] + u_inf * t, yc = P.vpos[1] + v_inf * t;
+  const double dx = x - xc, dy = y - yc;
+  const double r2 = dx * dx + dy * dy;
+  const double kk = P.vkap / (2.0 * pi);
+  const double e1 = exp(0.5 * (1.0 - r2));
+  pv[1] = u_inf - kk * dy * e1;
+  pv[2] = v_inf + kk * dx * e1;
+  const double temp = T_inf - kk * kk * (P.gamma - 1.0) / (2.0 * P.gamma) * (e1 * e1);
+  const double rho = pow_inv_gm1(P, temp);
+  pv[0] = rho;
+  pv[3] = rho * temp;  // rho^gamma = rho * rho^(gamma-1) = rho * temp
 }
 
 // Roe flux with Harten's entropy fix, primitive inputs (src/flux_invscid.f90:37-136).
@@ -470,13 +487,14 @@ __device__ __forceinline__ void stage_load(const StageParams &S, const int i, co
   dl = 0.0;
 #pragma unroll
   for (int v = 0; v < 4; v++) { q0[v] = 0.0; fo[v] = 0.0; }
-  if (UM == UM_RESID) return;
+  if constexpr (UM != UM_RESID) {
 #pragma unroll
-  for (int v = 0; v < 4; v++) q0[v] = q[v * np + i];
-  if (S.stage != 0) {
+    for (int v = 0; v < 4; v++) q0[v] = q[v * np + i];
+    if (S.stage != 0) {
 #pragma unroll
-    for (int v = 0; v < 4; v++) fo[v] = f[v * np + i];
-    if (STEADY) dl = dtl[i];
+      for (int v = 0; v < 4; v++) fo[v] = f[v * np + i];
+      if (STEADY) dl = dtl[i];
+    }
   }
 }
 
@@ -866,56 +884,42 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
 }
 
 // ------------------------------------------------------------------------------------------------
-// final reduction of per-CTA partial sums: out[v] = sum_b partial[b*NV+v], one CTA, fixed order
-template <int NV>
-__global__ void __launch_bounds__(256) k_finish_sum(const double *__restrict__ partial, int nblocks, double *__restrict__ logbuf,
-                                                    int stride, const StepClock *__restrict__ clk) {
-  __shared__ double sm[256];
-  double *out = logbuf + (size_t)stride * clk->istep;  // this step's row of the device log
-  for (int v = 0; v < NV; v++) {
-    double s = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += 256) s += partial[(size_t)b * NV + v];
-    sm[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) out[v] = sm[0];
-    __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
+constexpr int kVortexCtas = 6;  // resident CTAs per SM of k_vortex_err; its grid is exactly one such wave
 // K10: vortex error norms over the interior cells (src/mms.f90:315-361).  Per CTA:
 // partial[b*13 + 0..3] = max |dq_v|, [4..7] = sum |dq_v|, [8..11] = sum dq_v^2, [12] = best rho error;
 // best_id[b] = original id of the first cell attaining it.
-__global__ void __launch_bounds__(kBlock) k_vortex_err(const DevMesh m, const Phys P, const StepClock *__restrict__ clk,
-                                                       const double *__restrict__ q, double *__restrict__ partial,
-                                                       int *__restrict__ best_id) {
+__global__ void __launch_bounds__(kBlock, kVortexCtas) k_vortex_err(const DevMesh m, const Phys P, const StepClock *__restrict__ clk,
+                                                          const double *__restrict__ q, double *__restrict__ partial,
+                                                          int *__restrict__ best_id) {
   const double time = clock_told(clk) + clk->off_end;
-  // grid-stride over the owned cells with a fixed grid: the partial count is small and the summation
-  // order is a function of the launch configuration only (deterministic)
+  // grid-stride over the owned cells with a fixed grid (one resident wave): the partial count is small and the
+  // summation order is a function of the launch configuration only (deterministic)
   const int np = m.np;
   double dmx[4] = {0, 0, 0, 0}, ds1[4] = {0, 0, 0, 0}, ds2[4] = {0, 0, 0, 0};
   double bv = -1.0;
   int bi = 0x7fffffff;
   for (int i = blockIdx.x * kBlock + threadIdx.x; i < m.n_own; i += gridDim.x * kBlock) {
-    if (!m.is_intr[i]) continue;
-    double pv[4];
+    // all loads of the cell are issued together; boundary cells (few) are computed and masked out
+    const bool in = m.is_intr[i] != 0;
     const double2 cc = m.xy[i];
+    const double a0 = q[i], a1 = q[np + i], a2 = q[2 * np + i], a3 = q[3 * np + i];
+    double pv[4];
     vortex_exact(P, time, cc.x, cc.y, pv);
     const double ex0 = pv[0], ex1 = pv[0] * pv[1], ex2 = pv[0] * pv[2];
     const double ex3 = pv[3] / (P.gamma - 1.0) + 0.5 * pv[0] * (pv[1] * pv[1] + pv[2] * pv[2]);
     double d[4];
-    d[0] = fabs(q[i] - ex0);
-    d[1] = fabs(q[np + i] - ex1);
-    d[2] = fabs(q[2 * np + i] - ex2);
-    d[3] = fabs(q[3 * np + i] - ex3);
+    d[0] = fabs(a0 - ex0);
+    d[1] = fabs(a1 - ex1);
+    d[2] = fabs(a2 - ex2);
+    d[3] = fabs(a3 - ex3);
+    if (in) {
 #pragma unroll
-    for (int v = 0; v < 4; v++) { dmx[v] = fmax(dmx[v], d[v]); ds1[v] += d[v]; ds2[v] += d[v] * d[v]; }
-    const int oid = m.orig_id[i];
-    if (d[0] > bv || (d[0] == bv && oid < bi)) { bv = d[0]; bi = oid; }
+      for (int v = 0; v < 4; v++) { dmx[v] = fmax(dmx[v], d[v]); ds1[v] += d[v]; ds2[v] += d[v] * d[v]; }
+      if (d[0] >= bv) {  // rare after the first few cells: only then is the original id needed
+        const int oid = m.orig_id[i];
+        if (d[0] > bv || oid < bi) { bv = d[0]; bi = oid; }
+      }
+    }
   }
   __shared__ double smx[4][kBlock / 32], s1[4][kBlock / 32], s2[4][kBlock / 32], sb[kBlock / 32];
   __shared__ int sid[kBlock / 32];
@@ -956,49 +960,60 @@ __global__ void __launch_bounds__(kBlock) k_vortex_err(const DevMesh m, const Ph
   }
 }
 
-// out[0..3] max, [4..7] sum, [8..11] sum of squares, [12] best value; out_id[0] = original id of the best cell
-__global__ void __launch_bounds__(256) k_finish_vortex(const double *__restrict__ partial, const int *__restrict__ best_id,
-                                                        int nblocks, double *__restrict__ logbuf, int stride, int *__restrict__ logid,
-                                                        const StepClock *__restrict__ clk) {
-  __shared__ double sm[256];
-  __shared__ int si[256];
-  double *out = logbuf + (size_t)stride * clk->istep + 4;  // after the 4 residual sums of the step's row
-  int *out_id = logid + clk->istep;
-  for (int v = 0; v < 12; v++) {
+// Last kernel of a time step: the fixed-order final reductions of the per-CTA partials into this step's row of the
+// device log, then the step counter advances.  One warp per quantity (lane-strided partial sums, shuffle tree), so
+// there is no block-wide synchronisation until the clock update:
+//   warps 0..3   row[v]      = sum_b partial[b*4+v]        Sigma (q-q0)^2 of the step (src/runge_kutta.f90:169-184)
+//   warps 4..15  row[4+v]    = max (v<4) / sum of vpartial[b*13+v]                     (src/mms.f90:315-361)
+//   warp  16     row[16], logid = largest rho error and the original id of the first cell attaining it
+constexpr int kFinishThreads = 17 * 32;
+__global__ void __launch_bounds__(kFinishThreads) k_finish_step(const double *__restrict__ partial, const int nparts,
+                                                                const double *__restrict__ vpartial, const int *__restrict__ vbest,
+                                                                const int nvparts, double *__restrict__ logbuf, const int stride,
+                                                                int *__restrict__ logid, StepClock *__restrict__ clk) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int istep = clk->istep;
+  double *row = logbuf + (size_t)stride * istep;
+  if (warp < 4) {
     double s = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += 256) {
-      const double x = partial[(size_t)b * 13 + v];
-      s = v < 4 ? fmax(s, x) : s + x;
+    for (int b = lane; b < nparts; b += 32) s += partial[(size_t)b * 4 + warp];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) row[warp] = s;
+  } else if (warp < 16) {
+    const int v = warp - 4;
+    if (nvparts > 0) {
+      double s = 0.0;
+      for (int b = lane; b < nvparts; b += 32) {
+        const double x = vpartial[(size_t)b * 13 + v];
+        s = v < 4 ? fmax(s, x) : s + x;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double x = __shfl_down_sync(0xffffffffu, s, o);
+        s = v < 4 ? fmax(s, x) : s + x;
+      }
+      if (lane == 0) row[4 + v] = s;
     }
-    sm[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (threadIdx.x < o) sm[threadIdx.x] = v < 4 ? fmax(sm[threadIdx.x], sm[threadIdx.x + o]) : sm[threadIdx.x] + sm[threadIdx.x + o];
-      __syncthreads();
+  } else if (nvparts > 0) {
+    double bv = -1.0;
+    int bi = 0x7fffffff;
+    for (int b = lane; b < nvparts; b += 32) {
+      const double x = vpartial[(size_t)b * 13 + 12];
+      const int id = vbest[b];
+      if (x > bv || (x == bv && id < bi)) { bv = x; bi = id; }
     }
-    if (threadIdx.x == 0) out[v] = sm[0];
-    __syncthreads();
-  }
-  double bv = -1.0; int bi = 0x7fffffff;
-  for (int b = threadIdx.x; b < nblocks; b += 256) {
-    const double x = partial[(size_t)b * 13 + 12];
-    const int id = best_id[b];
-    if (x > bv || (x == bv && id < bi)) { bv = x; bi = id; }
-  }
-  sm[threadIdx.x] = bv; si[threadIdx.x] = bi;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      const double x = sm[threadIdx.x + o]; const int id = si[threadIdx.x + o];
-      if (x > sm[threadIdx.x] || (x == sm[threadIdx.x] && id < si[threadIdx.x])) { sm[threadIdx.x] = x; si[threadIdx.x] = id; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double x = __shfl_down_sync(0xffffffffu, bv, o);
+      const int id = __shfl_down_sync(0xffffffffu, bi, o);
+      if (x > bv || (x == bv && id < bi)) { bv = x; bi = id; }
     }
-    __syncthreads();
+    if (lane == 0) { row[16] = bv; logid[istep] = bi; }
   }
-  if (threadIdx.x == 0) { out[12] = sm[0]; out_id[0] = si[0]; }
+  __syncthreads();  // every warp has read istep
+  if (threadIdx.x == 0) clk->istep = istep + 1;
 }
-
-// last kernel of a time step
-__global__ void k_clock_advance(StepClock *clk) { clk->istep += 1; }
 
 // ------------------------------------------------------------------------------------------------
 // halo pack: buf[v*n + k] = a[v*np + idx[k]] for nv arrays of elements T (double2 for the pair-interleaved
