@@ -701,8 +701,11 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   // device log: per step 4 sums of squares, 13 vortex numbers, 1 id
   const size_t per = 4 + 13;
   if (C->log_cap < (size_t)nsub) {
-    if (dev_alloc(C->logbuf, per * (size_t)nsub) || dev_alloc(C->logid, (size_t)nsub)) return 1;
-    C->log_cap = nsub;
+    // at least 4096 rows (0.5 MB): the step graph is tied to this buffer, so growing it from call to call would
+    // force a re-capture inside the caller's time loop
+    const size_t cap = std::max<size_t>((size_t)nsub, 4096);
+    if (dev_alloc(C->logbuf, per * cap) || dev_alloc(C->logid, cap)) return 1;
+    C->log_cap = cap;
   }
   C->last_launches = 0;
   C->ev_used = 0;

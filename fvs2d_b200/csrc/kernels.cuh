@@ -96,26 +96,21 @@ __device__ __forceinline__ void mms_exact(const Phys &P, double x, double y, dou
   for (int v = 0; v < 4; v++) pv[v] = P.mms[v][0] + P.mms[v][1] * sin(P.mms[v][2] * x + P.mms[v][3] * y);
 }
 
-// Branch-free fp64 reciprocal and reciprocal square root for normal, positive arguments (densities,
-// 1+RT, a^2): hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~20 bits) + two Newton steps -> <= 1 ulp-level
-// error, no slow path (the IEEE division / sqrt sequences cost twice the instructions plus a branch).
+// Branch-free fp64 reciprocal and reciprocal square root for normal, positive arguments (densities, w+z, a^2):
+// hardware seed (MUFU.RCP64H / MUFU.RSQ64H, 20 mantissa bits) + ONE third-order step -> rounding-level error
+// (residual e ~ 2^-19, truncation ~ e^3 < 2^-56), no slow path.  The IEEE division / sqrt sequences cost twice
+// the instructions plus a branch, and two Newton steps are a dependent chain twice as long as this.
 __device__ __forceinline__ double fast_rcp(const double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  return y;
+  const double e = fma(-x, y, 1.0);   // 1/x = y / (1-e) = y (1 + e + e^2 + ...)
+  return fma(y, fma(e, e, e), y);
 }
 __device__ __forceinline__ double fast_rsqrt(const double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x * y, y, 1.0);
-  y = fma(0.5 * y, e, y);
-  e = fma(-x * y, y, 1.0);
-  y = fma(0.5 * y, e, y);
-  return y;
+  const double e = fma(-x * y, y, 1.0);  // x^-1/2 = y (1-e)^-1/2 = y (1 + e/2 + 3e^2/8 + ...)
+  return fma(y * e, fma(0.375, e, 0.5), y);
 }
 // sqrt(x) and 1/x from one rsqrt: s = x*r corrected by one Newton step, 1/x = r*r
 __device__ __forceinline__ void fast_sqrt_rcp(const double x, double &s, double &inv) {
