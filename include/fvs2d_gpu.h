@@ -137,7 +137,16 @@ int fvs2d_host_build(const fvs2d_config *cfg, int rank, int nranks, int nnodes, 
  * kernels, ms[3] = reductions/boundary/halo; launches = kernels launched by the call. */
 int fvs2d_gpu_last_timing(double ms[4], long *launches);
 
-/* Tuning knobs (kernel variant selection for benchmarking); unknown keys are an error. */
+/* Tuning knobs (kernel variant selection for benchmarking); unknown keys are an error.
+ *   "timing"   1: CUDA event pair around every kernel launch (fills ms[1..3] of fvs2d_gpu_last_timing; disables the
+ *              step graph); 0 (default): only the whole call is timed
+ *   "tile"     2 (default): pass B = persistent shared-memory pipeline k_flux_pipe; 0: direct-gather kernel k_flux_rk
+ *              (also chosen automatically when a mesh's tiles do not fit the pipeline's shared memory)
+ *   "graph"    1 (default): on one GPU, steps 2..nsub of a call replay a captured CUDA graph; 0: every step eager
+ *   "overlap"  1 (default): multi-GPU halo exchange on a second stream, overlapped with interior-tile work
+ *   "ctas"     resident CTAs per SM of k_flux_pipe (0 = occupancy API), "smem_pad" / "carveout": extra dynamic shared
+ *              memory per CTA / preferred shared-memory carve-out of k_flux_pipe, both in KB (the L1 experiments of
+ *              DESIGN.md section 5) */
 int fvs2d_gpu_set_option(const char *key, int value);
 
 const char *fvs2d_gpu_last_error(void);
