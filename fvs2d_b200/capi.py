@@ -23,6 +23,7 @@ SYMBOLS = [
     "fvs2d_gpu_initialize_solution", "fvs2d_gpu_set_state", "fvs2d_gpu_get_state", "fvs2d_gpu_set_state_local",
     "fvs2d_gpu_get_state_local",
     "fvs2d_gpu_time_integration", "fvs2d_gpu_compute_residual", "fvs2d_gpu_get_aux", "fvs2d_gpu_test_resid",
+    "fvs2d_gpu_interpolate_cell2node", "fvs2d_gpu_wall_values",
     "fvs2d_gpu_sizes", "fvs2d_gpu_scalars", "fvs2d_gpu_mesh_array", "fvs2d_host_build", "fvs2d_gpu_last_timing",
     "fvs2d_gpu_set_option", "fvs2d_gpu_last_error", "fvs2d_gpu_finalize",
 ]
@@ -57,6 +58,8 @@ def lib():
     L.fvs2d_gpu_compute_residual.argtypes = [cd, vp, vp]
     L.fvs2d_gpu_get_aux.argtypes = [vp, vp, vp]
     L.fvs2d_gpu_test_resid.argtypes = [ci, vp, vp]
+    L.fvs2d_gpu_interpolate_cell2node.argtypes = [vp, vp]
+    L.fvs2d_gpu_wall_values.argtypes = [ci, vp]
     L.fvs2d_gpu_sizes.argtypes = [vp]
     L.fvs2d_gpu_scalars.argtypes = [vp]
     L.fvs2d_gpu_mesh_array.argtypes = [ctypes.c_char_p, vp]

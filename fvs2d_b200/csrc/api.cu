@@ -95,6 +95,13 @@ struct Ctx {
   int n_int = 0, n_bnd = 0;
   bool bc_static_done = false;
   double rk_coef[4], h_rk[4], dts[4], dte[4];
+  // output path, uploaded on first use: node -> cell lists with inverse-distance weights, boundary-edge tables
+  const int *d_n2c_ptr = nullptr, *d_n2c = nullptr;
+  const double *d_idw = nullptr;
+  double *d_fnode = nullptr;
+  const int *d_be_cell = nullptr;
+  const double2 *d_be_xy = nullptr, *d_be_nxy = nullptr;
+  double *d_be_out = nullptr;
   // timing
   int opt_timing = 0;
   double last_ms[4] = {0, 0, 0, 0};
@@ -145,6 +152,8 @@ void free_device() {
   C->bytes = 0;
   C->stage_aos = nullptr; C->stage_aos_len = 0;
   C->logbuf = nullptr; C->log_cap = 0;
+  C->d_n2c_ptr = C->d_n2c = nullptr; C->d_idw = nullptr; C->d_fnode = nullptr;
+  C->d_be_cell = nullptr; C->d_be_xy = C->d_be_nxy = nullptr; C->d_be_out = nullptr;
 }
 
 // ---- event-based kernel timing (option "timing") ------------------------------------------------
@@ -267,8 +276,8 @@ int download_aos(const double *soa, int nvar, double *host_out, int pair = 0, in
   return 0;
 }
 
-int launch_gradient(const double *p, const int *list = nullptr, int nlist = 0) {
-  if (C->recon == RC_FIRST) return 0;
+int launch_gradient(const double *p, const int *list = nullptr, int nlist = 0, bool force = false) {
+  if (C->recon == RC_FIRST && !force) return 0;  // src/gradient.f90:49
   const int nb = list ? nlist : C->nblocks;
   if (nb == 0) return 0;
   Span sp(1);
@@ -688,6 +697,76 @@ int fvs2d_gpu_get_aux(double *pvar, double *grad, double *phi_lim) {
     if (download_aos(C->g, 4, grad, 1, 0)) return 1;
     if (download_aos(C->g, 4, grad + plane, 1, 4)) return 1;
   }
+  return 0;
+}
+
+int fvs2d_gpu_interpolate_cell2node(const int select[4], double *fnode) {
+  NEED(C && C->has_state, "fvs2d_gpu_interpolate_cell2node: no state");
+  NEED(select && fnode, "fvs2d_gpu_interpolate_cell2node: null argument");
+  NEED(C->nranks == 1, "fvs2d_gpu_interpolate_cell2node: single GPU only (a node's cells may live on several ranks)");
+  const HostMesh &m = C->mesh;
+  int mask = 0, nsel = 0;
+  for (int v = 0; v < 4; v++) if (select[v]) { mask |= 1 << v; nsel++; }
+  if (nsel == 0) return 0;
+  if (!C->d_n2c_ptr) {  // first use: node -> cell lists in local ids and the weights of cell2node_idw_setup
+    std::vector<int> iperm(m.ncells), n2c(m.n2c.size());
+    std::vector<double> idw(m.n2c.size());
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < m.ncells; i++) iperm[C->L.perm[i]] = i;
+#pragma omp parallel for schedule(static)
+    for (int in = 0; in < m.nnodes; in++) {  // src/interpolation.f90:62-101
+      double idt = 0.0;
+      for (int j = m.n2c_ptr[in]; j < m.n2c_ptr[in + 1]; j++) {
+        const int ic = m.n2c[j];
+        const double dx = m.xc[ic] - m.xn[in], dy = m.yc[ic] - m.yn[in];
+        idw[j] = std::sqrt(dx * dx + dy * dy);
+        idt = idt + 1.0 / idw[j];
+        n2c[j] = iperm[ic];
+      }
+      for (int j = m.n2c_ptr[in]; j < m.n2c_ptr[in + 1]; j++) idw[j] = 1.0 / idw[j] / idt;
+    }
+    if (dev_upload(C->d_n2c, n2c) || dev_upload(C->d_idw, idw) || dev_alloc(C->d_fnode, 4 * (size_t)m.nnodes)) return 1;
+    if (dev_upload(C->d_n2c_ptr, m.n2c_ptr)) return 1;
+  }
+  // C->pa is the primitive state of the current cvar (cvar2pvar of write_inst_ios, src/io.f90:135)
+  k_cell2node<<<cdiv(m.nnodes, 256), 256, 0, C->st>>>(m.nnodes, C->np, mask, C->d_n2c_ptr, C->d_n2c, C->d_idw, C->pa, C->d_fnode);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(fnode, C->d_fnode, (size_t)nsel * m.nnodes * 8, cudaMemcpyDeviceToHost, C->st));
+  CUDA_OK(cudaStreamSynchronize(C->st));
+  return 0;
+}
+
+int fvs2d_gpu_wall_values(int ib, double *vals) {
+  NEED(C && C->has_state, "fvs2d_gpu_wall_values: no state");
+  NEED(vals != nullptr, "fvs2d_gpu_wall_values: null argument");
+  NEED(C->nranks == 1, "fvs2d_gpu_wall_values: single GPU only");
+  const HostMesh &m = C->mesh;
+  NEED(ib >= 0 && ib < m.nb, "fvs2d_gpu_wall_values: boundary index out of range");
+  const int nbe = (int)m.b_edge.size();
+  if (!C->d_be_cell) {  // first use: every boundary edge in bndry(:)%edge order -> its cell (edge%c1) and geometry
+    std::vector<int> iperm(m.ncells), cell(nbe);
+    std::vector<double2> exy(nbe), enxy(nbe);
+    for (int i = 0; i < m.ncells; i++) iperm[C->L.perm[i]] = i;
+    for (int i = 0; i < nbe; i++) {
+      const int je = m.b_edge[i];
+      const EdgeGeom eg = edge_geom(m, je);
+      cell[i] = iperm[m.ec1[je]];
+      exy[i] = make_double2(eg.x, eg.y);
+      enxy[i] = make_double2(eg.nx, eg.ny);
+    }
+    if (dev_upload(C->d_be_cell, cell) || dev_upload(C->d_be_xy, exy) || dev_upload(C->d_be_nxy, enxy) ||
+        dev_alloc(C->d_be_out, 4 * (size_t)std::max(1, nbe))) return 1;
+  }
+  const int e0 = m.b_edge_ptr[ib], n = m.b_edge_ptr[ib + 1] - e0;
+  if (n == 0) return 0;
+  // gradient_cellcntr_1var (src/gradient.f90:74-96): the unlimited gradient of the selected scheme, also for
+  // first-order reconstruction, of the current primitive state
+  if (launch_gradient(C->pa, nullptr, 0, true)) return 1;
+  k_wall_values<<<cdiv(n, 128), 128, 0, C->st>>>(n, C->np, C->d_be_cell + e0, C->d_be_xy + e0, C->d_be_nxy + e0, C->dm.xy, C->pa, C->g,
+                                                 C->d_be_out);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(vals, C->d_be_out, (size_t)n * 32, cudaMemcpyDeviceToHost, C->st));
+  CUDA_OK(cudaStreamSynchronize(C->st));
   return 0;
 }
 

@@ -300,31 +300,13 @@ int main(int argc, char **argv) {
   itimes[0] = in.ntstart - 1 + nsub[0];
   for (int i = 1; i < in.nsaves; i++) itimes[i] = nsub[i] + itimes[i - 1];
   std::ofstream inst;
-  std::vector<double> idw;  // cell->node inverse-distance weights (src/interpolation.f90:62-101)
-  std::vector<int> n2c_ptr, n2c;
+  int lw_sel[4];
+  for (int v = 0; v < 4; v++) lw_sel[v] = in.lw[v];
   if (mp > 0) {
     // the header lists inf(1:mp) = the first mp of (rho,u,v,p) rather than the selected names (src/io.f90:72-87)
     std::vector<std::string> params(names, names + mp);
     writecd("inst", g.nnodes, nc, mp, in.nsaves, itimes, params, {});
     inst.open(in.s8 ? "inst.s8" : "inst.s4", std::ios::binary);
-    n2c_ptr.assign(g.nnodes + 1, 0);
-    for (int v : g.cnode) n2c_ptr[v + 1]++;
-    for (int i = 0; i < g.nnodes; i++) n2c_ptr[i + 1] += n2c_ptr[i];
-    n2c.resize(g.cnode.size()); idw.resize(g.cnode.size());
-    std::vector<int> fill(n2c_ptr.begin(), n2c_ptr.end() - 1);
-    std::vector<double> xc(nc), yc(nc);
-    fvs2d_gpu_mesh_array("xc", xc.data()); fvs2d_gpu_mesh_array("yc", yc.data());
-    for (int ic = 0; ic < nc; ic++)
-      for (int s = g.cptr[ic]; s < g.cptr[ic + 1]; s++) n2c[fill[g.cnode[s]]++] = ic;
-    for (int n = 0; n < g.nnodes; n++) {
-      double idt = 0;
-      for (int j = n2c_ptr[n]; j < n2c_ptr[n + 1]; j++) {
-        const double dx = xc[n2c[j]] - g.xy[2 * n], dy = yc[n2c[j]] - g.xy[2 * n + 1];
-        idw[j] = std::sqrt(dx * dx + dy * dy);
-        idt = idt + 1.0 / idw[j];
-      }
-      for (int j = n2c_ptr[n]; j < n2c_ptr[n + 1]; j++) idw[j] = 1.0 / idw[j] / idt;
-    }
   }
   {
     char dch[16]; std::snprintf(dch, sizeof dch, "%6d", in.ntimes);
@@ -352,44 +334,40 @@ int main(int argc, char **argv) {
   bool lcp = false;
   for (int t : g.bt) lcp = lcp || t == FVS2D_BC_SLIP_WALL || t == FVS2D_BC_SOLID_WALL;
   std::ofstream fcp, fun, fclcd;
-  std::vector<int> b_edge, b_edge_ptr, ec1;
-  std::vector<double> ex, ey, ea, enx, eny, xcc, ycc;
+  std::vector<int> b_edge, b_edge_ptr;
+  std::vector<double> ea, enx, eny;
   if (lcp) {
     fcp.open("log_cp.plt"); fun.open("log_un.plt"); fclcd.open("log_clcd.plt");
     fun << "VARIABLES = \"time\" \"|V<sub>n</sub>|<sub><math>%</math></sub>\",   \"|V<sub>n</sub>|<sub>2</sub>\" , \"|V<sub>n</sub>|<sub>1</sub>\"\n";
     fclcd << "VARIABLES = \"time\" \"c<sub>l</sub>\",   \"c<sub>d</sub>\", \"c<sub>l1</sub>\",   \"c<sub>d1</sub>\"\n";
     auto geti = [&](const char *n, std::vector<int> &v) { v.resize(fvs2d_gpu_mesh_array(n, nullptr)); fvs2d_gpu_mesh_array(n, v.data()); };
     auto getd = [&](const char *n, std::vector<double> &v) { v.resize(fvs2d_gpu_mesh_array(n, nullptr)); fvs2d_gpu_mesh_array(n, v.data()); };
-    geti("b_edge", b_edge); geti("b_edge_ptr", b_edge_ptr); geti("ec1", ec1);
-    getd("ex", ex); getd("ey", ey); getd("ea", ea); getd("enx", enx); getd("eny", eny); getd("xc", xcc); getd("yc", ycc);
+    geti("b_edge", b_edge); geti("b_edge_ptr", b_edge_ptr);
+    getd("ea", ea); getd("enx", enx); getd("eny", eny);
   }
-  // write_inst_cp_un (src/io.f90:340-449): wall pressure coefficient, normal-velocity norms and force coefficients from
-  // the cell values extrapolated to the wall faces with the (unlimited) cell gradients of p, u, v
+  // write_inst_cp_un (src/io.f90:340-449): wall pressure coefficient, normal-velocity norms and force coefficients.  The
+  // library extrapolates p, u, v to the wall-edge centres with the unlimited cell gradients on the device
+  // (fvs2d_gpu_wall_values: 4 doubles per wall edge come back instead of pvar + grad of every cell); the sums run
+  // here in the reference's edge order.
   auto write_inst_cp_un = [&](double sol_time) {
     if (!lcp) return;
-    std::vector<double> pv(4 * (size_t)nc), gr(8 * (size_t)nc);
-    check(fvs2d_gpu_compute_residual(sol_time, nullptr, nullptr));   // refreshes pvar and grad of the current state
-    check(fvs2d_gpu_get_aux(pv.data(), gr.data(), nullptr));
-    const double *gx = gr.data(), *gy = gr.data() + 4 * (size_t)nc;
     const double p_inf = 1.0 / in.gamma, q2 = 2.0 / (in.mach * in.mach);
     const double ca_ = in.aoa == 0.0 ? 1.0 : std::cos(in.aoa * pi / 180.0), sa_ = in.aoa == 0.0 ? 0.0 : std::sin(in.aoa * pi / 180.0);
     for (size_t ib = 0; ib < g.bt.size(); ib++) {
       if (g.bt[ib] != FVS2D_BC_SLIP_WALL && g.bt[ib] != FVS2D_BC_SOLID_WALL) continue;
       const int e0 = b_edge_ptr[ib], e1 = b_edge_ptr[ib + 1];
+      std::vector<double> wv(4 * (size_t)(e1 - e0));
+      check(fvs2d_gpu_wall_values((int)ib, wv.data()));
       fcp << "TITLE     = \"cp\"\nVARIABLES = \"x\" \"cp_w\" \"cp_cell\"\nZONE I=" << (e1 - e0) << " J=1\n"
           << "STRANDID=1, SOLUTIONTIME=" << fortran_e(sol_time, 16, 8) << "\n";
       double un_max = 0, un_l2 = 0, un_l1 = 0, cn = 0, ca = 0, cn1 = 0, ca1 = 0;
       for (int i = e0; i < e1; i++) {
-        const int ie = b_edge[i], ic = ec1[ie];  // the reference indexes bndry%cell by the edge counter
-        const double dx = ex[ie] - xcc[ic], dy = ey[ie] - ycc[ic];
-        const double pw = pv[4 * (size_t)ic + 3] + dx * gx[4 * (size_t)ic + 3] + dy * gy[4 * (size_t)ic + 3];
-        const double cp = q2 * (pw - p_inf), cp1 = q2 * (pv[4 * (size_t)ic + 3] - p_inf);
-        fcp << fortran_e(ex[ie], 16, 8) << " " << fortran_e(cp, 16, 8) << " " << fortran_e(cp1, 16, 8) << " \n";
+        const int ie = b_edge[i];
+        const double *w = &wv[4 * (size_t)(i - e0)];  // x_f, p_w, p_cell, u_n
+        const double cp = q2 * (w[1] - p_inf), cp1 = q2 * (w[2] - p_inf), un = w[3];
+        fcp << fortran_e(w[0], 16, 8) << " " << fortran_e(cp, 16, 8) << " " << fortran_e(cp1, 16, 8) << " \n";
         cn = cn + cp * eny[ie] * ea[ie];   ca = ca + cp * enx[ie] * ea[ie];
         cn1 = cn1 + cp1 * eny[ie] * ea[ie]; ca1 = ca1 + cp1 * enx[ie] * ea[ie];
-        const double uw = pv[4 * (size_t)ic + 1] + dx * gx[4 * (size_t)ic + 1] + dy * gy[4 * (size_t)ic + 1];
-        const double vw = pv[4 * (size_t)ic + 2] + dx * gx[4 * (size_t)ic + 2] + dy * gy[4 * (size_t)ic + 2];
-        const double un = uw * enx[ie] + vw * eny[ie];
         un_l2 += un * un; un_l1 += std::fabs(un); un_max = std::max(un_max, std::fabs(un));
       }
       const double n = (double)(e1 - e0);
@@ -425,23 +403,11 @@ int main(int argc, char **argv) {
     std::printf("%5d time-steps done \n", it_tot);
     std::fflush(stdout);
     t0 += in.dt * n;
-    if (mp > 0) {  // write_inst_ios (src/io.f90:122-150): node-interpolated primitive variables, one record per variable
-      std::vector<double> pv(4 * (size_t)nc), fv(g.nnodes);
-      check(fvs2d_gpu_get_state(cvar.data()));
-      for (int ic = 0; ic < nc; ic++) {  // cvar2pvar (src/data_solution.f90:72-86)
-        const double *q = &cvar[4 * (size_t)ic]; double *p = &pv[4 * (size_t)ic];
-        p[0] = q[0]; p[1] = q[1] / q[0]; p[2] = q[2] / q[0];
-        p[3] = (in.gamma - 1.0) * (q[3] - 0.5 * p[0] * (p[1] * p[1] + p[2] * p[2]));
-      }
-      for (int v = 0; v < 4; v++) {
-        if (!in.lw[v]) continue;
-        for (int nd = 0; nd < g.nnodes; nd++) {
-          double a = 0;
-          for (int j = n2c_ptr[nd]; j < n2c_ptr[nd + 1]; j++) a = a + idw[j] * pv[4 * (size_t)n2c[j] + v];
-          fv[nd] = a;
-        }
-        write_be(inst, fv.data(), fv.size(), !in.s8);
-      }
+    if (mp > 0) {  // write_inst_ios (src/io.f90:122-150): node-interpolated primitive variables, one record per variable;
+      // interpolated on the device, only the mp node records come back
+      std::vector<double> fv((size_t)mp * g.nnodes);
+      check(fvs2d_gpu_interpolate_cell2node(lw_sel, fv.data()));
+      write_be(inst, fv.data(), fv.size(), !in.s8);
     }
     write_inst_cp_un(t0);  // src/fvs2d.f90:157
   }

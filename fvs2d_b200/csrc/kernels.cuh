@@ -10,6 +10,8 @@
 //   k_finish_step   fixed-order final reductions of the per-CTA partials (no fp atomics anywhere) and the
 //                   device-side step counter (lets a time step be replayed as a CUDA graph)
 //   k_pack, k_scatter_in, k_gather_out   halo packing and AoS <-> device-layout copies
+//   k_cell2node     cell -> node inverse-distance interpolation of the primitive state (output path, per save)
+//   k_wall_values   wall pressure / normal velocity at the boundary-edge centres (output path, per save)
 //
 // Data layout: struct-of-arrays with pitch `np` (cells padded to a multiple of 32).  The arrays that other
 // cells gather -- primitive state p (4 vars), gradients g (8 vars: gx0-3, gy0-3), centroids xy, edge centres
@@ -1038,6 +1040,61 @@ __global__ void __launch_bounds__(256) k_gather_out(int n, int np, int nvar, con
   if (i >= n) return;
   const size_t o = orig_id ? orig_id[i] : i;
   for (int v = 0; v < nvar; v++) aos[o * nvar + v] = soa[pair ? pidx(v0 + v, np, i) : (size_t)(v0 + v) * np + i];
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Output path (per save interval, not per stage): the node-interpolated primitive variables of write_inst_ios
+// (src/io.f90:122-150, src/interpolation.f90:107-123).  One thread per node; the node's cells are visited in
+// ascending ORIGINAL cell id -- the reference's summation order -- through their local ids, with the
+// inverse-distance weights of cell2node_idw_setup (src/interpolation.f90:62-101) precomputed on upload.
+// mask bit v selects primitive variable v; the k-th selected variable goes to fv[k*nnodes + node].
+__global__ void __launch_bounds__(256) k_cell2node(const int nnodes, const int np, const int mask, const int *__restrict__ n2c_ptr,
+                                                    const int *__restrict__ n2c, const double *__restrict__ idw,
+                                                    const double *__restrict__ p, double *__restrict__ fv) {
+  const int in = blockIdx.x * blockDim.x + threadIdx.x;
+  if (in >= nnodes) return;
+  const double2 *p2 = reinterpret_cast<const double2 *>(p);
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  const int j1 = __ldg(&n2c_ptr[in + 1]);
+  for (int j = __ldg(&n2c_ptr[in]); j < j1; j++) {
+    const int ic = __ldg(&n2c[j]);
+    const double w = __ldg(&idw[j]);
+    double pv[4];
+    load4(p2, np, ic, pv);
+#pragma unroll
+    for (int v = 0; v < 4; v++) a[v] = a[v] + w * pv[v];
+  }
+  int k = 0;
+#pragma unroll
+  for (int v = 0; v < 4; v++)
+    if (mask >> v & 1) { fv[(size_t)k * nnodes + in] = a[v]; k++; }
+}
+
+// Output path: the numerical part of write_inst_cp_un (src/io.f90:340-449).  One thread per boundary edge of the
+// requested boundary: p, u, v of the edge's cell (c1) extrapolated to the edge centre with the cell's unlimited
+// gradient (pass A has just been run on the current state), out[4*i..] = x_f, p_w, p_cell, u_n.
+__global__ void __launch_bounds__(128) k_wall_values(const int n, const int np, const int *__restrict__ cell,
+                                                      const double2 *__restrict__ exy, const double2 *__restrict__ enxy,
+                                                      const double2 *__restrict__ xy, const double *__restrict__ p,
+                                                      const double *__restrict__ g, double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int ic = cell[i];
+  const double2 *p2 = reinterpret_cast<const double2 *>(p), *g2 = reinterpret_cast<const double2 *>(g);
+  double pv[4], gx[4], gy[4];
+  load4(p2, np, ic, pv);
+  load4(g2, np, ic, gx);
+  load4(g2 + 2 * (size_t)np, np, ic, gy);
+  const double2 fc = exy[i], fn = enxy[i], cc = xy[ic];
+  const double dx = fc.x - cc.x, dy = fc.y - cc.y;
+  const double pw = pv[3] + dx * gx[3] + dy * gy[3];
+  const double uw = pv[1] + dx * gx[1] + dy * gy[1];
+  const double vw = pv[2] + dx * gx[2] + dy * gy[2];
+  out[4 * (size_t)i + 0] = fc.x;
+  out[4 * (size_t)i + 1] = pw;
+  out[4 * (size_t)i + 2] = pv[3];
+  out[4 * (size_t)i + 3] = uw * fn.x + vw * fn.y;
 }
 
 }  // namespace fvs2d

@@ -116,6 +116,23 @@ class Fvs2dGpu:
         capi.check(self.L.fvs2d_gpu_test_resid(int(corrected), capi.ptr(l2), capi.ptr(li)))
         return l2, li
 
+    # -- output path (write_inst_ios / write_inst_cp_un numerics, src/io.f90:122-150, 340-449) --
+    def interpolate_cell2node(self, select=(1, 1, 1, 1)) -> np.ndarray:
+        """-> [nselected, nnodes]: the selected primitive variables (rho, u, v, p) of the current state at the
+        nodes, inverse-distance weighted (src/interpolation.f90:62-123)."""
+        sel = np.asarray([1 if s else 0 for s in select], dtype=np.int32)
+        out = np.zeros((int(sel.sum()), self.sizes()["nnodes"]))
+        if out.size:
+            capi.check(self.L.fvs2d_gpu_interpolate_cell2node(capi.ptr(sel), capi.ptr(out)))
+        return out
+
+    def wall_values(self, ib: int) -> np.ndarray:
+        """-> [nedges(ib), 4] = x_f, p_w, p_cell, u_n per edge of boundary ``ib`` (src/io.f90:340-449)."""
+        bptr = capi.mesh_array("b_edge_ptr")
+        out = np.zeros((int(bptr[ib + 1] - bptr[ib]), 4))
+        capi.check(self.L.fvs2d_gpu_wall_values(int(ib), capi.ptr(out)))
+        return out
+
     # -- instrumentation ---------------------------------------------------------------------
     def set_option(self, key: str, value: int):
         capi.check(self.L.fvs2d_gpu_set_option(key.encode(), int(value)))

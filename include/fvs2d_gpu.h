@@ -107,6 +107,22 @@ int fvs2d_gpu_get_aux(double *pvar, double *grad, double *phi_lim);
  * the reference's u*rx (src/mms.f90:169). */
 int fvs2d_gpu_test_resid(int corrected, double l2[4], double linf[4]);
 
+/* ---- output path (per save interval) ------------------------------- */
+
+/* Replaces: the numerical part of write_inst_ios (src/io.f90:122-150) = cvar2pvar + interpolate_cell2node
+ * (src/interpolation.f90:62-123: linear inverse-distance weights, summed over node%cell in ascending cell id) for
+ * every primitive variable v (0 rho, 1 u, 2 v, 3 p) with select[v] != 0 -- the lw_inst flags of fvs2d.input
+ * line 17.  fnode holds nselected records of nnodes doubles in variable order, ready for writed
+ * (src/ios_unstrc.f90:300-404).  Only the node records cross PCIe instead of cvar(4,ncells).  Single GPU only. */
+int fvs2d_gpu_interpolate_cell2node(const int select[4], double *fnode /* nselected * nnodes */);
+
+/* Replaces: the numerical part of write_inst_cp_un (src/io.f90:340-449) for boundary ib (0-based, .bc order): the
+ * unlimited gradient of the current primitive state (gradient_cellcntr_1var, src/gradient.f90:74-96) and, per edge i
+ * of bndry(ib)%edge, vals[4*i..4*i+3] = x_f, p_w, p_cell, u_n (pressure and normal velocity extrapolated to the edge
+ * centre from the edge's cell, the cell pressure).  cp, the |V_n| norms and cl/cd are sums of these in edge order, left
+ * to the caller exactly as the reference forms them.  Single GPU only. */
+int fvs2d_gpu_wall_values(int ib, double *vals /* 4 * nedges(ib) */);
+
 /* ---- queries ----------------------------------------------------------------------------- */
 
 /* sizes[0..9] = nnodes, ncells, nedges, nedges_intr, nedges_bndr, ncells_intr, ncells_bndr,

@@ -1155,6 +1155,54 @@ int orc_test_resid(orc *m, int which, double l2[4], double linf[4]) {
 
 void orc_vortex_error(orc *m, double time, double out[14], double xy[2]) { error_isentropic_vortex(m, time, out, xy); }
 
+/* write_inst_ios numerics (src/io.f90:122-150): cvar2pvar, then interpolate_cell2node of primitive variable ivar
+ * with the linear inverse-distance weights of cell2node_idw_setup (src/interpolation.f90:62-101: d = |x_c - x_v|,
+ * idw = 1/d/sum(1/d)), summed over node%cell in ascending cell id (src/interpolation.f90:107-123). */
+int orc_interpolate_cell2node(orc *m, int ivar, double *fv) {
+  if (ivar < 0 || ivar >= NVAR) { snprintf(m->err, sizeof m->err, "interpolate_cell2node: bad variable"); return 14; }
+  cvar2pvar(m);
+  for (int in = 0; in < m->nnodes; in++) {
+    double idt = 0.0;
+    for (int j = m->n2c_ptr[in]; j < m->n2c_ptr[in + 1]; j++) {
+      int ic = m->n2c[j];
+      double dx = m->xc[ic] - m->xn[in], dy = m->yc[ic] - m->yn[in];
+      idt = idt + 1.0 / sqrt(dx * dx + dy * dy);
+    }
+    double f = 0.0;
+    for (int j = m->n2c_ptr[in]; j < m->n2c_ptr[in + 1]; j++) {
+      int ic = m->n2c[j];
+      double dx = m->xc[ic] - m->xn[in], dy = m->yc[ic] - m->yn[in];
+      double idw = 1.0 / sqrt(dx * dx + dy * dy) / idt;
+      f = f + idw * m->pvar[4 * ic + ivar];
+    }
+    fv[in] = f;
+  }
+  return 0;
+}
+
+/* write_inst_cp_un numerics (src/io.f90:340-449) for boundary ib: the cell values of p, u, v extrapolated to the
+ * boundary-edge centres with the UNLIMITED cell gradients of gradient_cellcntr_1var (src/gradient.f90:74-96 -- computed
+ * by the selected scheme even for first-order reconstruction).  out[4*i..] = x_f, p_w, p_cell, u_n for edge i of
+ * bndry(ib)%edge; the cell is edge%c1 (the reference indexes bndry%cell by the edge counter).
+ * pvar is that of the current cvar (the reference calls cvar2pvar in write_inst_ios just before). */
+int orc_wall_values(orc *m, int ib, double *out) {
+  if (ib < 0 || ib >= m->nb) { snprintf(m->err, sizeof m->err, "wall_values: bad boundary"); return 15; }
+  cvar2pvar(m);
+  if (m->cfg.grad_method == 2) grad_ggnb(m);
+  else if (m->cfg.grad_method == 1) grad_ggcb(m);
+  else grad_lsq(m);
+  for (int i = m->b_edge_ptr[ib]; i < m->b_edge_ptr[ib + 1]; i++) {
+    int ie = m->b_edge[i], ic = m->ec1[ie];
+    double dx = m->ex[ie] - m->xc[ic], dy = m->ey[ie] - m->yc[ic];
+    double pw = m->pvar[4 * ic + 3] + dx * GRAD(m, 0, ic, 3) + dy * GRAD(m, 1, ic, 3);
+    double uw = m->pvar[4 * ic + 1] + dx * GRAD(m, 0, ic, 1) + dy * GRAD(m, 1, ic, 1);
+    double vw = m->pvar[4 * ic + 2] + dx * GRAD(m, 0, ic, 2) + dy * GRAD(m, 1, ic, 2);
+    double *o = out + 4 * (size_t)(i - m->b_edge_ptr[ib]);
+    o[0] = m->ex[ie]; o[1] = pw; o[2] = m->pvar[4 * ic + 3]; o[3] = uw * m->enx[ie] + vw * m->eny[ie];
+  }
+  return 0;
+}
+
 /* sizes: [nnodes,ncells,nedges,nedges_intr,nedges_bndr,ncells_intr,ncells_bndr,nslots,lsq_total,ggnb_total] */
 void orc_sizes(orc *m, int out[10]) {
   out[0] = m->nnodes; out[1] = m->ncells; out[2] = m->nedges; out[3] = m->nedges_intr; out[4] = m->nedges_bndr;

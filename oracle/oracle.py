@@ -45,6 +45,8 @@ def _lib(fast=False):
     L.orc_time_integration.argtypes = [vp, ctypes.c_double, ctypes.c_int, vp, vp, vp]
     L.orc_test_resid.argtypes = [vp, ctypes.c_int, vp, vp]
     L.orc_vortex_error.argtypes = [vp, ctypes.c_double, vp, vp]
+    L.orc_interpolate_cell2node.argtypes = [vp, ctypes.c_int, vp]
+    L.orc_wall_values.argtypes = [vp, ctypes.c_int, vp]
     L.orc_sizes.argtypes = [vp, vp]
     L.orc_scalars.argtypes = [vp, vp]
     L.orc_timers.argtypes = [vp, vp]
@@ -125,6 +127,19 @@ class Oracle:
         out, xy = np.zeros(14), np.zeros(2)
         self.L.orc_vortex_error(self.h, float(time), _p(out), _p(xy))
         return out, xy
+
+    def interpolate_cell2node(self, ivar: int) -> np.ndarray:
+        """Primitive variable ivar (0 rho, 1 u, 2 v, 3 p) of the current state at the nodes (src/io.f90:122-150)."""
+        fv = np.zeros(self.mesh.nnodes)
+        self._check(self.L.orc_interpolate_cell2node(self.h, int(ivar), _p(fv)))
+        return fv
+
+    def wall_values(self, ib: int) -> np.ndarray:
+        """[nedges(ib), 4] = x_f, p_w, p_cell, u_n per edge of boundary ib (src/io.f90:340-449)."""
+        bptr = self.array("b_edge_ptr")
+        out = np.zeros((int(bptr[ib + 1] - bptr[ib]), 4))
+        self._check(self.L.orc_wall_values(self.h, int(ib), _p(out)))
+        return out
 
     # -- data access ------------------------------------------------------------------------
     def array(self, name: str) -> np.ndarray:

@@ -179,3 +179,41 @@ def test_oracle_all_cores_variant_agrees(case, vortex_mesh, naca_mesh):
     assert (np.abs(ra - rb) / np.abs(ra).clip(1e-300)).max() < 1e-8
     if cfg.lvortex:
         assert np.abs(va - vb).max() < 1e-12
+
+
+def test_output_path_interpolation_and_wall_values(vortex_mesh, naca_mesh):
+    """The oracle's restatement of the output numerics (write_inst_ios src/io.f90:122-150 + src/interpolation.f90:62-123,
+    write_inst_cp_un src/io.f90:340-449) against their defining properties: the inverse-distance weights of a node sum
+    to one (a uniform field interpolates to itself), the interpolant is the independent numpy evaluation of the same
+    formula, and on a uniform freestream the wall values are p_w = p_cell = p_inf, u_n = u_inf . n (zero gradients)."""
+    r = run_input("vortex")
+    orc = _oracle(vortex_mesh, r.to_config())
+    orc.initialize_solution()
+    ptr, n2c = orc.array("n2c_ptr"), orc.array("n2c")
+    xc, yc = orc.array("xc"), orc.array("yc")
+    node = np.repeat(np.arange(vortex_mesh.nnodes), np.diff(ptr))
+    w = 1.0 / np.hypot(xc[n2c] - vortex_mesh.node_xy[node, 0], yc[n2c] - vortex_mesh.node_xy[node, 1])
+    w /= np.add.reduceat(w, ptr[:-1])[node]
+    q = orc.cvar
+    pv = np.stack([q[:, 0], q[:, 1] / q[:, 0], q[:, 2] / q[:, 0],
+                   (r.gamma - 1.0) * (q[:, 3] - 0.5 * (q[:, 1]**2 + q[:, 2]**2) / q[:, 0])], axis=1)
+    for v in range(4):
+        np.testing.assert_allclose(orc.interpolate_cell2node(v), np.add.reduceat(w * pv[n2c, v], ptr[:-1]), rtol=1e-13, atol=1e-15)
+    orc.set_state(np.tile([1.0, 0.3, -0.1, 2.5], (vortex_mesh.ncells, 1)))
+    np.testing.assert_allclose(orc.interpolate_cell2node(0), 1.0, rtol=1e-14)
+    np.testing.assert_allclose(orc.interpolate_cell2node(1), 0.3, rtol=1e-14)
+    # NACA: freestream state -> zero gradients (LSQ differences vanish identically)
+    rn = run_input("naca")
+    on = _oracle(naca_mesh, rn.to_config())
+    on.initialize_solution()
+    ib = naca_mesh.bndry_type.index("slip_wall")
+    wv = on.wall_values(ib)
+    bptr, bedge = on.array("b_edge_ptr"), on.array("b_edge")
+    ie = bedge[bptr[ib]:bptr[ib + 1]]
+    assert wv.shape == (256, 4)
+    np.testing.assert_array_equal(wv[:, 0], on.array("ex")[ie])
+    np.testing.assert_allclose(wv[:, 1], 1.0 / rn.gamma, rtol=1e-15)
+    np.testing.assert_allclose(wv[:, 2], 1.0 / rn.gamma, rtol=1e-15)
+    np.testing.assert_allclose(wv[:, 3], rn.mach_inf * on.array("enx")[ie], rtol=1e-14, atol=1e-16)
+    # closed wall: sum(n a) = 0, so the freestream pressure integrates to zero force
+    assert abs((on.array("enx")[ie] * on.array("ea")[ie]).sum()) < 1e-12
