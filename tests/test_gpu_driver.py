@@ -78,6 +78,15 @@ def test_vortex_example_files_and_restart(tmp_path, vortex_mesh):
     assert f"number of nodes = {vortex_mesh.nnodes}" in cd or f"number of nodes = {vortex_mesh.nnodes}" in icd
     assert "        10          20" in icd
     assert os.path.exists(os.path.join(d, "log.grid"))
+    # the files the host program wrote parse with the readcd / readd mirror and convert like utils/ios2tecplot
+    from fvs2d_b200 import ios2tecplot, iosfile
+    hd = iosfile.read_cd(os.path.join(d, "inst"))
+    assert (hd.mnodes, hd.mcells, hd.mp, hd.mt, hd.itimes) == (vortex_mesh.nnodes, vortex_mesh.ncells, 2, 2, [10, 20])
+    np.testing.assert_array_equal(iosfile.read_record(os.path.join(d, "inst"), hd, 2, 1), inst[2].astype(np.float64))
+    plt = ios2tecplot.convert(os.path.join(d, "vortex.grid"), os.path.join(d, "inst"), os.path.join(d, "vis"), (2, 2, 1))
+    assert open(plt[0]).read().split("\n")[1] == 'VARIABLES ="x", "y", "rho", "u"'
+    hs = iosfile.read_cd(os.path.join(d, "save"))
+    assert hs.m1 == vortex_mesh.ncells and hs.mp == 4 and hs.itimes == [20]
     # restart: save -> cont, ntstart = 21, 10 more steps == a straight 30-step oracle run
     shutil.copy(os.path.join(d, "save.cd"), os.path.join(d, "cont.cd"))
     shutil.copy(os.path.join(d, "save.s8"), os.path.join(d, "cont.s8"))
