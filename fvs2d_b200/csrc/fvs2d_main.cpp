@@ -8,8 +8,15 @@
 // (node-interpolated primitive variables, src/io.f90:60-144, src/interpolation.f90:62-123), save.cd + save.s8
 // (src/io.f90:95-113,156-178; ios format of src/ios_unstrc.f90:141-290: text header + big-endian
 // direct-access records), log_cp.plt / log_un.plt / log_clcd.plt when a wall boundary exists
-// (src/io.f90:340-449), log.grid, and in MMS mode (ntstart=0) the error_resid.plt row of test_resid
-// (src/test.f90:481-519).  All numerics of the hot path happen in libfvs2d_gpu.so; this file is I/O only.
+// (src/io.f90:340-449), log.fvs2d (src/input.f90:283-409), log.grid, and in MMS mode (ntstart=0) the error_resid.plt
+// row of test_resid (src/test.f90:481-519).  All numerics of the hot path happen in libfvs2d_gpu.so; this file is I/O only.
+//
+//   fvs2d_gpu.exe [device]     run (device = CUDA ordinal, default LOCAL_RANK / 0)
+//   fvs2d_gpu.exe --check      inputs + mesh pre-processing only (fvs2d_host_build: no GPU needed): writes log.fvs2d and
+//                              log.grid, prints the mesh counts and exits -- grid_data_verify of src/grid_procs.f90:800-878
+// Start-up at large meshes: the .grid text is parsed with a single-pass strtod/strtol scanner over the
+// whole file, and a binary image <base>.gridbin (magic, counts, node_xy, cell_node) is written next to it and used on
+// later runs while it is newer than the text file (FVS2D_NO_GRIDBIN=1 disables both).
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -18,6 +25,7 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <sys/stat.h>
 #include <string>
 #include <vector>
 
@@ -164,28 +172,85 @@ struct Grid {
   std::vector<int> cptr, cnode, bn, bt, bc;
 };
 
+// <base>.gridbin: "FVS2DGRD" | int32 version, nnodes, ntri, nquad | node_xy (2*nnodes f64) | cell_node (int32, 0-based)
+const char kGridBinMagic[8] = {'F', 'V', 'S', '2', 'D', 'G', 'R', 'D'};
+bool gridbin_read(const std::string &base, Grid &g) {
+  struct stat st_txt, st_bin;
+  if (stat((base + ".gridbin").c_str(), &st_bin) != 0) return false;
+  if (stat((base + ".grid").c_str(), &st_txt) == 0 &&
+      (st_txt.st_mtim.tv_sec > st_bin.st_mtim.tv_sec ||
+       (st_txt.st_mtim.tv_sec == st_bin.st_mtim.tv_sec && st_txt.st_mtim.tv_nsec > st_bin.st_mtim.tv_nsec)))
+    return false;  // the text file changed after the image was written
+  FILE *f = std::fopen((base + ".gridbin").c_str(), "rb");
+  if (!f) return false;
+  char magic[8]; int32_t hdr[4];
+  bool ok = std::fread(magic, 1, 8, f) == 8 && std::memcmp(magic, kGridBinMagic, 8) == 0 && std::fread(hdr, 4, 4, f) == 4 && hdr[0] == 1;
+  if (ok) {
+    g.nnodes = hdr[1]; g.ntri = hdr[2]; g.nquad = hdr[3];
+    const size_t nn = 3 * (size_t)g.ntri + 4 * (size_t)g.nquad;
+    g.xy.resize(2 * (size_t)g.nnodes); g.cnode.resize(nn);
+    ok = std::fread(g.xy.data(), 8, g.xy.size(), f) == g.xy.size() && std::fread(g.cnode.data(), 4, nn, f) == nn;
+  }
+  std::fclose(f);
+  return ok;
+}
+void gridbin_write(const std::string &base, const Grid &g) {
+  FILE *f = std::fopen((base + ".gridbin").c_str(), "wb");
+  if (!f) return;  // read-only directory: the image is an optimisation only
+  const int32_t hdr[4] = {1, g.nnodes, g.ntri, g.nquad};
+  std::fwrite(kGridBinMagic, 1, 8, f); std::fwrite(hdr, 4, 4, f);
+  std::fwrite(g.xy.data(), 8, g.xy.size(), f); std::fwrite(g.cnode.data(), 4, g.cnode.size(), f);
+  std::fclose(f);
+}
+
 Grid grid_read(const std::string &base) {  // src/grid_procs.f90:63-164
   Grid g;
-  FILE *f = std::fopen((base + ".grid").c_str(), "r");
-  if (!f) stop("cannot find " + base + ".grid file!");
-  char line[512];
-  if (!std::fgets(line, sizeof line, f)) stop("grid file empty");
-  if (std::fscanf(f, "%d %d %d", &g.nnodes, &g.ntri, &g.nquad) != 3) stop("grid header");
-  g.xy.resize(2 * (size_t)g.nnodes);
-  for (int i = 0; i < g.nnodes; i++) {
-    char a[64], b[64];
-    if (std::fscanf(f, "%63s %63s", a, b) != 2) stop("grid nodes");
-    g.xy[2 * i] = freal(a); g.xy[2 * i + 1] = freal(b);
+  const bool use_bin = !std::getenv("FVS2D_NO_GRIDBIN");
+  if (!(use_bin && gridbin_read(base, g))) {
+    // whole file in memory, one pass: list-directed reads accept blanks / commas / newlines as separators and D exponents
+    FILE *f = std::fopen((base + ".grid").c_str(), "rb");
+    if (!f) stop("cannot find " + base + ".grid file!");
+    std::fseek(f, 0, SEEK_END);
+    const long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    std::vector<char> buf((size_t)sz + 1);
+    if (std::fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) stop("grid file: short read");
+    std::fclose(f);
+    buf[sz] = 0;
+    char *p = buf.data();
+    while (*p && *p != '\n') p++;  // line 1 is a comment
+    auto skip = [&]() { while (*p == ' ' || *p == ',' || *p == '\n' || *p == '\r' || *p == '\t') p++; };
+    auto next_int = [&](const char *what) -> int {
+      skip();
+      char *e; const long v = std::strtol(p, &e, 10);
+      if (e == p) stop(std::string("grid ") + what);
+      p = e;
+      return (int)v;
+    };
+    auto next_real = [&](const char *what) -> double {
+      skip();
+      char *e; double v = std::strtod(p, &e);
+      if (e == p) stop(std::string("grid ") + what);
+      if (*e == 'd' || *e == 'D') {  // Fortran D exponent: strtod stopped at the mantissa
+        char *e2; const long ex = std::strtol(e + 1, &e2, 10);
+        if (e2 != e + 1) { v *= std::pow(10.0, (double)ex); e = e2; }
+      }
+      p = e;
+      return v;
+    };
+    g.nnodes = next_int("header"); g.ntri = next_int("header"); g.nquad = next_int("header");
+    if (g.nnodes <= 0 || g.ntri < 0 || g.nquad < 0) stop("grid header");
+    while (*p && *p != '\n') p++;  // a list-directed read ignores the rest of the header record
+    g.xy.resize(2 * (size_t)g.nnodes);
+    for (size_t i = 0; i < g.xy.size(); i++) g.xy[i] = next_real("nodes");
+    const size_t nn = 3 * (size_t)g.ntri + 4 * (size_t)g.nquad;
+    g.cnode.resize(nn);
+    for (size_t i = 0; i < nn; i++) g.cnode[i] = next_int("cells") - 1;
+    if (use_bin) gridbin_write(base, g);
   }
   const int nc = g.ntri + g.nquad;
   g.cptr.resize(nc + 1); g.cptr[0] = 0;
-  g.cnode.reserve(3 * (size_t)g.ntri + 4 * (size_t)g.nquad);
-  for (int i = 0; i < nc; i++) {
-    const int nv = i < g.ntri ? 3 : 4;
-    for (int k = 0; k < nv; k++) { int v; if (std::fscanf(f, "%d", &v) != 1) stop("grid cells"); g.cnode.push_back(v - 1); }
-    g.cptr[i + 1] = g.cptr[i] + nv;
-  }
-  std::fclose(f);
+  for (int i = 0; i < nc; i++) g.cptr[i + 1] = g.cptr[i] + (i < g.ntri ? 3 : 4);
   std::ifstream b(base + ".bc");
   if (!b) stop("cannot find " + base + ".bc file!");
   std::string s;
@@ -206,11 +271,72 @@ Grid grid_read(const std::string &base) {  // src/grid_procs.f90:63-164
   return g;
 }
 
+// log.fvs2d: the echo of the parsed input (src/input.f90:283-409), same lines and edit descriptors.  aN right-justifies a
+// shorter string in N columns (and keeps the leftmost N of a longer one).
+std::string fa(const std::string &t, size_t w) { return t.size() >= w ? t.substr(0, w) : std::string(w - t.size(), ' ') + t; }
+std::string ffix(double v, int w, int d) {
+  char b[64]; std::snprintf(b, sizeof b, "%*.*f", w, d, v);
+  std::string s = b;
+  return (int)s.size() > w ? std::string(w, '*') : s;  // Fortran fills an overflowing field with asterisks
+}
+void write_log_input(const Input &in) {
+  std::ofstream f("log.fvs2d");
+  const std::string bar(139, '='), dash(139, '-');
+  f << bar << "\n     FVM2D CODE                       \n" << bar << "\n";
+  f << fa("grid file name: ", 35) << in.base << ".grid\n" << fa("bc file name: ", 35) << in.base << ".bc\n";
+  f << fa("Reynolds number: ", 35) << fortran_e(in.rey, 16, 8) << "\n" << fa("Mach number: ", 35) << fortran_e(in.mach, 16, 8) << "\n"
+    << fa("Flow angle (deg): ", 35) << fortran_e(in.aoa, 16, 8) << "\n" << dash << "\n";
+  f << fa("Time-step: ", 35) << fortran_e(in.dt, 16, 8) << "\n" << fa("#s of total time-steps: ", 35) << in.ntimes << "\n"
+    << fa("#s of output solution files: ", 35) << in.nsaves << "\n";
+  if (in.nsaves > 0 && in.ntimes % in.nsaves == 0) f << fa("Interval to output solution files: ", 35) << in.ntimes / in.nsaves << "\n";
+  else if (in.nsaves > 0)
+    f << fa("Interval to output solution files: ", 35) << in.ntimes / in.nsaves + 1 << " & " << in.ntimes - (in.ntimes / in.nsaves + 1) * (in.nsaves - 1) << "\n";
+  if (in.steady) {
+    f << fa("Steady flow is computed: ", 35) << "local time-stepping is employed (input dt is ignored)\n";
+    f << fa("Local dt is computed based on CFL=", 35) << ffix(in.cfl, 4, 2) << "\n";
+  } else {
+    f << fa("Starting time-step: ", 35) << in.ntstart << "\n" << fa("t_inital: ", 35) << fortran_e((double)(in.ntstart - 1) * in.dt, 16, 8) << "\n"
+      << fa("t_final : ", 35) << fortran_e((double)(in.ntstart - 1) * in.dt + (double)in.ntimes * in.dt, 16, 8) << "\n";
+  }
+  const char *vort1 = " primative varialbes are initialized with isentropic vortex\n", *vort2 = " Code will read freestream parameters from fvs2d.vortex file\n";
+  if (in.ntstart < 1) f << " primative varialbes are initialized with manufactured solution\n";
+  else if (in.ntstart > 1) { f << " primative varialbes are initialized with continuation files\n"; if (in.vortex) f << vort1 << vort2; }
+  else if (in.vortex) f << vort1 << vort2;
+  else f << " primative varialbes are initialized with freestream values\n";
+  f << dash << "\n";
+  const bool any = in.lw[0] || in.lw[1] || in.lw[2] || in.lw[3];
+  if (any) f << fa(in.s8 ? " Write out following variables in double precision:" : " Write out following variables in single precision:", 52) << "\n";
+  const char *vn[4] = {" density", " u-velocity", " v-velcoity", " pressure"};
+  for (int v = 0; v < 4; v++) if (in.lw[v]) f << fa(vn[v], 52) << "\n";
+  f << " \n" << bar << "\n     Temporal & Spatial Discretization Schemes      \n" << bar << "\n";
+  const std::string gm = fa(" Cell-center gradient method:", 38);
+  if (in.grad == 1) f << gm << " Green-Gauss Cell-Base\n";
+  else if (in.grad == 2) f << gm << " Green-Gauss Node-Base\n";
+  else if (in.grad == 3) {
+    const std::string st = in.lsq_nn ? "node" : "face";
+    if (in.lsq_pow == 0.0) f << gm << " Unweigghted Least-Squeres based on " << st << " neighbor stencil\n";
+    else f << gm << " Weigghted (1/d^" << ffix(in.lsq_pow, 3, 1) << ") Least-Squeres based on " << st << " neighbor stencil\n";
+  }
+  const char *lim[4] = {" not applied", " Venkatakrishnan", " Barth and Jespersen", " Van Albada"};
+  if (in.limiter >= 0 && in.limiter <= 3) f << fa("Gradient limiter:", 38) << lim[in.limiter] << "\n";
+  const std::string fr = fa(" Face reconstruction method:", 38);
+  if (in.recon == 1) f << fr << " 1st-order upwind\n";
+  else if (in.recon == 2) f << fr << " 2nd-order upwind\n";
+  else if (in.recon == 3) f << fr << " UMUSCL with Kappa=" << ffix(in.umuscl, 8, 4) << "\n";
+  if (in.flux == 1) f << fa(" Inviscid flux discretization scheme:", 38) << " Roe\n";
+  f << dash << "\n" << fa(in.ssprk ? "Runge-Kutta SSP formualtion is employed" : "Runge-Kutta standard formualtion is employed", 50) << "\n";
+  f << fa("#s of stages for Runge-Kutta time-integration: ", 52) << in.rk_nstages << "\n"
+    << fa("Order of accuracy of Runge-Kutta time-integration: ", 52) << in.rk_order << "\n";
+  f << dash << "\n Transient output files         \n";
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
-  const int device = argc > 1 ? std::atoi(argv[1]) : -1;
+  const bool check_only = argc > 1 && std::string(argv[1]) == "--check";
+  const int device = (argc > 1 && !check_only) ? std::atoi(argv[1]) : -1;
   Input in = input_read();
+  write_log_input(in);
   Grid g = grid_read(in.base);
   const int nc = g.ntri + g.nquad;
 
@@ -233,9 +359,14 @@ int main(int argc, char **argv) {
   std::memcpy(c.mms_c, mms, sizeof mms);
   c.ngpus = 1;
 
-  check(fvs2d_gpu_init(&c, device));
-  check(fvs2d_gpu_set_mesh(g.nnodes, g.ntri, g.nquad, g.xy.data(), g.cptr.data(), g.cnode.data(), (int)g.bn.size(), g.bn.data(),
+  if (check_only)  // host half of set_mesh only: connectivity, geometry, gradient operator, renumbering (no CUDA call)
+    check(fvs2d_host_build(&c, 0, 1, g.nnodes, g.ntri, g.nquad, g.xy.data(), g.cptr.data(), g.cnode.data(), (int)g.bn.size(), g.bn.data(),
                            g.bt.data(), g.bc.data()));
+  else {
+    check(fvs2d_gpu_init(&c, device));
+    check(fvs2d_gpu_set_mesh(g.nnodes, g.ntri, g.nquad, g.xy.data(), g.cptr.data(), g.cnode.data(), (int)g.bn.size(), g.bn.data(),
+                             g.bt.data(), g.bc.data()));
+  }
   int sizes[10]; double scal[6];
   check(fvs2d_gpu_sizes(sizes)); check(fvs2d_gpu_scalars(scal));
   {  // log.grid (src/grid_procs.f90:857-878)
@@ -247,6 +378,13 @@ int main(int argc, char **argv) {
     std::snprintf(b, sizeof b, " Sum of the cell volumes via numerical cal: %.11E\n Sum of the cell volumes via Green theorem: %.11E\n\n"
                   " cell effective length, sqrt[sum(vol)/ncells]: %.11E\n cell effective length, sum[sqrt(vol)]/ncells: %.11E\n", scal[2], scal[3], scal[0], scal[1]);
     lg << b;
+  }
+
+  if (check_only) {
+    std::printf(" nodes=%d cells=%d (tri=%d quad=%d) edges=%d (interior=%d boundary=%d) interior cells=%d boundary cells=%d\n", sizes[0], sizes[1],
+                g.ntri, g.nquad, sizes[2], sizes[3], sizes[4], sizes[5], sizes[6]);
+    std::printf(" sum(vol)=%.11E green=%.11E lsq_verify=%.3E\n o.k. (check only)\n", scal[2], scal[3], scal[4]);
+    return 0;
   }
 
   // ---- initial condition or restart (src/initialize.f90:19-90)
