@@ -415,7 +415,8 @@ def main():
     if other:
         line["other_configs"] = other
     if not args.no_cpu_baseline:
-        cb, _ = cpu_baseline(args.workload, run, 4 if args.workload in ("c3", "c4") else 50)
+        # ~10 s of single-thread CPU work on the 1/16-size sibling (540 k cells x 24 RK4 steps at ~6.5 M cell-stages/s)
+        cb, _ = cpu_baseline(args.workload, run, 24 if args.workload in ("c3", "c4") else 300)
         line["cpu_baseline"] = cb
     print(json.dumps(line))
 
