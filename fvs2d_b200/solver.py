@@ -129,9 +129,10 @@ class Fvs2dGpu:
     def wall_values(self, ib: int) -> np.ndarray:
         """-> [nedges(ib), 4] = x_f, p_w, p_cell, u_n per edge of boundary ``ib`` (src/io.f90:340-449)."""
         bptr = capi.mesh_array("b_edge_ptr")
-        out = np.zeros((int(bptr[ib + 1] - bptr[ib]), 4))
+        n = int(bptr[ib + 1] - bptr[ib]) if 0 <= ib < len(bptr) - 1 else 0   # out of range: the library reports it
+        out = np.zeros((max(n, 1), 4))
         capi.check(self.L.fvs2d_gpu_wall_values(int(ib), capi.ptr(out)))
-        return out
+        return out[:n]
 
     # -- instrumentation ---------------------------------------------------------------------
     def set_option(self, key: str, value: int):
