@@ -300,7 +300,7 @@ template <int UM, bool STEADY, int RC>
 void launch_flux_one(const StageParams &S, const double *pin, double *pout) {
   const int nb = C->nblocks;
   if (C->tile_ok && C->opt_tile == 2) {
-    const size_t smem = kStages * pipe_stage_bytes<RC>(C->pm.S, C->pm.E) + 4 * sizeof(uint64_t) + (size_t)C->opt_smem_pad * 1024;
+    const size_t smem = kStages * pipe_stage_bytes<RC>(C->pm.S, C->pm.E) + 2 * kStages * sizeof(uint64_t) + (size_t)C->opt_smem_pad * 1024;
     static size_t configured = 0;
     if (configured < smem) {
       cudaFuncSetAttribute(k_flux_pipe<UM, STEADY, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -527,7 +527,10 @@ int fvs2d_gpu_set_mesh(int nnodes, int ntri, int nquad, const double *node_xy, c
     for (int i = 0; i < L.n_loc; i++) xy[i] = make_double2(L.xc[i], L.yc[i]);
     std::vector<double> vol(L.vol);
     vol.resize(C->np, 1.0);
-    if (dev_upload(d.exy, exy) || dev_upload(d.enxy, enxy) || dev_upload(d.ea, L.ea) || dev_upload(d.xy, xy) || dev_upload(d.vol, vol)) return 1;
+    std::vector<double> ivol(vol.size());
+    for (size_t i = 0; i < vol.size(); i++) ivol[i] = 1.0 / vol[i];
+    if (dev_upload(d.exy, exy) || dev_upload(d.enxy, enxy) || dev_upload(d.ea, L.ea) || dev_upload(d.xy, xy) || dev_upload(d.vol, vol) ||
+        dev_upload(d.ivol, ivol)) return 1;
   }
   C->tile_ok = L.tile_hc_max >= 0;
   if (C->tile_ok) {

@@ -50,6 +50,7 @@ struct DevMesh {
   const double *ea;           // edge length
   const double2 *xy;          // cell centroid
   const double *vol;
+  const double *ivol;         // 1/vol, rounded once on the host: -R/vol is a multiplication in the stage update
   const int *g_off, *g_idx;
   const double *g_cx, *g_cy, *c0x, *c0y;
   const int *bf_type, *bf_edge;
@@ -163,7 +164,9 @@ __device__ __forceinline__ void vortex_exact(const Phys &P, double t, double x, 
 // Roe flux with Harten's entropy fix, primitive inputs (src/flux_invscid.f90:37-136).
 // aL, aR only ever appear squared in the reference (HL = aL*aL/(gamma-1)+kL), so c2 = gamma*p/rho is
 // used directly; divisions are reciprocals shared between quotients; gog = gamma/(gamma-1).
-__device__ __forceinline__ void roe_flux(const Phys &P, const double L[4], const double R[4], const double nx,
+// Returns TWICE the flux and TWICE ws_max: the reference's factors 0.5 (:118-133) are folded by the callers into the
+// face area (0.5*a is exact, so the products are bitwise those of 0.5*(...)*a).
+__device__ __forceinline__ void roe_flux2(const Phys &P, const double L[4], const double R[4], const double nx,
                                          const double ny, double flux[4], double &ws_max) {
   const double gm1 = P.gm1, gog = P.gog;
   const double tx = -ny, ty = nx;
@@ -197,9 +200,10 @@ __device__ __forceinline__ void roe_flux(const Phys &P, const double L[4], const
   const double l4 = (dp + rad) * hia2;
   double w1 = fabs(un - a), w2 = fabs(un), w4 = fabs(un + a);
   const double dws = 1.0 / 5.0;
-  // Harten's entropy fix (src/flux_invscid.f90:97-101); 1/dws == 5 exactly
-  w1 = w1 < dws ? 0.5 * (w1 * w1 * 5.0 + dws) : w1;
-  w4 = w4 < dws ? 0.5 * (w4 * w4 * 5.0 + dws) : w4;
+  // Harten's entropy fix (src/flux_invscid.f90:97-101): 0.5*(w*w/dws + dws) = fma(w*w, 2.5, 0.5*dws) -- scaling by
+  // a power of two commutes with the rounding, so this is bitwise 0.5*fma(w*w, 5, dws)
+  w1 = w1 < dws ? fma(w1 * w1, 2.5, 0.5 * dws) : w1;
+  w4 = w4 < dws ? fma(w4 * w4, 2.5, 0.5 * dws) : w4;
   const double s1 = w1 * l1, s2 = w2 * l2, s3 = w2 * l3, s4 = w4 * l4;
   // diss_i = sum_j ws_j LdU_j R_ij, j = 1..4 in order (src/flux_invscid.f90:111-116)
   const double anx = a * nx, any = a * ny, una = un * a;
@@ -208,11 +212,16 @@ __device__ __forceinline__ void roe_flux(const Phys &P, const double L[4], const
   const double d2 = s1 * (v - any) + s2 * ty + s3 * v + s4 * (v + any);
   const double d3 = s1 * (H - una) + s2 * ut + s3 * tke + s4 * (H + una);
   const double mL = rhoL * unL, mR = rhoR * unR;
-  flux[0] = 0.5 * (mL + mR - d0);
-  flux[1] = 0.5 * (mL * uL + pL * nx + (mR * uR + pR * nx) - d1);
-  flux[2] = 0.5 * (mL * vL + pL * ny + (mR * vR + pR * ny) - d2);
-  flux[3] = 0.5 * (mL * HL + mR * HR - d3);
-  ws_max = 0.5 * (fabs(un) + a);
+  flux[0] = mL + mR - d0;
+  flux[1] = mL * uL + pL * nx + (mR * uR + pR * nx) - d1;
+  flux[2] = mL * vL + pL * ny + (mR * vR + pR * ny) - d2;
+  flux[3] = mL * HL + mR * HR - d3;
+  ws_max = fabs(un) + a;
+}
+
+// second-order upwind state (kappa = 0, no limiter): p + (x_f - x_c) . grad p as two fused multiply-adds
+__device__ __forceinline__ double recon_k0(const double p, const double gx, const double gy, const double dx, const double dy) {
+  return fma(dy, gy, fma(dx, gx, p));
 }
 
 // limiter function (src/gradient_limiter.f90:103-134); eps2 is precomputed per cell
@@ -229,7 +238,8 @@ __global__ void __launch_bounds__(256) k_prim(int n, int np, double gamma, const
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double r = q[i], ru = q[np + i], rv = q[2 * np + i], re = q[3 * np + i];
-  const double u = ru / r, v = rv / r;
+  const double ir = fast_rcp(r);  // the same reciprocal as the stage update, so a restart reproduces the run bitwise
+  const double u = ru * ir, v = rv * ir;
   double2 *p2 = reinterpret_cast<double2 *>(p);
   p2[i] = make_double2(r, u);
   p2[np + i] = make_double2(v, (gamma - 1.0) * (re - 0.5 * r * (u * u + v * v)));
@@ -369,6 +379,7 @@ __device__ __forceinline__ void block_sum_store(double val[NV], double *__restri
 
 // interior face: p0/me/phi0 = this cell's state, reconstruction increment and limiter; pj/ot/phij the
 // neighbour's.  The flux is evaluated in the edge's own orientation (L = c1, R = c2).
+// RC_K0: me / ot are the reconstructed STATES (recon_k0), for the other modes the increments (x_f - x_c) . grad p.
 template <int RC>
 __device__ __forceinline__ void interior_face(const Phys &P, const bool self_c1, const double p0[4], const double me[4],
                                               const double phi0, const double pj[4], const double ot[4], const double phij,
@@ -382,7 +393,7 @@ __device__ __forceinline__ void interior_face(const Phys &P, const bool self_c1,
     else {
       const double gL = self_c1 ? me[v] : ot[v], gR = self_c1 ? ot[v] : me[v];
       const double fL = self_c1 ? phi0 : phij, fR = self_c1 ? phij : phi0;
-      if (RC == RC_K0) { sL[v] = pL + gL; sR[v] = pR + gR; }
+      if (RC == RC_K0) { sL[v] = gL; sR[v] = gR; }
       else if (RC == RC_K0_PHI) { sL[v] = pL + fL * gL; sR[v] = pR + fR * gR; }
       else {
         const double gC = pR - pL;
@@ -392,11 +403,11 @@ __device__ __forceinline__ void interior_face(const Phys &P, const bool self_c1,
     }
   }
   double flux[4], ws;
-  roe_flux(P, sL, sR, nx, ny, flux, ws);
-  const double sa = self_c1 ? af : -af;
+  roe_flux2(P, sL, sR, nx, ny, flux, ws);
+  const double ha = 0.5 * af, sa = self_c1 ? ha : -ha;
 #pragma unroll
   for (int v = 0; v < 4; v++) acc[v] += flux[v] * sa;
-  wsacc += ws * af;
+  wsacc += ws * ha;
 }
 
 // boundary face: this cell is c1 (src/residual.f90:125-155); bcv = ghost state for freestream/dirichlet
@@ -406,7 +417,7 @@ __device__ __forceinline__ void boundary_face(const Phys &P, const int type, con
                                               const double af, double acc[4], double &wsacc) {
   double sL[4], sR[4];
 #pragma unroll
-  for (int v = 0; v < 4; v++) sL[v] = (RC == RC_FIRST) ? p0[v] : p0[v] + phi0 * me[v];
+  for (int v = 0; v < 4; v++) sL[v] = (RC == RC_FIRST) ? p0[v] : (RC == RC_K0) ? me[v] : p0[v] + phi0 * me[v];
   if (type == 2) {  // slip wall: mirror the normal velocity
     const double un = sL[1] * nx + sL[2] * ny;
     sR[0] = sL[0]; sR[3] = sL[3];
@@ -417,24 +428,28 @@ __device__ __forceinline__ void boundary_face(const Phys &P, const int type, con
     for (int v = 0; v < 4; v++) sR[v] = bcv[v];
   }
   double flux[4], ws;
-  roe_flux(P, sL, sR, nx, ny, flux, ws);
+  roe_flux2(P, sL, sR, nx, ny, flux, ws);
+  const double ha = 0.5 * af;
 #pragma unroll
-  for (int v = 0; v < 4; v++) acc[v] += flux[v] * af;
-  wsacc += ws * af;
+  for (int v = 0; v < 4; v++) acc[v] += flux[v] * ha;
+  wsacc += ws * ha;
 }
 
 // residual -> stage update of cell i with the cell's RK data already in registers (q0 = state at the
 // start of the step, fo = accumulated stage residuals, dl = dt_local of stages > 0);
 // returns (q_new - q0)^2 in dq2 on the last stage
+// ivol = 1/vol (rounded once on the host), vol_arr = the volumes (read only by the steady stage-0 local time step)
 template <int UM, bool STEADY>
-__device__ __forceinline__ void stage_update_pre(const Phys &P, const StageParams &S, const int i, const int np, const double vol,
+__device__ __forceinline__ void stage_update_pre(const Phys &P, const StageParams &S, const int i, const int np, const double ivol,
+                                                 const double *__restrict__ vol_arr,
                                                  const double q0[4], const double fo[4], const double dl_in, const double acc[4],
                                                  const double wsacc, double *__restrict__ q, double *__restrict__ f,
                                                  double *__restrict__ pout, double *__restrict__ dtl, double *__restrict__ resid_out,
                                                  double *__restrict__ ws_out, double dq2[4]) {
   double R[4];
+  const double niv = -ivol;
 #pragma unroll
-  for (int v = 0; v < 4; v++) R[v] = -acc[v] / vol;
+  for (int v = 0; v < 4; v++) R[v] = acc[v] * niv;
   if (UM == UM_RESID) {
 #pragma unroll
     for (int v = 0; v < 4; v++) resid_out[v * np + i] = R[v];
@@ -444,7 +459,7 @@ __device__ __forceinline__ void stage_update_pre(const Phys &P, const StageParam
   double h = S.h;
   if (STEADY) {
     double dl = dl_in;
-    if (S.stage == 0) { dl = P.cfl * vol / (0.5 * wsacc); dtl[i] = dl; }
+    if (S.stage == 0) { dl = P.cfl * vol_arr[i] / (0.5 * wsacc); dtl[i] = dl; }
     h = dl * S.h;
   }
   double qn[4];
@@ -462,8 +477,9 @@ __device__ __forceinline__ void stage_update_pre(const Phys &P, const StageParam
       if (!S.last) f[v * np + i] = fo[v] + R[v];
     }
   }
-  // primitive state for the next stage (cvar2pvar of the next compute_residual)
-  const double u = qn[1] / qn[0], vv = qn[2] / qn[0];
+  // primitive state for the next stage (cvar2pvar of the next compute_residual); 1/rho by fast_rcp
+  const double ir = fast_rcp(qn[0]);
+  const double u = qn[1] * ir, vv = qn[2] * ir;
   double2 *po = reinterpret_cast<double2 *>(pout);
   po[i] = make_double2(qn[0], u);
   po[np + i] = make_double2(vv, (P.gamma - 1.0) * (qn[3] - 0.5 * qn[0] * (u * u + vv * vv)));
@@ -496,13 +512,14 @@ __device__ __forceinline__ void stage_load(const StageParams &S, const int i, co
 }
 
 template <int UM, bool STEADY>
-__device__ __forceinline__ void stage_update(const Phys &P, const StageParams &S, const int i, const int np, const double vol,
+__device__ __forceinline__ void stage_update(const Phys &P, const StageParams &S, const int i, const int np, const double ivol,
+                                             const double *__restrict__ vol_arr,
                                              const double acc[4], const double wsacc, double *__restrict__ q,
                                              double *__restrict__ f, double *__restrict__ pout, double *__restrict__ dtl,
                                              double *__restrict__ resid_out, double *__restrict__ ws_out, double dq2[4]) {
   double q0[4], fo[4], dl;
   stage_load<UM, STEADY>(S, i, np, q, f, dtl, q0, fo, dl);
-  stage_update_pre<UM, STEADY>(P, S, i, np, vol, q0, fo, dl, acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
+  stage_update_pre<UM, STEADY>(P, S, i, np, ivol, vol_arr, q0, fo, dl, acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -539,11 +556,11 @@ __global__ void __launch_bounds__(kBlock) k_flux_rk(const DevMesh m, const Phys 
       const bool self_c1 = (fe & 1) == 0;
       const double2 fc = __ldg(&m.exy[ed]), fn = __ldg(&m.enxy[ed]);
       const double af = __ldg(&m.ea[ed]);
-      double me[4] = {0.0, 0.0, 0.0, 0.0};  // this cell's reconstruction increment (x_f - x_c) . grad p
+      double me[4] = {0.0, 0.0, 0.0, 0.0};  // this cell's reconstruction increment (x_f - x_c) . grad p (RC_K0: the state)
       if (RC != RC_FIRST) {
         const double dx = fc.x - c0.x, dy = fc.y - c0.y;
 #pragma unroll
-        for (int v = 0; v < 4; v++) me[v] = dx * g0x[v] + dy * g0y[v];
+        for (int v = 0; v < 4; v++) me[v] = RC == RC_K0 ? recon_k0(p0[v], g0x[v], g0y[v], dx, dy) : dx * g0x[v] + dy * g0y[v];
       }
       if (nb >= 0) {
         double pj[4], ot[4] = {0.0, 0.0, 0.0, 0.0};
@@ -556,7 +573,7 @@ __global__ void __launch_bounds__(kBlock) k_flux_rk(const DevMesh m, const Phys 
           const double2 cj = m.xy[nb];
           const double dx = fc.x - cj.x, dy = fc.y - cj.y;
 #pragma unroll
-          for (int v = 0; v < 4; v++) ot[v] = dx * gjx[v] + dy * gjy[v];
+          for (int v = 0; v < 4; v++) ot[v] = RC == RC_K0 ? recon_k0(pj[v], gjx[v], gjy[v], dx, dy) : dx * gjx[v] + dy * gjy[v];
           if (RC >= RC_K0_PHI) phij = phi[nb];
         }
         interior_face<RC>(P, self_c1, p0, me, phi0, pj, ot, phij, fn.x, fn.y, af, acc, wsacc);
@@ -569,7 +586,7 @@ __global__ void __launch_bounds__(kBlock) k_flux_rk(const DevMesh m, const Phys 
         boundary_face<RC>(P, type, p0, me, phi0, bcv, fn.x, fn.y, af, acc, wsacc);
       }
     }
-    stage_update<UM, STEADY>(P, S, i, np, m.vol[i], acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
+    stage_update<UM, STEADY>(P, S, i, np, m.ivol[i], m.vol, acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
   }
   if (UM != UM_RESID && S.last) block_sum_store<4>(dq2, partial);
 }
@@ -620,7 +637,14 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src) {  // L1-
 // line allocation -- pass B ran 25 % slower whenever 3 CTAs' shared memory pushed the carve-out from 196 to
 // 228 KB; the pair-interleaved layout exists to make every gather a 16-byte bypass copy.)
 constexpr int kPipeThreads = kBlock + 32;
-constexpr int kStages = 2;
+#ifndef FVS2D_STAGES
+#define FVS2D_STAGES 2
+#endif
+#ifndef FVS2D_FACE2
+#define FVS2D_FACE2 1   // two interior faces per loop iteration of a consumer thread (0: one; measured 2-3 % slower)
+#endif
+constexpr int kStages = FVS2D_STAGES;
+
 
 struct PipeMeta {
   const int4 *hdr;  // 2 x int4 per tile: {es, ne, hc_ptr, n_hc}, {he_ptr, n_he, fbase, fw}
@@ -709,7 +733,7 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
     int it = 0;
     for (int j = blockIdx.x; j < pm.ntiles; j += gridDim.x, it++) {
       const int t = tile_id(j);
-      const int s = it & (kStages - 1);
+      const int s = it % kStages;
       const uint32_t ph = (it / kStages) & 1;
       const int es = h0.x, ne = h0.y, hp = h0.z, nh = h0.w, ep = h1.x, nhe = h1.y, fbase = h1.z, fw = h1.w;
       const int jcc[3] = {jc[0], jc[1], jc[2]}, jee[3] = {je[0], je[1], je[2]};
@@ -753,16 +777,16 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
   int it = 0;
   for (int j = blockIdx.x; j < pm.ntiles; j += gridDim.x, it++) {
     const int t = pm.tile_list ? __ldg(&pm.tile_list[j]) : j;
-    const int s = it & (kStages - 1);
+    const int s = it % kStages;
     const uint32_t ph = (it / kStages) & 1;
     const int c0 = t * kBlock;
     const int ncell = min(kBlock, m.n_own - c0);
     const int i = c0 + tid;
     const bool live = tid < ncell;
-    double q0[4], fo[4], dl = 0.0, vol = 1.0;
+    double q0[4], fo[4], dl = 0.0, ivol = 1.0;
     if (live) {  // RK data of this cell: in flight while the faces are computed
       stage_load<UM, STEADY>(S, i, np, q, f, dtl, q0, fo, dl);
-      vol = m.vol[i];
+      ivol = m.ivol[i];
     }
     const double2 *c2 = st_c2(s), *e2 = st_e2(s);
     const double *sphi = st_phi(s), *sea = st_ea(s);
@@ -797,18 +821,28 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
           double gL[4], gR[4];
           {
             const double2 a = cl[2 * SS], b = cl[3 * SS], c = cl[4 * SS], d = cl[5 * SS];
-            gL[0] = dxL * a.x + dyL * c.x; gL[1] = dxL * a.y + dyL * c.y;
-            gL[2] = dxL * b.x + dyL * d.x; gL[3] = dxL * b.y + dyL * d.y;
+            if (RC == RC_K0) {
+              gL[0] = recon_k0(sL[0], a.x, c.x, dxL, dyL); gL[1] = recon_k0(sL[1], a.y, c.y, dxL, dyL);
+              gL[2] = recon_k0(sL[2], b.x, d.x, dxL, dyL); gL[3] = recon_k0(sL[3], b.y, d.y, dxL, dyL);
+            } else {
+              gL[0] = dxL * a.x + dyL * c.x; gL[1] = dxL * a.y + dyL * c.y;
+              gL[2] = dxL * b.x + dyL * d.x; gL[3] = dxL * b.y + dyL * d.y;
+            }
           }
           {
             const double2 a = cr[2 * SS], b = cr[3 * SS], c = cr[4 * SS], d = cr[5 * SS];
-            gR[0] = dxR * a.x + dyR * c.x; gR[1] = dxR * a.y + dyR * c.y;
-            gR[2] = dxR * b.x + dyR * d.x; gR[3] = dxR * b.y + dyR * d.y;
+            if (RC == RC_K0) {
+              gR[0] = recon_k0(sR[0], a.x, c.x, dxR, dyR); gR[1] = recon_k0(sR[1], a.y, c.y, dxR, dyR);
+              gR[2] = recon_k0(sR[2], b.x, d.x, dxR, dyR); gR[3] = recon_k0(sR[3], b.y, d.y, dxR, dyR);
+            } else {
+              gR[0] = dxR * a.x + dyR * c.x; gR[1] = dxR * a.y + dyR * c.y;
+              gR[2] = dxR * b.x + dyR * d.x; gR[3] = dxR * b.y + dyR * d.y;
+            }
           }
 #pragma unroll
           for (int v = 0; v < 4; v++) {
             const double pL = sL[v], pR = sR[v];
-            if (RC == RC_K0) { sL[v] = pL + gL[v]; sR[v] = pR + gR[v]; }
+            if (RC == RC_K0) { sL[v] = gL[v]; sR[v] = gR[v]; }  // already the states (recon_k0 above)
             else if (RC == RC_K0_PHI) { sL[v] = pL + fL * gL[v]; sR[v] = pR + fR * gR[v]; }
             else {
               // boundary faces carry no kappa term (src/residual.f90:128)
@@ -832,13 +866,40 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
           }
         }
         double flux[4], ws;
-        roe_flux(P, sL, sR, nx, ny, flux, ws);
-        const double sa = self_c1 ? af : -af;
+        roe_flux2(P, sL, sR, nx, ny, flux, ws);
+        const double ha = 0.5 * af, sa = self_c1 ? ha : -ha;
 #pragma unroll
         for (int v = 0; v < 4; v++) acc[v] += flux[v] * sa;
-        wsacc += ws * af;
+        wsacc += ws * ha;
       };
       bool has_bnd = false;
+#if FVS2D_FACE2
+      {
+        // two interior faces per iteration in one basic block, so the two independent flux evaluations interleave
+        int k = 0;
+#pragma unroll 1
+        for (; k + 1 < fw; k += 2) {
+          const uint32_t pk0 = sf[k * kBlock + tid], pk1 = sf[(k + 1) * kBlock + tid];
+          const uint32_t n0 = pk0 & 0xFFFFu, n1 = pk1 & 0xFFFFu;
+          has_bnd = has_bnd || n0 == 0xFFFFu || n1 == 0xFFFFu;
+          if (n0 < 0xFFFEu && n1 < 0xFFFEu) {
+            face(pk0, k, std::false_type{});
+            face(pk1, k + 1, std::false_type{});
+          } else {
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+              const uint32_t pk = h ? pk1 : pk0;
+              if ((pk & 0xFFFFu) < 0xFFFEu) face(pk, k + h, std::false_type{});
+            }
+          }
+        }
+        if (k < fw) {
+          const uint32_t pk = sf[k * kBlock + tid], ns = pk & 0xFFFFu;
+          if (ns == 0xFFFFu) has_bnd = true;
+          else if (ns != 0xFFFEu) face(pk, k, std::false_type{});
+        }
+      }
+#else
       uint32_t pk_next = fw > 0 ? sf[tid] : 0xFFFEu;
 #pragma unroll 1
       for (int k = 0; k < fw; k++) {
@@ -849,6 +910,7 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
         if (ns == 0xFFFFu) { has_bnd = true; continue; }
         face(pk, k, std::false_type{});
       }
+#endif
       if (has_bnd) {
 #pragma unroll 1
         for (int k = 0; k < fw; k++) {
@@ -858,7 +920,7 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
       }
     }
     mbar_arrive(&empty[s]);  // this thread is done reading stage s
-    if (live) stage_update_pre<UM, STEADY>(P, S, i, np, vol, q0, fo, dl, acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
+    if (live) stage_update_pre<UM, STEADY>(P, S, i, np, ivol, m.vol, q0, fo, dl, acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
   }
   if (UM != UM_RESID && S.last) {
     // sum of (q - q0)^2 over this CTA's cells: warp shuffles, then the consumer warps through smem
