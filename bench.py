@@ -397,7 +397,7 @@ def main():
         tr = json.load(open(tpath)).get(args.workload)
         if tr:
             roof["traffic"] = tr / 1e9  # GB per launch, from the committed ncu capture
-            roof["traffic_unit"] = "GB per launch (ncu dram__bytes_read+write, profiles/r1_ncu_summary.md)"
+            roof["traffic_unit"] = "GB per launch (ncu dram__bytes_read+write, profiles/r1e_ncu_summary.md)"
             roof["alg_GB_per_launch"] = bB * n_own / 1e9
     roof["frac"] = roof["achieved"] / peak
     stage = {"alg_bytes_per_cell_stage": bA + bB, "achieved_GBs": (bA + bB) * ncells * 4 * K / (dev_ms * 1e-3) / 1e9}
