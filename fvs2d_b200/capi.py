@@ -89,8 +89,9 @@ def ptr(a):
 _INT_ARRAYS = {"en1", "en2", "ec1", "ec2", "cedge", "nghbre", "cell_intr", "b_edge", "b_edge_ptr", "grad_ptr", "grad_idx",
                "perm", "f_off", "f_nbr", "f_edge", "g_off", "g_idx", "orig_id", "loc2new", "bf_type", "bf_edge", "peers",
                "send_ptr", "send_idx", "recv_begin", "recv_count", "tile_es", "tile_ne", "tile_hc_ptr", "tile_he_ptr",
-               "tile_hc_idx", "tile_he_idx", "f_bf", "tile_hdr", "t_bf"}
-_U32_ARRAYS = {"f_pack"}
+               "tile_hc_idx", "tile_he_idx", "f_bf", "tile_hdr", "t_bf", "fz_hdr", "fz_h2_idx", "fz_info"}
+_U32_ARRAYS = {"f_pack", "t_pack"}
+_U16_ARRAYS = {"fz_gslot"}
 _BYTE_ARRAYS = {"is_intr"}
 
 
@@ -99,7 +100,7 @@ def mesh_array(name: str) -> np.ndarray:
     n = L.fvs2d_gpu_mesh_array(name.encode(), None)
     if n < 0:
         raise Fvs2dError(L.fvs2d_gpu_last_error().decode())
-    dt = np.int32 if name in _INT_ARRAYS else np.uint8 if name in _BYTE_ARRAYS else np.uint32 if name in _U32_ARRAYS else np.float64
+    dt = np.int32 if name in _INT_ARRAYS else np.uint8 if name in _BYTE_ARRAYS else np.uint32 if name in _U32_ARRAYS else np.uint16 if name in _U16_ARRAYS else np.float64
     out = np.zeros(n, dtype=dt)
     if n:
         L.fvs2d_gpu_mesh_array(name.encode(), ptr(out))

@@ -18,6 +18,7 @@
 #include "../../include/fvs2d_gpu.h"
 #include "host_mesh.hpp"
 #include "kernels.cuh"
+#include "kernels_fused.cuh"
 #include "layout.hpp"
 
 using namespace fvs2d;
@@ -89,6 +90,9 @@ struct Ctx {
   int opt_overlap = 1;   // multi-GPU: overlap the halo exchanges with interior-tile work (second stream)
   int opt_smem_pad = 0;  // experiment: extra dynamic shared memory (KB) per pass-B CTA (shrinks the L1 carve-out)
   int opt_carveout = -1; // experiment: preferred shared-memory carve-out of the pass-B kernel in KB (-1: driver default)
+  int opt_fuse = 0;      // one kernel per stage (k_stage_fused) where it applies: single GPU, kappa = 0, no limiter
+  int fz_state = 0;      // 0 not prepared, 1 ready, -1 not applicable to this mesh / scheme
+  FusedMeta fm{};
   cudaStream_t sx = nullptr;  // exchange stream
   cudaEvent_t e_a = nullptr, e_g = nullptr, e_b = nullptr, e_p = nullptr;
   const int *d_tile_int = nullptr, *d_tile_bnd = nullptr;
@@ -154,6 +158,7 @@ void free_device() {
   C->logbuf = nullptr; C->log_cap = 0;
   C->d_n2c_ptr = C->d_n2c = nullptr; C->d_idw = nullptr; C->d_fnode = nullptr;
   C->d_be_cell = nullptr; C->d_be_xy = C->d_be_nxy = nullptr; C->d_be_out = nullptr;
+  C->fz_state = 0;
 }
 
 // ---- event-based kernel timing (option "timing") ------------------------------------------------
@@ -345,6 +350,86 @@ int launch_flux(int um, const StageParams &S, const double *pin, double *pout, c
   if (um == UM_RESID) launch_flux_rc<UM_RESID, false>(S, pin, pout);
   else if (um == UM_RK) { if (steady) launch_flux_rc<UM_RK, true>(S, pin, pout); else launch_flux_rc<UM_RK, false>(S, pin, pout); }
   else { if (steady) launch_flux_rc<UM_SSPRK, true>(S, pin, pout); else launch_flux_rc<UM_SSPRK, false>(S, pin, pout); }
+  C->last_launches++;
+  return 0;
+}
+
+// ---- one kernel per stage (option "fuse"): tables on first use, then k_stage_fused instead of pass A + pass B
+size_t fused_smem() {
+  const FusedMeta &fm = C->fm;
+  return kStages * fused_stage_bytes(fm.S1, fm.S2, fm.E, fm.TW, fm.W, fm.CG) + 2 * kStages * sizeof(uint64_t);
+}
+
+int ensure_fused() {
+  if (C->fz_state) return 0;
+  C->fz_state = -1;
+  if (C->nranks != 1 || !C->tile_ok || C->recon != RC_K0) return 0;
+  const std::string err = build_fused_tables(C->L);
+  if (!err.empty()) return fail("%s", err.c_str());
+  const Layout &L = C->L;
+  if (L.fz_built != 1) return 0;
+  FusedMeta &fm = C->fm;
+  const int F0 = L.g_form == 0 ? 1 : 0, nt = L.ntiles;
+  fm.W = L.fz_w; fm.CG = std::max(4, L.fz_w + F0);
+  fm.S1 = C->pm.S; fm.S2 = (L.fz_s2_max + 1) & ~1; fm.E = C->pm.E; fm.TW = L.fz_tw_max; fm.ntiles = nt;
+  if (fused_smem() > 227 * 1024) return 0;  // wide stencils (GGNB, LSQ-nn on some meshes): two-pass path
+  std::vector<int> hdr(12 * (size_t)nt);
+  for (int t = 0; t < nt; t++) {
+    std::copy(&L.tile_hdr[8 * (size_t)t], &L.tile_hdr[8 * (size_t)t] + 8, &hdr[12 * (size_t)t]);
+    std::copy(&L.fz_hdr[4 * (size_t)t], &L.fz_hdr[4 * (size_t)t] + 4, &hdr[12 * (size_t)t + 8]);
+  }
+  std::vector<double> gc;
+  fused_coeff_rows(L, (size_t)C->np, gc);
+  static_assert(sizeof(double2) == 2 * sizeof(double), "double2 layout");
+  const int *dh;
+  if (dev_upload(dh, hdr) || dev_upload(fm.h2_idx, L.fz_h2_idx) || dev_upload(fm.gslot, L.fz_gslot)) return 1;
+  {
+    const double *dgc;
+    if (dev_upload(dgc, gc)) return 1;
+    fm.gc2 = reinterpret_cast<const double2 *>(dgc);
+  }
+  fm.hdr = reinterpret_cast<const int4 *>(dh);
+  fm.hc_idx = C->pm.hc_idx; fm.he_idx = C->pm.he_idx; fm.t_pack = C->pm.t_pack; fm.t_bf = C->pm.t_bf;
+  C->fz_state = 1;
+  return 0;
+}
+
+template <int UM, bool STEADY, int FORM>
+void launch_fused_one(const StageParams &S, const double *pin, double *pout) {
+  const size_t smem = fused_smem();
+  auto k3 = k_stage_fused<UM, STEADY, FORM, 3>;
+  auto k2 = k_stage_fused<UM, STEADY, FORM, 2>;
+  static size_t configured = 0;
+  static int per3 = 0, per2 = 0;
+  if (configured != smem) {  // the 128-register build when three CTAs fit an SM, else the build with more registers
+    cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per3, k3, kPipeThreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, k2, kPipeThreads, smem);
+    configured = smem;
+    if (getenv("FVS2D_DEBUG")) fprintf(stderr, "[fvs2d] k_stage_fused: %zu B smem/CTA, CTAs/SM %d (128 regs) / %d\n", smem, per3, per2);
+  }
+  const bool use3 = per3 >= 3 && (C->opt_ctas == 0 || C->opt_ctas >= 3);
+  int per_sm = std::max(1, use3 ? per3 : per2);
+  if (C->opt_ctas > 0) per_sm = std::min(per_sm, C->opt_ctas);
+  const int grid = std::min(C->fm.ntiles, C->nsm * per_sm);
+  if (grid > 0) {
+    if (use3) k3<<<grid, kPipeThreads, smem, C->st>>>(C->dm, C->fm, C->phys, S, pin, C->bc, C->q, C->f, pout, C->dtl, C->partial);
+    else k2<<<grid, kPipeThreads, smem, C->st>>>(C->dm, C->fm, C->phys, S, pin, C->bc, C->q, C->f, pout, C->dtl, C->partial);
+  }
+  C->nparts = grid;
+}
+
+int launch_fused(int um, const StageParams &S, const double *pin, double *pout) {
+  Span sp(2);
+  const bool steady = C->cfg.steady != 0, gg = C->L.g_form == 0;
+  if (um == UM_RK) {
+    if (steady) { if (gg) launch_fused_one<UM_RK, true, 0>(S, pin, pout); else launch_fused_one<UM_RK, true, 1>(S, pin, pout); }
+    else { if (gg) launch_fused_one<UM_RK, false, 0>(S, pin, pout); else launch_fused_one<UM_RK, false, 1>(S, pin, pout); }
+  } else {
+    if (steady) { if (gg) launch_fused_one<UM_SSPRK, true, 0>(S, pin, pout); else launch_fused_one<UM_SSPRK, true, 1>(S, pin, pout); }
+    else { if (gg) launch_fused_one<UM_SSPRK, false, 0>(S, pin, pout); else launch_fused_one<UM_SSPRK, false, 1>(S, pin, pout); }
+  }
   C->last_launches++;
   return 0;
 }
@@ -794,6 +879,8 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   for (auto &s : C->ev_spans) s.clear();
   const bool overlap = C->nranks > 1 && C->opt_overlap && C->tile_ok && C->opt_tile == 2;
   bool p_pending = false;
+  if (C->opt_fuse && ensure_fused()) return 1;
+  const bool fused = C->opt_fuse && C->fz_state == 1 && C->opt_tile == 2;
   {  // device step clock (src/runge_kutta.f90:135-145, 218-221): stage times are told + off[stage]
     StepClock hc{};
     hc.t1 = t1; hc.dt = dt; hc.istep = 0;
@@ -811,7 +898,9 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
       if (c.steady) S.h = c.ssprk ? (rk == 3 ? 1.0 / 4.0 : 1.0 / 3.0) : (rk == 2 ? 1.0 : rk == 3 ? 1.0 / 6.0 : 1.0 / 2.0);
       else S.h = C->h_rk[rk];
       if (launch_bc(rk)) return 1;
-      if (overlap) {
+      if (fused) {
+        if (launch_fused(um, S, C->pa, C->pb)) return 1;
+      } else if (overlap) {
         // interior tiles never read a ghost: they run while the exchanges are in flight on the second stream
         const bool grad = C->recon != RC_FIRST;
         if (grad) {
@@ -866,7 +955,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   int done = 0;
   if (nsub > 0) { if (run_step()) return 1; done = 1; }
   if (use_graph) {
-    if (C->graph_exec && (C->graph_logbuf != C->logbuf || C->graph_um != um * 16 + C->opt_tile * 4 + C->opt_ctas)) {
+    if (C->graph_exec && (C->graph_logbuf != C->logbuf || C->graph_um != (fused ? 256 : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas)) {
       cudaGraphExecDestroy(C->graph_exec);
       C->graph_exec = nullptr;
     }
@@ -881,7 +970,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
       CUDA_OK(cudaGraphInstantiate(&C->graph_exec, graph, 0));
       cudaGraphDestroy(graph);
       C->graph_logbuf = C->logbuf;
-      C->graph_um = um * 16 + C->opt_tile * 4 + C->opt_ctas;
+      C->graph_um = (fused ? 256 : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas;
     }
     const long per_step = C->last_launches;
     for (; done < nsub; done++) CUDA_OK(cudaGraphLaunch(C->graph_exec, C->st));
@@ -1042,10 +1131,27 @@ long fvs2d_gpu_mesh_array(const char *name, void *out) {
   RET("f_off", C->L.f_off) RET("f_nbr", C->L.f_nbr) RET("f_edge", C->L.f_edge) RET("g_off", C->L.g_off) RET("g_idx", C->L.g_idx)
   RET("g_cx", C->L.g_cx) RET("g_cy", C->L.g_cy) RET("orig_id", C->L.orig_id) RET("bf_type", C->L.bf_type) RET("bf_edge", C->L.bf_edge)
   RET("lex", C->L.ex) RET("ley", C->L.ey) RET("is_intr", C->L.is_intr)
+  RET("lea", C->L.ea) RET("lenx", C->L.enx) RET("leny", C->L.eny) RET("lxc", C->L.xc) RET("lyc", C->L.yc) RET("lvol", C->L.vol)
   RET("tile_es", C->L.tile_es) RET("tile_ne", C->L.tile_ne) RET("tile_hc_ptr", C->L.tile_hc_ptr) RET("tile_he_ptr", C->L.tile_he_ptr)
   RET("tile_hdr", C->L.tile_hdr) RET("t_pack", C->L.t_pack) RET("t_bf", C->L.t_bf)
   RET("tile_hc_idx", C->L.tile_hc_idx) RET("tile_he_idx", C->L.tile_he_idx) RET("f_pack", C->L.f_pack) RET("f_bf", C->L.f_bf)
   RET("grad_idx", C->grad.idx)
+  if (n.rfind("fz_", 0) == 0) {  // tables of the fused stage kernel, built on first request (single rank)
+    const std::string err = build_fused_tables(C->L);
+    if (!err.empty()) { fail("%s", err.c_str()); return -1; }
+    RET("fz_hdr", C->L.fz_hdr) RET("fz_h2_idx", C->L.fz_h2_idx) RET("fz_gslot", C->L.fz_gslot)
+    if (n == "fz_gc") {  // coefficient rows at the pitch the device uses (cells padded to 32)
+      std::vector<double> gc;
+      fused_coeff_rows(C->L, (size_t)(C->L.n_loc + 31) / 32 * 32, gc);
+      if (out) memcpy(out, gc.data(), gc.size() * 8);
+      return (long)gc.size();
+    }
+    if (n == "fz_info") {
+      const int info[5] = {C->L.fz_built, C->L.fz_w, C->L.fz_s2_max, C->L.fz_tw_max, C->L.fz_h2_max};
+      if (out) memcpy(out, info, sizeof info);
+      return 5;
+    }
+  }
 #undef RET
   if (n == "grad_ptr") {
     if (out) for (size_t i = 0; i < C->grad.ptr.size(); i++) ((int *)out)[i] = (int)C->grad.ptr[i];
@@ -1072,6 +1178,7 @@ int fvs2d_gpu_set_option(const char *key, int value) {
   if (k == "graph") { C->opt_graph = value; return 0; }
   if (k == "smem_pad") { C->opt_smem_pad = value; return 0; }
   if (k == "carveout") { C->opt_carveout = value; return 0; }
+  if (k == "fuse") { C->opt_fuse = value; return 0; }
   return fail("fvs2d_gpu_set_option: unknown option '%s'", key);
 }
 

@@ -1,0 +1,317 @@
+// kernels_fused.cuh -- ONE kernel per Runge-Kutta stage (option "fuse", single GPU, second-order upwind
+// reconstruction without limiter): pass A (gradients) folded into the persistent pass-B pipeline of kernels.cuh.
+//
+// Why: the two-pass schedule writes the gradients (64 B/cell) in pass A and reads them back in pass B, and reads the
+// primitive state twice -- 160 of the 512-528 algorithmic bytes of a stage ("B_alg - 128 B" is the
+// single-pass lower bound).  Here a tile stages, besides what k_flux_pipe stages,
+//   * the primitive state of "ring 2" (gradient-stencil members of the tile's cells and of its halo cells),
+//   * the gradient operator (coefficient rows + a per-tile table of 16-bit stencil slots) of tile + halo cells,
+// rebuilds the gradients of tile + halo in shared memory (phase 1; ~35 % redundant gradient evaluations, a few
+// per cent of the flux arithmetic), and after a consumer-side barrier runs the face loop of k_flux_pipe on them
+// (phase 2).  The gradient of a cell is evaluated with explicit fma() in one fixed order wherever it is rebuilt, so
+// every copy is bit-identical and both evaluations of an interior face flux still agree bitwise (discrete
+// conservation), and the result equals the two-pass path's bitwise as long as nvcc contracts k_gradient's
+// `a += c*d` into the same fma (it does).
+//
+// Reference: src/gradient_ggcb.f90:116-138, src/gradient_ggnb.f90:183-210, src/gradient_lsq.f90:393-401 (phase 1);
+// src/residual.f90:66-166, src/flux_invscid.f90:37-136, src/runge_kutta.f90:156-162,225-226,299-313,383-387 (phase 2).
+//
+// The face code is a copy of k_flux_pipe's RC_K0 branch on purpose: the production kernel stays untouched while this
+// variant is being measured.
+#pragma once
+#include "kernels.cuh"
+
+namespace fvs2d {
+
+struct FusedMeta {
+  const int4 *hdr;  // 3 x int4 per tile: {es, ne, hc_ptr, n1}, {he_ptr, n_he, fbase, fw}, {h2_ptr, n2, gs_base, gw}
+  const int *hc_idx, *he_idx, *h2_idx;
+  const uint32_t *t_pack;
+  const int *t_bf;
+  const uint16_t *gslot;  // per tile gw rows of pitch TW = roundup8(kBlock + n1)
+  const double2 *gc2;     // gradient coefficients (cx, cy), rows of pitch np: [c0 (FORM 0)], entry 0, entry 1, ...
+  int S1, S2, E, TW, W;   // smem pitches in elements: cells with gradient (tile + ring 1), all cells, edges; max TW; max entries
+  int CG;                 // rows of the coefficient / gradient block = max(4, W + (FORM == 0))
+  int ntiles;
+};
+
+// bytes of one stage:  p [2][S2] | coefficients -> gradients [CG][S1] | xy [S1] | exy, enxy [2][E] | ea [E] |
+//                      face table [4][kBlock] | {fw, fbase, gw, n1} | stencil slots [W][TW] (16 bit)
+__host__ __device__ inline size_t fused_stage_bytes(int S1, int S2, int E, int TW, int W, int CG) {
+  return (size_t)2 * S2 * 16 + (size_t)CG * S1 * 16 + (size_t)S1 * 16 + (size_t)E * 40 + 4 * kBlock * sizeof(uint32_t) + 16 +
+         (((size_t)W * TW * 2 + 15) & ~(size_t)15);
+}
+
+template <int UM, bool STEADY, int FORM, int CTAS>
+__global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused(const DevMesh m, const FusedMeta fm, const Phys P, const StageParams S,
+                                                                    const double *__restrict__ p, const double *__restrict__ bc,
+                                                                    double *__restrict__ q, double *__restrict__ f,
+                                                                    double *__restrict__ pout, double *__restrict__ dtl,
+                                                                    double *__restrict__ partial) {
+  constexpr int F0 = FORM == 0 ? 1 : 0;  // coefficient row 0 is c0 for the Green-Gauss form
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int S1 = fm.S1, S2 = fm.S2, EE = fm.E, CG = fm.CG, np = m.np;
+  const size_t stage_bytes = fused_stage_bytes(S1, S2, EE, fm.TW, fm.W, CG);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kStages * stage_bytes);
+  uint64_t *empty = full + kStages;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  auto st_p = [&](int s) { return reinterpret_cast<double2 *>(smem_raw + s * stage_bytes); };
+  auto st_cg = [&](int s) { return st_p(s) + 2 * S2; };
+  auto st_xy = [&](int s) { return st_cg(s) + CG * S1; };
+  auto st_e2 = [&](int s) { return st_xy(s) + S1; };
+  auto st_ea = [&](int s) { return reinterpret_cast<double *>(st_e2(s) + 2 * EE); };
+  auto st_f = [&](int s) { return reinterpret_cast<uint32_t *>(st_ea(s) + EE); };
+  auto st_misc = [&](int s) { return reinterpret_cast<int *>(st_f(s) + 4 * kBlock); };
+  auto st_gs = [&](int s) { return reinterpret_cast<uint16_t *>(st_misc(s) + 4); };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 33); mbar_init(&empty[s], kBlock); }
+  }
+  __syncthreads();
+
+  if (warp == kBlock / 32) {
+    // ================================ producer warp ================================
+    const double2 *p2 = reinterpret_cast<const double2 *>(p);
+    int4 h0 = make_int4(0, 0, 0, 0), h1 = make_int4(0, 0, 0, 0), h2 = make_int4(0, 0, 0, 0);
+    int jc[3] = {0, 0, 0}, je[3] = {0, 0, 0}, j2[3] = {0, 0, 0};
+    auto fetch_meta = [&](int t) {
+      h0 = __ldg(&fm.hdr[3 * t]);
+      h1 = __ldg(&fm.hdr[3 * t + 1]);
+      h2 = __ldg(&fm.hdr[3 * t + 2]);
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        jc[r] = (lane + 32 * r < h0.w) ? __ldg(&fm.hc_idx[h0.z + lane + 32 * r]) : 0;
+        je[r] = (lane + 32 * r < h1.y) ? __ldg(&fm.he_idx[h1.x + lane + 32 * r]) : 0;
+        j2[r] = (lane + 32 * r < h2.y) ? __ldg(&fm.h2_idx[h2.x + lane + 32 * r]) : 0;
+      }
+    };
+    if ((int)blockIdx.x < fm.ntiles) fetch_meta(blockIdx.x);
+    int it = 0;
+    for (int t = blockIdx.x; t < fm.ntiles; t += gridDim.x, it++) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      const int es = h0.x, ne = h0.y, hp = h0.z, n1 = h0.w, ep = h1.x, nhe = h1.y, fbase = h1.z, fw = h1.w;
+      const int h2p = h2.x, n2 = h2.y, gsb = h2.z, gw = h2.w;
+      const int rows = gw + F0;                  // coefficient rows of this tile
+      const int tw = (kBlock + n1 + 7) & ~7;     // pitch of its stencil-slot table
+      const int jcc[3] = {jc[0], jc[1], jc[2]}, jee[3] = {je[0], je[1], je[2]}, j22[3] = {j2[0], j2[1], j2[2]};
+      mbar_wait(&empty[s], ph ^ 1);
+      const int c0 = t * kBlock;
+      const int ncell = min(kBlock, m.n_own - c0);
+      double2 *sp = st_p(s), *scg = st_cg(s), *sxy = st_xy(s), *e2 = st_e2(s);
+      if (lane == 0) {
+        uint32_t *sf = st_f(s);
+        int *sh = st_misc(s);
+        sh[0] = fw; sh[1] = fbase; sh[2] = gw; sh[3] = n1;  // published to the consumers by the arrive below (release)
+        const uint32_t bytes_c = (uint32_t)ncell * 16u;
+        const uint32_t bytes_e = (uint32_t)ne * 16u, bytes_ea = (uint32_t)ne * 8u, bytes_f = (uint32_t)fw * kBlock * 4u;
+        const uint32_t bytes_gs = (uint32_t)gw * (uint32_t)tw * 2u;
+        mbar_expect_tx(&full[s], (3u + (uint32_t)rows) * bytes_c + 2u * bytes_e + bytes_ea + bytes_f + bytes_gs);
+        bulk_g2s(sp, p2 + c0, bytes_c, &full[s]);
+        bulk_g2s(sp + S2, p2 + (size_t)np + c0, bytes_c, &full[s]);
+        bulk_g2s(sxy, m.xy + c0, bytes_c, &full[s]);
+        for (int r = 0; r < rows; r++) bulk_g2s(scg + r * S1, fm.gc2 + (size_t)r * np + c0, bytes_c, &full[s]);
+        if (ne > 0) {
+          bulk_g2s(e2, m.exy + es, bytes_e, &full[s]);
+          bulk_g2s(e2 + EE, m.enxy + es, bytes_e, &full[s]);
+          bulk_g2s(st_ea(s), m.ea + es, bytes_ea, &full[s]);
+        }
+        if (fw > 0) bulk_g2s(sf, fm.t_pack + fbase, bytes_f, &full[s]);
+        if (gw > 0) bulk_g2s(st_gs(s), fm.gslot + gsb, bytes_gs, &full[s]);
+      }
+      auto gather_h1 = [&](int h, int j) {  // ring 1: state, centroid, gradient operator
+        cp_async16(sp + kBlock + h, p2 + j);
+        cp_async16(sp + S2 + kBlock + h, p2 + (size_t)np + j);
+        cp_async16(sxy + kBlock + h, m.xy + j);
+        for (int r = 0; r < rows; r++) cp_async16(scg + r * S1 + kBlock + h, fm.gc2 + (size_t)r * np + j);
+      };
+      auto gather_h2 = [&](int h, int j) {  // ring 2: state only
+        cp_async16(sp + kBlock + n1 + h, p2 + j);
+        cp_async16(sp + S2 + kBlock + n1 + h, p2 + (size_t)np + j);
+      };
+      auto gather_edge = [&](int h, int j) {
+        cp_async16(e2 + ne + h, m.exy + j);
+        cp_async16(e2 + EE + ne + h, m.enxy + j);
+        cp_async8(st_ea(s) + ne + h, m.ea + j);
+      };
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const int h = lane + 32 * r;
+        if (h < n1) gather_h1(h, jcc[r]);
+        if (h < n2) gather_h2(h, j22[r]);
+        if (h < nhe) gather_edge(h, jee[r]);
+      }
+      for (int h = lane + 96; h < n1; h += 32) gather_h1(h, __ldg(&fm.hc_idx[hp + h]));  // rare: more than 96 entries
+      for (int h = lane + 96; h < n2; h += 32) gather_h2(h, __ldg(&fm.h2_idx[h2p + h]));
+      for (int h = lane + 96; h < nhe; h += 32) gather_edge(h, __ldg(&fm.he_idx[ep + h]));
+      cp_async_mbar_arrive_noinc(&full[s]);
+      if (t + (int)gridDim.x < fm.ntiles) fetch_meta(t + gridDim.x);
+    }
+    return;
+  }
+
+  // ================================== consumer warps ==================================
+  double dq2[4] = {0.0, 0.0, 0.0, 0.0};
+  int it = 0;
+  for (int t = blockIdx.x; t < fm.ntiles; t += gridDim.x, it++) {
+    const int s = it % kStages;
+    const uint32_t ph = (it / kStages) & 1;
+    const int c0 = t * kBlock;
+    const int ncell = min(kBlock, m.n_own - c0);
+    const int i = c0 + tid;
+    const bool live = tid < ncell;
+    double q0[4], fo[4], dl = 0.0, ivol = 1.0;
+    if (live) {  // RK data of this cell: in flight while the gradients and the faces are computed
+      stage_load<UM, STEADY>(S, i, np, q, f, dtl, q0, fo, dl);
+      ivol = m.ivol[i];
+    }
+    const double2 *sp = st_p(s), *sxy = st_xy(s), *e2 = st_e2(s);
+    double2 *scg = st_cg(s);
+    const double *sea = st_ea(s);
+    const uint32_t *sf = st_f(s);
+    const uint16_t *sgs = st_gs(s);
+    mbar_wait(&full[s], ph);
+    const int fw = st_misc(s)[0], fbase = st_misc(s)[1], gw = st_misc(s)[2], n1 = st_misc(s)[3];
+    const int tw = (kBlock + n1 + 7) & ~7;
+
+    // ---- phase 1: gradients of the tile's cells and of ring 1, into the block that held their coefficients.
+    // Column c of that block is read and then overwritten by this thread only; every coefficient of the column has
+    // been consumed when the gradient is stored.
+    for (int c = tid; c < kBlock + n1; c += kBlock) {
+      if (c < kBlock && c >= ncell) continue;
+      double p0[4], ax[4], ay[4];
+      {
+        const double2 a = sp[c], b = sp[S2 + c];
+        p0[0] = a.x; p0[1] = a.y; p0[2] = b.x; p0[3] = b.y;
+      }
+      if (FORM == 0) {
+        const double2 cc = scg[c];
+#pragma unroll
+        for (int v = 0; v < 4; v++) { ax[v] = cc.x * p0[v]; ay[v] = cc.y * p0[v]; }
+      } else {
+#pragma unroll
+        for (int v = 0; v < 4; v++) { ax[v] = 0.0; ay[v] = 0.0; }
+      }
+      for (int k = 0; k < gw; k++) {
+        const int js = sgs[k * tw + c];
+        const double2 cf = scg[(k + F0) * S1 + c];
+        const double2 a = sp[js], b = sp[S2 + js];
+        const double pj[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+          const double d = FORM == 0 ? pj[v] : pj[v] - p0[v];
+          ax[v] = fma(cf.x, d, ax[v]);
+          ay[v] = fma(cf.y, d, ay[v]);
+        }
+      }
+      scg[c] = make_double2(ax[0], ax[1]);
+      scg[S1 + c] = make_double2(ax[2], ax[3]);
+      scg[2 * S1 + c] = make_double2(ay[0], ay[1]);
+      scg[3 * S1 + c] = make_double2(ay[2], ay[3]);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");  // consumer warps only: all gradients are in place
+
+    // ---- phase 2: faces (k_flux_pipe's RC_K0 path on the rebuilt gradients)
+    double acc[4] = {0.0, 0.0, 0.0, 0.0}, wsacc = 0.0;
+    if (live) {
+      auto face = [&](const uint32_t pk, const int k, const auto bnd_tag) {
+        constexpr bool BND = decltype(bnd_tag)::value;
+        const int ns = pk & 0xFFFFu, eslot = (pk >> 16) & 0x7FFF;
+        const bool self_c1 = BND || (pk >> 31) == 0;
+        const double2 fc = e2[eslot], fn = e2[EE + eslot];
+        const double af = sea[eslot], nx = fn.x, ny = fn.y;
+        const int sl_ = self_c1 ? tid : ns, sr_ = (self_c1 && !BND) ? ns : tid;
+        double sL[4], sR[4];
+        {
+          const double2 a = sp[sl_], b = sp[S2 + sl_], xl = sxy[sl_];
+          const double2 ga = scg[sl_], gb = scg[S1 + sl_], gc = scg[2 * S1 + sl_], gd = scg[3 * S1 + sl_];
+          const double dx = fc.x - xl.x, dy = fc.y - xl.y;
+          sL[0] = recon_k0(a.x, ga.x, gc.x, dx, dy); sL[1] = recon_k0(a.y, ga.y, gc.y, dx, dy);
+          sL[2] = recon_k0(b.x, gb.x, gd.x, dx, dy); sL[3] = recon_k0(b.y, gb.y, gd.y, dx, dy);
+        }
+        if (!BND) {
+          const double2 a = sp[sr_], b = sp[S2 + sr_], xr = sxy[sr_];
+          const double2 ga = scg[sr_], gb = scg[S1 + sr_], gc = scg[2 * S1 + sr_], gd = scg[3 * S1 + sr_];
+          const double dx = fc.x - xr.x, dy = fc.y - xr.y;
+          sR[0] = recon_k0(a.x, ga.x, gc.x, dx, dy); sR[1] = recon_k0(a.y, ga.y, gc.y, dx, dy);
+          sR[2] = recon_k0(b.x, gb.x, gd.x, dx, dy); sR[3] = recon_k0(b.y, gb.y, gd.y, dx, dy);
+        } else {
+          const int b = __ldg(&fm.t_bf[fbase + k * kBlock + tid]);
+          const int type = __ldg(&m.bf_type[b]);
+          if (type == 2) {  // slip wall: mirror the normal velocity (src/residual.f90:200-204)
+            const double un = sL[1] * nx + sL[2] * ny;
+            sR[0] = sL[0]; sR[3] = sL[3];
+            sR[1] = sL[1] - 2.0 * un * nx;
+            sR[2] = sL[2] - 2.0 * un * ny;
+          } else {
+#pragma unroll
+            for (int v = 0; v < 4; v++) sR[v] = __ldg(&bc[v * m.nbf + b]);
+          }
+        }
+        double flux[4], ws;
+        roe_flux2(P, sL, sR, nx, ny, flux, ws);
+        const double ha = 0.5 * af, sa = self_c1 ? ha : -ha;
+#pragma unroll
+        for (int v = 0; v < 4; v++) acc[v] += flux[v] * sa;
+        wsacc += ws * ha;
+      };
+      bool has_bnd = false;
+      {
+        // two interior faces per iteration in one basic block, so the two independent flux evaluations interleave
+        int k = 0;
+#pragma unroll 1
+        for (; k + 1 < fw; k += 2) {
+          const uint32_t pk0 = sf[k * kBlock + tid], pk1 = sf[(k + 1) * kBlock + tid];
+          const uint32_t n0 = pk0 & 0xFFFFu, n1_ = pk1 & 0xFFFFu;
+          has_bnd = has_bnd || n0 == 0xFFFFu || n1_ == 0xFFFFu;
+          if (n0 < 0xFFFEu && n1_ < 0xFFFEu) {
+            face(pk0, k, std::false_type{});
+            face(pk1, k + 1, std::false_type{});
+          } else {
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+              const uint32_t pk = h ? pk1 : pk0;
+              if ((pk & 0xFFFFu) < 0xFFFEu) face(pk, k + h, std::false_type{});
+            }
+          }
+        }
+        if (k < fw) {
+          const uint32_t pk = sf[k * kBlock + tid], ns = pk & 0xFFFFu;
+          if (ns == 0xFFFFu) has_bnd = true;
+          else if (ns != 0xFFFEu) face(pk, k, std::false_type{});
+        }
+      }
+      if (has_bnd) {
+#pragma unroll 1
+        for (int k = 0; k < fw; k++) {
+          const uint32_t pk = sf[k * kBlock + tid];
+          if ((pk & 0xFFFFu) == 0xFFFFu) face(pk, k, std::true_type{});
+        }
+      }
+    }
+    // this thread's gradient stores (generic proxy) are ordered before the bulk copies (async proxy) that refill the stage
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive(&empty[s]);  // this thread is done with stage s
+    if (live) stage_update_pre<UM, STEADY>(P, S, i, np, ivol, m.vol, q0, fo, dl, acc, wsacc, q, f, pout, dtl, nullptr, nullptr, dq2);
+  }
+  if (S.last) {
+    // sum of (q - q0)^2 over this CTA's cells: warp shuffles, then the consumer warps through smem
+    __shared__ double red[4][kBlock / 32];
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      double x = dq2[v];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (lane == 0) red[v][warp] = x;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");
+    if (tid < 4) {
+      double ssum = 0.0;
+#pragma unroll
+      for (int w = 0; w < kBlock / 32; w++) ssum += red[tid][w];
+      partial[blockIdx.x * 4 + tid] = ssum;
+    }
+  }
+}
+
+}  // namespace fvs2d

@@ -350,4 +350,100 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
   return "";
 }
 
+std::string build_fused_tables(Layout &L) {
+  if (L.fz_built) return "";
+  L.fz_built = -1;
+  if (L.nranks != 1) return "build_fused_tables: single rank only";
+  if (L.tile_hc_max < 0) return "";  // no tile kernel for this mesh
+  const int nt = L.ntiles, nsl = L.nslices;
+  // stencil entries of a local cell: the live prefix of its sliced-ELL column (padding entries carry a zero
+  // coefficient and the cell's own id; an interior zero coefficient is kept, it costs nothing)
+  auto width = [&](int i) { return (L.g_off[(i >> 5) + 1] - L.g_off[i >> 5]) >> 5; };
+  int wmax = 0;
+  for (int s = 0; s < nsl; s++) wmax = std::max(wmax, (L.g_off[s + 1] - L.g_off[s]) >> 5);
+  L.fz_w = wmax;
+  std::vector<std::vector<int>> h2(nt);
+  std::vector<int> gw(nt, 0);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int t = 0; t < nt; t++) {
+    const int c0 = t * kTile, c1 = std::min(L.n_own, c0 + kTile);
+    const int *h1 = L.tile_hc_idx.data() + L.tile_hc_ptr[t];
+    const int n1 = L.tile_hc_ptr[t + 1] - L.tile_hc_ptr[t];
+    std::vector<int> &v = h2[t];
+    int w = 0;
+    auto visit = [&](int i) {
+      const int wi = width(i);
+      w = std::max(w, wi);
+      for (int k = 0; k < wi; k++) {
+        const int j = L.g_idx[L.g_off[i >> 5] + 32 * k + (i & 31)];
+        if (j >= c0 && j < c1) continue;
+        if (std::binary_search(h1, h1 + n1, j)) continue;
+        v.push_back(j);
+      }
+    };
+    for (int i = c0; i < c1; i++) visit(i);
+    for (int h = 0; h < n1; h++) visit(h1[h]);
+    std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end());
+    gw[t] = w;
+  }
+  L.fz_hdr.assign(4 * (size_t)nt, 0);
+  int64_t hp = 0, gs = 0;
+  for (int t = 0; t < nt; t++) {
+    const int n1 = L.tile_hc_ptr[t + 1] - L.tile_hc_ptr[t], n2 = (int)h2[t].size();
+    const int tw = (kTile + n1 + 7) & ~7;
+    int *h = &L.fz_hdr[4 * (size_t)t];
+    h[0] = (int)hp; h[1] = n2; h[2] = (int)gs; h[3] = gw[t];
+    hp += n2; gs += (int64_t)gw[t] * tw;
+    L.fz_h2_max = std::max(L.fz_h2_max, n2);
+    L.fz_s2_max = std::max(L.fz_s2_max, kTile + n1 + n2);
+    L.fz_tw_max = std::max(L.fz_tw_max, tw);
+    if (hp > INT32_MAX || gs > INT32_MAX) return "";  // tables too large for 32-bit offsets: stay on the two-pass path
+  }
+  if (L.fz_s2_max >= 0xFFFF) return "";
+  L.fz_h2_idx.resize(hp);
+  L.fz_gslot.assign(gs, 0);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int t = 0; t < nt; t++) {
+    const int c0 = t * kTile, c1 = std::min(L.n_own, c0 + kTile);
+    const int *h1 = L.tile_hc_idx.data() + L.tile_hc_ptr[t];
+    const int n1 = L.tile_hc_ptr[t + 1] - L.tile_hc_ptr[t];
+    const int tw = (kTile + n1 + 7) & ~7;
+    const std::vector<int> &v = h2[t];
+    const int *h = &L.fz_hdr[4 * (size_t)t];
+    std::copy(v.begin(), v.end(), L.fz_h2_idx.begin() + h[0]);
+    uint16_t *tab = L.fz_gslot.data() + h[2];
+    for (int k = 0; k < h[3]; k++)
+      for (int c = 0; c < tw; c++) tab[(size_t)k * tw + c] = (uint16_t)std::min(c, kTile + n1 - 1);  // default: itself
+    auto slot_of = [&](int j) -> int {
+      if (j >= c0 && j < c1) return j - c0;
+      const int *p1 = std::lower_bound(h1, h1 + n1, j);
+      if (p1 != h1 + n1 && *p1 == j) return kTile + (int)(p1 - h1);
+      return kTile + n1 + (int)(std::lower_bound(v.begin(), v.end(), j) - v.begin());
+    };
+    auto fill = [&](int i, int c) {
+      const int wi = width(i);
+      for (int k = 0; k < wi; k++) tab[(size_t)k * tw + c] = (uint16_t)slot_of(L.g_idx[L.g_off[i >> 5] + 32 * k + (i & 31)]);
+    };
+    for (int i = c0; i < c1; i++) fill(i, i - c0);
+    for (int hh = 0; hh < n1; hh++) fill(h1[hh], kTile + hh);
+  }
+  L.fz_built = 1;
+  return "";
+}
+
+void fused_coeff_rows(const Layout &L, size_t np, std::vector<double> &rows) {
+  const int F0 = L.g_form == 0 ? 1 : 0;
+  rows.assign((size_t)(L.fz_w + F0) * np * 2, 0.0);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < L.n_own; i++) {
+    const int sl = i >> 5, lane = i & 31, w = (L.g_off[sl + 1] - L.g_off[sl]) >> 5;
+    if (F0) { rows[2 * (size_t)i] = L.c0x[i]; rows[2 * (size_t)i + 1] = L.c0y[i]; }
+    for (int k = 0; k < w; k++) {
+      const int e = L.g_off[sl] + 32 * k + lane;
+      const size_t o = 2 * ((size_t)(k + F0) * np + i);
+      rows[o] = L.g_cx[e]; rows[o + 1] = L.g_cy[e];
+    }
+  }
+}
+
 }  // namespace fvs2d

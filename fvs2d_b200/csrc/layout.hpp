@@ -75,9 +75,28 @@ struct Layout {
   // peer or reads a ghost (through a face or the gradient stencil); all other tiles are "interior"
   std::vector<int> tile_int, tile_bnd;
   double lsq_verify_err = 0;  // max linear-exactness error over the owned cells (src/gradient_lsq.f90:490-529)
+  // ---- one-kernel-per-stage variant (k_stage_fused, single rank): the gradients of a tile's cells AND of its halo
+  // cells ("ring 1", tile_hc_idx) are rebuilt in shared memory, so a tile also stages "ring 2" = the gradient-stencil
+  // members of tile + ring 1 that are in neither (primitive state only) and the gradient operator of tile + ring 1.
+  // Slots of a tile: own cells [0, kTile), ring 1 [kTile, kTile+n1), ring 2 [kTile+n1, kTile+n1+n2).
+  // fz_gslot = per tile gw rows of pitch TW = roundup8(kTile+n1): entry (k, c) = slot of the k-th stencil member of
+  // the cell in slot c (same k order as g_idx; cells with fewer entries point at themselves, their coefficient is 0).
+  int fz_built = 0;            // 0 not built, 1 usable, -1 built but unusable for this mesh
+  int fz_w = 0;                // stencil entries per cell, maximum over the mesh (coefficient rows)
+  int fz_s2_max = 0, fz_tw_max = 0, fz_h2_max = 0;
+  std::vector<int> fz_hdr;     // 4 ints per tile {h2_ptr, n_h2, gs_base, gw}
+  std::vector<int> fz_h2_idx;  // ring-2 cells (local ids, ascending) of all tiles
+  std::vector<uint16_t> fz_gslot;
 };
 
 // Builds the layout of `rank` out of `nranks` (equal contiguous chunks of the Hilbert order).
 std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<int> &perm, int rank, int nranks, Layout &L);
+
+// Adds the fz_* tables of the fused stage kernel to a single-rank layout (on demand: they are only needed when the
+// "fuse" option is on).  Returns "" (then L.fz_built is 1 or -1) or an error message.
+std::string build_fused_tables(Layout &L);
+// Gradient coefficients in the fused kernel's form: rows of `np` (cx, cy) pairs -- row 0 = c0 for the Green-Gauss form,
+// then one row per stencil entry k (the sliced-ELL entry k of every cell; missing entries are zero).
+void fused_coeff_rows(const Layout &L, size_t np, std::vector<double> &rows);
 
 }  // namespace fvs2d
