@@ -93,6 +93,8 @@ struct Ctx {
   int opt_fuse = 0;      // one kernel per stage (k_stage_fused) where it applies: single GPU, kappa = 0, no limiter
   int fz_state = 0;      // 0 not prepared, 1 ready, -1 not applicable to this mesh / scheme
   FusedMeta fm{};
+  Fused2Meta fm2{};
+  bool fz2_ok = false;   // "fuse" = 2 (published face states) usable
   cudaStream_t sx = nullptr;  // exchange stream
   cudaEvent_t e_a = nullptr, e_g = nullptr, e_b = nullptr, e_p = nullptr;
   const int *d_tile_int = nullptr, *d_tile_bnd = nullptr;
@@ -376,7 +378,7 @@ int ensure_fused() {
   std::vector<int> hdr(12 * (size_t)nt);
   for (int t = 0; t < nt; t++) {
     std::copy(&L.tile_hdr[8 * (size_t)t], &L.tile_hdr[8 * (size_t)t] + 8, &hdr[12 * (size_t)t]);
-    std::copy(&L.fz_hdr[4 * (size_t)t], &L.fz_hdr[4 * (size_t)t] + 4, &hdr[12 * (size_t)t + 8]);
+    std::copy(&L.fz_hdr[8 * (size_t)t], &L.fz_hdr[8 * (size_t)t] + 4, &hdr[12 * (size_t)t + 8]);
   }
   std::vector<double> gc;
   fused_coeff_rows(L, (size_t)C->np, gc);
@@ -391,33 +393,62 @@ int ensure_fused() {
   fm.hdr = reinterpret_cast<const int4 *>(dh);
   fm.hc_idx = C->pm.hc_idx; fm.he_idx = C->pm.he_idx; fm.t_pack = C->pm.t_pack; fm.t_bf = C->pm.t_bf;
   C->fz_state = 1;
+  C->fz2_ok = false;
+  if (L.fz_v2) {  // second variant: published face states
+    Fused2Meta &f2 = C->fm2;
+    f2.hc_idx = fm.hc_idx; f2.he_idx = fm.he_idx; f2.h2_idx = fm.h2_idx; f2.t_bf = fm.t_bf; f2.gslot = fm.gslot; f2.gc2 = fm.gc2;
+    f2.H1 = fm.S1 - kBlock; f2.HP = fm.S2 - kBlock; f2.E = fm.E; f2.TW = fm.TW; f2.W = fm.W; f2.CG = fm.CG; f2.ntiles = nt;
+    f2.FW = 0;
+    for (int t = 0; t < nt; t++) f2.FW = std::max(f2.FW, L.tile_hdr[8 * (size_t)t + 7]);
+    f2.HF = (L.fz_hf_max + 3) & ~3;
+    f2.XR = std::max(3 + fm.W + F0, 2 * f2.FW + (2 * f2.HF + kBlock - 1) / kBlock);
+    if (kStages * fused2_stage_bytes(f2) + 2 * kStages * sizeof(uint64_t) <= 227 * 1024) {
+      std::vector<int> hdr4(16 * (size_t)nt, 0);
+      for (int t = 0; t < nt; t++) {
+        std::copy(&hdr[12 * (size_t)t], &hdr[12 * (size_t)t] + 12, &hdr4[16 * (size_t)t]);
+        hdr4[16 * (size_t)t + 12] = L.fz_hdr[8 * (size_t)t + 4];
+        hdr4[16 * (size_t)t + 13] = L.fz_hdr[8 * (size_t)t + 5];
+      }
+      const int *dh4;
+      if (dev_upload(dh4, hdr4) || dev_upload(f2.pack2, L.fz_pack2) || dev_upload(f2.hf, L.fz_hf)) return 1;
+      f2.hdr = reinterpret_cast<const int4 *>(dh4);
+      C->fz2_ok = true;
+    }
+  }
   return 0;
 }
 
-template <int UM, bool STEADY, int FORM>
-void launch_fused_one(const StageParams &S, const double *pin, double *pout) {
-  const size_t smem = fused_smem();
-  auto k3 = k_stage_fused<UM, STEADY, FORM, 3>;
-  auto k2 = k_stage_fused<UM, STEADY, FORM, 2>;
-  static size_t configured = 0;
-  static int per3 = 0, per2 = 0;
-  if (configured != smem) {  // the 128-register build when three CTAs fit an SM, else the build with more registers
+// persistent launch of one of the fused kernels: the 128-register build when three CTAs fit an SM, else the build
+// compiled for two CTAs per SM (more registers)
+template <class K, class Meta>
+void launch_persistent(K k3, K k2, const Meta &meta, size_t smem, const char *name, size_t &configured, int &per3, int &per2,
+                       const StageParams &S, const double *pin, double *pout) {
+  if (configured != smem) {
     cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per3, k3, kPipeThreads, smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, k2, kPipeThreads, smem);
     configured = smem;
-    if (getenv("FVS2D_DEBUG")) fprintf(stderr, "[fvs2d] k_stage_fused: %zu B smem/CTA, CTAs/SM %d (128 regs) / %d\n", smem, per3, per2);
+    if (getenv("FVS2D_DEBUG")) fprintf(stderr, "[fvs2d] %s: %zu B smem/CTA, CTAs/SM %d (128 regs) / %d\n", name, smem, per3, per2);
   }
   const bool use3 = per3 >= 3 && (C->opt_ctas == 0 || C->opt_ctas >= 3);
   int per_sm = std::max(1, use3 ? per3 : per2);
   if (C->opt_ctas > 0) per_sm = std::min(per_sm, C->opt_ctas);
-  const int grid = std::min(C->fm.ntiles, C->nsm * per_sm);
-  if (grid > 0) {
-    if (use3) k3<<<grid, kPipeThreads, smem, C->st>>>(C->dm, C->fm, C->phys, S, pin, C->bc, C->q, C->f, pout, C->dtl, C->partial);
-    else k2<<<grid, kPipeThreads, smem, C->st>>>(C->dm, C->fm, C->phys, S, pin, C->bc, C->q, C->f, pout, C->dtl, C->partial);
-  }
+  const int grid = std::min(meta.ntiles, C->nsm * per_sm);
+  if (grid > 0) (use3 ? k3 : k2)<<<grid, kPipeThreads, smem, C->st>>>(C->dm, meta, C->phys, S, pin, C->bc, C->q, C->f, pout, C->dtl, C->partial);
   C->nparts = grid;
+}
+
+template <int UM, bool STEADY, int FORM>
+void launch_fused_one(const StageParams &S, const double *pin, double *pout) {
+  static size_t conf1 = 0, conf2 = 0;
+  static int p3a = 0, p2a = 0, p3b = 0, p2b = 0;
+  if (C->opt_fuse == 2 && C->fz2_ok)
+    launch_persistent(k_stage_fused2<UM, STEADY, FORM, 3>, k_stage_fused2<UM, STEADY, FORM, 2>, C->fm2,
+                      kStages * fused2_stage_bytes(C->fm2) + 2 * kStages * sizeof(uint64_t), "k_stage_fused2", conf2, p3b, p2b, S, pin, pout);
+  else
+    launch_persistent(k_stage_fused<UM, STEADY, FORM, 3>, k_stage_fused<UM, STEADY, FORM, 2>, C->fm, fused_smem(), "k_stage_fused",
+                      conf1, p3a, p2a, S, pin, pout);
 }
 
 int launch_fused(int um, const StageParams &S, const double *pin, double *pout) {
@@ -955,7 +986,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   int done = 0;
   if (nsub > 0) { if (run_step()) return 1; done = 1; }
   if (use_graph) {
-    if (C->graph_exec && (C->graph_logbuf != C->logbuf || C->graph_um != (fused ? 256 : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas)) {
+    if (C->graph_exec && (C->graph_logbuf != C->logbuf || C->graph_um != (fused ? 256 * C->opt_fuse : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas)) {
       cudaGraphExecDestroy(C->graph_exec);
       C->graph_exec = nullptr;
     }
@@ -970,7 +1001,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
       CUDA_OK(cudaGraphInstantiate(&C->graph_exec, graph, 0));
       cudaGraphDestroy(graph);
       C->graph_logbuf = C->logbuf;
-      C->graph_um = (fused ? 256 : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas;
+      C->graph_um = (fused ? 256 * C->opt_fuse : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas;
     }
     const long per_step = C->last_launches;
     for (; done < nsub; done++) CUDA_OK(cudaGraphLaunch(C->graph_exec, C->st));
@@ -1140,6 +1171,7 @@ long fvs2d_gpu_mesh_array(const char *name, void *out) {
     const std::string err = build_fused_tables(C->L);
     if (!err.empty()) { fail("%s", err.c_str()); return -1; }
     RET("fz_hdr", C->L.fz_hdr) RET("fz_h2_idx", C->L.fz_h2_idx) RET("fz_gslot", C->L.fz_gslot)
+    RET("fz_pack2", C->L.fz_pack2) RET("fz_hf", C->L.fz_hf)
     if (n == "fz_gc") {  // coefficient rows at the pitch the device uses (cells padded to 32)
       std::vector<double> gc;
       fused_coeff_rows(C->L, (size_t)(C->L.n_loc + 31) / 32 * 32, gc);
@@ -1147,9 +1179,9 @@ long fvs2d_gpu_mesh_array(const char *name, void *out) {
       return (long)gc.size();
     }
     if (n == "fz_info") {
-      const int info[5] = {C->L.fz_built, C->L.fz_w, C->L.fz_s2_max, C->L.fz_tw_max, C->L.fz_h2_max};
+      const int info[7] = {C->L.fz_built, C->L.fz_w, C->L.fz_s2_max, C->L.fz_tw_max, C->L.fz_h2_max, C->L.fz_v2, C->L.fz_hf_max};
       if (out) memcpy(out, info, sizeof info);
-      return 5;
+      return 7;
     }
   }
 #undef RET

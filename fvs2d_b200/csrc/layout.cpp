@@ -386,12 +386,12 @@ std::string build_fused_tables(Layout &L) {
     std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end());
     gw[t] = w;
   }
-  L.fz_hdr.assign(4 * (size_t)nt, 0);
+  L.fz_hdr.assign(8 * (size_t)nt, 0);
   int64_t hp = 0, gs = 0;
   for (int t = 0; t < nt; t++) {
     const int n1 = L.tile_hc_ptr[t + 1] - L.tile_hc_ptr[t], n2 = (int)h2[t].size();
     const int tw = (kTile + n1 + 7) & ~7;
-    int *h = &L.fz_hdr[4 * (size_t)t];
+    int *h = &L.fz_hdr[8 * (size_t)t];
     h[0] = (int)hp; h[1] = n2; h[2] = (int)gs; h[3] = gw[t];
     hp += n2; gs += (int64_t)gw[t] * tw;
     L.fz_h2_max = std::max(L.fz_h2_max, n2);
@@ -409,7 +409,7 @@ std::string build_fused_tables(Layout &L) {
     const int n1 = L.tile_hc_ptr[t + 1] - L.tile_hc_ptr[t];
     const int tw = (kTile + n1 + 7) & ~7;
     const std::vector<int> &v = h2[t];
-    const int *h = &L.fz_hdr[4 * (size_t)t];
+    const int *h = &L.fz_hdr[8 * (size_t)t];
     std::copy(v.begin(), v.end(), L.fz_h2_idx.begin() + h[0]);
     uint16_t *tab = L.fz_gslot.data() + h[2];
     for (int k = 0; k < h[3]; k++)
@@ -428,6 +428,48 @@ std::string build_fused_tables(Layout &L) {
     for (int hh = 0; hh < n1; hh++) fill(h1[hh], kTile + hh);
   }
   L.fz_built = 1;
+
+  // ---- second variant: face table with reverse face indices + the list of tile/ring-1 faces
+  if (L.tile_e_max >= 0x1000) return "";
+  std::vector<std::vector<uint32_t>> hf(nt);
+  L.fz_pack2.assign(L.t_pack.size(), 0xFFFEu);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int t = 0; t < nt; t++) {
+    const int c0 = t * kTile, c1 = std::min(L.n_own, c0 + kTile);
+    const int *th = &L.tile_hdr[8 * (size_t)t];
+    const int fbase = th[6];
+    for (int k = 0; k < th[7]; k++)
+      for (int j = 0; j < c1 - c0; j++) {
+        const uint32_t pk = L.t_pack[fbase + kTile * k + j];
+        uint32_t code = pk & 0xFFFFu, rev = 0;
+        const uint32_t es = (pk >> 16) & 0x7FFFu;
+        if (code < (uint32_t)kTile) {
+          // the same local edge in the neighbour's face list
+          const int i = c0 + j, nb = c0 + (int)code;
+          const int le = L.f_edge[L.f_off[i >> 5] + 32 * k + (i & 31)] >> 1;
+          const int wn = (L.f_off[(nb >> 5) + 1] - L.f_off[nb >> 5]) >> 5;
+          for (int kk = 0; kk < wn; kk++) {
+            const int e = L.f_off[nb >> 5] + 32 * kk + (nb & 31);
+            if (L.f_nbr[e] != kFacePad && (L.f_edge[e] >> 1) == le) rev = (uint32_t)kk;
+          }
+        } else if (code < 0xFFFEu) {
+          hf[t].push_back((code - kTile) | (es << 16));
+          code = (uint32_t)(kTile + hf[t].size() - 1);
+        }
+        L.fz_pack2[fbase + kTile * k + j] = code | (es << 16) | (rev << 28) | (pk & 0x80000000u);
+      }
+  }
+  int64_t fp = 0;
+  for (int t = 0; t < nt; t++) {
+    int *h = &L.fz_hdr[8 * (size_t)t];
+    h[4] = (int)fp; h[5] = (int)hf[t].size();
+    fp += ((int64_t)hf[t].size() + 3) & ~3;  // 16-byte granules (bulk copy)
+    L.fz_hf_max = std::max(L.fz_hf_max, (int)hf[t].size());
+    if (fp > INT32_MAX) return "";
+  }
+  L.fz_hf.assign(fp, 0);
+  for (int t = 0; t < nt; t++) std::copy(hf[t].begin(), hf[t].end(), L.fz_hf.begin() + L.fz_hdr[8 * (size_t)t + 4]);
+  L.fz_v2 = 1;
   return "";
 }
 

@@ -84,9 +84,17 @@ struct Layout {
   int fz_built = 0;            // 0 not built, 1 usable, -1 built but unusable for this mesh
   int fz_w = 0;                // stencil entries per cell, maximum over the mesh (coefficient rows)
   int fz_s2_max = 0, fz_tw_max = 0, fz_h2_max = 0;
-  std::vector<int> fz_hdr;     // 4 ints per tile {h2_ptr, n_h2, gs_base, gw}
+  std::vector<int> fz_hdr;     // 8 ints per tile {h2_ptr, n_h2, gs_base, gw, hf_ptr, n_hf, 0, 0}
   std::vector<int> fz_h2_idx;  // ring-2 cells (local ids, ascending) of all tiles
   std::vector<uint16_t> fz_gslot;
+  // second variant (k_stage_fused2, "fuse" = 2): every reconstructed face state is evaluated once, by the thread that
+  // holds the cell's gradient, and published in shared memory.  fz_pack2 = t_pack with the neighbour code of bits 0-15
+  // redefined -- < kTile: neighbour's slot in the tile, and bits 28-29 = index of this face in the NEIGHBOUR's face
+  // list; >= kTile: kTile + index into the tile's list of tile/ring-1 faces (fz_hf: ring-1 index | edge slot << 16);
+  // 0xFFFF boundary, 0xFFFE padding -- and the edge slot in bits 16-27.
+  int fz_v2 = 0;               // 1 when the tables below exist (edge slots fit 12 bits)
+  int fz_hf_max = 0;
+  std::vector<uint32_t> fz_pack2, fz_hf;
 };
 
 // Builds the layout of `rank` out of `nranks` (equal contiguous chunks of the Hilbert order).

@@ -13,6 +13,7 @@ sys.path.insert(0, ROOT)
 from fvs2d_b200 import config, meshgen, meshio, solver  # noqa: E402
 
 OUT = os.path.join(ROOT, "gpurun_out", "fused_check.txt")
+FUSE = tuple(int(x) for x in os.environ.get("FUSE", "1,2").split(","))
 os.makedirs(os.path.dirname(OUT), exist_ok=True)
 
 
@@ -51,14 +52,15 @@ def parity():
         gpu = solver.Fvs2dGpu(cfg, device=0)
         gpu.set_mesh(mesh)
         q0, r0, v0 = run(gpu, 10, 0)
-        q1, r1, v1 = run(gpu, 10, 1)
-        used = gpu.last_timing()["launches"]
-        dq = float(np.abs(q1 - q0).max() / np.abs(q0).max())
-        dr = float(np.abs(r1 - r0).max() / np.abs(r0).max())
-        good = dq <= 1e-12 and dr <= 1e-10 and np.isfinite(q1).all()
-        ok = ok and good
-        say("PARITY", name, f"cells {mesh.ncells} fused-vs-twopass state {dq:.3e} log_res {dr:.3e} bitwise {bool(np.array_equal(q0, q1))} "
-            f"launches/10 steps {used}", "ok" if good else "FAILED")
+        for fuse in FUSE:
+            q1, r1, v1 = run(gpu, 10, fuse)
+            used = gpu.last_timing()["launches"]
+            dq = float(np.abs(q1 - q0).max() / np.abs(q0).max())
+            dr = float(np.abs(r1 - r0).max() / np.abs(r0).max())
+            good = dq <= 1e-12 and dr <= 1e-10 and np.isfinite(q1).all()
+            ok = ok and good
+            say("PARITY", name, f"cells {mesh.ncells} fuse={fuse} vs two-pass: state {dq:.3e} log_res {dr:.3e} bitwise "
+                f"{bool(np.array_equal(q0, q1))} launches/10 steps {used}", "ok" if good else "FAILED")
         gpu.close()
     say("PARITY_OK" if ok else "PARITY_FAILED")
     return ok
@@ -78,7 +80,7 @@ def timing(which):
         gpu.set_mesh(mesh)
         say("TIME", w, f"cells {mesh.ncells} mesh+setup {time.time() - t:.1f}s")
         gpu.initialize_solution()
-        for fuse in (0, 1, 0, 1):
+        for fuse in (0,) + FUSE + (0,) + FUSE:
             gpu.set_option("fuse", fuse)
             gpu.set_option("timing", 0)
             gpu.time_integration(0.0, 5, logs=False)

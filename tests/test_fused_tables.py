@@ -25,7 +25,7 @@ def _emulate_residual(mesh, cfg, orc, time):
     np_ = (n_own + 31) // 32 * 32
     gc = A("fz_gc").reshape(W + F0, np_, 2)
     hdr = A("tile_hdr").reshape(-1, 8)
-    fz = A("fz_hdr").reshape(-1, 4)
+    fz = A("fz_hdr").reshape(-1, 8)[:, :4]
     hc_idx, he_idx, h2_idx = A("tile_hc_idx"), A("tile_he_idx"), A("fz_h2_idx")
     gslot, t_pack, t_bf = A("fz_gslot"), A("t_pack"), A("t_bf")
     bf_type, bf_edge = A("bf_type"), A("bf_edge")
@@ -34,6 +34,9 @@ def _emulate_residual(mesh, cfg, orc, time):
     p = orc.array("pvar").reshape(-1, 4)[orig]          # primitive state in the library's cell order
     resid = np.zeros((n_own, 4))
     n2_seen = 0
+    assert info[5] == 1, "tables of the second fused variant missing"
+    pack2, hf_all = A("fz_pack2"), A("fz_hf")
+    fz8 = A("fz_hdr").reshape(-1, 8)
     for t in range(len(hdr)):
         es, ne, hp, n1, ep, nhe, fbase, fw = (int(x) for x in hdr[t])
         h2p, n2, gsb, gw = (int(x) for x in fz[t])
@@ -48,6 +51,30 @@ def _emulate_residual(mesh, cfg, orc, time):
         ids[TILE + n1:] = h2_idx[h2p:h2p + n2]
         eids = np.concatenate([np.arange(es, es + ne), he_idx[ep:ep + nhe]])
         tab = gslot[gsb:gsb + gw * tw].reshape(gw, tw).astype(np.int64)
+        # second variant: the face words point back at each other / at the list of tile/ring-1 faces
+        hfp, nhf = int(fz8[t, 4]), int(fz8[t, 5])
+        assert hfp % 4 == 0 and nhf <= int(info[6])
+        seen = set()
+        for j in range(ncell):
+            for k in range(fw):
+                w1, w2 = int(t_pack[fbase + k * TILE + j]), int(pack2[fbase + k * TILE + j])
+                ns, code = w1 & 0xFFFF, w2 & 0xFFFF
+                assert (w2 >> 31) == (w1 >> 31)
+                if ns >= 0xFFFE:
+                    assert code == ns
+                    continue
+                assert ((w2 >> 16) & 0xFFF) == ((w1 >> 16) & 0x7FFF)
+                if ns < TILE:
+                    kr = (w2 >> 28) & 3
+                    back = int(pack2[fbase + kr * TILE + ns])
+                    assert code == ns and (back & 0xFFFF) == j and ((back >> 16) & 0xFFF) == ((w2 >> 16) & 0xFFF)
+                    assert ((back >> 28) & 3) == k and (back >> 31) != (w2 >> 31)
+                else:
+                    e = code - TILE
+                    assert 0 <= e < nhf and e not in seen
+                    seen.add(e)
+                    assert int(hf_all[hfp + e]) == (ns - TILE) | (((w1 >> 16) & 0x7FFF) << 16)
+        assert len(seen) == nhf
         # phase 1: gradients of the columns of tile + ring 1
         cols = np.concatenate([np.arange(ncell), np.arange(TILE, TILE + n1)])
         cid = ids[cols]
