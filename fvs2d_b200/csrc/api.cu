@@ -90,11 +90,14 @@ struct Ctx {
   int opt_overlap = 1;   // multi-GPU: overlap the halo exchanges with interior-tile work (second stream)
   int opt_smem_pad = 0;  // experiment: extra dynamic shared memory (KB) per pass-B CTA (shrinks the L1 carve-out)
   int opt_carveout = -1; // experiment: preferred shared-memory carve-out of the pass-B kernel in KB (-1: driver default)
-  int opt_fuse = 0;      // one kernel per stage (k_stage_fused) where it applies: single GPU, kappa = 0, no limiter
+  int opt_fuse = -1;     // one kernel per stage where it applies (single GPU, kappa = 0, no limiter): 0 never, -1 automatic
+                         // (second variant, only where three CTAs per SM fit), 1 / 2 / 3 force k_stage_fused / its variants
   int fz_state = 0;      // 0 not prepared, 1 ready, -1 not applicable to this mesh / scheme
   FusedMeta fm{};
   Fused2Meta fm2{};
   bool fz2_ok = false;   // "fuse" = 2 (published face states) usable
+  bool fz3_ok = false;   // "fuse" = 3 (+ every face flux once) usable
+  bool fz_auto_ok = false;  // the automatic setting uses the fused kernel on this mesh
   cudaStream_t sx = nullptr;  // exchange stream
   cudaEvent_t e_a = nullptr, e_g = nullptr, e_b = nullptr, e_p = nullptr;
   const int *d_tile_int = nullptr, *d_tile_bnd = nullptr;
@@ -365,16 +368,38 @@ size_t fused_smem() {
 int ensure_fused() {
   if (C->fz_state) return 0;
   C->fz_state = -1;
+  C->fz2_ok = C->fz3_ok = C->fz_auto_ok = false;
   if (C->nranks != 1 || !C->tile_ok || C->recon != RC_K0) return 0;
   const std::string err = build_fused_tables(C->L);
   if (!err.empty()) return fail("%s", err.c_str());
   const Layout &L = C->L;
   if (L.fz_built != 1) return 0;
   FusedMeta &fm = C->fm;
+  Fused2Meta &f2 = C->fm2;
   const int F0 = L.g_form == 0 ? 1 : 0, nt = L.ntiles;
   fm.W = L.fz_w; fm.CG = std::max(4, L.fz_w + F0);
   fm.S1 = C->pm.S; fm.S2 = (L.fz_s2_max + 1) & ~1; fm.E = C->pm.E; fm.TW = L.fz_tw_max; fm.ntiles = nt;
   if (fused_smem() > 227 * 1024) return 0;  // wide stencils (GGNB, LSQ-nn on some meshes): two-pass path
+  bool v2 = L.fz_v2 != 0;
+  size_t smem2 = 0;
+  if (v2) {  // second / third variant: published face states
+    f2.H1 = fm.S1 - kBlock; f2.HP = fm.S2 - kBlock; f2.E = fm.E; f2.TW = fm.TW; f2.W = fm.W; f2.CG = fm.CG; f2.ntiles = nt;
+    f2.FW = 0;
+    for (int t = 0; t < nt; t++) f2.FW = std::max(f2.FW, L.tile_hdr[8 * (size_t)t + 7]);
+    f2.HF = (L.fz_hf_max + 3) & ~3;
+    f2.XR = std::max(3 + fm.W + F0, 2 * f2.FW + (2 * f2.HF + kBlock - 1) / kBlock);
+    smem2 = kStages * fused2_stage_bytes(f2) + 2 * kStages * sizeof(uint64_t);
+    v2 = smem2 <= 227 * 1024;
+  }
+  {
+    // automatic: the fused kernel replaces the two passes where it was measured to win clearly -- the variant with
+    // published face states at three CTAs per SM (triangle meshes with face-neighbour stencils: C3 1.44 -> 1.21-1.27 ms
+    // per step).  At two CTAs per SM (meshes with quadrilaterals) it only matches the two-pass path: stay there.
+    int sm_smem = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, C->device));
+    C->fz_auto_ok = v2 && 3 * (smem2 + 1024) <= (size_t)sm_smem;
+    if (C->opt_fuse < 0 && !C->fz_auto_ok) return 0;
+  }
   std::vector<int> hdr(12 * (size_t)nt);
   for (int t = 0; t < nt; t++) {
     std::copy(&L.tile_hdr[8 * (size_t)t], &L.tile_hdr[8 * (size_t)t] + 8, &hdr[12 * (size_t)t]);
@@ -392,29 +417,23 @@ int ensure_fused() {
   }
   fm.hdr = reinterpret_cast<const int4 *>(dh);
   fm.hc_idx = C->pm.hc_idx; fm.he_idx = C->pm.he_idx; fm.t_pack = C->pm.t_pack; fm.t_bf = C->pm.t_bf;
-  C->fz_state = 1;
-  C->fz2_ok = false;
-  if (L.fz_v2) {  // second variant: published face states
-    Fused2Meta &f2 = C->fm2;
+  if (v2) {
     f2.hc_idx = fm.hc_idx; f2.he_idx = fm.he_idx; f2.h2_idx = fm.h2_idx; f2.t_bf = fm.t_bf; f2.gslot = fm.gslot; f2.gc2 = fm.gc2;
-    f2.H1 = fm.S1 - kBlock; f2.HP = fm.S2 - kBlock; f2.E = fm.E; f2.TW = fm.TW; f2.W = fm.W; f2.CG = fm.CG; f2.ntiles = nt;
-    f2.FW = 0;
-    for (int t = 0; t < nt; t++) f2.FW = std::max(f2.FW, L.tile_hdr[8 * (size_t)t + 7]);
-    f2.HF = (L.fz_hf_max + 3) & ~3;
-    f2.XR = std::max(3 + fm.W + F0, 2 * f2.FW + (2 * f2.HF + kBlock - 1) / kBlock);
-    if (kStages * fused2_stage_bytes(f2) + 2 * kStages * sizeof(uint64_t) <= 227 * 1024) {
-      std::vector<int> hdr4(16 * (size_t)nt, 0);
-      for (int t = 0; t < nt; t++) {
-        std::copy(&hdr[12 * (size_t)t], &hdr[12 * (size_t)t] + 12, &hdr4[16 * (size_t)t]);
-        hdr4[16 * (size_t)t + 12] = L.fz_hdr[8 * (size_t)t + 4];
-        hdr4[16 * (size_t)t + 13] = L.fz_hdr[8 * (size_t)t + 5];
-      }
-      const int *dh4;
-      if (dev_upload(dh4, hdr4) || dev_upload(f2.pack2, L.fz_pack2) || dev_upload(f2.hf, L.fz_hf)) return 1;
-      f2.hdr = reinterpret_cast<const int4 *>(dh4);
-      C->fz2_ok = true;
+    std::vector<int> hdr4(16 * (size_t)nt, 0);
+    for (int t = 0; t < nt; t++) {
+      std::copy(&hdr[12 * (size_t)t], &hdr[12 * (size_t)t] + 12, &hdr4[16 * (size_t)t]);
+      std::copy(&L.fz_hdr[8 * (size_t)t + 4], &L.fz_hdr[8 * (size_t)t + 4] + 4, &hdr4[16 * (size_t)t + 12]);
     }
+    const int *dh4;
+    const uint32_t *duf;
+    if (dev_upload(dh4, hdr4) || dev_upload(f2.pack2, L.fz_pack2) || dev_upload(f2.hf, L.fz_hf) || dev_upload(duf, L.fz_uf)) return 1;
+    f2.hdr = reinterpret_cast<const int4 *>(dh4);
+    f2.uf = reinterpret_cast<const uint2 *>(duf);
+    C->fz2_ok = true;
+    // the wave speeds of the steady third variant live in the ring blocks, which are dead by then
+    C->fz3_ok = L.fz_uf_max > 0 && (size_t)f2.FW * kBlock * 8 <= (size_t)(2 * f2.HP + (f2.CG + 1) * f2.H1) * 16;
   }
+  C->fz_state = 1;
   return 0;
 }
 
@@ -441,11 +460,14 @@ void launch_persistent(K k3, K k2, const Meta &meta, size_t smem, const char *na
 
 template <int UM, bool STEADY, int FORM>
 void launch_fused_one(const StageParams &S, const double *pin, double *pout) {
-  static size_t conf1 = 0, conf2 = 0;
-  static int p3a = 0, p2a = 0, p3b = 0, p2b = 0;
-  if (C->opt_fuse == 2 && C->fz2_ok)
-    launch_persistent(k_stage_fused2<UM, STEADY, FORM, 3>, k_stage_fused2<UM, STEADY, FORM, 2>, C->fm2,
-                      kStages * fused2_stage_bytes(C->fm2) + 2 * kStages * sizeof(uint64_t), "k_stage_fused2", conf2, p3b, p2b, S, pin, pout);
+  static size_t conf1 = 0, conf2 = 0, conf3 = 0;
+  static int p3a = 0, p2a = 0, p3b = 0, p2b = 0, p3c = 0, p2c = 0;
+  if (C->opt_fuse == 3 && C->fz3_ok)
+    launch_persistent(k_stage_fused2<UM, STEADY, FORM, 3, 3>, k_stage_fused2<UM, STEADY, FORM, 2, 3>, C->fm2,
+                      kStages * fused2_stage_bytes(C->fm2) + 2 * kStages * sizeof(uint64_t), "k_stage_fused2<VAR 3>", conf3, p3c, p2c, S, pin, pout);
+  else if (C->opt_fuse != 1 && C->fz2_ok)
+    launch_persistent(k_stage_fused2<UM, STEADY, FORM, 3, 2>, k_stage_fused2<UM, STEADY, FORM, 2, 2>, C->fm2,
+                      kStages * fused2_stage_bytes(C->fm2) + 2 * kStages * sizeof(uint64_t), "k_stage_fused2<VAR 2>", conf2, p3b, p2b, S, pin, pout);
   else
     launch_persistent(k_stage_fused<UM, STEADY, FORM, 3>, k_stage_fused<UM, STEADY, FORM, 2>, C->fm, fused_smem(), "k_stage_fused",
                       conf1, p3a, p2a, S, pin, pout);
@@ -911,7 +933,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   const bool overlap = C->nranks > 1 && C->opt_overlap && C->tile_ok && C->opt_tile == 2;
   bool p_pending = false;
   if (C->opt_fuse && ensure_fused()) return 1;
-  const bool fused = C->opt_fuse && C->fz_state == 1 && C->opt_tile == 2;
+  const bool fused = (C->opt_fuse > 0 || (C->opt_fuse < 0 && C->fz_auto_ok)) && C->fz_state == 1 && C->opt_tile == 2;
   {  // device step clock (src/runge_kutta.f90:135-145, 218-221): stage times are told + off[stage]
     StepClock hc{};
     hc.t1 = t1; hc.dt = dt; hc.istep = 0;
@@ -986,7 +1008,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   int done = 0;
   if (nsub > 0) { if (run_step()) return 1; done = 1; }
   if (use_graph) {
-    if (C->graph_exec && (C->graph_logbuf != C->logbuf || C->graph_um != (fused ? 256 * C->opt_fuse : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas)) {
+    if (C->graph_exec && (C->graph_logbuf != C->logbuf || C->graph_um != (fused ? 256 * (C->opt_fuse & 7) : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas)) {
       cudaGraphExecDestroy(C->graph_exec);
       C->graph_exec = nullptr;
     }
@@ -1001,7 +1023,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
       CUDA_OK(cudaGraphInstantiate(&C->graph_exec, graph, 0));
       cudaGraphDestroy(graph);
       C->graph_logbuf = C->logbuf;
-      C->graph_um = (fused ? 256 * C->opt_fuse : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas;
+      C->graph_um = (fused ? 256 * (C->opt_fuse & 7) : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas;
     }
     const long per_step = C->last_launches;
     for (; done < nsub; done++) CUDA_OK(cudaGraphLaunch(C->graph_exec, C->st));
@@ -1171,7 +1193,7 @@ long fvs2d_gpu_mesh_array(const char *name, void *out) {
     const std::string err = build_fused_tables(C->L);
     if (!err.empty()) { fail("%s", err.c_str()); return -1; }
     RET("fz_hdr", C->L.fz_hdr) RET("fz_h2_idx", C->L.fz_h2_idx) RET("fz_gslot", C->L.fz_gslot)
-    RET("fz_pack2", C->L.fz_pack2) RET("fz_hf", C->L.fz_hf)
+    RET("fz_pack2", C->L.fz_pack2) RET("fz_hf", C->L.fz_hf) RET("fz_uf", C->L.fz_uf)
     if (n == "fz_gc") {  // coefficient rows at the pitch the device uses (cells padded to 32)
       std::vector<double> gc;
       fused_coeff_rows(C->L, (size_t)(C->L.n_loc + 31) / 32 * 32, gc);
@@ -1179,9 +1201,9 @@ long fvs2d_gpu_mesh_array(const char *name, void *out) {
       return (long)gc.size();
     }
     if (n == "fz_info") {
-      const int info[7] = {C->L.fz_built, C->L.fz_w, C->L.fz_s2_max, C->L.fz_tw_max, C->L.fz_h2_max, C->L.fz_v2, C->L.fz_hf_max};
+      const int info[8] = {C->L.fz_built, C->L.fz_w, C->L.fz_s2_max, C->L.fz_tw_max, C->L.fz_h2_max, C->L.fz_v2, C->L.fz_hf_max, C->L.fz_uf_max};
       if (out) memcpy(out, info, sizeof info);
-      return 7;
+      return 8;
     }
   }
 #undef RET
@@ -1210,7 +1232,11 @@ int fvs2d_gpu_set_option(const char *key, int value) {
   if (k == "graph") { C->opt_graph = value; return 0; }
   if (k == "smem_pad") { C->opt_smem_pad = value; return 0; }
   if (k == "carveout") { C->opt_carveout = value; return 0; }
-  if (k == "fuse") { C->opt_fuse = value; return 0; }
+  if (k == "fuse") {
+    if (value != C->opt_fuse && C->fz_state == -1) C->fz_state = 0;  // decide again under the new setting
+    C->opt_fuse = value;
+    return 0;
+  }
   return fail("fvs2d_gpu_set_option: unknown option '%s'", key);
 }
 

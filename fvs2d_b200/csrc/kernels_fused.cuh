@@ -330,9 +330,10 @@ __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused(const DevMes
 // [2][HP] | coefficients -> gradients of ring 1 [CG][H1] | centroids of ring 1 [H1] | exy, enxy [2][E] | ea [E] |
 // face words [4][kBlock] | 8 ints | stencil slots [W][TW] u16 | tile/ring-1 faces [HF] u32
 struct Fused2Meta {
-  const int4 *hdr;  // 4 x int4 per tile: k_stage_fused's three + {hf_ptr, n_hf, 0, 0}
+  const int4 *hdr;  // 4 x int4 per tile: k_stage_fused's three + {hf_ptr, n_hf, uf_ptr, n_uf}
   const int *hc_idx, *he_idx, *h2_idx;
   const uint32_t *pack2, *hf;
+  const uint2 *uf;  // unique faces of all tiles (VAR 3), see layout.hpp
   const int *t_bf;
   const uint16_t *gslot;
   const double2 *gc2;
@@ -345,7 +346,16 @@ __host__ __device__ inline size_t fused2_stage_bytes(const Fused2Meta &f) {
          4 * kBlock * sizeof(uint32_t) + 32 + (((size_t)f.W * f.TW * 2 + 15) & ~(size_t)15) + (size_t)f.HF * 4;
 }
 
-template <int UM, bool STEADY, int FORM, int CTAS>
+// VAR 3 ("fuse" = 3) additionally evaluates every face flux of the tile ONCE: after the states are published, the
+// tile's unique faces (list fz_uf: tile/tile faces once, tile/ring-1 faces, boundary faces) are dealt out evenly to the
+// threads, two per thread and round -- a triangle tile has ~215 unique faces against 384 cell-faces, so the flux
+// arithmetic (the dominant cost: ~190 dependent fp64 instructions per face) drops by ~40 % and a thread's faces fit one
+// interleaved pair instead of a pair plus a single.  The flux is written IN PLACE over the two states it consumed (each
+// published state belongs to exactly one unique face, so no other thread reads them), in the edge's own orientation;
+// after a third barrier every thread sums the fluxes of its cell in face order with the sign of its side -- the same
+// values in the same order as the other kernels, so the result is still bitwise theirs.  The wave speeds (needed by
+// the local time step only) go to the dead ring-state block.
+template <int UM, bool STEADY, int FORM, int CTAS, int VAR>
 __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused2(const DevMesh m, const Fused2Meta fm, const Phys P, const StageParams S,
                                                                      const double *__restrict__ p, const double *__restrict__ bc,
                                                                      double *__restrict__ q, double *__restrict__ f,
@@ -472,6 +482,14 @@ __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused2(const DevMe
       stage_load<UM, STEADY>(S, i, np, q, f, dtl, q0, fo, dl);
       ivol = m.ivol[i];
     }
+    uint2 u0 = make_uint2(0u, 0u), u1 = make_uint2(0u, 0u);
+    int ufb = 0, nuf = 0;
+    if (VAR == 3) {  // this thread's first two unique faces: in flight like the RK data
+      const int4 h3 = __ldg(&fm.hdr[4 * t + 3]);
+      ufb = h3.z; nuf = h3.w;
+      if (tid < nuf) u0 = __ldg(&fm.uf[ufb + tid]);
+      if (tid + kBlock < nuf) u1 = __ldg(&fm.uf[ufb + tid + kBlock]);
+    }
     double2 *sx = st_x(s), *scg = st_cg(s);
     const double2 *sph = st_ph(s), *sxy = st_xy(s), *e2 = st_e2(s);
     const double *sea = st_ea(s);
@@ -567,7 +585,7 @@ __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused2(const DevMe
 
     // ---- phase 2: faces
     double acc[4] = {0.0, 0.0, 0.0, 0.0}, wsacc = 0.0;
-    if (live) {
+    if (VAR == 2 && live) {
       auto face = [&](const uint32_t pk, const int k, const auto bnd_tag) {
         constexpr bool BND = decltype(bnd_tag)::value;
         const int code = pk & 0xFFFFu, eslot = (pk >> 16) & 0xFFFu, kr = (pk >> 28) & 3;
@@ -635,6 +653,82 @@ __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused2(const DevMe
         for (int k = 0; k < fw; k++) {
           const uint32_t pk = sf[k * kBlock + tid];
           if ((pk & 0xFFFFu) == 0xFFFFu) face(pk, k, std::true_type{});
+        }
+      }
+    }
+    if (VAR == 3) {
+      // ---- phase 2a: the tile's unique faces, two per thread and round
+      double *sws = reinterpret_cast<double *>(st_ph(s));  // wave speeds [fw][kBlock] over the dead ring-state block
+      auto st_addr = [&](const int loc) { return loc < 0x400 ? ((loc / kBlock) * 2 * kBlock + (loc % kBlock)) : hst0 + 2 * (loc - 0x400); };
+      auto uface = [&](const uint2 u, const auto bnd_tag) {
+        constexpr bool BND = decltype(bnd_tag)::value;
+        const int locL = u.x & 0xFFFFu, locR = u.x >> 16, eslot = u.y & 0xFFFu, outL = (u.y >> 12) & 0x3FFu, outR = u.y >> 22;
+        const double2 fn = e2[EE + eslot];
+        const double nx = fn.x, ny = fn.y;
+        double sL[4], sR[4];
+        {
+          const int a0 = st_addr(locL), a1 = a0 + (locL < 0x400 ? kBlock : 1);
+          const double2 a = sx[a0], b = sx[a1];
+          sL[0] = a.x; sL[1] = a.y; sL[2] = b.x; sL[3] = b.y;
+        }
+        if (!BND) {
+          const int a0 = st_addr(locR), a1 = a0 + (locR < 0x400 ? kBlock : 1);
+          const double2 c = sx[a0], d = sx[a1];
+          sR[0] = c.x; sR[1] = c.y; sR[2] = d.x; sR[3] = d.y;
+        } else {
+          const int b = __ldg(&fm.t_bf[fbase + outL]);
+          const int type = __ldg(&m.bf_type[b]);
+          if (type == 2) {  // slip wall: mirror the normal velocity (src/residual.f90:200-204)
+            const double un = sL[1] * nx + sL[2] * ny;
+            sR[0] = sL[0]; sR[3] = sL[3];
+            sR[1] = sL[1] - 2.0 * un * nx;
+            sR[2] = sL[2] - 2.0 * un * ny;
+          } else {
+#pragma unroll
+            for (int v = 0; v < 4; v++) sR[v] = __ldg(&bc[v * m.nbf + b]);
+          }
+        }
+        double flux[4], ws;
+        roe_flux2(P, sL, sR, nx, ny, flux, ws);
+        if (outL != 0x3FF) {
+          const int o = (outL / kBlock) * 2 * kBlock + (outL % kBlock);
+          sx[o] = make_double2(flux[0], flux[1]);
+          sx[o + kBlock] = make_double2(flux[2], flux[3]);
+          if (STEADY) sws[outL] = ws;
+        }
+        if (!BND && outR != 0x3FF) {
+          const int o = (outR / kBlock) * 2 * kBlock + (outR % kBlock);
+          sx[o] = make_double2(flux[0], flux[1]);
+          sx[o + kBlock] = make_double2(flux[2], flux[3]);
+          if (STEADY) sws[outR] = ws;
+        }
+      };
+#pragma unroll 1
+      for (int e0 = tid; e0 < nuf; e0 += 2 * kBlock) {
+        const bool first = e0 == tid, two = e0 + kBlock < nuf;
+        const uint2 ua = first ? u0 : __ldg(&fm.uf[ufb + e0]);
+        const uint2 ub = !two ? ua : first ? u1 : __ldg(&fm.uf[ufb + e0 + kBlock]);
+        const bool ba = (ua.x >> 16) == 0xFFFFu, bb = (ub.x >> 16) == 0xFFFFu;
+        if (two && !ba && !bb) {  // one basic block: the two independent flux evaluations interleave
+          uface(ua, std::false_type{});
+          uface(ub, std::false_type{});
+        } else {
+          if (ba) uface(ua, std::true_type{}); else uface(ua, std::false_type{});
+          if (two) { if (bb) uface(ub, std::true_type{}); else uface(ub, std::false_type{}); }
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");  // every flux of the tile is in place
+      // ---- phase 2b: this cell's fluxes, in face order, with the sign of its side
+      if (live) {
+        for (int k = 0; k < fw; k++) {
+          const uint32_t pk = sf[k * kBlock + tid];
+          if ((pk & 0xFFFFu) == 0xFFFEu) continue;
+          const double2 fa = sx[(2 * k) * kBlock + tid], fb = sx[(2 * k + 1) * kBlock + tid];
+          const double ha = 0.5 * sea[(pk >> 16) & 0xFFFu];
+          const double sa = (pk >> 31) == 0 ? ha : -ha;
+          acc[0] = fma(fa.x, sa, acc[0]); acc[1] = fma(fa.y, sa, acc[1]);
+          acc[2] = fma(fb.x, sa, acc[2]); acc[3] = fma(fb.y, sa, acc[3]);
+          if (STEADY) wsacc = fma(sws[k * kBlock + tid], ha, wsacc);
         }
       }
     }

@@ -431,7 +431,7 @@ std::string build_fused_tables(Layout &L) {
 
   // ---- second variant: face table with reverse face indices + the list of tile/ring-1 faces
   if (L.tile_e_max >= 0x1000) return "";
-  std::vector<std::vector<uint32_t>> hf(nt);
+  std::vector<std::vector<uint32_t>> hf(nt), uf(nt);
   L.fz_pack2.assign(L.t_pack.size(), 0xFFFEu);
 #pragma omp parallel for schedule(dynamic, 64)
   for (int t = 0; t < nt; t++) {
@@ -458,6 +458,28 @@ std::string build_fused_tables(Layout &L) {
         }
         L.fz_pack2[fbase + kTile * k + j] = code | (es << 16) | (rev << 28) | (pk & 0x80000000u);
       }
+    // unique faces: interior ones in (k, j) order, boundary faces last
+    if (kTile * 4 > 0x3FF || hf[t].size() >= 0x400) continue;  // (checked again below through fz_uf_max)
+    for (int pass = 0; pass < 2; pass++)
+      for (int k = 0; k < th[7]; k++)
+        for (int j = 0; j < c1 - c0; j++) {
+          const uint32_t w = L.fz_pack2[fbase + kTile * k + j];
+          const uint32_t code = w & 0xFFFFu, es = (w >> 16) & 0xFFFu, me = (uint32_t)(k * kTile + j);
+          const bool c2 = (w >> 31) != 0;
+          if (code == 0xFFFEu || (code == 0xFFFFu) != (pass == 1)) continue;
+          uint32_t w0, w1;
+          if (code == 0xFFFFu) { w0 = me | (0xFFFFu << 16); w1 = es | (me << 12) | (0x3FFu << 22); }
+          else if (code < (uint32_t)kTile) {
+            if (c2) continue;  // emitted from the c1 side
+            const uint32_t other = ((w >> 28) & 3u) * kTile + code;
+            w0 = me | (other << 16); w1 = es | (me << 12) | (other << 22);
+          } else {
+            const uint32_t hs = 0x400u + (code - kTile);
+            if (!c2) { w0 = me | (hs << 16); w1 = es | (me << 12) | (0x3FFu << 22); }
+            else { w0 = hs | (me << 16); w1 = es | (0x3FFu << 12) | (me << 22); }
+          }
+          uf[t].push_back(w0); uf[t].push_back(w1);
+        }
   }
   int64_t fp = 0;
   for (int t = 0; t < nt; t++) {
@@ -469,6 +491,16 @@ std::string build_fused_tables(Layout &L) {
   }
   L.fz_hf.assign(fp, 0);
   for (int t = 0; t < nt; t++) std::copy(hf[t].begin(), hf[t].end(), L.fz_hf.begin() + L.fz_hdr[8 * (size_t)t + 4]);
+  int64_t up = 0;
+  for (int t = 0; t < nt; t++) {
+    int *h = &L.fz_hdr[8 * (size_t)t];
+    h[6] = (int)up; h[7] = (int)(uf[t].size() / 2);
+    up += h[7];
+    L.fz_uf_max = std::max(L.fz_uf_max, h[7]);
+    if (2 * up > INT32_MAX) return "";
+  }
+  L.fz_uf.resize(2 * up);
+  for (int t = 0; t < nt; t++) std::copy(uf[t].begin(), uf[t].end(), L.fz_uf.begin() + 2 * (size_t)L.fz_hdr[8 * (size_t)t + 6]);
   L.fz_v2 = 1;
   return "";
 }

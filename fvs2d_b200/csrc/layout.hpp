@@ -95,6 +95,14 @@ struct Layout {
   int fz_v2 = 0;               // 1 when the tables below exist (edge slots fit 12 bits)
   int fz_hf_max = 0;
   std::vector<uint32_t> fz_pack2, fz_hf;
+  // third variant (k_stage_fused3, "fuse" = 3): every face flux of a tile is evaluated once.  fz_uf = per tile the
+  // list of its unique faces (tile/tile faces once, tile/ring-1 faces, boundary faces last), two words per face:
+  //   w0 = locL | locR << 16   where a state lives: k*kTile + j (face k of own cell j), 0x400 + i (i-th tile/ring-1
+  //                            face: the ring-1 side), 0xFFFF (right state from the boundary condition)
+  //   w1 = edge slot | outL << 12 | outR << 22   where the flux goes: k*kTile + j of the c1 / c2 cell, 0x3FF = nowhere
+  // fz_hdr[6], [7] = offset (in faces) and count of the tile's list
+  int fz_uf_max = 0;
+  std::vector<uint32_t> fz_uf;
 };
 
 // Builds the layout of `rank` out of `nranks` (equal contiguous chunks of the Hilbert order).

@@ -35,7 +35,7 @@ def _emulate_residual(mesh, cfg, orc, time):
     resid = np.zeros((n_own, 4))
     n2_seen = 0
     assert info[5] == 1, "tables of the second fused variant missing"
-    pack2, hf_all = A("fz_pack2"), A("fz_hf")
+    pack2, hf_all, uf_all = A("fz_pack2"), A("fz_hf"), A("fz_uf")
     fz8 = A("fz_hdr").reshape(-1, 8)
     for t in range(len(hdr)):
         es, ne, hp, n1, ep, nhe, fbase, fw = (int(x) for x in hdr[t])
@@ -75,6 +75,37 @@ def _emulate_residual(mesh, cfg, orc, time):
                     seen.add(e)
                     assert int(hf_all[hfp + e]) == (ns - TILE) | (((w1 >> 16) & 0x7FFF) << 16)
         assert len(seen) == nhf
+        # third variant: every cell-face is the c1 or c2 output of exactly one unique face
+        ufp, nuf = int(fz8[t, 6]), int(fz8[t, 7])
+        assert nuf <= int(info[7])
+        covered = {}
+        bnd_started = False
+        for e in range(nuf):
+            w0, w1 = int(uf_all[2 * (ufp + e)]), int(uf_all[2 * (ufp + e) + 1])
+            locL, locR, es, outL, outR = w0 & 0xFFFF, w0 >> 16, w1 & 0xFFF, (w1 >> 12) & 0x3FF, w1 >> 22
+            bnd_started = bnd_started or locR == 0xFFFF
+            assert (locR == 0xFFFF) == bnd_started, "boundary faces must come last"
+            for out, loc, side in ((outL, locL, 0), (outR, locR, 1)):
+                if out == 0x3FF and loc == 0xFFFF:
+                    continue                           # right side of a boundary face
+                if out == 0x3FF:
+                    assert 0x400 <= loc < 0x400 + nhf and int(hf_all[hfp + loc - 0x400]) >> 16 == es
+                    continue
+                assert out == loc and out not in covered
+                k, j = out >> 7, out & 127
+                w = int(pack2[fbase + k * TILE + j])
+                assert (w >> 31) == side and ((w >> 16) & 0xFFF) == es and (w & 0xFFFF) != 0xFFFE
+                covered[out] = e
+            if locR == 0xFFFF:
+                assert outR == 0x3FF and (int(pack2[fbase + (outL >> 7) * TILE + (outL & 127)]) & 0xFFFF) == 0xFFFF
+            elif outL != 0x3FF and outR != 0x3FF:      # tile/tile face: the two words point at each other
+                wl = int(pack2[fbase + (outL >> 7) * TILE + (outL & 127)])
+                assert (wl & 0xFFFF) == (outR & 127) and ((wl >> 28) & 3) == outR >> 7
+            else:                                       # tile/ring-1 face: the ring-1 state is the one the face word names
+                a, h = (outL, locR) if outR == 0x3FF else (outR, locL)
+                assert (int(pack2[fbase + (a >> 7) * TILE + (a & 127)]) & 0xFFFF) == TILE + h - 0x400
+        nfaces = sum(1 for j in range(ncell) for k in range(fw) if (int(t_pack[fbase + k * TILE + j]) & 0xFFFF) != 0xFFFE)
+        assert len(covered) == nfaces
         # phase 1: gradients of the columns of tile + ring 1
         cols = np.concatenate([np.arange(ncell), np.arange(TILE, TILE + n1)])
         cid = ids[cols]
