@@ -356,6 +356,7 @@ def main():
         for key, wname, kk in (("c3", "c3", K), ("c2", "naca", 100 * K)):
             meshx, runx, descx, (ax, bx) = make_workload(wname, 1)
             gx = solver.Fvs2dGpu(runx.to_config(1), device=local_rank)
+            gx.set_option("fuse", -1)               # one kernel per stage where it fits three CTAs per SM (C3: yes; C2: limiter, no)
             gx.set_mesh(meshx)
             ncx = meshx.ncells
             del meshx
@@ -379,6 +380,12 @@ def main():
                           "pass_b_avg_launch_ms": tt["flux_ms"] / (4 * kk), "pass_a_avg_launch_ms": tt["grad_ms"] / (4 * kk),
                           "pass_b_roofline_frac": bx * ncx / (tt["flux_ms"] / (4 * kk) * 1e-3) / 1e9 / pk,
                           "stage_roofline_frac": (ax + bx) * ncx * 4 * kk / (tv["total_ms"] * 1e-3) / 1e9 / pk}
+            if tt["grad_ms"] == 0.0 and tt["flux_ms"] > 0.0:
+                # k_stage_fused2 ran: no pass A; "pass_b_*" is the fused stage kernel, which moves neither the gradients
+                # (64 B written + 64 B read per cell) nor the primitive state a second time (32 B)
+                fb = ax + bx - 160.0
+                other[key].update({"fused_stage_kernel": True, "fused_alg_bytes_per_cell": fb,
+                                   "pass_b_roofline_frac": fb * ncx / (tt["flux_ms"] / (4 * kk) * 1e-3) / 1e9 / pk})
         other["c2"]["note"] = "65 536 cells fit in L2 and one step is ~10 dependent launches of a few us: launch/latency-bound, not HBM-bound"
     if world > 1:
         dist.destroy_process_group()

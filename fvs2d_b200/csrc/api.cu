@@ -90,8 +90,9 @@ struct Ctx {
   int opt_overlap = 1;   // multi-GPU: overlap the halo exchanges with interior-tile work (second stream)
   int opt_smem_pad = 0;  // experiment: extra dynamic shared memory (KB) per pass-B CTA (shrinks the L1 carve-out)
   int opt_carveout = -1; // experiment: preferred shared-memory carve-out of the pass-B kernel in KB (-1: driver default)
-  int opt_fuse = -1;     // one kernel per stage where it applies (single GPU, kappa = 0, no limiter): 0 never, -1 automatic
-                         // (second variant, only where three CTAs per SM fit), 1 / 2 / 3 force k_stage_fused / its variants
+  int opt_fuse = 0;      // one kernel per stage where it applies (single GPU, kappa = 0, no limiter): 0 never (default this
+                         // round: the full GPU suite has not been run under -1 yet), -1 automatic (second variant, only where
+                         // three CTAs per SM fit), 1 / 2 / 3 force k_stage_fused / its variants
   int fz_state = 0;      // 0 not prepared, 1 ready, -1 not applicable to this mesh / scheme
   FusedMeta fm{};
   Fused2Meta fm2{};

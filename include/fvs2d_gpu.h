@@ -160,8 +160,8 @@ int fvs2d_gpu_last_timing(double ms[4], long *launches);
  *              (also chosen automatically when a mesh's tiles do not fit the pipeline's shared memory)
  *   "fuse"     one kernel per Runge-Kutta stage (gradients rebuilt in shared memory inside the pass-B pipeline; single GPU,
  *              second-order upwind reconstruction without limiter; results are bitwise those of the two-pass path):
- *              -1 (default) automatic = k_stage_fused2 where three CTAs per SM fit (triangle meshes with face-neighbour
- *              stencils), 0 never, 1 k_stage_fused (neighbour data gathered per face), 2 k_stage_fused2 (face states
+ *              0 (default) never, -1 automatic = k_stage_fused2 where three CTAs per SM fit (triangle meshes with
+ *              face-neighbour stencils; what bench.py selects), 1 k_stage_fused (neighbour data gathered per face), 2 k_stage_fused2 (face states
  *              evaluated once and published), 3 k_stage_fused2 + every face flux evaluated once (measured slower)
  *   "graph"    1 (default): on one GPU, steps 2..nsub of a call replay a captured CUDA graph; 0: every step eager
  *   "overlap"  1 (default): multi-GPU halo exchange on a second stream, overlapped with interior-tile work
