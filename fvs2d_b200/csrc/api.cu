@@ -99,6 +99,10 @@ struct Ctx {
   bool fz2_ok = false;   // "fuse" = 2 (published face states) usable
   bool fz3_ok = false;   // "fuse" = 3 (+ every face flux once) usable
   bool fz_auto_ok = false;  // the automatic setting uses the fused kernel on this mesh
+  // "fuse" = 4: two launches per stage of k_stage_fused2<2> -- the tiles whose staging fits three CTAs per SM (group A:
+  // triangle tiles) with shared memory sized for them, the rest (tiles with quadrilaterals) with theirs
+  Fused2Meta fm2a{}, fm2b{};
+  bool fz_split = false;
   cudaStream_t sx = nullptr;  // exchange stream
   cudaEvent_t e_a = nullptr, e_g = nullptr, e_b = nullptr, e_p = nullptr;
   const int *d_tile_int = nullptr, *d_tile_bnd = nullptr;
@@ -366,10 +370,53 @@ size_t fused_smem() {
   return kStages * fused_stage_bytes(fm.S1, fm.S2, fm.E, fm.TW, fm.W, fm.CG) + 2 * kStages * sizeof(uint64_t);
 }
 
+// "fuse" = 4: split the tiles into the group whose staging fits three CTAs per SM and the rest; each group gets a
+// Fused2Meta with pitches sized for its own tiles and a tile list
+int build_fused_split() {
+  const Layout &L = C->L;
+  const int nt = L.ntiles, F0 = L.g_form == 0 ? 1 : 0;
+  int sm_smem = 0;
+  CUDA_OK(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, C->device));
+  auto group_meta = [&](const std::vector<int> &tiles) {
+    Fused2Meta g = C->fm2;  // pointers
+    int n1m = 0, s2m = 0, em = 0, twm = 0, wm = 0, fwm = 0, hfm = 0;
+    for (int t : tiles) {
+      const int *th = &L.tile_hdr[8 * (size_t)t], *fh = &L.fz_hdr[8 * (size_t)t];
+      n1m = std::max(n1m, th[3]); s2m = std::max(s2m, th[3] + fh[1]); em = std::max(em, th[1] + th[5]);
+      twm = std::max(twm, (kBlock + th[3] + 7) & ~7); wm = std::max(wm, fh[3]); fwm = std::max(fwm, th[7]); hfm = std::max(hfm, fh[5]);
+    }
+    g.H1 = (n1m + 1) & ~1; g.HP = (s2m + 1) & ~1; g.E = (em + 1) & ~1; g.TW = twm; g.W = wm; g.CG = std::max(4, wm + F0);
+    g.FW = fwm; g.HF = (hfm + 3) & ~3;
+    g.XR = std::max(3 + wm + F0, 2 * fwm + (2 * g.HF + kBlock - 1) / kBlock);
+    g.ntiles = (int)tiles.size();
+    return g;
+  };
+  auto cta_bytes = [&](const Fused2Meta &g) { return kStages * fused2_stage_bytes(g) + 2 * kStages * sizeof(uint64_t); };
+  const size_t cap = (size_t)sm_smem / 3 - 1024;  // per CTA for three CTAs per SM
+  std::vector<size_t> need(nt);
+  for (int t = 0; t < nt; t++) need[t] = cta_bytes(group_meta(std::vector<int>(1, t)));
+  std::vector<int> ta, tb;
+  double thr = (double)cap;
+  for (int iter = 0; iter < 24; iter++, thr *= 0.985) {  // the group's pitches are maxima per array: tighten until the group fits
+    ta.clear(); tb.clear();
+    for (int t = 0; t < nt; t++) (need[t] <= (size_t)thr ? ta : tb).push_back(t);
+    if (ta.empty() || cta_bytes(group_meta(ta)) <= cap) break;
+  }
+  if (ta.empty() || tb.empty() || cta_bytes(group_meta(ta)) > cap) return 0;  // nothing to split
+  C->fm2a = group_meta(ta);
+  C->fm2b = group_meta(tb);
+  if (dev_upload(C->fm2a.tile_list, ta) || dev_upload(C->fm2b.tile_list, tb)) return 1;
+  C->fz_split = true;
+  if (getenv("FVS2D_DEBUG"))
+    fprintf(stderr, "[fvs2d] fused split: %d tiles at %zu B/CTA (3 CTAs/SM), %d tiles at %zu B/CTA\n", (int)ta.size(), cta_bytes(C->fm2a),
+            (int)tb.size(), cta_bytes(C->fm2b));
+  return 0;
+}
+
 int ensure_fused() {
   if (C->fz_state) return 0;
   C->fz_state = -1;
-  C->fz2_ok = C->fz3_ok = C->fz_auto_ok = false;
+  C->fz2_ok = C->fz3_ok = C->fz_auto_ok = C->fz_split = false;
   if (C->nranks != 1 || !C->tile_ok || C->recon != RC_K0) return 0;
   const std::string err = build_fused_tables(C->L);
   if (!err.empty()) return fail("%s", err.c_str());
@@ -435,6 +482,7 @@ int ensure_fused() {
     C->fz3_ok = L.fz_uf_max > 0 && (size_t)f2.FW * kBlock * 8 <= (size_t)(2 * f2.HP + (f2.CG + 1) * f2.H1) * 16;
   }
   C->fz_state = 1;
+  if (C->fz2_ok && build_fused_split()) return 1;
   return 0;
 }
 
@@ -459,8 +507,45 @@ void launch_persistent(K k3, K k2, const Meta &meta, size_t smem, const char *na
   C->nparts = grid;
 }
 
+struct OccCache { size_t smem = 0; int per3 = 0, per2 = 0; };
+// one launch of k_stage_fused2<2> over a group of tiles ("fuse" = 4); its partial sums start at part_off
+template <class K>
+int launch_group(K k3, K k2, const Fused2Meta &meta, OccCache &oc, size_t &attr_set, int part_off, const StageParams &S,
+                 const double *pin, double *pout) {
+  const size_t smem = kStages * fused2_stage_bytes(meta) + 2 * kStages * sizeof(uint64_t);
+  if (smem > attr_set) {
+    cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = smem;
+  }
+  if (oc.smem != smem) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc.per3, k3, kPipeThreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc.per2, k2, kPipeThreads, smem);
+    oc.smem = smem;
+    if (getenv("FVS2D_DEBUG")) fprintf(stderr, "[fvs2d] k_stage_fused2 group: %zu B smem/CTA, CTAs/SM %d (128 regs) / %d\n", smem, oc.per3, oc.per2);
+  }
+  const bool use3 = oc.per3 >= 3;
+  const int per_sm = std::max(1, use3 ? oc.per3 : oc.per2);
+  const int grid = std::min(meta.ntiles, C->nsm * per_sm);
+  if (grid > 0)
+    (use3 ? k3 : k2)<<<grid, kPipeThreads, smem, C->st>>>(C->dm, meta, C->phys, S, pin, C->bc, C->q, C->f, pout, C->dtl,
+                                                          C->partial + 4 * (size_t)part_off);
+  return grid;
+}
+
 template <int UM, bool STEADY, int FORM>
 void launch_fused_one(const StageParams &S, const double *pin, double *pout) {
+  if (C->opt_fuse == 4 && C->fz_split) {
+    static OccCache oa, ob;
+    static size_t attr_set = 0;
+    auto k3 = k_stage_fused2<UM, STEADY, FORM, 3, 2>;
+    auto k2 = k_stage_fused2<UM, STEADY, FORM, 2, 2>;
+    const int ga = launch_group(k3, k2, C->fm2a, oa, attr_set, 0, S, pin, pout);
+    const int gb = launch_group(k3, k2, C->fm2b, ob, attr_set, ga, S, pin, pout);
+    C->nparts = ga + gb;
+    C->last_launches++;
+    return;
+  }
   static size_t conf1 = 0, conf2 = 0, conf3 = 0;
   static int p3a = 0, p2a = 0, p3b = 0, p2b = 0, p3c = 0, p2c = 0;
   if (C->opt_fuse == 3 && C->fz3_ok)
@@ -718,8 +803,10 @@ int fvs2d_gpu_set_mesh(int nnodes, int ntri, int nquad, const double *node_xy, c
     C->send_idx = const_cast<int *>(si);
     if (dev_alloc(C->sendbuf, (size_t)std::max(1, nsend) * 9)) return 1;
   }
-  C->ev_pool.resize(8192);
-  for (auto &e : C->ev_pool) CUDA_OK(cudaEventCreate(&e));
+  if (C->ev_pool.empty()) {  // once per context (a second set_mesh reuses them)
+    C->ev_pool.assign(8192, nullptr);
+    for (auto &e : C->ev_pool) CUDA_OK(cudaEventCreate(&e));
+  }
   C->has_mesh = true;
   return 0;
 }
@@ -1058,7 +1145,8 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   std::vector<double> all;  // [rank][step][per]
   std::vector<int> allid;
   if (nr > 1) {
-    double *dall; int *dallid;
+    double *dall = nullptr; int *dallid = nullptr;
+    struct Scratch { double *&a; int *&b; ~Scratch() { cudaFree(a); cudaFree(b); } } scratch{dall, dallid};  // freed on every path
     CUDA_OK(cudaMalloc(&dall, lg.size() * 8 * nr));
     CUDA_OK(cudaMalloc(&dallid, ids.size() * 4 * nr));
     NCCL_OK(g_nccl.AllGather(C->logbuf, dall, lg.size(), ncclDouble, C->comm, C->st));
@@ -1067,7 +1155,6 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
     CUDA_OK(cudaMemcpyAsync(all.data(), dall, all.size() * 8, cudaMemcpyDeviceToHost, C->st));
     CUDA_OK(cudaMemcpyAsync(allid.data(), dallid, allid.size() * 4, cudaMemcpyDeviceToHost, C->st));
     CUDA_OK(cudaStreamSynchronize(C->st));
-    cudaFree(dall); cudaFree(dallid);
   } else { all = lg; allid = ids; }
   const double ncg = (double)C->L.nc_global, nin = (double)C->mesh.ncells_intr;
   for (int s = 0; s < nsub; s++) {
@@ -1249,7 +1336,7 @@ int fvs2d_gpu_finalize(void) {
     if (C->st) cudaStreamSynchronize(C->st);
     free_device();
   }
-  for (auto &e : C->ev_pool) cudaEventDestroy(e);
+  for (auto &e : C->ev_pool) if (e) cudaEventDestroy(e);
   if (C->ev0) cudaEventDestroy(C->ev0);
   if (C->ev1) cudaEventDestroy(C->ev1);
   if (C->graph_exec) cudaGraphExecDestroy(C->graph_exec);

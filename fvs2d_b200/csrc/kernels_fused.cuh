@@ -340,6 +340,7 @@ struct Fused2Meta {
   int H1, HP, E, TW, W, CG, XR, FW, HF;  // pitches: ring 1, rings 1+2, edges, slot table; max stencil entries; rows of the
                                          // ring-1 block and of X; max faces per cell; max tile/ring-1 faces (multiple of 4)
   int ntiles;
+  const int *tile_list;  // null: tiles 0..ntiles-1; else the ntiles tile ids to process (a launch over a subset of the tiles)
 };
 __host__ __device__ inline size_t fused2_stage_bytes(const Fused2Meta &f) {
   return (size_t)f.XR * kBlock * 16 + (size_t)2 * f.HP * 16 + (size_t)f.CG * f.H1 * 16 + (size_t)f.H1 * 16 + (size_t)f.E * 40 +
@@ -401,9 +402,11 @@ __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused2(const DevMe
         j2[r] = (lane + 32 * r < h2.y) ? __ldg(&fm.h2_idx[h2.x + lane + 32 * r]) : 0;
       }
     };
-    if ((int)blockIdx.x < fm.ntiles) fetch_meta(blockIdx.x);
+    auto tile_id = [&](int j) { return fm.tile_list ? __ldg(&fm.tile_list[j]) : j; };
+    if ((int)blockIdx.x < fm.ntiles) fetch_meta(tile_id(blockIdx.x));
     int it = 0;
-    for (int t = blockIdx.x; t < fm.ntiles; t += gridDim.x, it++) {
+    for (int j = blockIdx.x; j < fm.ntiles; j += gridDim.x, it++) {
+      const int t = tile_id(j);
       const int s = it % kStages;
       const uint32_t ph = (it / kStages) & 1;
       const int es = h0.x, ne = h0.y, hp = h0.z, n1 = h0.w, ep = h1.x, nhe = h1.y, fbase = h1.z, fw = h1.w;
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused2(const DevMe
       for (int h = lane + 96; h < n2; h += 32) gather_h2(h, __ldg(&fm.h2_idx[h2p + h]));
       for (int h = lane + 96; h < nhe; h += 32) gather_edge(h, __ldg(&fm.he_idx[ep + h]));
       cp_async_mbar_arrive_noinc(&full[s]);
-      if (t + (int)gridDim.x < fm.ntiles) fetch_meta(t + gridDim.x);
+      if (j + (int)gridDim.x < fm.ntiles) fetch_meta(tile_id(j + gridDim.x));
     }
     return;
   }
@@ -470,7 +473,8 @@ __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused2(const DevMe
   double dq2[4] = {0.0, 0.0, 0.0, 0.0};
   const int hst0 = 2 * fm.FW * kBlock;  // first double2 of the ring-1 face states inside X
   int it = 0;
-  for (int t = blockIdx.x; t < fm.ntiles; t += gridDim.x, it++) {
+  for (int j = blockIdx.x; j < fm.ntiles; j += gridDim.x, it++) {
+    const int t = fm.tile_list ? __ldg(&fm.tile_list[j]) : j;
     const int s = it % kStages;
     const uint32_t ph = (it / kStages) & 1;
     const int c0 = t * kBlock;
