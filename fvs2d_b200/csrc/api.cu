@@ -711,7 +711,10 @@ int host_build(int nnodes, int ntri, int nquad, const double *node_xy, const int
   if (!err.empty()) return fail("%s", err.c_str());
   std::vector<int> perm;
   hilbert_order(m, perm);
-  err = build_layout(m, C->grad, perm, C->rank, C->nranks, C->L);
+  // several ranks + the fused stage kernel: one more ghost layer (the stencils of the face-neighbour ghosts); the
+  // environment variable lets the CPU-side verification (fvs2d_host_build) ask for it
+  const bool deep = C->nranks > 1 && (C->opt_fuse != 0 || getenv("FVS2D_DEEP_GHOSTS") != nullptr);
+  err = build_layout(m, C->grad, perm, C->rank, C->nranks, C->L, deep);
   if (!err.empty()) return fail("%s", err.c_str());
   C->has_mesh = true;
   return 0;
@@ -1272,6 +1275,7 @@ long fvs2d_gpu_mesh_array(const char *name, void *out) {
   RET("f_off", C->L.f_off) RET("f_nbr", C->L.f_nbr) RET("f_edge", C->L.f_edge) RET("g_off", C->L.g_off) RET("g_idx", C->L.g_idx)
   RET("g_cx", C->L.g_cx) RET("g_cy", C->L.g_cy) RET("orig_id", C->L.orig_id) RET("bf_type", C->L.bf_type) RET("bf_edge", C->L.bf_edge)
   RET("lex", C->L.ex) RET("ley", C->L.ey) RET("is_intr", C->L.is_intr)
+  RET("fz_tile_int", C->L.fz_tile_int) RET("fz_tile_bnd", C->L.fz_tile_bnd) RET("gh_ptr", C->L.gh_ptr) RET("gh_idx", C->L.gh_idx)
   RET("lea", C->L.ea) RET("lenx", C->L.enx) RET("leny", C->L.eny) RET("lxc", C->L.xc) RET("lyc", C->L.yc) RET("lvol", C->L.vol)
   RET("tile_es", C->L.tile_es) RET("tile_ne", C->L.tile_ne) RET("tile_hc_ptr", C->L.tile_hc_ptr) RET("tile_he_ptr", C->L.tile_he_ptr)
   RET("tile_hdr", C->L.tile_hdr) RET("t_pack", C->L.t_pack) RET("t_bf", C->L.t_bf)

@@ -14,9 +14,12 @@ struct FaceTmp {
 };
 }  // namespace
 
-std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<int> &perm, int rank, int nranks, Layout &L) {
+std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<int> &perm, int rank, int nranks, Layout &L,
+                         bool deep) {
   const int nc = m.ncells;
   L = Layout();
+  L.deep = deep && nranks > 1;
+  deep = L.deep != 0;
   L.rank = rank; L.nranks = nranks; L.nc_global = nc;
   L.perm = perm;
   std::vector<int> iperm(nc);
@@ -33,20 +36,43 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
   std::vector<int> new2loc;
   std::vector<int> ghosts;
   if (nranks > 1) {
-    std::vector<unsigned char> mark(nc, 0);
+    std::vector<unsigned char> mark(nc, 0);  // bit 0: ghost, bit 1: face-neighbour ghost (concurrent writes store the same bits)
 #pragma omp parallel for schedule(static)
     for (int i = b0; i < b1; i++) {
       const int o = perm[i];
       for (int s = m.cptr[o]; s < m.cptr[o + 1]; s++) {
         const int j = m.nghbre[s];
-        if (j >= 0) { const int jn = iperm[j]; if (jn < b0 || jn >= b1) mark[jn] = 1; }
+        if (j >= 0) { const int jn = iperm[j]; if (jn < b0 || jn >= b1) mark[jn] = 3; }
       }
+    }
+#pragma omp parallel for schedule(static)
+    for (int i = b0; i < b1; i++) {
+      const int o = perm[i];
       for (int64_t t = g.ptr[o]; t < g.ptr[o + 1]; t++) {
         const int jn = iperm[g.idx[t]];
-        if (jn < b0 || jn >= b1) mark[jn] = 1;
+        if ((jn < b0 || jn >= b1) && !mark[jn]) mark[jn] = 1;
+      }
+    }
+    if (deep) {  // the stencils of the face-neighbour ghosts must be local too
+      std::vector<int> g1;
+      for (int i = 0; i < nc; i++) if (mark[i] & 2) g1.push_back(i);
+      for (int jn : g1) {
+        const int o = perm[jn];
+        for (int64_t t = g.ptr[o]; t < g.ptr[o + 1]; t++) {
+          const int kn = iperm[g.idx[t]];
+          if ((kn < b0 || kn >= b1) && !mark[kn]) mark[kn] = 1;
+        }
       }
     }
     for (int i = 0; i < nc; i++) if (mark[i]) ghosts.push_back(i);
+    if (deep) {
+      // gradient operator of the face-neighbour ghosts (local ids; the members are local by construction)
+      const int ng = (int)ghosts.size();
+      L.gh_ptr.assign(ng + 1, 0);
+      for (int k = 0; k < ng; k++) L.gh_ptr[k + 1] = L.gh_ptr[k] + ((mark[ghosts[k]] & 2) ? (int)(g.ptr[perm[ghosts[k]] + 1] - g.ptr[perm[ghosts[k]]]) : 0);
+      L.gh_idx.resize(L.gh_ptr[ng]); L.gh_cx.resize(L.gh_ptr[ng]); L.gh_cy.resize(L.gh_ptr[ng]);
+      L.gh_c0x.assign(ng, 0.0); L.gh_c0y.assign(ng, 0.0);
+    }
   }
   L.n_loc = L.n_own + (int)ghosts.size();
   L.loc2new.resize(L.n_loc);
@@ -59,6 +85,25 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
   if (nranks > 1) {
     new2loc.assign(nc, -1);
     for (size_t k = 0; k < ghosts.size(); k++) new2loc[ghosts[k]] = L.n_own + (int)k;
+  }
+  if (deep) {
+    const int ng = (int)ghosts.size();
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : bad)
+    for (int k = 0; k < ng; k++) {
+      const int n = L.gh_ptr[k + 1] - L.gh_ptr[k];
+      if (n == 0) continue;
+      const int o = perm[ghosts[k]];
+      double cx[kMaxStencil], cy[kMaxStencil], c0x = 0, c0y = 0;
+      if (grad_cell_coeffs(m, g, o, cx, cy, c0x, c0y) < 0) bad++;
+      for (int e = 0; e < n; e++) {
+        L.gh_idx[L.gh_ptr[k] + e] = to_local(iperm[g.idx[g.ptr[o] + e]]);
+        L.gh_cx[L.gh_ptr[k] + e] = cx[e];
+        L.gh_cy[L.gh_ptr[k] + e] = cy[e];
+      }
+      L.gh_c0x[k] = c0x; L.gh_c0y[k] = c0y;
+    }
+    if (bad) return "gradient_lsq: singular least-squares system";
   }
 
   // ---- per-cell data
@@ -313,6 +358,17 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
           const int jn = iperm[g.idx[t]];
           if (jn >= b0 && jn < b1) { mask[jn - b0] = 1; any = true; }
         }
+        if (deep)  // p also stores the stencil members of its face-neighbour ghosts
+          for (int s = m.cptr[o]; s < m.cptr[o + 1]; s++) {
+            const int j = m.nghbre[s];
+            if (j < 0) continue;
+            const int jn = iperm[j];
+            if (jn >= p0 && jn < p1) continue;
+            for (int64_t t = g.ptr[j]; t < g.ptr[j + 1]; t++) {
+              const int kn = iperm[g.idx[t]];
+              if (kn >= b0 && kn < b1) { mask[kn - b0] = 1; any = true; }
+            }
+          }
       }
       if (!any) mask.clear();
     }
@@ -353,14 +409,17 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
 std::string build_fused_tables(Layout &L) {
   if (L.fz_built) return "";
   L.fz_built = -1;
-  if (L.nranks != 1) return "build_fused_tables: single rank only";
+  if (L.nranks != 1 && !L.deep) return "";  // several ranks need the deep ghost layers (build_layout(..., deep))
   if (L.tile_hc_max < 0) return "";  // no tile kernel for this mesh
-  const int nt = L.ntiles, nsl = L.nslices;
-  // stencil entries of a local cell: the live prefix of its sliced-ELL column (padding entries carry a zero
-  // coefficient and the cell's own id; an interior zero coefficient is kept, it costs nothing)
-  auto width = [&](int i) { return (L.g_off[(i >> 5) + 1] - L.g_off[i >> 5]) >> 5; };
+  const int nt = L.ntiles, nsl = L.nslices, n_own = L.n_own;
+  // stencil entries of a local cell: owned cells -- the live prefix of the sliced-ELL column (padding entries carry a
+  // zero coefficient and the cell's own id; an interior zero coefficient is kept, it costs nothing); face-neighbour
+  // ghosts -- their CSR list
+  auto width = [&](int i) { return i < n_own ? (L.g_off[(i >> 5) + 1] - L.g_off[i >> 5]) >> 5 : L.gh_ptr[i - n_own + 1] - L.gh_ptr[i - n_own]; };
+  auto member = [&](int i, int k) { return i < n_own ? L.g_idx[L.g_off[i >> 5] + 32 * k + (i & 31)] : L.gh_idx[L.gh_ptr[i - n_own] + k]; };
   int wmax = 0;
   for (int s = 0; s < nsl; s++) wmax = std::max(wmax, (L.g_off[s + 1] - L.g_off[s]) >> 5);
+  for (size_t k = 0; k + 1 < L.gh_ptr.size(); k++) wmax = std::max(wmax, L.gh_ptr[k + 1] - L.gh_ptr[k]);
   L.fz_w = wmax;
   std::vector<std::vector<int>> h2(nt);
   std::vector<int> gw(nt, 0);
@@ -375,7 +434,7 @@ std::string build_fused_tables(Layout &L) {
       const int wi = width(i);
       w = std::max(w, wi);
       for (int k = 0; k < wi; k++) {
-        const int j = L.g_idx[L.g_off[i >> 5] + 32 * k + (i & 31)];
+        const int j = member(i, k);
         if (j >= c0 && j < c1) continue;
         if (std::binary_search(h1, h1 + n1, j)) continue;
         v.push_back(j);
@@ -422,12 +481,23 @@ std::string build_fused_tables(Layout &L) {
     };
     auto fill = [&](int i, int c) {
       const int wi = width(i);
-      for (int k = 0; k < wi; k++) tab[(size_t)k * tw + c] = (uint16_t)slot_of(L.g_idx[L.g_off[i >> 5] + 32 * k + (i & 31)]);
+      for (int k = 0; k < wi; k++) tab[(size_t)k * tw + c] = (uint16_t)slot_of(member(i, k));
     };
     for (int i = c0; i < c1; i++) fill(i, i - c0);
     for (int hh = 0; hh < n1; hh++) fill(h1[hh], kTile + hh);
   }
   L.fz_built = 1;
+  if (L.nranks > 1) {  // overlap of the state exchange: tiles that neither read a ghost (rings 1, 2) nor hold a sent cell
+    std::vector<unsigned char> bnd(nt, 0);
+    for (int i : L.send_idx) bnd[i / kTile] = 1;
+    for (int t = 0; t < nt; t++) {
+      const int *h1 = L.tile_hc_idx.data() + L.tile_hc_ptr[t];
+      const int n1 = L.tile_hc_ptr[t + 1] - L.tile_hc_ptr[t];
+      if (n1 > 0 && h1[n1 - 1] >= n_own) bnd[t] = 1;               // lists are ascending: the last entry decides
+      if (!h2[t].empty() && h2[t].back() >= n_own) bnd[t] = 1;
+      (bnd[t] ? L.fz_tile_bnd : L.fz_tile_int).push_back(t);
+    }
+  }
 
   // ---- second variant: face table with reverse face indices + the list of tile/ring-1 faces
   if (L.tile_e_max >= 0x1000) return "";
@@ -516,6 +586,15 @@ void fused_coeff_rows(const Layout &L, size_t np, std::vector<double> &rows) {
       const int e = L.g_off[sl] + 32 * k + lane;
       const size_t o = 2 * ((size_t)(k + F0) * np + i);
       rows[o] = L.g_cx[e]; rows[o + 1] = L.g_cy[e];
+    }
+  }
+  for (size_t k = 0; k + 1 < L.gh_ptr.size(); k++) {  // face-neighbour ghosts (several ranks, deep ghost layers)
+    const size_t i = (size_t)L.n_own + k;
+    if (L.gh_ptr[k + 1] == L.gh_ptr[k]) continue;
+    if (F0) { rows[2 * i] = L.gh_c0x[k]; rows[2 * i + 1] = L.gh_c0y[k]; }
+    for (int e = L.gh_ptr[k]; e < L.gh_ptr[k + 1]; e++) {
+      const size_t o = 2 * ((size_t)(e - L.gh_ptr[k] + F0) * np + i);
+      rows[o] = L.gh_cx[e]; rows[o + 1] = L.gh_cy[e];
     }
   }
 }

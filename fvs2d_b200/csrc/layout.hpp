@@ -81,6 +81,14 @@ struct Layout {
   // Slots of a tile: own cells [0, kTile), ring 1 [kTile, kTile+n1), ring 2 [kTile+n1, kTile+n1+n2).
   // fz_gslot = per tile gw rows of pitch TW = roundup8(kTile+n1): entry (k, c) = slot of the k-th stencil member of
   // the cell in slot c (same k order as g_idx; cells with fewer entries point at themselves, their coefficient is 0).
+  // Several ranks: the fused kernel rebuilds the gradients of ring-1 cells that are GHOSTS, so with `deep` ghost layers
+  // (build_layout(..., deep = true)) a rank also stores the gradient-stencil members of its face-neighbour ghosts (one
+  // state exchange per stage instead of state + gradients: SURVEY 8e variant 2a) and their gradient operator:
+  // gh_ptr/gh_idx/gh_cx/gh_cy = CSR over the ghosts (only face-neighbour ghosts have entries; local ids), gh_c0x/y.
+  int deep = 0;
+  std::vector<int> gh_ptr, gh_idx;
+  std::vector<double> gh_cx, gh_cy, gh_c0x, gh_c0y;
+  std::vector<int> fz_tile_int, fz_tile_bnd;  // tiles whose rings hold no ghost and none of whose cells is sent / the rest
   int fz_built = 0;            // 0 not built, 1 usable, -1 built but unusable for this mesh
   int fz_w = 0;                // stencil entries per cell, maximum over the mesh (coefficient rows)
   int fz_s2_max = 0, fz_tw_max = 0, fz_h2_max = 0;
@@ -106,7 +114,8 @@ struct Layout {
 };
 
 // Builds the layout of `rank` out of `nranks` (equal contiguous chunks of the Hilbert order).
-std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<int> &perm, int rank, int nranks, Layout &L);
+std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<int> &perm, int rank, int nranks, Layout &L,
+                         bool deep = false);
 
 // Adds the fz_* tables of the fused stage kernel to a single-rank layout (on demand: they are only needed when the
 // "fuse" option is on).  Returns "" (then L.fz_built is 1 or -1) or an error message.

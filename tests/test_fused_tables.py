@@ -11,18 +11,21 @@ from conftest import run_input  # noqa: F401
 TILE = 128
 
 
-def _emulate_residual(mesh, cfg, orc, time):
+def _emulate_residual(mesh, cfg, orc, time, rank=0, nranks=1):
     from fvs2d_b200 import capi, solver
     from oracle import oracle as om
-    solver.host_build(cfg, mesh)
+    solver.host_build(cfg, mesh, rank, nranks)
     A = capi.mesh_array
     info = A("fz_info")
     assert info[0] == 1, "fused tables unusable for this mesh"
     W = int(info[1])
     F0 = 1 if cfg.grad_method in (1, 2) else 0
-    orig = A("orig_id")
-    n_own = len(orig)
-    np_ = (n_own + 31) // 32 * 32
+    orig = A("orig_id")                                # owned cells, then ghosts
+    sz = np.zeros(10, dtype=np.int32)
+    capi.lib().fvs2d_gpu_sizes(capi.ptr(sz))
+    n_own, n_loc = int(sz[7]), int(sz[8])
+    assert len(orig) == n_loc
+    np_ = (n_loc + 31) // 32 * 32
     gc = A("fz_gc").reshape(W + F0, np_, 2)
     hdr = A("tile_hdr").reshape(-1, 8)
     fz = A("fz_hdr").reshape(-1, 8)[:, :4]
@@ -155,8 +158,8 @@ def _emulate_residual(mesh, cfg, orc, time):
                     fl, _ = om.roe_flux(cfg.gamma, recon(sl_), recon(sr_), nx, ny)
                     acc += fl * af if c2flag == 0 else -fl * af
             resid[c0 + j] = -acc / vol[c0 + j]
-    out = np.zeros_like(resid)
-    out[orig] = resid
+    out = np.full((mesh.ncells, 4), np.nan)
+    out[orig[:n_own]] = resid
     return out, n2_seen
 
 
@@ -194,3 +197,39 @@ def test_fused_tables_slip_wall_and_freestream(naca_mesh):
     r_e, _ = _emulate_residual(naca_mesh, cfg, orc, 0.0)
     scale = np.abs(r_o).max(axis=0)
     assert (np.abs(r_e - r_o) / scale).max() < 1e-11
+
+
+@pytest.mark.parametrize("grad,stencil,nranks", [(1, "fn", 2), (3, "nn", 3)])
+def test_fused_tables_with_deep_ghost_layers(grad, stencil, nranks, monkeypatch):
+    """several ranks: with the extra ghost layer every tile's rings are local, ring-1 ghosts carry their gradient
+    operator, and the ranks' emulated residuals tile the oracle's; the halo plans still match pairwise."""
+    from fvs2d_b200 import capi, config, meshgen, solver
+    from oracle.oracle import Oracle
+    monkeypatch.setenv("FVS2D_DEEP_GHOSTS", "1")
+    mesh = meshgen.vortex_mixed_mesh(32)
+    cfg = config.RunInput(grad_cellcntr_imethd=grad, grad_cellcntr_lsq_nghbr=stencil, lvortex=True, dt=0.01).to_config()
+    orc = Oracle(mesh, cfg)
+    orc.initialize_solution()
+    r_o = orc.compute_residual(0.3).copy()
+    total = np.full_like(r_o, np.nan)
+    plans = []
+    for r in range(nranks):
+        r_e, _ = _emulate_residual(mesh, cfg, orc, 0.3, r, nranks)
+        own = ~np.isnan(r_e[:, 0])
+        assert np.isnan(total[own]).all()
+        total[own] = r_e[own]
+        A = capi.mesh_array
+        ti, tb = A("fz_tile_int"), A("fz_tile_bnd")
+        assert len(ti) + len(tb) == len(A("tile_hdr")) // 8 and len(tb) > 0
+        plans.append(dict(loc2new=A("loc2new").copy(), peers=A("peers").copy(), send_ptr=A("send_ptr").copy(), send_idx=A("send_idx").copy(),
+                          recv_begin=A("recv_begin").copy(), recv_count=A("recv_count").copy()))
+    assert not np.isnan(total).any()
+    scale = np.abs(r_o).max(axis=0)
+    assert (np.abs(total - r_o) / scale).max() < 1e-11
+    for r, p in enumerate(plans):
+        for k, peer in enumerate(p["peers"]):
+            q = plans[peer]
+            kk = list(q["peers"]).index(r)
+            sent = p["loc2new"][p["send_idx"][p["send_ptr"][k]:p["send_ptr"][k + 1]]]
+            recv = q["loc2new"][q["recv_begin"][kk]:q["recv_begin"][kk] + q["recv_count"][kk]]
+            assert np.array_equal(sent, recv)
