@@ -103,6 +103,8 @@ struct Ctx {
   // triangle tiles) with shared memory sized for them, the rest (tiles with quadrilaterals) with theirs
   Fused2Meta fm2a{}, fm2b{};
   bool fz_split = false;
+  const int *d_fz_int = nullptr, *d_fz_bnd = nullptr;  // several ranks: tiles without / with ghost or sent cells (fused path)
+  int n_fz_int = 0, n_fz_bnd = 0;
   cudaStream_t sx = nullptr;  // exchange stream
   cudaEvent_t e_a = nullptr, e_g = nullptr, e_b = nullptr, e_p = nullptr;
   const int *d_tile_int = nullptr, *d_tile_bnd = nullptr;
@@ -417,7 +419,7 @@ int ensure_fused() {
   if (C->fz_state) return 0;
   C->fz_state = -1;
   C->fz2_ok = C->fz3_ok = C->fz_auto_ok = C->fz_split = false;
-  if (C->nranks != 1 || !C->tile_ok || C->recon != RC_K0) return 0;
+  if ((C->nranks != 1 && !C->L.deep) || !C->tile_ok || C->recon != RC_K0) return 0;
   const std::string err = build_fused_tables(C->L);
   if (!err.empty()) return fail("%s", err.c_str());
   const Layout &L = C->L;
@@ -481,6 +483,13 @@ int ensure_fused() {
     // the wave speeds of the steady third variant live in the ring blocks, which are dead by then
     C->fz3_ok = L.fz_uf_max > 0 && (size_t)f2.FW * kBlock * 8 <= (size_t)(2 * f2.HP + (f2.CG + 1) * f2.H1) * 16;
   }
+  if (C->nranks > 1) {  // several ranks: only the published-state variant, launched over interior / boundary tiles
+    if (!C->fz2_ok) return 0;
+    if (dev_upload(C->d_fz_int, L.fz_tile_int) || dev_upload(C->d_fz_bnd, L.fz_tile_bnd)) return 1;
+    C->n_fz_int = (int)L.fz_tile_int.size(); C->n_fz_bnd = (int)L.fz_tile_bnd.size();
+    C->fz_state = 1;
+    return 0;
+  }
   C->fz_state = 1;
   if (C->fz2_ok && build_fused_split()) return 1;
   return 0;
@@ -490,7 +499,7 @@ int ensure_fused() {
 // compiled for two CTAs per SM (more registers)
 template <class K, class Meta>
 void launch_persistent(K k3, K k2, const Meta &meta, size_t smem, const char *name, size_t &configured, int &per3, int &per2,
-                       const StageParams &S, const double *pin, double *pout) {
+                       const StageParams &S, const double *pin, double *pout, int part_off = 0) {
   if (configured != smem) {
     cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -503,8 +512,10 @@ void launch_persistent(K k3, K k2, const Meta &meta, size_t smem, const char *na
   int per_sm = std::max(1, use3 ? per3 : per2);
   if (C->opt_ctas > 0) per_sm = std::min(per_sm, C->opt_ctas);
   const int grid = std::min(meta.ntiles, C->nsm * per_sm);
-  if (grid > 0) (use3 ? k3 : k2)<<<grid, kPipeThreads, smem, C->st>>>(C->dm, meta, C->phys, S, pin, C->bc, C->q, C->f, pout, C->dtl, C->partial);
-  C->nparts = grid;
+  if (grid > 0)
+    (use3 ? k3 : k2)<<<grid, kPipeThreads, smem, C->st>>>(C->dm, meta, C->phys, S, pin, C->bc, C->q, C->f, pout, C->dtl,
+                                                          C->partial + 4 * (size_t)part_off);
+  C->nparts = part_off + grid;
 }
 
 struct OccCache { size_t smem = 0; int per3 = 0, per2 = 0; };
@@ -548,18 +559,24 @@ void launch_fused_one(const StageParams &S, const double *pin, double *pout) {
   }
   static size_t conf1 = 0, conf2 = 0, conf3 = 0;
   static int p3a = 0, p2a = 0, p3b = 0, p2b = 0, p3c = 0, p2c = 0;
-  if (C->opt_fuse == 3 && C->fz3_ok)
+  if (C->opt_fuse == 3 && C->fz3_ok && !g_sel.list)
     launch_persistent(k_stage_fused2<UM, STEADY, FORM, 3, 3>, k_stage_fused2<UM, STEADY, FORM, 2, 3>, C->fm2,
                       kStages * fused2_stage_bytes(C->fm2) + 2 * kStages * sizeof(uint64_t), "k_stage_fused2<VAR 3>", conf3, p3c, p2c, S, pin, pout);
-  else if (C->opt_fuse != 1 && C->fz2_ok)
-    launch_persistent(k_stage_fused2<UM, STEADY, FORM, 3, 2>, k_stage_fused2<UM, STEADY, FORM, 2, 2>, C->fm2,
-                      kStages * fused2_stage_bytes(C->fm2) + 2 * kStages * sizeof(uint64_t), "k_stage_fused2<VAR 2>", conf2, p3b, p2b, S, pin, pout);
+  else if ((C->opt_fuse != 1 || g_sel.list) && C->fz2_ok) {
+    Fused2Meta meta = C->fm2;
+    if (g_sel.list) { meta.tile_list = g_sel.list; meta.ntiles = g_sel.n; }  // several ranks: interior / boundary tiles
+    launch_persistent(k_stage_fused2<UM, STEADY, FORM, 3, 2>, k_stage_fused2<UM, STEADY, FORM, 2, 2>, meta,
+                      kStages * fused2_stage_bytes(meta) + 2 * kStages * sizeof(uint64_t), "k_stage_fused2<VAR 2>", conf2, p3b, p2b, S, pin, pout,
+                      g_sel.part_off);
+  }
   else
     launch_persistent(k_stage_fused<UM, STEADY, FORM, 3>, k_stage_fused<UM, STEADY, FORM, 2>, C->fm, fused_smem(), "k_stage_fused",
                       conf1, p3a, p2a, S, pin, pout);
 }
 
-int launch_fused(int um, const StageParams &S, const double *pin, double *pout) {
+int launch_fused(int um, const StageParams &S, const double *pin, double *pout, const int *list = nullptr, int nlist = 0, int part_off = 0) {
+  g_sel.list = list; g_sel.n = nlist; g_sel.part_off = part_off;
+  if (list && nlist == 0) { C->nparts = part_off; return 0; }
   Span sp(2);
   const bool steady = C->cfg.steady != 0, gg = C->L.g_form == 0;
   if (um == UM_RK) {
@@ -1042,7 +1059,26 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
       if (c.steady) S.h = c.ssprk ? (rk == 3 ? 1.0 / 4.0 : 1.0 / 3.0) : (rk == 2 ? 1.0 : rk == 3 ? 1.0 / 6.0 : 1.0 / 2.0);
       else S.h = C->h_rk[rk];
       if (launch_bc(rk)) return 1;
-      if (fused) {
+      if (fused && C->nranks > 1) {
+        // one exchange per stage (the state); tiles that read no ghost run while the previous one is in flight
+        if (C->opt_overlap) {
+          if (launch_fused(um, S, C->pa, C->pb, C->d_fz_int, C->n_fz_int, 0)) return 1;
+          const int parts_int = C->nparts;
+          if (p_pending) CUDA_OK(cudaStreamWaitEvent(C->st, C->e_p, 0));
+          if (launch_fused(um, S, C->pa, C->pb, C->d_fz_bnd, C->n_fz_bnd, parts_int)) return 1;
+          CUDA_OK(cudaEventRecord(C->e_b, C->st));
+          CUDA_OK(cudaStreamWaitEvent(C->sx, C->e_b, 0));
+          HaloItem itp{C->pb, 4, 1};
+          if (halo_exchange(&itp, 1, C->sx)) return 1;
+          CUDA_OK(cudaEventRecord(C->e_p, C->sx));
+          p_pending = true;
+        } else {
+          if (launch_fused(um, S, C->pa, C->pb)) return 1;
+          Span sp(0);
+          HaloItem it{C->pb, 4, 1};
+          if (halo_exchange(&it, 1)) return 1;
+        }
+      } else if (fused) {
         if (launch_fused(um, S, C->pa, C->pb)) return 1;
       } else if (overlap) {
         // interior tiles never read a ghost: they run while the exchanges are in flight on the second stream

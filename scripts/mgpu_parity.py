@@ -1,6 +1,7 @@
 """Run under torchrun (one rank per GPU): the domain-decomposed run (NCCL halo exchange) against the CPU oracle
 and, bit for bit, against ... itself is not possible across partitionings, so the reference is the oracle.
-Prints PARITY_OK on rank 0."""
+Prints PARITY_OK on rank 0.  FUSE=<n> in the environment selects the library's "fuse" option before set_mesh (the fused
+stage kernel on several ranks needs the deep ghost layers, which are decided when the mesh is set)."""
 import os
 import sys
 
@@ -35,6 +36,8 @@ def main():
     for name, mesh, run, nsteps in cases:
         cfg = run.to_config(world)
         gpu = solver.Fvs2dGpu(cfg, device=local, comm=new_comm())
+        if os.environ.get("FUSE"):
+            gpu.set_option("fuse", int(os.environ["FUSE"]))
         gpu.set_mesh(mesh)
         gpu.initialize_solution()
         res, ve, vxy = gpu.time_integration(0.0, nsteps)
