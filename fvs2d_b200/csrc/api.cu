@@ -103,6 +103,8 @@ struct Ctx {
   // triangle tiles) with shared memory sized for them, the rest (tiles with quadrilaterals) with theirs
   Fused2Meta fm2a{}, fm2b{};
   bool fz_split = false;
+  const int *sp_list[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // [group][all | interior | boundary tiles]
+  int sp_n[2][3] = {{0, 0, 0}, {0, 0, 0}};
   const int *d_fz_int = nullptr, *d_fz_bnd = nullptr;  // several ranks: tiles without / with ghost or sent cells (fused path)
   int n_fz_int = 0, n_fz_bnd = 0;
   cudaStream_t sx = nullptr;  // exchange stream
@@ -407,7 +409,21 @@ int build_fused_split() {
   if (ta.empty() || tb.empty() || cta_bytes(group_meta(ta)) > cap) return 0;  // nothing to split
   C->fm2a = group_meta(ta);
   C->fm2b = group_meta(tb);
-  if (dev_upload(C->fm2a.tile_list, ta) || dev_upload(C->fm2b.tile_list, tb)) return 1;
+  {  // per group: all its tiles, and (several ranks) its interior / boundary tiles
+    std::vector<unsigned char> is_bnd(nt, 0);
+    for (int t : L.fz_tile_bnd) is_bnd[t] = 1;
+    const std::vector<int> *grp[2] = {&ta, &tb};
+    for (int gi = 0; gi < 2; gi++) {
+      std::vector<int> sub[3];
+      for (int t : *grp[gi]) { sub[0].push_back(t); sub[is_bnd[t] ? 2 : 1].push_back(t); }
+      for (int k = 0; k < 3; k++) {
+        if (dev_upload(C->sp_list[gi][k], sub[k])) return 1;
+        C->sp_n[gi][k] = (int)sub[k].size();
+      }
+    }
+    C->fm2a.tile_list = C->sp_list[0][0];
+    C->fm2b.tile_list = C->sp_list[1][0];
+  }
   C->fz_split = true;
   if (getenv("FVS2D_DEBUG"))
     fprintf(stderr, "[fvs2d] fused split: %d tiles at %zu B/CTA (3 CTAs/SM), %d tiles at %zu B/CTA\n", (int)ta.size(), cta_bytes(C->fm2a),
@@ -488,7 +504,7 @@ int ensure_fused() {
     if (dev_upload(C->d_fz_int, L.fz_tile_int) || dev_upload(C->d_fz_bnd, L.fz_tile_bnd)) return 1;
     C->n_fz_int = (int)L.fz_tile_int.size(); C->n_fz_bnd = (int)L.fz_tile_bnd.size();
     C->fz_state = 1;
-    return 0;
+    return build_fused_split();
   }
   C->fz_state = 1;
   if (C->fz2_ok && build_fused_split()) return 1;
@@ -551,9 +567,13 @@ void launch_fused_one(const StageParams &S, const double *pin, double *pout) {
     static size_t attr_set = 0;
     auto k3 = k_stage_fused2<UM, STEADY, FORM, 3, 2>;
     auto k2 = k_stage_fused2<UM, STEADY, FORM, 2, 2>;
-    const int ga = launch_group(k3, k2, C->fm2a, oa, attr_set, 0, S, pin, pout);
-    const int gb = launch_group(k3, k2, C->fm2b, ob, attr_set, ga, S, pin, pout);
-    C->nparts = ga + gb;
+    const int sub = !g_sel.list ? 0 : g_sel.list == C->d_fz_int ? 1 : 2;  // several ranks: interior / boundary tiles of each group
+    Fused2Meta ma = C->fm2a, mb = C->fm2b;
+    ma.tile_list = C->sp_list[0][sub]; ma.ntiles = C->sp_n[0][sub];
+    mb.tile_list = C->sp_list[1][sub]; mb.ntiles = C->sp_n[1][sub];
+    const int ga = launch_group(k3, k2, ma, oa, attr_set, g_sel.part_off, S, pin, pout);
+    const int gb = launch_group(k3, k2, mb, ob, attr_set, g_sel.part_off + ga, S, pin, pout);
+    C->nparts = g_sel.part_off + ga + gb;
     C->last_launches++;
     return;
   }
