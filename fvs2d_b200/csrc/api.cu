@@ -653,6 +653,7 @@ int fvs2d_gpu_init(const fvs2d_config *cfg, int device) {
   C = new Ctx();
   C->cfg = *cfg;
   C->device = device;
+  if (const char *ev = getenv("FVS2D_FUSE")) C->opt_fuse = atoi(ev);  // "fuse" option for hosts that cannot call set_option
   CUDA_OK(cudaSetDevice(device));
   CUDA_OK(cudaStreamCreateWithFlags(&C->st, cudaStreamNonBlocking));
   CUDA_OK(cudaDeviceGetAttribute(&C->nsm, cudaDevAttrMultiProcessorCount, device));
