@@ -101,6 +101,8 @@ struct Ctx {
   bool fz_auto_ok = false;  // the automatic setting uses the fused kernel on this mesh
   // "fuse" = 4: two launches per stage of k_stage_fused2<2> -- the tiles whose staging fits three CTAs per SM (group A:
   // triangle tiles) with shared memory sized for them, the rest (tiles with quadrilaterals) with theirs
+  Fused2cMeta fm2c{};    // "fuse" = 5: the published-state kernel on a shared-memory diet (k_stage_fused2c)
+  bool fz2c_ok = false;
   Fused2Meta fm2a{}, fm2b{};
   bool fz_split = false;
   const int *sp_list[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // [group][all | interior | boundary tiles]
@@ -434,7 +436,7 @@ int build_fused_split() {
 int ensure_fused() {
   if (C->fz_state) return 0;
   C->fz_state = -1;
-  C->fz2_ok = C->fz3_ok = C->fz_auto_ok = C->fz_split = false;
+  C->fz2_ok = C->fz3_ok = C->fz_auto_ok = C->fz_split = C->fz2c_ok = false;
   if ((C->nranks != 1 && !C->L.deep) || !C->tile_ok || C->recon != RC_K0) return 0;
   const std::string err = build_fused_tables(C->L);
   if (!err.empty()) return fail("%s", err.c_str());
@@ -498,6 +500,20 @@ int ensure_fused() {
     C->fz2_ok = true;
     // the wave speeds of the steady third variant live in the ring blocks, which are dead by then
     C->fz3_ok = L.fz_uf_max > 0 && (size_t)f2.FW * kBlock * 8 <= (size_t)(2 * f2.HP + (f2.CG + 1) * f2.H1) * 16;
+    if (fm.W <= 4 && f2.FW <= 4) {  // k_stage_fused2c keeps the own cell's rows in registers: face-neighbour stencils only
+      Fused2cMeta &fc = C->fm2c;
+      fc.hdr = f2.hdr; fc.hc_idx = f2.hc_idx; fc.he_idx = f2.he_idx; fc.h2_idx = f2.h2_idx; fc.pack2 = f2.pack2; fc.hf = f2.hf;
+      fc.t_bf = f2.t_bf; fc.gslot = f2.gslot; fc.gc2 = f2.gc2;
+      fc.H1 = f2.H1; fc.HP = f2.HP; fc.E = f2.E; fc.TW = f2.TW; fc.W = f2.W; fc.CG = f2.CG; fc.FW = f2.FW; fc.HF = f2.HF;
+      fc.ntiles = nt; fc.tile_list = nullptr;
+      std::vector<double> fdxy, hfd;
+      fused_face_disp(L, (size_t)C->np, 4, fdxy, hfd);
+      const double *d1, *d2;
+      if (dev_upload(d1, fdxy) || dev_upload(d2, hfd)) return 1;
+      fc.fdxy = reinterpret_cast<const double2 *>(d1);
+      fc.hfd = reinterpret_cast<const double2 *>(d2);
+      C->fz2c_ok = fused2c_x_bytes(fc) + kStages * fused2c_stage_bytes(fc) + 2 * kStages * sizeof(uint64_t) <= 227 * 1024;
+    }
   }
   if (C->nranks > 1) {  // several ranks: only the published-state variant, launched over interior / boundary tiles
     if (!C->fz2_ok) return 0;
@@ -575,6 +591,16 @@ void launch_fused_one(const StageParams &S, const double *pin, double *pout) {
     const int gb = launch_group(k3, k2, mb, ob, attr_set, g_sel.part_off + ga, S, pin, pout);
     C->nparts = g_sel.part_off + ga + gb;
     C->last_launches++;
+    return;
+  }
+  if (C->opt_fuse == 5 && C->fz2c_ok) {
+    static size_t conf5 = 0;
+    static int p3e = 0, p2e = 0;
+    Fused2cMeta meta = C->fm2c;
+    if (g_sel.list) { meta.tile_list = g_sel.list; meta.ntiles = g_sel.n; }
+    launch_persistent(k_stage_fused2c<UM, STEADY, FORM, 3>, k_stage_fused2c<UM, STEADY, FORM, 2>, meta,
+                      fused2c_x_bytes(meta) + kStages * fused2c_stage_bytes(meta) + 2 * kStages * sizeof(uint64_t), "k_stage_fused2c", conf5, p3e,
+                      p2e, S, pin, pout, g_sel.part_off);
     return;
   }
   static size_t conf1 = 0, conf2 = 0, conf3 = 0;
@@ -1348,6 +1374,13 @@ long fvs2d_gpu_mesh_array(const char *name, void *out) {
       fused_coeff_rows(C->L, (size_t)(C->L.n_loc + 31) / 32 * 32, gc);
       if (out) memcpy(out, gc.data(), gc.size() * 8);
       return (long)gc.size();
+    }
+    if (n == "fz_fdxy" || n == "fz_hfd") {  // face displacements of k_stage_fused2c
+      std::vector<double> fdxy, hfd;
+      fused_face_disp(C->L, (size_t)(C->L.n_loc + 31) / 32 * 32, 4, fdxy, hfd);
+      const std::vector<double> &v = n == "fz_fdxy" ? fdxy : hfd;
+      if (out) memcpy(out, v.data(), v.size() * 8);
+      return (long)v.size();
     }
     if (n == "fz_info") {
       const int info[8] = {C->L.fz_built, C->L.fz_w, C->L.fz_s2_max, C->L.fz_tw_max, C->L.fz_h2_max, C->L.fz_v2, C->L.fz_hf_max, C->L.fz_uf_max};

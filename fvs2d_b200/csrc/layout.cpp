@@ -599,4 +599,32 @@ void fused_coeff_rows(const Layout &L, size_t np, std::vector<double> &rows) {
   }
 }
 
+void fused_face_disp(const Layout &L, size_t np, int nrows, std::vector<double> &fdxy, std::vector<double> &hfd) {
+  fdxy.assign((size_t)nrows * np * 2, 0.0);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < L.n_own; i++) {
+    const int sl = i >> 5, lane = i & 31, w = (L.f_off[sl + 1] - L.f_off[sl]) >> 5;
+    for (int k = 0; k < w && k < nrows; k++) {
+      const int e = L.f_off[sl] + 32 * k + lane;
+      if (L.f_nbr[e] == kFacePad) continue;
+      const int le = L.f_edge[e] >> 1;
+      const size_t o = 2 * ((size_t)k * np + i);
+      fdxy[o] = L.ex[le] - L.xc[i]; fdxy[o + 1] = L.ey[le] - L.yc[i];
+    }
+  }
+  hfd.assign(2 * L.fz_hf.size(), 0.0);
+#pragma omp parallel for schedule(static)
+  for (int t = 0; t < L.ntiles; t++) {
+    const int *th = &L.tile_hdr[8 * (size_t)t], *fh = &L.fz_hdr[8 * (size_t)t];
+    for (int e = 0; e < fh[5]; e++) {
+      const uint32_t w = L.fz_hf[fh[4] + e];
+      const int h = (int)(w & 0xFFFFu), es = (int)(w >> 16);
+      const int cell = L.tile_hc_idx[th[2] + h];
+      const int le = es < th[1] ? th[0] + es : L.tile_he_idx[th[4] + es - th[1]];
+      hfd[2 * (size_t)(fh[4] + e)] = L.ex[le] - L.xc[cell];
+      hfd[2 * (size_t)(fh[4] + e) + 1] = L.ey[le] - L.yc[cell];
+    }
+  }
+}
+
 }  // namespace fvs2d

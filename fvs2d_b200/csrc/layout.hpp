@@ -123,5 +123,8 @@ std::string build_fused_tables(Layout &L);
 // Gradient coefficients in the fused kernel's form: rows of `np` (cx, cy) pairs -- row 0 = c0 for the Green-Gauss form,
 // then one row per stencil entry k (the sliced-ELL entry k of every cell; missing entries are zero).
 void fused_coeff_rows(const Layout &L, size_t np, std::vector<double> &rows);
+// Face displacements for k_stage_fused2c: fdxy = rows [k][np] of (x_f - x_c, y_f - y_c) for face k of an owned cell
+// (zero where a cell has fewer faces); hfd = the same for the ring-1 cell of every tile/ring-1 face, aligned with fz_hf.
+void fused_face_disp(const Layout &L, size_t np, int nrows, std::vector<double> &fdxy, std::vector<double> &hfd);
 
 }  // namespace fvs2d

@@ -164,7 +164,11 @@ int fvs2d_gpu_last_timing(double ms[4], long *launches);
  *              face-neighbour stencils; what bench.py selects), 1 k_stage_fused (neighbour data gathered per face), 2 k_stage_fused2 (face states
  *              evaluated once and published), 3 k_stage_fused2 + every face flux evaluated once (measured slower),
  *              4 k_stage_fused2 in two launches per stage: the tiles whose staging fits three CTAs per SM with shared
- *              memory sized for them, then the rest (meshes with quadrilaterals; not yet measured)
+ *              memory sized for them, then the rest (meshes with quadrilaterals; not yet measured),
+ *              5 k_stage_fused2c: the published-state kernel with everything only the owning thread reads (coefficient
+ *              rows, stencil slots, face words, face displacements) loaded straight into registers and one state buffer
+ *              per CTA -- 68 KB instead of 97 KB per CTA on the C4 mix, i.e. three CTAs per SM also for quadrilateral
+ *              tiles (face-neighbour stencils only; not yet measured)
  *   "graph"    1 (default): on one GPU, steps 2..nsub of a call replay a captured CUDA graph; 0: every step eager
  *   "overlap"  1 (default): multi-GPU halo exchange on a second stream, overlapped with interior-tile work
  *   "ctas"     resident CTAs per SM of k_flux_pipe (0 = occupancy API), "smem_pad" / "carveout": extra dynamic shared

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 from fvs2d_b200 import config, meshgen, meshio, solver  # noqa: E402
 
 OUT = os.path.join(ROOT, "gpurun_out", "fused_check.txt")
-FUSE = tuple(int(x) for x in os.environ.get("FUSE", "2,4").split(","))
+FUSE = tuple(int(x) for x in os.environ.get("FUSE", "2,4,5").split(","))
 os.makedirs(os.path.dirname(OUT), exist_ok=True)
 
 

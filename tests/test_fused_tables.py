@@ -39,6 +39,7 @@ def _emulate_residual(mesh, cfg, orc, time, rank=0, nranks=1):
     n2_seen = 0
     assert info[5] == 1, "tables of the second fused variant missing"
     pack2, hf_all, uf_all = A("fz_pack2"), A("fz_hf"), A("fz_uf")
+    fdxy, hfd = A("fz_fdxy").reshape(4, np_, 2), A("fz_hfd").reshape(-1, 2)
     fz8 = A("fz_hdr").reshape(-1, 8)
     for t in range(len(hdr)):
         es, ne, hp, n1, ep, nhe, fbase, fw = (int(x) for x in hdr[t])
@@ -78,6 +79,19 @@ def _emulate_residual(mesh, cfg, orc, time, rank=0, nranks=1):
                     seen.add(e)
                     assert int(hf_all[hfp + e]) == (ns - TILE) | (((w1 >> 16) & 0x7FFF) << 16)
         assert len(seen) == nhf
+        # k_stage_fused2c: the face displacements are bitwise the differences the other kernels form
+        for e in range(nhf):
+            w = int(hf_all[hfp + e])
+            cell, le = int(hc_idx[hp + (w & 0xFFFF)]), int(eids[w >> 16])
+            assert hfd[hfp + e, 0] == ex[le] - xc[cell] and hfd[hfp + e, 1] == ey[le] - yc[cell]
+        for j in range(0, ncell, 5):
+            for k in range(fw):
+                w = int(t_pack[fbase + k * TILE + j])
+                if (w & 0xFFFF) == 0xFFFE:
+                    assert fdxy[k, c0 + j, 0] == 0.0
+                    continue
+                le = int(eids[(w >> 16) & 0x7FFF])
+                assert fdxy[k, c0 + j, 0] == ex[le] - xc[c0 + j] and fdxy[k, c0 + j, 1] == ey[le] - yc[c0 + j]
         # third variant: every cell-face is the c1 or c2 output of exactly one unique face
         ufp, nuf = int(fz8[t, 6]), int(fz8[t, 7])
         assert nuf <= int(info[7])
