@@ -102,7 +102,7 @@ struct Ctx {
   // "fuse" = 4: two launches per stage of k_stage_fused2<2> -- the tiles whose staging fits three CTAs per SM (group A:
   // triangle tiles) with shared memory sized for them, the rest (tiles with quadrilaterals) with theirs
   Fused2cMeta fm2c{};    // "fuse" = 5: the published-state kernel on a shared-memory diet (k_stage_fused2c)
-  bool fz2c_ok = false;
+  bool fz2c_ok = false, fz2c_built = false;
   Fused2Meta fm2a{}, fm2b{};
   bool fz_split = false;
   const int *sp_list[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // [group][all | interior | boundary tiles]
@@ -433,10 +433,32 @@ int build_fused_split() {
   return 0;
 }
 
+// "fuse" = 5: tables of k_stage_fused2c (built only when asked for: fdxy alone is 64 B per cell)
+int build_fused2c() {
+  if (C->fz2c_built || !C->fz2_ok) return 0;
+  C->fz2c_built = true;
+  const Layout &L = C->L;
+  const Fused2Meta &f2 = C->fm2;
+  if (f2.W > 4 || f2.FW > 4) return 0;  // the own cell's rows are held in registers: face-neighbour stencils only
+  Fused2cMeta &fc = C->fm2c;
+  fc.hdr = f2.hdr; fc.hc_idx = f2.hc_idx; fc.he_idx = f2.he_idx; fc.h2_idx = f2.h2_idx; fc.pack2 = f2.pack2; fc.hf = f2.hf;
+  fc.t_bf = f2.t_bf; fc.gslot = f2.gslot; fc.gc2 = f2.gc2;
+  fc.H1 = f2.H1; fc.HP = f2.HP; fc.E = f2.E; fc.TW = f2.TW; fc.W = f2.W; fc.CG = f2.CG; fc.FW = f2.FW; fc.HF = f2.HF;
+  fc.ntiles = L.ntiles; fc.tile_list = nullptr;
+  std::vector<double> fdxy, hfd;
+  fused_face_disp(L, (size_t)C->np, 4, fdxy, hfd);
+  const double *d1, *d2;
+  if (dev_upload(d1, fdxy) || dev_upload(d2, hfd)) return 1;
+  fc.fdxy = reinterpret_cast<const double2 *>(d1);
+  fc.hfd = reinterpret_cast<const double2 *>(d2);
+  C->fz2c_ok = fused2c_x_bytes(fc) + kStages * fused2c_stage_bytes(fc) + 2 * kStages * sizeof(uint64_t) <= 227 * 1024;
+  return 0;
+}
+
 int ensure_fused() {
   if (C->fz_state) return 0;
   C->fz_state = -1;
-  C->fz2_ok = C->fz3_ok = C->fz_auto_ok = C->fz_split = C->fz2c_ok = false;
+  C->fz2_ok = C->fz3_ok = C->fz_auto_ok = C->fz_split = C->fz2c_ok = C->fz2c_built = false;
   if ((C->nranks != 1 && !C->L.deep) || !C->tile_ok || C->recon != RC_K0) return 0;
   const std::string err = build_fused_tables(C->L);
   if (!err.empty()) return fail("%s", err.c_str());
@@ -500,20 +522,7 @@ int ensure_fused() {
     C->fz2_ok = true;
     // the wave speeds of the steady third variant live in the ring blocks, which are dead by then
     C->fz3_ok = L.fz_uf_max > 0 && (size_t)f2.FW * kBlock * 8 <= (size_t)(2 * f2.HP + (f2.CG + 1) * f2.H1) * 16;
-    if (fm.W <= 4 && f2.FW <= 4) {  // k_stage_fused2c keeps the own cell's rows in registers: face-neighbour stencils only
-      Fused2cMeta &fc = C->fm2c;
-      fc.hdr = f2.hdr; fc.hc_idx = f2.hc_idx; fc.he_idx = f2.he_idx; fc.h2_idx = f2.h2_idx; fc.pack2 = f2.pack2; fc.hf = f2.hf;
-      fc.t_bf = f2.t_bf; fc.gslot = f2.gslot; fc.gc2 = f2.gc2;
-      fc.H1 = f2.H1; fc.HP = f2.HP; fc.E = f2.E; fc.TW = f2.TW; fc.W = f2.W; fc.CG = f2.CG; fc.FW = f2.FW; fc.HF = f2.HF;
-      fc.ntiles = nt; fc.tile_list = nullptr;
-      std::vector<double> fdxy, hfd;
-      fused_face_disp(L, (size_t)C->np, 4, fdxy, hfd);
-      const double *d1, *d2;
-      if (dev_upload(d1, fdxy) || dev_upload(d2, hfd)) return 1;
-      fc.fdxy = reinterpret_cast<const double2 *>(d1);
-      fc.hfd = reinterpret_cast<const double2 *>(d2);
-      C->fz2c_ok = fused2c_x_bytes(fc) + kStages * fused2c_stage_bytes(fc) + 2 * kStages * sizeof(uint64_t) <= 227 * 1024;
-    }
+    if (C->opt_fuse == 5 && build_fused2c()) return 1;
   }
   if (C->nranks > 1) {  // several ranks: only the published-state variant, launched over interior / boundary tiles
     if (!C->fz2_ok) return 0;
@@ -1088,6 +1097,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   const bool overlap = C->nranks > 1 && C->opt_overlap && C->tile_ok && C->opt_tile == 2;
   bool p_pending = false;
   if (C->opt_fuse && ensure_fused()) return 1;
+  if (C->opt_fuse == 5 && C->fz_state == 1 && build_fused2c()) return 1;
   const bool fused = (C->opt_fuse > 0 || (C->opt_fuse < 0 && C->fz_auto_ok)) && C->fz_state == 1 && C->opt_tile == 2;
   {  // device step clock (src/runge_kutta.f90:135-145, 218-221): stage times are told + off[stage]
     StepClock hc{};
