@@ -1066,24 +1066,31 @@ __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused2c(const DevM
         for (int v = 0; v < 4; v++) acc[v] += flux[v] * sa;
         wsacc += ws * ha;
       };
-      // face pairs (0,1) and (2,3): two interior faces in one basic block so that the two flux evaluations interleave
+      // face pairs (0,1) and (2,3): two interior faces in one basic block so that the two flux evaluations interleave;
+      // the loops stay rolled (the face words are picked out of their registers by selects) to keep the code small
       bool has_bnd = false;
-#pragma unroll
-      for (int k = 0; k < 4; k += 2) {
-        const uint32_t n0 = pk[k] & 0xFFFFu, n1_ = pk[k + 1] & 0xFFFFu;
+#pragma unroll 1
+      for (int kk = 0; kk < 2; kk++) {
+        const uint32_t w0 = kk ? pk[2] : pk[0], w1 = kk ? pk[3] : pk[1];
+        const uint32_t n0 = w0 & 0xFFFFu, n1_ = w1 & 0xFFFFu;
         has_bnd = has_bnd || n0 == 0xFFFFu || n1_ == 0xFFFFu;
         if (n0 < 0xFFFEu && n1_ < 0xFFFEu) {
-          face(pk[k], k, std::false_type{});
-          face(pk[k + 1], k + 1, std::false_type{});
+          face(w0, 2 * kk, std::false_type{});
+          face(w1, 2 * kk + 1, std::false_type{});
         } else {
-          if (n0 < 0xFFFEu) face(pk[k], k, std::false_type{});
-          if (n1_ < 0xFFFEu) face(pk[k + 1], k + 1, std::false_type{});
+#pragma unroll 1
+          for (int h = 0; h < 2; h++) {
+            const uint32_t w = h ? w1 : w0;
+            if ((w & 0xFFFFu) < 0xFFFEu) face(w, 2 * kk + h, std::false_type{});
+          }
         }
       }
       if (has_bnd) {
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-          if ((pk[k] & 0xFFFFu) == 0xFFFFu) face(pk[k], k, std::true_type{});
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) {
+          const uint32_t w = k == 0 ? pk[0] : k == 1 ? pk[1] : k == 2 ? pk[2] : pk[3];
+          if ((w & 0xFFFFu) == 0xFFFFu) face(w, k, std::true_type{});
+        }
       }
     }
     // (no proxy fence: the regions the bulk copies refill are never written by generic stores -- the gradients go over
