@@ -4,6 +4,8 @@
 //   k_flux_pipe     pass B: face-flux gather + residual + RK stage update; persistent, warp-specialised
 //                   TMA / cp.async shared-memory pipeline (production path)                    [reference K4-K9]
 //   k_flux_rk       pass B, direct global gathers (fallback for meshes whose tiles do not fit the pipeline)
+//   (kernels_fused.cuh: k_stage_fused / k_stage_fused2 / k_stage_fused2c -- pass A folded into the pass-B pipeline,
+//    one kernel per stage, option "fuse")
 //   k_bc_state      Dirichlet / freestream ghost states of the boundary faces for one stage time
 //   k_prim          conserved -> primitive
 //   k_vortex_err    isentropic-vortex error norms                                             [reference K10]
