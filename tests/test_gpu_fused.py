@@ -57,3 +57,19 @@ def test_fuse_is_ignored_where_it_does_not_apply():
     q1, r1, _, l1 = _run(gpu, 2, 4)
     assert np.array_equal(q0, q1) and np.array_equal(r0, r1) and l0 == l1
     gpu.close()
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("FVS2D_TEST_EXPERIMENTAL"),
+                    reason="fuse=4/5 were written after the round's last GPU run; set FVS2D_TEST_EXPERIMENTAL=1 to include them")
+@pytest.mark.parametrize("fuse", [4, 5])
+def test_unmeasured_fused_variants_bitwise(fuse):
+    """split launch (4) and the shared-memory-diet kernel (5): bits of the two-pass path on a triangle and a mixed mesh."""
+    from fvs2d_b200 import config, meshgen, solver
+    for mesh in (meshgen.vortex_tri_mesh(44), meshgen.vortex_mixed_mesh(64)):
+        cfg = config.RunInput(grad_cellcntr_imethd=1, lvortex=True, dt=0.01).to_config()
+        gpu = solver.Fvs2dGpu(cfg, device=0)
+        gpu.set_mesh(mesh)
+        q0, r0, _, l0 = _run(gpu, 0, 8)
+        q, r, _, l = _run(gpu, fuse, 8)
+        assert np.array_equal(q, q0) and np.allclose(r, r0, rtol=1e-13, atol=0.0) and l < l0
+        gpu.close()
