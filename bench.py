@@ -406,6 +406,14 @@ def main():
             roof["traffic"] = tr / 1e9  # GB per launch, from the committed ncu capture
             roof["traffic_unit"] = "GB per launch (ncu dram__bytes_read+write, profiles/r1e_ncu_summary.md)"
             roof["alg_GB_per_launch"] = bB * n_own / 1e9
+    if grad_ms == 0.0 and flux_ms > 0.0:
+        # a fused stage kernel ran (--opt fuse=N): no pass A; its own algorithmic bytes are B_alg - 160 (no gradient write +
+        # read, state read once); the committed ncu traffic figure belongs to k_flux_pipe, not to this kernel
+        fb = bA + bB - 160.0
+        roof.update({"kernel": "k_stage_fused* (one kernel per RK stage: gradients rebuilt in shared memory inside the pass-B pipeline)",
+                     "alg_bytes_per_cell": fb, "achieved": fb * n_own / (flux_ms * 1e-3) / 1e9, "traffic": None})
+        roof.pop("traffic_unit", None)
+        roof.pop("alg_GB_per_launch", None)
     roof["frac"] = roof["achieved"] / peak
     stage = {"alg_bytes_per_cell_stage": bA + bB, "achieved_GBs": (bA + bB) * ncells * 4 * K / (dev_ms * 1e-3) / 1e9}
     stage["frac"] = stage["achieved_GBs"] / (peak * world)
