@@ -51,6 +51,14 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 
+struct FusedLaunch {  // one launch of k_stage_fused over a subset of the tiles
+  FusedMeta meta{};
+  int n_bnd = 0;            // leading boundary tiles of meta.tile_list (several ranks)
+  std::vector<int> tiles;   // host copy of meta.tile_list
+  const void *attr_key = nullptr;
+  int per3 = 0, per2 = 0;
+};
+
 struct Ctx {
   bool inited = false, has_mesh = false, has_state = false;
   fvs2d_config cfg{};
@@ -90,25 +98,25 @@ struct Ctx {
   int opt_overlap = 1;   // multi-GPU: overlap the halo exchanges with interior-tile work (second stream)
   int opt_smem_pad = 0;  // experiment: extra dynamic shared memory (KB) per pass-B CTA (shrinks the L1 carve-out)
   int opt_carveout = -1; // experiment: preferred shared-memory carve-out of the pass-B kernel in KB (-1: driver default)
-  int opt_fuse = 0;      // one kernel per stage where it applies (single GPU, kappa = 0, no limiter): 0 never (default this
-                         // round: the full GPU suite has not been run under -1 yet), -1 automatic (second variant, only where
-                         // three CTAs per SM fit), 1 / 2 / 3 force k_stage_fused / its variants
-  int fz_state = 0;      // 0 not prepared, 1 ready, -1 not applicable to this mesh / scheme
-  FusedMeta fm{};
-  Fused2Meta fm2{};
-  bool fz2_ok = false;   // "fuse" = 2 (published face states) usable
-  bool fz3_ok = false;   // "fuse" = 3 (+ every face flux once) usable
-  bool fz_auto_ok = false;  // the automatic setting uses the fused kernel on this mesh
-  // "fuse" = 4: two launches per stage of k_stage_fused2<2> -- the tiles whose staging fits three CTAs per SM (group A:
-  // triangle tiles) with shared memory sized for them, the rest (tiles with quadrilaterals) with theirs
-  Fused2cMeta fm2c{};    // "fuse" = 5: the published-state kernel on a shared-memory diet (k_stage_fused2c)
-  bool fz2c_ok = false, fz2c_built = false;
-  Fused2Meta fm2a{}, fm2b{};
-  bool fz_split = false;
-  const int *sp_list[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // [group][all | interior | boundary tiles]
-  int sp_n[2][3] = {{0, 0, 0}, {0, 0, 0}};
-  const int *d_fz_int = nullptr, *d_fz_bnd = nullptr;  // several ranks: tiles without / with ghost or sent cells (fused path)
-  int n_fz_int = 0, n_fz_bnd = 0;
+  int opt_fuse = -1;     // one kernel per stage (k_stage_fused) where it applies -- second-order upwind reconstruction without
+                         // limiter, gradient tables that fit shared memory: -1 automatic (default), 0 never (two-pass path),
+                         // 2 force a single launch per stage (no split by shared-memory need)
+  int fz_state = 0;      // launch plan: 0 not prepared, 1 ready, -1 not applicable to this mesh / scheme
+  int fz_tables = 0;     // device tables: 0 not uploaded, 1 uploaded, -1 this mesh has none
+  FusedMeta fm{};        // table pointers shared by the launches of a stage
+  FusedLaunch fl[2];     // the launch plan of a stage (build_fused_plan)
+  int n_fl = 0;
+  // in-kernel halo exchange of the fused path (several ranks): peers' arrays mapped with CUDA IPC
+  bool p2p_ok = false;
+  double *p_buf[2] = {nullptr, nullptr};    // the two primitive-state buffers (pa / pb swap every stage)
+  double2 *peer_p[kMaxPeers][2] = {};       // the same two buffers of every peer
+  int peer_np[kMaxPeers] = {}, peer_recv_begin[kMaxPeers] = {};
+  unsigned *peer_flag[kMaxPeers] = {};
+  unsigned *flags = nullptr, *done_ctr = nullptr;  // flags[r]: stages rank r has delivered to this rank
+  std::vector<void *> ipc_open;
+  const uint32_t *d_rs_word = nullptr;
+  const int2 *d_rs_ent = nullptr;
+  unsigned epoch_total = 0;  // Runge-Kutta stages run through the in-kernel exchange so far (all ranks agree)
   cudaStream_t sx = nullptr;  // exchange stream
   cudaEvent_t e_a = nullptr, e_g = nullptr, e_b = nullptr, e_p = nullptr;
   const int *d_tile_int = nullptr, *d_tile_bnd = nullptr;
@@ -166,7 +174,14 @@ int dev_upload(const T *&p, const std::vector<T> &h) {
 }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+void close_p2p();
+int all_ranks_agree(int mine, int &all);
 void free_device() {
+  if (C->p2p_ok) {  // peers have this rank's buffers mapped: everybody unmaps before anybody frees
+    close_p2p();
+    int dummy = 0;
+    if (C->comm && C->st) all_ranks_agree(1, dummy);
+  }
   for (void *p : C->allocs) cudaFree(p);
   C->allocs.clear();
   C->bytes = 0;
@@ -174,7 +189,8 @@ void free_device() {
   C->logbuf = nullptr; C->log_cap = 0;
   C->d_n2c_ptr = C->d_n2c = nullptr; C->d_idw = nullptr; C->d_fnode = nullptr;
   C->d_be_cell = nullptr; C->d_be_xy = C->d_be_nxy = nullptr; C->d_be_out = nullptr;
-  C->fz_state = 0;
+  C->fz_state = 0; C->n_fl = 0; C->fz_tables = 0;
+  C->flags = nullptr; C->done_ctr = nullptr; C->d_rs_word = nullptr; C->d_rs_ent = nullptr;
 }
 
 // ---- event-based kernel timing (option "timing") ------------------------------------------------
@@ -193,6 +209,13 @@ struct Span {
     C->ev_spans[bucket].push_back({a, a + 1});
   }
 };
+
+int recon_mode(const fvs2d_config &c) {
+  const double kap = c.recon == 3 ? c.umuscl_cst : 0.0;  // src/input.f90:248-254
+  if (c.recon == 1) return RC_FIRST;
+  if (kap == 0.0) return c.limiter > 0 ? RC_K0_PHI : RC_K0;
+  return RC_GENERAL;
+}
 
 int rk_setup() {  // src/runge_kutta.f90:25-88
   const fvs2d_config &c = C->cfg;
@@ -371,267 +394,191 @@ int launch_flux(int um, const StageParams &S, const double *pin, double *pout, c
 }
 
 // ---- one kernel per stage (option "fuse"): tables on first use, then k_stage_fused instead of pass A + pass B
-size_t fused_smem() {
-  const FusedMeta &fm = C->fm;
-  return kStages * fused_stage_bytes(fm.S1, fm.S2, fm.E, fm.TW, fm.W, fm.CG) + 2 * kStages * sizeof(uint64_t);
+size_t fused_cta_bytes(const FusedMeta &g) { return kStages * fused_stage_bytes(g) + 2 * kStages * sizeof(uint64_t); }
+
+// Pitches of a launch over `tiles`: the maxima over those tiles only, so that a launch over the triangle tiles of a mixed
+// mesh needs less shared memory (three CTAs per SM) than one that also holds quadrilateral tiles (two).
+FusedMeta fused_group_meta(const std::vector<int> &tiles) {
+  const Layout &L = C->L;
+  const int F0 = L.g_form == 0 ? 1 : 0;
+  FusedMeta g = C->fm;  // pointers
+  int n1m = 0, s2m = 0, em = 0, twm = 0, wm = 0, fwm = 0, hfm = 0;
+  for (int t : tiles) {
+    const int *th = &L.tile_hdr[8 * (size_t)t], *fh = &L.fz_hdr[8 * (size_t)t];
+    n1m = std::max(n1m, th[3]); s2m = std::max(s2m, th[3] + fh[1]); em = std::max(em, th[1] + th[5]);
+    twm = std::max(twm, (kBlock + th[3] + 7) & ~7); wm = std::max(wm, fh[3]); fwm = std::max(fwm, th[7]); hfm = std::max(hfm, fh[5]);
+  }
+  g.H1 = (n1m + 1) & ~1; g.HP = (s2m + 1) & ~1; g.E = (em + 1) & ~1; g.TW = twm; g.W = wm; g.CG = std::max(4, wm + F0);
+  g.FW = fwm; g.HF = (hfm + 3) & ~3;
+  g.XR = std::max(3 + wm + F0, 2 * fwm + (2 * g.HF + kBlock - 1) / kBlock);
+  g.ntiles = (int)tiles.size();
+  return g;
 }
 
-// "fuse" = 4: split the tiles into the group whose staging fits three CTAs per SM and the rest; each group gets a
-// Fused2Meta with pitches sized for its own tiles and a tile list
-int build_fused_split() {
+// The launch plan of a stage: at most two launches of k_stage_fused.
+//   one rank      [tiles that fit three CTAs per SM] , [the rest]               (either may be empty)
+//   several ranks [interior tiles that fit three CTAs per SM] , [boundary tiles (all of them, first) + the other interior tiles]
+// Boundary tiles = tiles that read a ghost or hold a cell a peer needs (fz_tile_bnd); only the launch that holds them
+// takes part in the in-kernel halo exchange, and the other one runs first, so the peers get a whole interior phase.
+int build_fused_plan() {
   const Layout &L = C->L;
-  const int nt = L.ntiles, F0 = L.g_form == 0 ? 1 : 0;
+  const int nt = L.ntiles;
   int sm_smem = 0;
   CUDA_OK(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, C->device));
-  auto group_meta = [&](const std::vector<int> &tiles) {
-    Fused2Meta g = C->fm2;  // pointers
-    int n1m = 0, s2m = 0, em = 0, twm = 0, wm = 0, fwm = 0, hfm = 0;
-    for (int t : tiles) {
-      const int *th = &L.tile_hdr[8 * (size_t)t], *fh = &L.fz_hdr[8 * (size_t)t];
-      n1m = std::max(n1m, th[3]); s2m = std::max(s2m, th[3] + fh[1]); em = std::max(em, th[1] + th[5]);
-      twm = std::max(twm, (kBlock + th[3] + 7) & ~7); wm = std::max(wm, fh[3]); fwm = std::max(fwm, th[7]); hfm = std::max(hfm, fh[5]);
-    }
-    g.H1 = (n1m + 1) & ~1; g.HP = (s2m + 1) & ~1; g.E = (em + 1) & ~1; g.TW = twm; g.W = wm; g.CG = std::max(4, wm + F0);
-    g.FW = fwm; g.HF = (hfm + 3) & ~3;
-    g.XR = std::max(3 + wm + F0, 2 * fwm + (2 * g.HF + kBlock - 1) / kBlock);
-    g.ntiles = (int)tiles.size();
-    return g;
-  };
-  auto cta_bytes = [&](const Fused2Meta &g) { return kStages * fused2_stage_bytes(g) + 2 * kStages * sizeof(uint64_t); };
   const size_t cap = (size_t)sm_smem / 3 - 1024;  // per CTA for three CTAs per SM
+  std::vector<unsigned char> is_bnd(nt, 0);
+  if (C->nranks > 1) for (int t : L.fz_tile_bnd) is_bnd[t] = 1;
   std::vector<size_t> need(nt);
-  for (int t = 0; t < nt; t++) need[t] = cta_bytes(group_meta(std::vector<int>(1, t)));
+  for (int t = 0; t < nt; t++) need[t] = fused_cta_bytes(fused_group_meta(std::vector<int>(1, t)));
   std::vector<int> ta, tb;
   double thr = (double)cap;
-  for (int iter = 0; iter < 24; iter++, thr *= 0.985) {  // the group's pitches are maxima per array: tighten until the group fits
+  for (int iter = 0; iter < 24; iter++, thr *= 0.985) {  // a group's pitches are maxima per array: tighten until group A fits
     ta.clear(); tb.clear();
-    for (int t = 0; t < nt; t++) (need[t] <= (size_t)thr ? ta : tb).push_back(t);
-    if (ta.empty() || cta_bytes(group_meta(ta)) <= cap) break;
+    for (int t = 0; t < nt; t++) ((!is_bnd[t] && need[t] <= (size_t)thr) ? ta : tb).push_back(t);
+    if (ta.empty() || fused_cta_bytes(fused_group_meta(ta)) <= cap) break;
   }
-  if (ta.empty() || tb.empty() || cta_bytes(group_meta(ta)) > cap) return 0;  // nothing to split
-  C->fm2a = group_meta(ta);
-  C->fm2b = group_meta(tb);
-  {  // per group: all its tiles, and (several ranks) its interior / boundary tiles
-    std::vector<unsigned char> is_bnd(nt, 0);
-    for (int t : L.fz_tile_bnd) is_bnd[t] = 1;
-    const std::vector<int> *grp[2] = {&ta, &tb};
-    for (int gi = 0; gi < 2; gi++) {
-      std::vector<int> sub[3];
-      for (int t : *grp[gi]) { sub[0].push_back(t); sub[is_bnd[t] ? 2 : 1].push_back(t); }
-      for (int k = 0; k < 3; k++) {
-        if (dev_upload(C->sp_list[gi][k], sub[k])) return 1;
-        C->sp_n[gi][k] = (int)sub[k].size();
-      }
-    }
-    C->fm2a.tile_list = C->sp_list[0][0];
-    C->fm2b.tile_list = C->sp_list[1][0];
+  if (!ta.empty() && fused_cta_bytes(fused_group_meta(ta)) > cap) { tb.insert(tb.end(), ta.begin(), ta.end()); ta.clear(); }
+  if (C->opt_fuse == 2 || ta.size() * 8 < (size_t)nt) { tb.insert(tb.end(), ta.begin(), ta.end()); ta.clear(); }  // not worth a launch
+  // group B: boundary tiles first
+  std::stable_sort(tb.begin(), tb.end(), [&](int x, int y) { return is_bnd[x] > is_bnd[y] || (is_bnd[x] == is_bnd[y] && x < y); });
+  int nb = 0;
+  for (int t : tb) nb += is_bnd[t];
+  C->n_fl = 0;
+  for (const std::vector<int> *grp : {&ta, &tb}) {
+    if (grp->empty()) continue;
+    FusedLaunch &fl = C->fl[C->n_fl++];
+    fl = FusedLaunch();
+    fl.meta = fused_group_meta(*grp);
+    if (fused_cta_bytes(fl.meta) > 227 * 1024) { C->n_fl = 0; return 0; }  // wide stencils: two-pass path
+    if (dev_upload(fl.meta.tile_list, *grp)) return 1;
+    fl.n_bnd = grp == &tb ? nb : 0;
+    fl.tiles = *grp;
   }
-  C->fz_split = true;
   if (getenv("FVS2D_DEBUG"))
-    fprintf(stderr, "[fvs2d] fused split: %d tiles at %zu B/CTA (3 CTAs/SM), %d tiles at %zu B/CTA\n", (int)ta.size(), cta_bytes(C->fm2a),
-            (int)tb.size(), cta_bytes(C->fm2b));
+    for (int k = 0; k < C->n_fl; k++)
+      fprintf(stderr, "[fvs2d] rank %d fused launch %d: %d tiles (%d boundary first) at %zu B/CTA\n", C->rank, k, C->fl[k].meta.ntiles,
+              C->fl[k].n_bnd, fused_cta_bytes(C->fl[k].meta));
   return 0;
 }
 
-// "fuse" = 5: tables of k_stage_fused2c (built only when asked for: fdxy alone is 64 B per cell)
-int build_fused2c() {
-  if (C->fz2c_built || !C->fz2_ok) return 0;
-  C->fz2c_built = true;
+int upload_fused_tables();
+
+// several ranks: which peer ghost slots every cell of a boundary tile is stored to (HaloP2P::rs_word / rs_ent)
+int build_remote_store_tables() {
   const Layout &L = C->L;
-  const Fused2Meta &f2 = C->fm2;
-  if (f2.W > 4 || f2.FW > 4) return 0;  // the own cell's rows are held in registers: face-neighbour stencils only
-  Fused2cMeta &fc = C->fm2c;
-  fc.hdr = f2.hdr; fc.hc_idx = f2.hc_idx; fc.he_idx = f2.he_idx; fc.h2_idx = f2.h2_idx; fc.pack2 = f2.pack2; fc.hf = f2.hf;
-  fc.t_bf = f2.t_bf; fc.gslot = f2.gslot; fc.gc2 = f2.gc2;
-  fc.H1 = f2.H1; fc.HP = f2.HP; fc.E = f2.E; fc.TW = f2.TW; fc.W = f2.W; fc.CG = f2.CG; fc.FW = f2.FW; fc.HF = f2.HF;
-  fc.ntiles = L.ntiles; fc.tile_list = nullptr;
-  std::vector<double> fdxy, hfd;
-  fused_face_disp(L, (size_t)C->np, 4, fdxy, hfd);
-  const double *d1, *d2;
-  if (dev_upload(d1, fdxy) || dev_upload(d2, hfd)) return 1;
-  fc.fdxy = reinterpret_cast<const double2 *>(d1);
-  fc.hfd = reinterpret_cast<const double2 *>(d2);
-  C->fz2c_ok = fused2c_x_bytes(fc) + kStages * fused2c_stage_bytes(fc) + 2 * kStages * sizeof(uint64_t) <= 227 * 1024;
+  C->d_rs_word = nullptr; C->d_rs_ent = nullptr;
+  if (C->nranks == 1 || !C->p2p_ok || C->n_fl == 0) return 0;
+  const FusedLaunch &fl = C->fl[C->n_fl - 1];
+  std::vector<std::vector<int2>> ent(L.n_own);
+  for (size_t k = 0; k < L.peers.size(); k++)
+    for (int pos = L.send_ptr[k]; pos < L.send_ptr[k + 1]; pos++)
+      ent[L.send_idx[pos]].push_back(make_int2((int)k, C->peer_recv_begin[k] + pos - L.send_ptr[k]));
+  std::vector<uint32_t> word((size_t)std::max(1, fl.n_bnd) * kBlock, 0u);
+  std::vector<int2> flat;
+  for (int j = 0; j < fl.n_bnd; j++) {
+    const int c0 = fl.tiles[j] * kBlock;
+    for (int c = c0; c < std::min(L.n_own, c0 + kBlock); c++) {
+      if (ent[c].empty()) continue;
+      NEED(ent[c].size() <= 7 && flat.size() < (1u << 28), "in-kernel halo exchange: a cell is sent to more than 7 peers");
+      word[(size_t)j * kBlock + (c - c0)] = (uint32_t)(flat.size() << 3) | (uint32_t)ent[c].size();
+      flat.insert(flat.end(), ent[c].begin(), ent[c].end());
+    }
+  }
+  // every sent cell must sit in a boundary tile of this launch
+  size_t nsend = L.send_idx.size();
+  NEED(flat.size() == nsend, "in-kernel halo exchange: a sent cell lies outside the boundary tiles");
+  if (flat.empty()) flat.push_back(make_int2(0, 0));
+  if (dev_upload(C->d_rs_word, word) || dev_upload(C->d_rs_ent, flat)) return 1;
   return 0;
 }
 
 int ensure_fused() {
   if (C->fz_state) return 0;
   C->fz_state = -1;
-  C->fz2_ok = C->fz3_ok = C->fz_auto_ok = C->fz_split = C->fz2c_ok = C->fz2c_built = false;
-  if ((C->nranks != 1 && !C->L.deep) || !C->tile_ok || C->recon != RC_K0) return 0;
+  C->n_fl = 0;
+  if ((C->nranks != 1 && (!C->L.deep || !C->p2p_ok)) || !C->tile_ok || C->recon != RC_K0) return 0;
+  if (C->fz_tables == 0 && upload_fused_tables()) return 1;
+  if (C->fz_tables != 1) return 0;
+  if (build_fused_plan()) return 1;  // (again after a change of the "fuse" option: the tile lists are small)
+  if (C->n_fl == 0) return 0;
+  if (build_remote_store_tables()) return 1;
+  C->fz_state = 1;
+  return 0;
+}
+
+int upload_fused_tables() {
+  C->fz_tables = -1;
   const std::string err = build_fused_tables(C->L);
   if (!err.empty()) return fail("%s", err.c_str());
   const Layout &L = C->L;
-  if (L.fz_built != 1) return 0;
+  if (L.fz_built != 1 || !L.fz_v2) return 0;
+  const int nt = L.ntiles;
   FusedMeta &fm = C->fm;
-  Fused2Meta &f2 = C->fm2;
-  const int F0 = L.g_form == 0 ? 1 : 0, nt = L.ntiles;
-  fm.W = L.fz_w; fm.CG = std::max(4, L.fz_w + F0);
-  fm.S1 = C->pm.S; fm.S2 = (L.fz_s2_max + 1) & ~1; fm.E = C->pm.E; fm.TW = L.fz_tw_max; fm.ntiles = nt;
-  if (fused_smem() > 227 * 1024) return 0;  // wide stencils (GGNB, LSQ-nn on some meshes): two-pass path
-  bool v2 = L.fz_v2 != 0;
-  size_t smem2 = 0;
-  if (v2) {  // second / third variant: published face states
-    f2.H1 = fm.S1 - kBlock; f2.HP = fm.S2 - kBlock; f2.E = fm.E; f2.TW = fm.TW; f2.W = fm.W; f2.CG = fm.CG; f2.ntiles = nt;
-    f2.FW = 0;
-    for (int t = 0; t < nt; t++) f2.FW = std::max(f2.FW, L.tile_hdr[8 * (size_t)t + 7]);
-    f2.HF = (L.fz_hf_max + 3) & ~3;
-    f2.XR = std::max(3 + fm.W + F0, 2 * f2.FW + (2 * f2.HF + kBlock - 1) / kBlock);
-    smem2 = kStages * fused2_stage_bytes(f2) + 2 * kStages * sizeof(uint64_t);
-    v2 = smem2 <= 227 * 1024;
-  }
-  {
-    // automatic: the fused kernel replaces the two passes where it was measured to win clearly -- the variant with
-    // published face states at three CTAs per SM (triangle meshes with face-neighbour stencils: C3 1.44 -> 1.21-1.27 ms
-    // per step).  At two CTAs per SM (meshes with quadrilaterals) it only matches the two-pass path: stay there.
-    int sm_smem = 0;
-    CUDA_OK(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, C->device));
-    C->fz_auto_ok = v2 && 3 * (smem2 + 1024) <= (size_t)sm_smem;
-    if (C->opt_fuse < 0 && !C->fz_auto_ok) return 0;
-  }
-  std::vector<int> hdr(12 * (size_t)nt);
+  std::vector<int> hdr4(16 * (size_t)nt, 0);
   for (int t = 0; t < nt; t++) {
-    std::copy(&L.tile_hdr[8 * (size_t)t], &L.tile_hdr[8 * (size_t)t] + 8, &hdr[12 * (size_t)t]);
-    std::copy(&L.fz_hdr[8 * (size_t)t], &L.fz_hdr[8 * (size_t)t] + 4, &hdr[12 * (size_t)t + 8]);
+    std::copy(&L.tile_hdr[8 * (size_t)t], &L.tile_hdr[8 * (size_t)t] + 8, &hdr4[16 * (size_t)t]);
+    std::copy(&L.fz_hdr[8 * (size_t)t], &L.fz_hdr[8 * (size_t)t] + 6, &hdr4[16 * (size_t)t + 8]);
   }
   std::vector<double> gc;
   fused_coeff_rows(L, (size_t)C->np, gc);
   static_assert(sizeof(double2) == 2 * sizeof(double), "double2 layout");
   const int *dh;
-  if (dev_upload(dh, hdr) || dev_upload(fm.h2_idx, L.fz_h2_idx) || dev_upload(fm.gslot, L.fz_gslot)) return 1;
-  {
-    const double *dgc;
-    if (dev_upload(dgc, gc)) return 1;
-    fm.gc2 = reinterpret_cast<const double2 *>(dgc);
-  }
+  const double *dgc;
+  if (dev_upload(dh, hdr4) || dev_upload(fm.h2_idx, L.fz_h2_idx) || dev_upload(fm.gslot, L.fz_gslot) || dev_upload(dgc, gc) ||
+      dev_upload(fm.pack2, L.fz_pack2) || dev_upload(fm.hf, L.fz_hf)) return 1;
   fm.hdr = reinterpret_cast<const int4 *>(dh);
-  fm.hc_idx = C->pm.hc_idx; fm.he_idx = C->pm.he_idx; fm.t_pack = C->pm.t_pack; fm.t_bf = C->pm.t_bf;
-  if (v2) {
-    f2.hc_idx = fm.hc_idx; f2.he_idx = fm.he_idx; f2.h2_idx = fm.h2_idx; f2.t_bf = fm.t_bf; f2.gslot = fm.gslot; f2.gc2 = fm.gc2;
-    std::vector<int> hdr4(16 * (size_t)nt, 0);
-    for (int t = 0; t < nt; t++) {
-      std::copy(&hdr[12 * (size_t)t], &hdr[12 * (size_t)t] + 12, &hdr4[16 * (size_t)t]);
-      std::copy(&L.fz_hdr[8 * (size_t)t + 4], &L.fz_hdr[8 * (size_t)t + 4] + 4, &hdr4[16 * (size_t)t + 12]);
-    }
-    const int *dh4;
-    const uint32_t *duf;
-    if (dev_upload(dh4, hdr4) || dev_upload(f2.pack2, L.fz_pack2) || dev_upload(f2.hf, L.fz_hf) || dev_upload(duf, L.fz_uf)) return 1;
-    f2.hdr = reinterpret_cast<const int4 *>(dh4);
-    f2.uf = reinterpret_cast<const uint2 *>(duf);
-    C->fz2_ok = true;
-    // the wave speeds of the steady third variant live in the ring blocks, which are dead by then
-    C->fz3_ok = L.fz_uf_max > 0 && (size_t)f2.FW * kBlock * 8 <= (size_t)(2 * f2.HP + (f2.CG + 1) * f2.H1) * 16;
-    if (C->opt_fuse == 5 && build_fused2c()) return 1;
-  }
-  if (C->nranks > 1) {  // several ranks: only the published-state variant, launched over interior / boundary tiles
-    if (!C->fz2_ok) return 0;
-    if (dev_upload(C->d_fz_int, L.fz_tile_int) || dev_upload(C->d_fz_bnd, L.fz_tile_bnd)) return 1;
-    C->n_fz_int = (int)L.fz_tile_int.size(); C->n_fz_bnd = (int)L.fz_tile_bnd.size();
-    C->fz_state = 1;
-    return build_fused_split();
-  }
-  C->fz_state = 1;
-  if (C->fz2_ok && build_fused_split()) return 1;
+  fm.gc2 = reinterpret_cast<const double2 *>(dgc);
+  fm.hc_idx = C->pm.hc_idx; fm.he_idx = C->pm.he_idx; fm.t_bf = C->pm.t_bf;
+  fm.tile_list = nullptr;
+  C->fz_tables = 1;
   return 0;
-}
-
-// persistent launch of one of the fused kernels: the 128-register build when three CTAs fit an SM, else the build
-// compiled for two CTAs per SM (more registers)
-template <class K, class Meta>
-void launch_persistent(K k3, K k2, const Meta &meta, size_t smem, const char *name, size_t &configured, int &per3, int &per2,
-                       const StageParams &S, const double *pin, double *pout, int part_off = 0) {
-  if (configured != smem) {
-    cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per3, k3, kPipeThreads, smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, k2, kPipeThreads, smem);
-    configured = smem;
-    if (getenv("FVS2D_DEBUG")) fprintf(stderr, "[fvs2d] %s: %zu B smem/CTA, CTAs/SM %d (128 regs) / %d\n", name, smem, per3, per2);
-  }
-  const bool use3 = per3 >= 3 && (C->opt_ctas == 0 || C->opt_ctas >= 3);
-  int per_sm = std::max(1, use3 ? per3 : per2);
-  if (C->opt_ctas > 0) per_sm = std::min(per_sm, C->opt_ctas);
-  const int grid = std::min(meta.ntiles, C->nsm * per_sm);
-  if (grid > 0)
-    (use3 ? k3 : k2)<<<grid, kPipeThreads, smem, C->st>>>(C->dm, meta, C->phys, S, pin, C->bc, C->q, C->f, pout, C->dtl,
-                                                          C->partial + 4 * (size_t)part_off);
-  C->nparts = part_off + grid;
-}
-
-struct OccCache { size_t smem = 0; int per3 = 0, per2 = 0; };
-// one launch of k_stage_fused2<2> over a group of tiles ("fuse" = 4); its partial sums start at part_off
-template <class K>
-int launch_group(K k3, K k2, const Fused2Meta &meta, OccCache &oc, size_t &attr_set, int part_off, const StageParams &S,
-                 const double *pin, double *pout) {
-  const size_t smem = kStages * fused2_stage_bytes(meta) + 2 * kStages * sizeof(uint64_t);
-  if (smem > attr_set) {
-    cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = smem;
-  }
-  if (oc.smem != smem) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc.per3, k3, kPipeThreads, smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc.per2, k2, kPipeThreads, smem);
-    oc.smem = smem;
-    if (getenv("FVS2D_DEBUG")) fprintf(stderr, "[fvs2d] k_stage_fused2 group: %zu B smem/CTA, CTAs/SM %d (128 regs) / %d\n", smem, oc.per3, oc.per2);
-  }
-  const bool use3 = oc.per3 >= 3;
-  const int per_sm = std::max(1, use3 ? oc.per3 : oc.per2);
-  const int grid = std::min(meta.ntiles, C->nsm * per_sm);
-  if (grid > 0)
-    (use3 ? k3 : k2)<<<grid, kPipeThreads, smem, C->st>>>(C->dm, meta, C->phys, S, pin, C->bc, C->q, C->f, pout, C->dtl,
-                                                          C->partial + 4 * (size_t)part_off);
-  return grid;
 }
 
 template <int UM, bool STEADY, int FORM>
 void launch_fused_one(const StageParams &S, const double *pin, double *pout) {
-  if (C->opt_fuse == 4 && C->fz_split) {
-    static OccCache oa, ob;
-    static size_t attr_set = 0;
-    auto k3 = k_stage_fused2<UM, STEADY, FORM, 3, 2>;
-    auto k2 = k_stage_fused2<UM, STEADY, FORM, 2, 2>;
-    const int sub = !g_sel.list ? 0 : g_sel.list == C->d_fz_int ? 1 : 2;  // several ranks: interior / boundary tiles of each group
-    Fused2Meta ma = C->fm2a, mb = C->fm2b;
-    ma.tile_list = C->sp_list[0][sub]; ma.ntiles = C->sp_n[0][sub];
-    mb.tile_list = C->sp_list[1][sub]; mb.ntiles = C->sp_n[1][sub];
-    const int ga = launch_group(k3, k2, ma, oa, attr_set, g_sel.part_off, S, pin, pout);
-    const int gb = launch_group(k3, k2, mb, ob, attr_set, g_sel.part_off + ga, S, pin, pout);
-    C->nparts = g_sel.part_off + ga + gb;
+  int part_off = 0;
+  for (int k = 0; k < C->n_fl; k++) {
+    FusedLaunch &fl = C->fl[k];
+    auto k3 = k_stage_fused<UM, STEADY, FORM, 3>;
+    auto k2 = k_stage_fused<UM, STEADY, FORM, 2>;  // more registers, for launches that only fit two CTAs per SM anyway
+    const size_t smem = fused_cta_bytes(fl.meta);
+    const void *key = (const void *)k3;
+    if (fl.attr_key != key) {  // per context and kernel instance: function attributes are per device
+      cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fl.per3, k3, kPipeThreads, smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fl.per2, k2, kPipeThreads, smem);
+      fl.attr_key = key;
+      if (getenv("FVS2D_DEBUG")) fprintf(stderr, "[fvs2d] k_stage_fused launch %d: %zu B smem/CTA, CTAs/SM %d (128 regs) / %d\n", k, smem, fl.per3, fl.per2);
+    }
+    const bool use3 = fl.per3 >= 3 && (C->opt_ctas == 0 || C->opt_ctas >= 3);
+    int per_sm = std::max(1, use3 ? fl.per3 : fl.per2);
+    if (C->opt_ctas > 0) per_sm = std::min(per_sm, C->opt_ctas);
+    const int grid = std::min(fl.meta.ntiles, C->nsm * per_sm);
+    HaloP2P hx{};
+    if (C->nranks > 1 && fl.n_bnd > 0) {
+      const int which = pout == C->p_buf[0] ? 0 : 1;
+      hx.n_peers = (int)C->L.peers.size();
+      hx.n_bnd = fl.n_bnd; hx.n_bnd_ctas = std::min(fl.n_bnd, grid);
+      hx.stage = S.stage; hx.clk = C->clk;
+      for (int q = 0; q < hx.n_peers; q++) {
+        hx.peer_out[q] = C->peer_p[q][which];
+        hx.peer_np[q] = C->peer_np[q];
+        hx.peer_flag[q] = C->peer_flag[q];
+        hx.my_flag[q] = C->flags + C->L.peers[q];
+      }
+      hx.rs_word = C->d_rs_word; hx.rs_ent = C->d_rs_ent; hx.done_ctr = C->done_ctr;
+    }
+    if (grid > 0)
+      (use3 ? k3 : k2)<<<grid, kPipeThreads, smem, C->st>>>(C->dm, fl.meta, C->phys, S, pin, C->bc, C->q, C->f, pout, C->dtl,
+                                                            C->partial + 4 * (size_t)part_off, hx);
+    part_off += grid;
     C->last_launches++;
-    return;
   }
-  if (C->opt_fuse == 5 && C->fz2c_ok) {
-    static size_t conf5 = 0;
-    static int p3e = 0, p2e = 0;
-    Fused2cMeta meta = C->fm2c;
-    if (g_sel.list) { meta.tile_list = g_sel.list; meta.ntiles = g_sel.n; }
-    launch_persistent(k_stage_fused2c<UM, STEADY, FORM, 3>, k_stage_fused2c<UM, STEADY, FORM, 2>, meta,
-                      fused2c_x_bytes(meta) + kStages * fused2c_stage_bytes(meta) + 2 * kStages * sizeof(uint64_t), "k_stage_fused2c", conf5, p3e,
-                      p2e, S, pin, pout, g_sel.part_off);
-    return;
-  }
-  static size_t conf1 = 0, conf2 = 0, conf3 = 0;
-  static int p3a = 0, p2a = 0, p3b = 0, p2b = 0, p3c = 0, p2c = 0;
-  if (C->opt_fuse == 3 && C->fz3_ok && !g_sel.list)
-    launch_persistent(k_stage_fused2<UM, STEADY, FORM, 3, 3>, k_stage_fused2<UM, STEADY, FORM, 2, 3>, C->fm2,
-                      kStages * fused2_stage_bytes(C->fm2) + 2 * kStages * sizeof(uint64_t), "k_stage_fused2<VAR 3>", conf3, p3c, p2c, S, pin, pout);
-  else if ((C->opt_fuse != 1 || g_sel.list) && C->fz2_ok) {
-    Fused2Meta meta = C->fm2;
-    if (g_sel.list) { meta.tile_list = g_sel.list; meta.ntiles = g_sel.n; }  // several ranks: interior / boundary tiles
-    launch_persistent(k_stage_fused2<UM, STEADY, FORM, 3, 2>, k_stage_fused2<UM, STEADY, FORM, 2, 2>, meta,
-                      kStages * fused2_stage_bytes(meta) + 2 * kStages * sizeof(uint64_t), "k_stage_fused2<VAR 2>", conf2, p3b, p2b, S, pin, pout,
-                      g_sel.part_off);
-  }
-  else
-    launch_persistent(k_stage_fused<UM, STEADY, FORM, 3>, k_stage_fused<UM, STEADY, FORM, 2>, C->fm, fused_smem(), "k_stage_fused",
-                      conf1, p3a, p2a, S, pin, pout);
+  C->nparts = part_off;
 }
 
-int launch_fused(int um, const StageParams &S, const double *pin, double *pout, const int *list = nullptr, int nlist = 0, int part_off = 0) {
-  g_sel.list = list; g_sel.n = nlist; g_sel.part_off = part_off;
-  if (list && nlist == 0) { C->nparts = part_off; return 0; }
+int launch_fused(int um, const StageParams &S, const double *pin, double *pout) {
   Span sp(2);
   const bool steady = C->cfg.steady != 0, gg = C->L.g_form == 0;
   if (um == UM_RK) {
@@ -641,7 +588,6 @@ int launch_fused(int um, const StageParams &S, const double *pin, double *pout, 
     if (steady) { if (gg) launch_fused_one<UM_SSPRK, true, 0>(S, pin, pout); else launch_fused_one<UM_SSPRK, true, 1>(S, pin, pout); }
     else { if (gg) launch_fused_one<UM_SSPRK, false, 0>(S, pin, pout); else launch_fused_one<UM_SSPRK, false, 1>(S, pin, pout); }
   }
-  C->last_launches++;
   return 0;
 }
 
@@ -654,6 +600,99 @@ int launch_bc(int stage) {
   C->last_launches++;
   C->bc_static_done = true;
   return 0;
+}
+
+// ---- in-kernel halo exchange of the fused path: map the peers' state buffers and flag words (CUDA IPC) ----------
+constexpr int kMaxRanks = 16;
+struct P2PInfo {
+  cudaIpcMemHandle_t h[3];   // primitive-state buffers 0 / 1, flag words
+  long long off[3];          // offset of the array inside the exported allocation (small cudaMallocs are sub-allocated)
+  int np, ok;
+  int recv_begin[kMaxRanks], recv_count[kMaxRanks];  // by sender rank: where its cells land in this rank's numbering
+};
+
+void close_p2p() {
+  for (void *b : C->ipc_open) cudaIpcCloseMemHandle(b);
+  C->ipc_open.clear();
+  C->p2p_ok = false;
+}
+
+int all_ranks_agree(int mine, int &all) {  // min over the communicator (also a barrier)
+  int *d = nullptr;
+  CUDA_OK(cudaMalloc(&d, sizeof(int)));
+  CUDA_OK(cudaMemcpyAsync(d, &mine, sizeof(int), cudaMemcpyHostToDevice, C->st));
+  NCCL_OK(g_nccl.AllReduce(d, d, 1, ncclInt, ncclMin, C->comm, C->st));
+  CUDA_OK(cudaMemcpyAsync(&all, d, sizeof(int), cudaMemcpyDeviceToHost, C->st));
+  CUDA_OK(cudaStreamSynchronize(C->st));
+  cudaFree(d);
+  return 0;
+}
+
+int setup_p2p() {
+  close_p2p();
+  C->epoch_total = 0;
+  if (C->nranks == 1) return 0;
+  const Layout &L = C->L;
+  const int nr = C->nranks, npeer = (int)L.peers.size();
+  if (dev_alloc(C->flags, (size_t)kMaxRanks) || dev_alloc(C->done_ctr, 1)) return 1;
+  CUDA_OK(cudaMemset(C->flags, 0, kMaxRanks * sizeof(unsigned)));
+  CUDA_OK(cudaMemset(C->done_ctr, 0, sizeof(unsigned)));
+  P2PInfo mine{};
+  mine.ok = npeer <= kMaxPeers && nr <= kMaxRanks && !getenv("FVS2D_NO_P2P");
+  mine.np = C->np;
+  {
+    typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);  // cuMemGetAddressRange (driver API, no link dependency)
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) { mine.ok = 0; cudaGetLastError(); }
+    void *arr[3] = {C->p_buf[0], C->p_buf[1], C->flags};
+    for (int k = 0; k < 3 && mine.ok; k++) {
+      unsigned long long base = 0;
+      size_t size = 0;
+      if (((range_fn)fn)(&base, &size, (unsigned long long)arr[k]) != 0) { mine.ok = 0; break; }
+      mine.off[k] = (long long)((unsigned long long)arr[k] - base);
+      if (cudaIpcGetMemHandle(&mine.h[k], (void *)base) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
+    }
+  }
+  for (int k = 0; k < npeer && L.peers[k] < kMaxRanks; k++) { mine.recv_begin[L.peers[k]] = L.recv_begin[k]; mine.recv_count[L.peers[k]] = L.recv_count[k]; }
+  std::vector<P2PInfo> all(nr);
+  {
+    char *d = nullptr;
+    CUDA_OK(cudaMalloc(&d, sizeof(P2PInfo) * (size_t)(nr + 1)));
+    CUDA_OK(cudaMemcpyAsync(d + sizeof(P2PInfo) * (size_t)nr, &mine, sizeof mine, cudaMemcpyHostToDevice, C->st));
+    NCCL_OK(g_nccl.AllGather(d + sizeof(P2PInfo) * (size_t)nr, d, sizeof(P2PInfo), ncclChar, C->comm, C->st));
+    CUDA_OK(cudaMemcpyAsync(all.data(), d, sizeof(P2PInfo) * (size_t)nr, cudaMemcpyDeviceToHost, C->st));
+    CUDA_OK(cudaStreamSynchronize(C->st));
+    cudaFree(d);
+  }
+  int ok = 1;
+  for (int r = 0; r < nr; r++) ok = ok && all[r].ok;
+  for (int k = 0; k < npeer && ok; k++) {
+    const P2PInfo &pi = all[L.peers[k]];
+    void *base[3] = {nullptr, nullptr, nullptr};
+    for (int a = 0; a < 3 && ok; a++) {
+      if (cudaIpcOpenMemHandle(&base[a], pi.h[a], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+      C->ipc_open.push_back(base[a]);
+    }
+    if (!ok) break;
+    C->peer_p[k][0] = reinterpret_cast<double2 *>((char *)base[0] + pi.off[0]);
+    C->peer_p[k][1] = reinterpret_cast<double2 *>((char *)base[1] + pi.off[1]);
+    C->peer_flag[k] = reinterpret_cast<unsigned *>((char *)base[2] + pi.off[2]) + C->rank;
+    C->peer_np[k] = pi.np;
+    C->peer_recv_begin[k] = pi.recv_begin[C->rank];
+    if (pi.recv_count[C->rank] != L.send_ptr[k + 1] - L.send_ptr[k]) return fail("halo plan mismatch between ranks %d and %d", C->rank, L.peers[k]);
+  }
+  int agreed = 0;
+  if (all_ranks_agree(ok, agreed)) return 1;
+  if (!agreed) { close_p2p(); return 0; }  // no peer access on this box: the two-pass path with NCCL send/recv
+  C->p2p_ok = true;
+  return 0;
+}
+
+// spins (one warp) until every peer has delivered stage `epoch`: the ghost slots are complete when this kernel retires
+struct PeerList { int n; int r[kMaxPeers]; };
+__global__ void k_wait_peers(const unsigned *__restrict__ flags, const PeerList pl, unsigned epoch) {
+  if ((int)threadIdx.x < pl.n) while ((int)(ld_acquire_sys(flags + pl.r[threadIdx.x]) - epoch) < 0) __nanosleep(128);
 }
 
 // one residual evaluation's worth of pass A (+ halo) for state p
@@ -703,9 +742,7 @@ int fvs2d_gpu_init(const fvs2d_config *cfg, int device) {
     NEED(cfg->grad_method == 3, "gradient limiter needs the LSQ stencil (src/gradient_limiter.f90:54-58): use grad_method 3");
   if (rk_setup()) return 1;
   const double kap = cfg->recon == 3 ? cfg->umuscl_cst : 0.0;  // src/input.f90:248-254
-  if (cfg->recon == 1) C->recon = RC_FIRST;
-  else if (kap == 0.0) C->recon = cfg->limiter > 0 ? RC_K0_PHI : RC_K0;
-  else C->recon = RC_GENERAL;
+  C->recon = recon_mode(*cfg);
   Phys &P = C->phys;
   P.gamma = cfg->gamma; P.kappa = kap; P.cfl = cfg->cfl_user;
   P.gm1 = cfg->gamma - 1.0; P.gog = cfg->gamma / (cfg->gamma - 1.0);
@@ -786,7 +823,8 @@ int host_build(int nnodes, int ntri, int nquad, const double *node_xy, const int
   hilbert_order(m, perm);
   // several ranks + the fused stage kernel: one more ghost layer (the stencils of the face-neighbour ghosts); the
   // environment variable lets the CPU-side verification (fvs2d_host_build) ask for it
-  const bool deep = C->nranks > 1 && (C->opt_fuse != 0 || getenv("FVS2D_DEEP_GHOSTS") != nullptr);
+  // (decided before the tables exist: if they turn out not to fit, the two-pass path runs on the deeper layout)
+  const bool deep = C->nranks > 1 && ((C->opt_fuse != 0 && C->recon == RC_K0 && !getenv("FVS2D_NO_P2P")) || getenv("FVS2D_DEEP_GHOSTS") != nullptr);
   err = build_layout(m, C->grad, perm, C->rank, C->nranks, C->L, deep);
   if (!err.empty()) return fail("%s", err.c_str());
   C->has_mesh = true;
@@ -803,6 +841,8 @@ int fvs2d_host_build(const fvs2d_config *cfg, int rank, int nranks, int nnodes, 
   if (C) fvs2d_gpu_finalize();
   C = new Ctx();
   C->cfg = *cfg;
+  C->recon = recon_mode(*cfg);
+  if (const char *ev = getenv("FVS2D_FUSE")) C->opt_fuse = atoi(ev);
   C->rank = rank; C->nranks = nranks;
   return host_build(nnodes, ntri, nquad, node_xy, cell_ptr, cell_node, nb, b_ncells, b_type, b_cell);
 }
@@ -851,6 +891,7 @@ int fvs2d_gpu_set_mesh(int nnodes, int ntri, int nquad, const double *node_xy, c
   if (dev_upload(d.is_intr, L.is_intr) || dev_upload(d.orig_id, L.orig_id)) return 1;
   const size_t np = C->np;
   if (dev_alloc(C->q, 4 * np) || dev_alloc(C->f, 4 * np) || dev_alloc(C->pa, 4 * np) || dev_alloc(C->pb, 4 * np)) return 1;
+  C->p_buf[0] = C->pa; C->p_buf[1] = C->pb;
   if (dev_alloc(C->g, 8 * np) || dev_alloc(C->phi, np)) return 1;
   if (C->cfg.steady && dev_alloc(C->dtl, np)) return 1;
   if (dev_alloc(C->bc, 4 * (size_t)std::max(1, L.nbf))) return 1;
@@ -879,6 +920,7 @@ int fvs2d_gpu_set_mesh(int nnodes, int ntri, int nquad, const double *node_xy, c
     C->send_idx = const_cast<int *>(si);
     if (dev_alloc(C->sendbuf, (size_t)std::max(1, nsend) * 9)) return 1;
   }
+  if (setup_p2p()) return 1;
   if (C->ev_pool.empty()) {  // once per context (a second set_mesh reuses them)
     C->ev_pool.assign(8192, nullptr);
     for (auto &e : C->ev_pool) CUDA_OK(cudaEventCreate(&e));
@@ -1097,11 +1139,10 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   const bool overlap = C->nranks > 1 && C->opt_overlap && C->tile_ok && C->opt_tile == 2;
   bool p_pending = false;
   if (C->opt_fuse && ensure_fused()) return 1;
-  if (C->opt_fuse == 5 && C->fz_state == 1 && build_fused2c()) return 1;
-  const bool fused = (C->opt_fuse > 0 || (C->opt_fuse < 0 && C->fz_auto_ok)) && C->fz_state == 1 && C->opt_tile == 2;
+  const bool fused = C->opt_fuse != 0 && C->fz_state == 1 && C->opt_tile == 2;
   {  // device step clock (src/runge_kutta.f90:135-145, 218-221): stage times are told + off[stage]
     StepClock hc{};
-    hc.t1 = t1; hc.dt = dt; hc.istep = 0;
+    hc.t1 = t1; hc.dt = dt; hc.istep = 0; hc.epoch0 = C->epoch_total;
     for (int rk = 0; rk < 4; rk++) hc.off[rk] = c.ssprk ? C->dts[rk] : (rk == 0 ? 0.0 : rk == 3 ? dt : 0.5 * dt);
     hc.off_end = c.ssprk ? C->dte[3] : dt;
     CUDA_OK(cudaMemcpyAsync(C->clk, &hc, sizeof hc, cudaMemcpyHostToDevice, C->st));
@@ -1116,26 +1157,8 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
       if (c.steady) S.h = c.ssprk ? (rk == 3 ? 1.0 / 4.0 : 1.0 / 3.0) : (rk == 2 ? 1.0 : rk == 3 ? 1.0 / 6.0 : 1.0 / 2.0);
       else S.h = C->h_rk[rk];
       if (launch_bc(rk)) return 1;
-      if (fused && C->nranks > 1) {
-        // one exchange per stage (the state); tiles that read no ghost run while the previous one is in flight
-        if (C->opt_overlap) {
-          if (launch_fused(um, S, C->pa, C->pb, C->d_fz_int, C->n_fz_int, 0)) return 1;
-          const int parts_int = C->nparts;
-          if (p_pending) CUDA_OK(cudaStreamWaitEvent(C->st, C->e_p, 0));
-          if (launch_fused(um, S, C->pa, C->pb, C->d_fz_bnd, C->n_fz_bnd, parts_int)) return 1;
-          CUDA_OK(cudaEventRecord(C->e_b, C->st));
-          CUDA_OK(cudaStreamWaitEvent(C->sx, C->e_b, 0));
-          HaloItem itp{C->pb, 4, 1};
-          if (halo_exchange(&itp, 1, C->sx)) return 1;
-          CUDA_OK(cudaEventRecord(C->e_p, C->sx));
-          p_pending = true;
-        } else {
-          if (launch_fused(um, S, C->pa, C->pb)) return 1;
-          Span sp(0);
-          HaloItem it{C->pb, 4, 1};
-          if (halo_exchange(&it, 1)) return 1;
-        }
-      } else if (fused) {
+      if (fused) {
+        // one kernel per stage; on several ranks it also delivers the new state into the peers' ghost slots (HaloP2P)
         if (launch_fused(um, S, C->pa, C->pb)) return 1;
       } else if (overlap) {
         // interior tiles never read a ghost: they run while the exchanges are in flight on the second stream
@@ -1188,11 +1211,12 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   };
   // Small meshes are launch-bound (a 65 k-cell step is ~10 kernels of ~10 us): the first step runs eagerly (it also
   // configures the kernels), the remaining ones replay a CUDA graph captured from the same sequence.
-  const bool use_graph = C->opt_graph && C->nranks == 1 && !C->opt_timing && nsub >= 3;
+  // (several ranks: only the fused path, whose halo exchange lives inside the stage kernel -- no NCCL call in the step)
+  const bool use_graph = C->opt_graph && (C->nranks == 1 || fused) && !C->opt_timing && nsub >= 3;
   int done = 0;
   if (nsub > 0) { if (run_step()) return 1; done = 1; }
   if (use_graph) {
-    if (C->graph_exec && (C->graph_logbuf != C->logbuf || C->graph_um != (fused ? 256 * (C->opt_fuse & 7) : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas)) {
+    if (C->graph_exec && (C->graph_logbuf != C->logbuf || C->graph_um != (fused ? 256 * ((C->opt_fuse & 3) + 1) : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas)) {
       cudaGraphExecDestroy(C->graph_exec);
       C->graph_exec = nullptr;
     }
@@ -1207,7 +1231,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
       CUDA_OK(cudaGraphInstantiate(&C->graph_exec, graph, 0));
       cudaGraphDestroy(graph);
       C->graph_logbuf = C->logbuf;
-      C->graph_um = (fused ? 256 * (C->opt_fuse & 7) : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas;
+      C->graph_um = (fused ? 256 * ((C->opt_fuse & 3) + 1) : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas;
     }
     const long per_step = C->last_launches;
     for (; done < nsub; done++) CUDA_OK(cudaGraphLaunch(C->graph_exec, C->st));
@@ -1216,6 +1240,15 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
     for (; done < nsub; done++) if (run_step()) return 1;
   }
   if (p_pending) CUDA_OK(cudaStreamWaitEvent(C->st, C->e_p, 0));  // the last exchange belongs to this call
+  if (fused && C->nranks > 1) {
+    // the peers' last stage lands in this rank's ghost slots: complete before the call returns (compute_residual,
+    // the output path and the next call's first gather read them)
+    C->epoch_total += 4u * (unsigned)nsub;
+    PeerList pl{};
+    pl.n = (int)C->L.peers.size();
+    for (int k = 0; k < pl.n; k++) pl.r[k] = C->L.peers[k];
+    if (nsub > 0) k_wait_peers<<<1, 32, 0, C->st>>>(C->flags, pl, C->epoch_total);
+  }
   CUDA_OK(cudaEventRecord(C->ev1, C->st));
   CUDA_OK(cudaGetLastError());
   // ---- logs back to the host (the only device->host traffic of the call)
@@ -1378,22 +1411,15 @@ long fvs2d_gpu_mesh_array(const char *name, void *out) {
     const std::string err = build_fused_tables(C->L);
     if (!err.empty()) { fail("%s", err.c_str()); return -1; }
     RET("fz_hdr", C->L.fz_hdr) RET("fz_h2_idx", C->L.fz_h2_idx) RET("fz_gslot", C->L.fz_gslot)
-    RET("fz_pack2", C->L.fz_pack2) RET("fz_hf", C->L.fz_hf) RET("fz_uf", C->L.fz_uf)
+    RET("fz_pack2", C->L.fz_pack2) RET("fz_hf", C->L.fz_hf)
     if (n == "fz_gc") {  // coefficient rows at the pitch the device uses (cells padded to 32)
       std::vector<double> gc;
       fused_coeff_rows(C->L, (size_t)(C->L.n_loc + 31) / 32 * 32, gc);
       if (out) memcpy(out, gc.data(), gc.size() * 8);
       return (long)gc.size();
     }
-    if (n == "fz_fdxy" || n == "fz_hfd") {  // face displacements of k_stage_fused2c
-      std::vector<double> fdxy, hfd;
-      fused_face_disp(C->L, (size_t)(C->L.n_loc + 31) / 32 * 32, 4, fdxy, hfd);
-      const std::vector<double> &v = n == "fz_fdxy" ? fdxy : hfd;
-      if (out) memcpy(out, v.data(), v.size() * 8);
-      return (long)v.size();
-    }
     if (n == "fz_info") {
-      const int info[8] = {C->L.fz_built, C->L.fz_w, C->L.fz_s2_max, C->L.fz_tw_max, C->L.fz_h2_max, C->L.fz_v2, C->L.fz_hf_max, C->L.fz_uf_max};
+      const int info[8] = {C->L.fz_built, C->L.fz_w, C->L.fz_s2_max, C->L.fz_tw_max, C->L.fz_h2_max, C->L.fz_v2, C->L.fz_hf_max, 0};
       if (out) memcpy(out, info, sizeof info);
       return 8;
     }
@@ -1425,7 +1451,7 @@ int fvs2d_gpu_set_option(const char *key, int value) {
   if (k == "smem_pad") { C->opt_smem_pad = value; return 0; }
   if (k == "carveout") { C->opt_carveout = value; return 0; }
   if (k == "fuse") {
-    if (value != C->opt_fuse && C->fz_state == -1) C->fz_state = 0;  // decide again under the new setting
+    if (value != C->opt_fuse) C->fz_state = 0;  // plan again under the new setting
     C->opt_fuse = value;
     return 0;
   }

@@ -76,7 +76,8 @@ struct Phys {
 // told = t1 + istep*dt (src/runge_kutta.f90:135), stage time = told + off[stage], end-of-step time = told + off_end
 struct StepClock {
   double t1, dt, off[4], off_end;
-  int istep, pad;
+  int istep;
+  unsigned epoch0;  // Runge-Kutta stages completed before this call (numbering of the in-kernel halo exchange)
 };
 __device__ __forceinline__ double clock_told(const StepClock *c) { return c->t1 + (double)c->istep * c->dt; }
 
@@ -447,7 +448,7 @@ __device__ __forceinline__ void stage_update_pre(const Phys &P, const StageParam
                                                  const double q0[4], const double fo[4], const double dl_in, const double acc[4],
                                                  const double wsacc, double *__restrict__ q, double *__restrict__ f,
                                                  double *__restrict__ pout, double *__restrict__ dtl, double *__restrict__ resid_out,
-                                                 double *__restrict__ ws_out, double dq2[4]) {
+                                                 double *__restrict__ ws_out, double dq2[4], double2 *prim_new = nullptr) {
   double R[4];
   const double niv = -ivol;
 #pragma unroll
@@ -483,8 +484,10 @@ __device__ __forceinline__ void stage_update_pre(const Phys &P, const StageParam
   const double ir = fast_rcp(qn[0]);
   const double u = qn[1] * ir, vv = qn[2] * ir;
   double2 *po = reinterpret_cast<double2 *>(pout);
-  po[i] = make_double2(qn[0], u);
-  po[np + i] = make_double2(vv, (P.gamma - 1.0) * (qn[3] - 0.5 * qn[0] * (u * u + vv * vv)));
+  const double2 pr0 = make_double2(qn[0], u), pr1 = make_double2(vv, (P.gamma - 1.0) * (qn[3] - 0.5 * qn[0] * (u * u + vv * vv)));
+  po[i] = pr0;
+  po[np + i] = pr1;
+  if (prim_new) { prim_new[0] = pr0; prim_new[1] = pr1; }  // for the in-kernel halo exchange (kernels_fused.cuh)
   if (S.last) {
 #pragma unroll
     for (int v = 0; v < 4; v++) {

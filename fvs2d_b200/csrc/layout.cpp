@@ -501,7 +501,7 @@ std::string build_fused_tables(Layout &L) {
 
   // ---- second variant: face table with reverse face indices + the list of tile/ring-1 faces
   if (L.tile_e_max >= 0x1000) return "";
-  std::vector<std::vector<uint32_t>> hf(nt), uf(nt);
+  std::vector<std::vector<uint32_t>> hf(nt);
   L.fz_pack2.assign(L.t_pack.size(), 0xFFFEu);
 #pragma omp parallel for schedule(dynamic, 64)
   for (int t = 0; t < nt; t++) {
@@ -528,28 +528,6 @@ std::string build_fused_tables(Layout &L) {
         }
         L.fz_pack2[fbase + kTile * k + j] = code | (es << 16) | (rev << 28) | (pk & 0x80000000u);
       }
-    // unique faces: interior ones in (k, j) order, boundary faces last
-    if (kTile * 4 > 0x3FF || hf[t].size() >= 0x400) continue;  // (checked again below through fz_uf_max)
-    for (int pass = 0; pass < 2; pass++)
-      for (int k = 0; k < th[7]; k++)
-        for (int j = 0; j < c1 - c0; j++) {
-          const uint32_t w = L.fz_pack2[fbase + kTile * k + j];
-          const uint32_t code = w & 0xFFFFu, es = (w >> 16) & 0xFFFu, me = (uint32_t)(k * kTile + j);
-          const bool c2 = (w >> 31) != 0;
-          if (code == 0xFFFEu || (code == 0xFFFFu) != (pass == 1)) continue;
-          uint32_t w0, w1;
-          if (code == 0xFFFFu) { w0 = me | (0xFFFFu << 16); w1 = es | (me << 12) | (0x3FFu << 22); }
-          else if (code < (uint32_t)kTile) {
-            if (c2) continue;  // emitted from the c1 side
-            const uint32_t other = ((w >> 28) & 3u) * kTile + code;
-            w0 = me | (other << 16); w1 = es | (me << 12) | (other << 22);
-          } else {
-            const uint32_t hs = 0x400u + (code - kTile);
-            if (!c2) { w0 = me | (hs << 16); w1 = es | (me << 12) | (0x3FFu << 22); }
-            else { w0 = hs | (me << 16); w1 = es | (0x3FFu << 12) | (me << 22); }
-          }
-          uf[t].push_back(w0); uf[t].push_back(w1);
-        }
   }
   int64_t fp = 0;
   for (int t = 0; t < nt; t++) {
@@ -561,16 +539,6 @@ std::string build_fused_tables(Layout &L) {
   }
   L.fz_hf.assign(fp, 0);
   for (int t = 0; t < nt; t++) std::copy(hf[t].begin(), hf[t].end(), L.fz_hf.begin() + L.fz_hdr[8 * (size_t)t + 4]);
-  int64_t up = 0;
-  for (int t = 0; t < nt; t++) {
-    int *h = &L.fz_hdr[8 * (size_t)t];
-    h[6] = (int)up; h[7] = (int)(uf[t].size() / 2);
-    up += h[7];
-    L.fz_uf_max = std::max(L.fz_uf_max, h[7]);
-    if (2 * up > INT32_MAX) return "";
-  }
-  L.fz_uf.resize(2 * up);
-  for (int t = 0; t < nt; t++) std::copy(uf[t].begin(), uf[t].end(), L.fz_uf.begin() + 2 * (size_t)L.fz_hdr[8 * (size_t)t + 6]);
   L.fz_v2 = 1;
   return "";
 }
@@ -595,34 +563,6 @@ void fused_coeff_rows(const Layout &L, size_t np, std::vector<double> &rows) {
     for (int e = L.gh_ptr[k]; e < L.gh_ptr[k + 1]; e++) {
       const size_t o = 2 * ((size_t)(e - L.gh_ptr[k] + F0) * np + i);
       rows[o] = L.gh_cx[e]; rows[o + 1] = L.gh_cy[e];
-    }
-  }
-}
-
-void fused_face_disp(const Layout &L, size_t np, int nrows, std::vector<double> &fdxy, std::vector<double> &hfd) {
-  fdxy.assign((size_t)nrows * np * 2, 0.0);
-#pragma omp parallel for schedule(static)
-  for (int i = 0; i < L.n_own; i++) {
-    const int sl = i >> 5, lane = i & 31, w = (L.f_off[sl + 1] - L.f_off[sl]) >> 5;
-    for (int k = 0; k < w && k < nrows; k++) {
-      const int e = L.f_off[sl] + 32 * k + lane;
-      if (L.f_nbr[e] == kFacePad) continue;
-      const int le = L.f_edge[e] >> 1;
-      const size_t o = 2 * ((size_t)k * np + i);
-      fdxy[o] = L.ex[le] - L.xc[i]; fdxy[o + 1] = L.ey[le] - L.yc[i];
-    }
-  }
-  hfd.assign(2 * L.fz_hf.size(), 0.0);
-#pragma omp parallel for schedule(static)
-  for (int t = 0; t < L.ntiles; t++) {
-    const int *th = &L.tile_hdr[8 * (size_t)t], *fh = &L.fz_hdr[8 * (size_t)t];
-    for (int e = 0; e < fh[5]; e++) {
-      const uint32_t w = L.fz_hf[fh[4] + e];
-      const int h = (int)(w & 0xFFFFu), es = (int)(w >> 16);
-      const int cell = L.tile_hc_idx[th[2] + h];
-      const int le = es < th[1] ? th[0] + es : L.tile_he_idx[th[4] + es - th[1]];
-      hfd[2 * (size_t)(fh[4] + e)] = L.ex[le] - L.xc[cell];
-      hfd[2 * (size_t)(fh[4] + e) + 1] = L.ey[le] - L.yc[cell];
     }
   }
 }

@@ -95,22 +95,14 @@ struct Layout {
   std::vector<int> fz_hdr;     // 8 ints per tile {h2_ptr, n_h2, gs_base, gw, hf_ptr, n_hf, 0, 0}
   std::vector<int> fz_h2_idx;  // ring-2 cells (local ids, ascending) of all tiles
   std::vector<uint16_t> fz_gslot;
-  // second variant (k_stage_fused2, "fuse" = 2): every reconstructed face state is evaluated once, by the thread that
-  // holds the cell's gradient, and published in shared memory.  fz_pack2 = t_pack with the neighbour code of bits 0-15
+  // every reconstructed face state is evaluated once, by the thread that holds the cell's gradient, and published in
+  // shared memory.  fz_pack2 = t_pack with the neighbour code of bits 0-15
   // redefined -- < kTile: neighbour's slot in the tile, and bits 28-29 = index of this face in the NEIGHBOUR's face
   // list; >= kTile: kTile + index into the tile's list of tile/ring-1 faces (fz_hf: ring-1 index | edge slot << 16);
   // 0xFFFF boundary, 0xFFFE padding -- and the edge slot in bits 16-27.
   int fz_v2 = 0;               // 1 when the tables below exist (edge slots fit 12 bits)
   int fz_hf_max = 0;
   std::vector<uint32_t> fz_pack2, fz_hf;
-  // third variant (k_stage_fused3, "fuse" = 3): every face flux of a tile is evaluated once.  fz_uf = per tile the
-  // list of its unique faces (tile/tile faces once, tile/ring-1 faces, boundary faces last), two words per face:
-  //   w0 = locL | locR << 16   where a state lives: k*kTile + j (face k of own cell j), 0x400 + i (i-th tile/ring-1
-  //                            face: the ring-1 side), 0xFFFF (right state from the boundary condition)
-  //   w1 = edge slot | outL << 12 | outR << 22   where the flux goes: k*kTile + j of the c1 / c2 cell, 0x3FF = nowhere
-  // fz_hdr[6], [7] = offset (in faces) and count of the tile's list
-  int fz_uf_max = 0;
-  std::vector<uint32_t> fz_uf;
 };
 
 // Builds the layout of `rank` out of `nranks` (equal contiguous chunks of the Hilbert order).
@@ -123,8 +115,5 @@ std::string build_fused_tables(Layout &L);
 // Gradient coefficients in the fused kernel's form: rows of `np` (cx, cy) pairs -- row 0 = c0 for the Green-Gauss form,
 // then one row per stencil entry k (the sliced-ELL entry k of every cell; missing entries are zero).
 void fused_coeff_rows(const Layout &L, size_t np, std::vector<double> &rows);
-// Face displacements for k_stage_fused2c: fdxy = rows [k][np] of (x_f - x_c, y_f - y_c) for face k of an owned cell
-// (zero where a cell has fewer faces); hfd = the same for the ring-1 cell of every tile/ring-1 face, aligned with fz_hf.
-void fused_face_disp(const Layout &L, size_t np, int nrows, std::vector<double> &fdxy, std::vector<double> &hfd);
 
 }  // namespace fvs2d

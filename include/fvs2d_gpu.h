@@ -158,18 +158,15 @@ int fvs2d_gpu_last_timing(double ms[4], long *launches);
  *              step graph); 0 (default): only the whole call is timed
  *   "tile"     2 (default): pass B = persistent shared-memory pipeline k_flux_pipe; 0: direct-gather kernel k_flux_rk
  *              (also chosen automatically when a mesh's tiles do not fit the pipeline's shared memory)
- *   "fuse"     one kernel per Runge-Kutta stage (gradients rebuilt in shared memory inside the pass-B pipeline; single GPU,
- *              second-order upwind reconstruction without limiter; results are bitwise those of the two-pass path):
- *              0 (default) never, -1 automatic = k_stage_fused2 where three CTAs per SM fit (triangle meshes with
- *              face-neighbour stencils; what bench.py selects), 1 k_stage_fused (neighbour data gathered per face), 2 k_stage_fused2 (face states
- *              evaluated once and published), 3 k_stage_fused2 + every face flux evaluated once (measured slower),
- *              4 k_stage_fused2 in two launches per stage: the tiles whose staging fits three CTAs per SM with shared
- *              memory sized for them, then the rest (meshes with quadrilaterals; not yet measured),
- *              5 k_stage_fused2c: the published-state kernel with everything only the owning thread reads (coefficient
- *              rows, stencil slots, face words, face displacements) loaded straight into registers and one state buffer
- *              per CTA -- 68 KB instead of 97 KB per CTA on the C4 mix, i.e. three CTAs per SM also for quadrilateral
- *              tiles (face-neighbour stencils only; not yet measured)
- *   "graph"    1 (default): on one GPU, steps 2..nsub of a call replay a captured CUDA graph; 0: every step eager
+ *   "fuse"     one kernel per Runge-Kutta stage (k_stage_fused: gradients rebuilt in shared memory inside the pass-B
+ *              pipeline; on several ranks the halo exchange happens inside the same kernel as stores to peer memory).
+ *              Applies to second-order upwind reconstruction without limiter when the gradient tables fit shared memory;
+ *              results are bitwise those of the two-pass path.  -1 (default) automatic: used wherever it applies, tiles split
+ *              into two launches per stage by shared-memory need (triangle tiles at three CTAs per SM, quadrilateral tiles
+ *              at two); 2: a single launch per stage; 0: never (two-pass path, NCCL send/recv on several ranks).
+ *              On several ranks the option must be set before fvs2d_gpu_set_mesh (it decides the ghost layers).
+ *   "graph"    1 (default): steps 2..nsub of a call replay a captured CUDA graph (one GPU, or the fused path on several:
+ *              its time step contains no NCCL call); 0: every step eager
  *   "overlap"  1 (default): multi-GPU halo exchange on a second stream, overlapped with interior-tile work
  *   "ctas"     resident CTAs per SM of k_flux_pipe (0 = occupancy API), "smem_pad" / "carveout": extra dynamic shared
  *              memory per CTA / preferred shared-memory carve-out of k_flux_pipe, both in KB (the L1 experiments of

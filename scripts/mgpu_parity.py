@@ -33,6 +33,9 @@ def main():
         ("mixed ggnb umuscl", meshgen.vortex_mixed_mesh(48),
          config.RunInput(grad_cellcntr_imethd=2, face_reconst_imethd=3, umuscl_cst=1.0 / 3.0, lvortex=True, dt=0.005), 6),
     ]
+    if os.environ.get("BIG"):  # the C4 sibling bench.py's parity block uses: >= 4 tiles per persistent CTA on 2 ranks
+        cases.append(("c4 sibling 540k mixed ggcb rk4", meshgen.make_mesh(2400, 150, 20.0, 10.0, (600, 1800)),
+                      config.RunInput(grad_cellcntr_imethd=1, lvortex=True, dt=1.6e-3), 10))
     for name, mesh, run, nsteps in cases:
         cfg = run.to_config(world)
         gpu = solver.Fvs2dGpu(cfg, device=local, comm=new_comm())
@@ -47,6 +50,7 @@ def main():
         dist.all_reduce(qt)                   # disjoint ownership -> sum assembles the global state
         q = qt.cpu().numpy()
         sizes = gpu.sizes()
+        launches = gpu.last_timing()["launches"]
         gpu.close()
         if rank == 0:
             from oracle.oracle import Oracle
@@ -60,7 +64,7 @@ def main():
             exy = float(np.abs(vxy - vxy_o).max())
             good = eq <= 1e-10 and er <= 1e-9 and ev <= 1e-8 and exy == 0.0
             ok = ok and good
-            print(f"[{world} ranks] {name}: cells {mesh.ncells} own(rank0) {sizes['ncells_own']} local {sizes['ncells_local']} "
+            print(f"[{world} ranks fuse={os.environ.get('FUSE', 'default')}] {name}: cells {mesh.ncells} own(rank0) {sizes['ncells_own']} local {sizes['ncells_local']} launches {launches} "
                   f"state {eq:.2e} log_res {er:.2e} vortex {ev:.2e} xy {exy:.1e} -> {'ok' if good else 'FAIL'}", flush=True)
     if rank == 0:
         print("PARITY_OK" if ok else "PARITY_FAIL", flush=True)

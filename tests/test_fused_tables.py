@@ -38,8 +38,7 @@ def _emulate_residual(mesh, cfg, orc, time, rank=0, nranks=1):
     resid = np.zeros((n_own, 4))
     n2_seen = 0
     assert info[5] == 1, "tables of the second fused variant missing"
-    pack2, hf_all, uf_all = A("fz_pack2"), A("fz_hf"), A("fz_uf")
-    fdxy, hfd = A("fz_fdxy").reshape(4, np_, 2), A("fz_hfd").reshape(-1, 2)
+    pack2, hf_all = A("fz_pack2"), A("fz_hf")
     fz8 = A("fz_hdr").reshape(-1, 8)
     for t in range(len(hdr)):
         es, ne, hp, n1, ep, nhe, fbase, fw = (int(x) for x in hdr[t])
@@ -55,7 +54,7 @@ def _emulate_residual(mesh, cfg, orc, time, rank=0, nranks=1):
         ids[TILE + n1:] = h2_idx[h2p:h2p + n2]
         eids = np.concatenate([np.arange(es, es + ne), he_idx[ep:ep + nhe]])
         tab = gslot[gsb:gsb + gw * tw].reshape(gw, tw).astype(np.int64)
-        # second variant: the face words point back at each other / at the list of tile/ring-1 faces
+        # published face states: the face words point back at each other / at the list of tile/ring-1 faces
         hfp, nhf = int(fz8[t, 4]), int(fz8[t, 5])
         assert hfp % 4 == 0 and nhf <= int(info[6])
         seen = set()
@@ -79,50 +78,6 @@ def _emulate_residual(mesh, cfg, orc, time, rank=0, nranks=1):
                     seen.add(e)
                     assert int(hf_all[hfp + e]) == (ns - TILE) | (((w1 >> 16) & 0x7FFF) << 16)
         assert len(seen) == nhf
-        # k_stage_fused2c: the face displacements are bitwise the differences the other kernels form
-        for e in range(nhf):
-            w = int(hf_all[hfp + e])
-            cell, le = int(hc_idx[hp + (w & 0xFFFF)]), int(eids[w >> 16])
-            assert hfd[hfp + e, 0] == ex[le] - xc[cell] and hfd[hfp + e, 1] == ey[le] - yc[cell]
-        for j in range(0, ncell, 5):
-            for k in range(fw):
-                w = int(t_pack[fbase + k * TILE + j])
-                if (w & 0xFFFF) == 0xFFFE:
-                    assert fdxy[k, c0 + j, 0] == 0.0
-                    continue
-                le = int(eids[(w >> 16) & 0x7FFF])
-                assert fdxy[k, c0 + j, 0] == ex[le] - xc[c0 + j] and fdxy[k, c0 + j, 1] == ey[le] - yc[c0 + j]
-        # third variant: every cell-face is the c1 or c2 output of exactly one unique face
-        ufp, nuf = int(fz8[t, 6]), int(fz8[t, 7])
-        assert nuf <= int(info[7])
-        covered = {}
-        bnd_started = False
-        for e in range(nuf):
-            w0, w1 = int(uf_all[2 * (ufp + e)]), int(uf_all[2 * (ufp + e) + 1])
-            locL, locR, es, outL, outR = w0 & 0xFFFF, w0 >> 16, w1 & 0xFFF, (w1 >> 12) & 0x3FF, w1 >> 22
-            bnd_started = bnd_started or locR == 0xFFFF
-            assert (locR == 0xFFFF) == bnd_started, "boundary faces must come last"
-            for out, loc, side in ((outL, locL, 0), (outR, locR, 1)):
-                if out == 0x3FF and loc == 0xFFFF:
-                    continue                           # right side of a boundary face
-                if out == 0x3FF:
-                    assert 0x400 <= loc < 0x400 + nhf and int(hf_all[hfp + loc - 0x400]) >> 16 == es
-                    continue
-                assert out == loc and out not in covered
-                k, j = out >> 7, out & 127
-                w = int(pack2[fbase + k * TILE + j])
-                assert (w >> 31) == side and ((w >> 16) & 0xFFF) == es and (w & 0xFFFF) != 0xFFFE
-                covered[out] = e
-            if locR == 0xFFFF:
-                assert outR == 0x3FF and (int(pack2[fbase + (outL >> 7) * TILE + (outL & 127)]) & 0xFFFF) == 0xFFFF
-            elif outL != 0x3FF and outR != 0x3FF:      # tile/tile face: the two words point at each other
-                wl = int(pack2[fbase + (outL >> 7) * TILE + (outL & 127)])
-                assert (wl & 0xFFFF) == (outR & 127) and ((wl >> 28) & 3) == outR >> 7
-            else:                                       # tile/ring-1 face: the ring-1 state is the one the face word names
-                a, h = (outL, locR) if outR == 0x3FF else (outR, locL)
-                assert (int(pack2[fbase + (a >> 7) * TILE + (a & 127)]) & 0xFFFF) == TILE + h - 0x400
-        nfaces = sum(1 for j in range(ncell) for k in range(fw) if (int(t_pack[fbase + k * TILE + j]) & 0xFFFF) != 0xFFFE)
-        assert len(covered) == nfaces
         # phase 1: gradients of the columns of tile + ring 1
         cols = np.concatenate([np.arange(ncell), np.arange(TILE, TILE + n1)])
         cid = ids[cols]

@@ -146,7 +146,8 @@ def test_layout_single_rank(vortex_mesh):
 
 @pytest.mark.parametrize("nranks", [2, 3])
 def test_partition_and_halo_plan(nranks):
-    """contiguous Hilbert chunks; ghosts = everything an owned cell reads; the send list of rank a for rank b
+    """contiguous Hilbert chunks; ghosts = everything an owned cell (or, deep layout, a face-neighbour ghost's gradient)
+    reads; the send list of rank a for rank b
     is exactly rank b's ghost run owned by a, in the same order."""
     from fvs2d_b200 import capi, config, meshgen, solver
     mesh = meshgen.vortex_mixed_mesh(32)
@@ -157,13 +158,17 @@ def test_partition_and_halo_plan(nranks):
         A = capi.mesh_array
         plans.append(dict(n_own=n_own, n_loc=n_loc, loc2new=A("loc2new").copy(), peers=A("peers").copy(), send_ptr=A("send_ptr").copy(),
                           send_idx=A("send_idx").copy(), recv_begin=A("recv_begin").copy(), recv_count=A("recv_count").copy(),
-                          g_idx=A("g_idx").copy(), f_nbr=A("f_nbr").copy()))
+                          g_idx=A("g_idx").copy(), f_nbr=A("f_nbr").copy(), gh_idx=A("gh_idx").copy()))
     assert sum(p["n_own"] for p in plans) == mesh.ncells
     for r, p in enumerate(plans):
         assert p["g_idx"].max() < p["n_loc"] and p["f_nbr"].max() < p["n_loc"]  # stencil closure
         used = np.zeros(p["n_loc"], bool)
         used[p["g_idx"]] = True
         used[p["f_nbr"][p["f_nbr"] >= 0]] = True
+        # default on several ranks for this scheme: the deep layout of the fused stage kernel -- the face-neighbour ghosts
+        # carry their own gradient stencils (gh_idx), whose members are ghosts too
+        assert len(p["gh_idx"]) > 0
+        used[p["gh_idx"]] = True
         assert used[p["n_own"]:].all()  # no useless ghost
         for k, peer in enumerate(p["peers"]):
             q = plans[peer]
