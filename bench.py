@@ -6,6 +6,8 @@
 One "step" = one full RK time step (4 stages: gradient -> Roe flux gather -> residual -> RK update, plus
 the per-step residual / vortex-error norms) of `time_integration` over the whole mesh.
 Metric = ncells * 4 * K / seconds (BASELINE.json: "cell-RK-stage updates/sec").
+Besides the contract's keys the line carries `parity` (GPU on all ranks vs the CPU oracle on a sibling mesh, run before
+the timed region), `state_check` (isfinite + conservation of the timed state) and `sustained` (>= --sustain-s seconds).
 
 Workloads:
   c4     (default) synthetic mixed tri/quad vortex mesh, 8.64 M cells per GPU (9600 x 600*N background quads;
@@ -149,17 +151,18 @@ class ClockSampler:
                 "power_w_max": max(r[1] for r in self.rows), "reasons": [n for b, n in self.REASONS.items() if mask & b]}
 
 
-def cpu_baseline(name: str, run, steps: int, warmup: int = 0):
+def cpu_baseline(name: str, run, steps: int, warmup: int = 0, full: bool = False, scale: float = 1.0):
     """The CPU oracle (C restatement of the reference algorithm, -Ofast, ONE thread: the reference's only
-    multi-thread mode is racy, src/residual.f90:65) on a bounded sample of the workload."""
+    multi-thread mode is racy, src/residual.f90:65) on a bounded sample of the workload: the 1/16-size sibling
+    (cpu_baseline leg of the GPU arm, ~10 s) or, full=True (the --impl reference arm), the whole single-GPU mesh."""
     from oracle.oracle import Oracle, build
     build()
-    if name in ("c4", "c3"):
+    if name in ("c4", "c3") and not full:
         mesh, run_s, desc, _ = make_workload(name, 1, scale=0.25)
         sample = f"1/16-size sibling of the workload ({mesh.ncells} cells, same generator/seed/scheme), {steps} RK4 steps"
     else:
-        mesh, run_s, desc, _ = make_workload(name, 1)
-        sample = f"the full {name} mesh ({mesh.ncells} cells), {steps} steps"
+        mesh, run_s, desc, _ = make_workload(name, 1, scale=scale)
+        sample = f"the full single-GPU {name} mesh ({mesh.ncells} cells), {steps} steps"
     orc = Oracle(mesh, run_s.to_config(), fast=True)
     orc.initialize_solution()
     if warmup:
@@ -181,14 +184,60 @@ def cpu_baseline(name: str, run, steps: int, warmup: int = 0):
         omp = Oracle(mesh, run_s.to_config(), fast="omp")
         omp.initialize_solution()
         omp.time_integration(0.0, 1)
+        so = max(2, min(steps, 6)) if full else steps
         t0 = time.perf_counter()
-        omp.time_integration(run_s.dt, steps)
+        omp.time_integration(run_s.dt, so)
         dto = time.perf_counter() - t0
-        out["all_cores_variant"] = {"value": mesh.ncells * 4 * steps / dto, "cores": nthr, "seconds": dto,
+        out["all_cores_variant"] = {"value": mesh.ncells * 4 * so / dto, "cores": nthr, "seconds": dto,
                                     "note": "OpenMP gather variant of the oracle; not the reference algorithm"}
     except Exception as e:  # the context number must never break the bench line
         out["all_cores_variant"] = {"unavailable": str(e)[:200]}
     return out, dt / steps * 1e3
+
+
+def parity_block(workload: str, world: int, rank: int, local_rank: int, new_comm, opts):
+    """GPU (all `world` ranks) against the CPU oracle (parity build, rank 0) on a sibling of the workload small enough for
+    the oracle, same generator / seed / scheme, state and log_res after `steps` RK4 steps.  c4 / c3: the 1/16-size sibling
+    (540 000 / 250 000 cells; >= 4 tiles per persistent CTA on one GPU), 1/4-size from 4 ranks on."""
+    import torch
+    import torch.distributed as dist
+    from fvs2d_b200 import solver
+    if workload in ("c4", "c3"):
+        scale, steps = (0.25, 10) if world < 4 else (0.5, 6)
+    else:
+        scale, steps = 1.0, 10
+    mesh, run_s, desc, _ = make_workload(workload, 1, scale=scale)
+    cfg = run_s.to_config(world)
+    gpu = solver.Fvs2dGpu(cfg, device=local_rank, comm=new_comm())
+    for k, v in opts:
+        gpu.set_option(k, v)
+    gpu.set_mesh(mesh)
+    gpu.initialize_solution()
+    res, _, _ = gpu.time_integration(0.0, steps)
+    q = np.zeros((mesh.ncells, 4))
+    gpu.get_state(q)                       # several ranks: fills the owned cells only
+    launches = gpu.last_timing()["launches"]
+    gpu.close()
+    if world > 1:
+        qt = torch.from_numpy(q).cuda()
+        dist.all_reduce(qt)                # disjoint ownership: the sum assembles the global state
+        q = qt.cpu().numpy()
+    out = None
+    if rank == 0:
+        from oracle.oracle import Oracle
+        orc = Oracle(mesh, cfg)
+        orc.initialize_solution()
+        res_o, _, _ = orc.time_integration(0.0, steps)
+        q_o = orc.cvar
+        out = {"max_rel_state": float((np.abs(q - q_o) / np.abs(q_o).max(axis=0)).max()),
+               "max_rel_log_res": float((np.abs(res - res_o) / np.abs(res_o)).max()), "ranks": world, "steps": steps,
+               "ncells": mesh.ncells, "finite": bool(np.isfinite(q).all()), "launches": launches,
+               "against": "CPU oracle (oracle/liboracle.so, -O2 -ffp-contract=off) on the same mesh and inputs; tolerance 1e-10",
+               "mesh": desc}
+        out["ok"] = out["finite"] and out["max_rel_state"] <= 1e-10 and out["max_rel_log_res"] <= 1e-10
+    if world > 1:
+        dist.barrier()
+    return out
 
 
 def main():
@@ -203,6 +252,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the additional C3 measurement at N=1")
     ap.add_argument("--opt", action="append", default=[], help="library tuning option key=value (fvs2d_gpu_set_option)")
+    ap.add_argument("--sustain-s", type=float, default=2.0, help="length of the second, sustained timed region in seconds (0: skip)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the GPU-vs-oracle parity block")
     args = ap.parse_args()
     K, W = args.steps, max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
@@ -215,13 +266,14 @@ def main():
         if rank != 0:
             return
         desc = workload_desc(args.workload, max(args.gpus, 1), args.scale)
-        cb, ms_step = cpu_baseline(args.workload, None, max(K, 1), W)
+        cb, ms_step = cpu_baseline(args.workload, None, max(K, 1), W, full=True, scale=args.scale)
         line = {"metric": metric, "value": cb["value"], "unit": "cell-stage updates/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "impl": "reference",
                 "config": {"workload": desc, "parallelism": "1 host thread (the reference's OpenMP flux loop races, src/residual.f90:65)",
                            "note": "reference algorithm on the host (C restatement in oracle/, -Ofast; the Fortran reference cannot be "
-                                   "compiled in this image); each step is a bounded sample of the workload: " + cb["sample"]},
+                                   "compiled in this image); each step is one RK4 step over " + cb["sample"] +
+                                   (" = the workload itself" if args.gpus <= 1 else " = one GPU's share of the workload (a bounded sample)")},
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "cell-stage updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -236,29 +288,51 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    comm = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def new_comm():  # one NCCL unique id per library context
+        if world == 1:
+            return None
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             uid.copy_(torch.frombuffer(bytearray(solver.Fvs2dGpu.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
-        comm = (rank, world, bytes(uid.cpu().numpy().tobytes()))
+        return (rank, world, bytes(uid.cpu().numpy().tobytes()))
     ngpus = world
+    opts = [(kv.split("=")[0], int(kv.split("=")[1])) for kv in args.opt]
+
+    # ---- parity first (its own library context): the configuration that is about to be timed, on a mesh the oracle can do
+    parity = None
+    if not args.no_parity and args.scale == 1.0:
+        parity = parity_block(args.workload, world, rank, local_rank, new_comm, opts)
+    comm = new_comm()
 
     t_setup = time.perf_counter()
     mesh, run, desc, (bA, bB) = make_workload(args.workload, ngpus, args.scale)
     cfg = run.to_config(ngpus)
     gpu = solver.Fvs2dGpu(cfg, device=local_rank, comm=comm)
-    for kv in args.opt:
-        k, v = kv.split("=")
-        gpu.set_option(k, int(v))
+    for k, v in opts:
+        gpu.set_option(k, v)
     gpu.set_mesh(mesh)
     ncells = mesh.ncells
     del mesh                                          # the library holds its own copy
     gpu.initialize_solution()
     sizes, scal = gpu.sizes(), gpu.scalars()
     t_setup = time.perf_counter() - t_setup
+    from fvs2d_b200 import capi
+    vol_own = capi.mesh_array("lvol")[:sizes["ncells_own"]]
+
+    def conserved_totals():
+        """sum over the owned cells of vol * (rho, rho u, rho v, rho E), summed over the ranks; isfinite of the state"""
+        qo = np.zeros((sizes["ncells_own"], 4))
+        gpu.get_state_local(qo)
+        t = torch.tensor(np.concatenate([(vol_own[:, None] * qo).sum(axis=0), [float(np.isfinite(qo).all())]]), dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t)
+        t = t.cpu().numpy()
+        return t[:4], bool(t[4] == world)
+    tot0, _ = conserved_totals()
 
     def barrier():
         if world > 1:
@@ -289,6 +363,28 @@ def main():
         wall = time.perf_counter() - w0
         tm = gpu.last_timing()
         t_sim += K * dt
+    # ---- what the timed region left behind: finite, and conservative (interior fluxes cancel bit for bit -- the change of
+    # the totals is the boundary flux of a vortex far from the boundary plus summation round-off)
+    tot1, finite = conserved_totals()
+    state_check = {"finite": finite, "steps_from_initial_state": W + K,
+                   "conserved_totals_rel_drift": [float(x) for x in np.abs(tot1 - tot0) / np.abs(tot0).max()]}
+    # ---- sustained: the same call repeated for >= --sustain-s seconds (the shipped examples run 4 000-50 000 steps; the
+    # fp64-heavy kernels reach the power cap of this pool after ~100 ms and the SM clock settles lower)
+    sustained = None
+    if args.sustain_s > 0:
+        ks = max(K, 20)
+        reps = max(1, int(np.ceil(args.sustain_s / (max(tm["total_ms"], 1e-3) * 1e-3 * ks / K))))
+        with ClockSampler(local_rank) as clk_s:
+            barrier()
+            ms_s = 0.0
+            for r in range(reps):
+                gpu.time_integration(t_sim, ks, logs=False)
+                ms_s += gpu.last_timing()["total_ms"]
+                t_sim += ks * dt
+            barrier()
+        ms_s = max_over_ranks(ms_s)
+        sustained = {"value": ncells * 4 * ks * reps / (ms_s * 1e-3), "ms_per_step": ms_s / (ks * reps), "steps": ks * reps,
+                     "seconds": ms_s * 1e-3, "clocks": clk_s.summary()}
     # ---- second pass of K steps with a CUDA event pair around every kernel launch (no graph): the average launch
     # durations of pass A / pass B for the roofline.  It starts after a short idle: on this pool the fp64-heavy
     # pass B trips sw_power_cap after ~100 ms of sustained load, so a second pass run back to back would time the
@@ -399,21 +495,24 @@ def main():
             "alg_bytes_per_cell": bB, "avg_launch_ms": flux_ms, "traffic": None,
             "measured": "CUDA event pair around every launch on the library stream, second pass of the same K steps started after a 2 s idle",
             "clocks": clk2.summary()}
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if world == 1 and args.scale == 1.0 and os.path.exists(tpath):
-        tr = json.load(open(tpath)).get(args.workload)
-        if tr:
-            roof["traffic"] = tr / 1e9  # GB per launch, from the committed ncu capture
-            roof["traffic_unit"] = "GB per launch (ncu dram__bytes_read+write, profiles/r1e_ncu_summary.md)"
-            roof["alg_GB_per_launch"] = bB * n_own / 1e9
-    if grad_ms == 0.0 and flux_ms > 0.0:
-        # a fused stage kernel ran (--opt fuse=N): no pass A; its own algorithmic bytes are B_alg - 160 (no gradient write +
-        # read, state read once); the committed ncu traffic figure belongs to k_flux_pipe, not to this kernel
+    fused_ran = grad_ms == 0.0 and flux_ms > 0.0
+    if fused_ran:
+        # the default schedule: k_stage_fused, no pass A; its algorithmic bytes are B_alg - 160 (no gradient write + read,
+        # state read once).  avg_launch_ms is the kernel time per STAGE (a stage is one launch on triangle meshes, two on
+        # mixed meshes: triangle tiles at three CTAs per SM, then the tiles with quadrilaterals at two)
         fb = bA + bB - 160.0
-        roof.update({"kernel": "k_stage_fused* (one kernel per RK stage: gradients rebuilt in shared memory inside the pass-B pipeline)",
-                     "alg_bytes_per_cell": fb, "achieved": fb * n_own / (flux_ms * 1e-3) / 1e9, "traffic": None})
-        roof.pop("traffic_unit", None)
-        roof.pop("alg_GB_per_launch", None)
+        roof.update({"kernel": "k_stage_fused (one kernel per RK stage: gradients rebuilt in shared memory inside the persistent TMA/cp.async "
+                               "pass-B pipeline; on several ranks the halo exchange is stores to peer memory from the same kernel)",
+                     "alg_bytes_per_cell": fb, "achieved": fb * n_own / (flux_ms * 1e-3) / 1e9})
+    # DRAM traffic per stage of the same kernel(s) from the committed ncu --set full capture of this workload (ncu cannot
+    # run inside a timed bench; the file names the capture and the commit it was taken at)
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if world == 1 and args.scale == 1.0 and os.path.exists(tpath):
+        tr = json.load(open(tpath)).get(("fused:" if fused_ran else "twopass:") + args.workload)
+        if tr:
+            roof["traffic"] = tr["dram_bytes_per_stage"] / 1e9
+            roof["traffic_unit"] = "GB per stage (ncu dram__bytes_read.sum + dram__bytes_write.sum), " + tr["source"]
+            roof["alg_GB_per_stage"] = roof["alg_bytes_per_cell"] * n_own / 1e9
     roof["frac"] = roof["achieved"] / peak
     stage = {"alg_bytes_per_cell_stage": bA + bB, "achieved_GBs": (bA + bB) * ncells * 4 * K / (dev_ms * 1e-3) / 1e9}
     stage["frac"] = stage["achieved_GBs"] / (peak * world)
@@ -426,7 +525,8 @@ def main():
                        f"({scal['device_bytes'] / 1e9:.2f} GB resident per GPU vs 126 MB L2)", "parallelism": f"dd{ngpus}",
                        "setup_s": round(t_setup, 1)},
             "roofline": roof, "stage_roofline": stage, "gradient_kernel": gradk,
-            "wall_ms_per_step": wall * 1e3 / K, "gpu_launches": launches, "clocks": clk.summary(), "e2e": e2e}
+            "wall_ms_per_step": wall * 1e3 / K, "gpu_launches": launches, "clocks": clk.summary(), "e2e": e2e,
+            "parity": parity, "state_check": state_check, "sustained": sustained}
     if other:
         line["other_configs"] = other
     if not args.no_cpu_baseline:

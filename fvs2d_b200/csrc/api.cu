@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -114,6 +115,8 @@ struct Ctx {
   unsigned *peer_flag[kMaxPeers] = {};
   unsigned *flags = nullptr, *done_ctr = nullptr;  // flags[r]: stages rank r has delivered to this rank
   std::vector<void *> ipc_open;
+  std::map<const void *, size_t> smem_attr;  // kernel -> dynamic shared memory it is configured for (per context: function
+                                             // attributes are per device)
   const uint32_t *d_rs_word = nullptr;
   const int2 *d_rs_ent = nullptr;
   unsigned epoch_total = 0;  // Runge-Kutta stages run through the in-kernel exchange so far (all ranks agree)
@@ -137,6 +140,7 @@ struct Ctx {
   std::vector<cudaEvent_t> ev_pool;
   std::vector<std::pair<int, int>> ev_spans[3];
   size_t ev_used = 0;
+  long ev_dropped = 0;   // spans not recorded because the event pool was in use (time_integration drains it every 256 steps)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 Ctx *C = nullptr;
@@ -172,7 +176,24 @@ int dev_upload(const T *&p, const std::vector<T> &h) {
   p = d;
   return 0;
 }
+template <class T>
+void dev_free(T *&p, size_t bytes) {  // release one tracked allocation before free_device
+  if (!p) return;
+  cudaFree(p);
+  C->allocs.erase(std::remove(C->allocs.begin(), C->allocs.end(), (void *)p), C->allocs.end());
+  C->bytes -= std::min(C->bytes, bytes);
+  p = nullptr;
+}
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// raise a kernel's dynamic shared-memory limit to `bytes` (never lowers it: several launch configurations share a kernel)
+template <class K>
+void ensure_smem_attr(K kernel, size_t bytes) {
+  size_t &have = C->smem_attr[(const void *)kernel];
+  if (have >= bytes) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  have = bytes;
+}
 
 void close_p2p();
 int all_ranks_agree(int mine, int &all);
@@ -198,7 +219,7 @@ struct Span {
   int bucket, a = -1;
   Span(int b) : bucket(b) {
     if (!C->opt_timing) return;
-    if (C->ev_used + 2 > C->ev_pool.size()) return;
+    if (C->ev_used + 2 > C->ev_pool.size()) { C->ev_dropped++; return; }
     a = (int)C->ev_used;
     C->ev_used += 2;
     cudaEventRecord(C->ev_pool[a], C->st);
@@ -345,11 +366,7 @@ void launch_flux_one(const StageParams &S, const double *pin, double *pout) {
   const int nb = C->nblocks;
   if (C->tile_ok && C->opt_tile == 2) {
     const size_t smem = kStages * pipe_stage_bytes<RC>(C->pm.S, C->pm.E) + 2 * kStages * sizeof(uint64_t) + (size_t)C->opt_smem_pad * 1024;
-    static size_t configured = 0;
-    if (configured < smem) {
-      cudaFuncSetAttribute(k_flux_pipe<UM, STEADY, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      configured = smem;
-    }
+    ensure_smem_attr(k_flux_pipe<UM, STEADY, RC>, smem);
     if (C->opt_carveout >= 0)
       cudaFuncSetAttribute(k_flux_pipe<UM, STEADY, RC>, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(100, C->opt_carveout * 100 / 228 + 1));
     int per_sm = 0;  // persistent kernel: exactly as many CTAs as are co-resident
@@ -462,6 +479,7 @@ int build_fused_plan() {
 }
 
 int upload_fused_tables();
+int all_ranks_agree(int mine, int &all);
 
 // several ranks: which peer ghost slots every cell of a boundary tile is stored to (HaloP2P::rs_word / rs_ent)
 int build_remote_store_tables() {
@@ -492,18 +510,29 @@ int build_remote_store_tables() {
   return 0;
 }
 
-int ensure_fused() {
-  if (C->fz_state) return 0;
-  C->fz_state = -1;
+int ensure_fused_local() {
   C->n_fl = 0;
   if ((C->nranks != 1 && (!C->L.deep || !C->p2p_ok)) || !C->tile_ok || C->recon != RC_K0) return 0;
   if (C->fz_tables == 0 && upload_fused_tables()) return 1;
   if (C->fz_tables != 1) return 0;
   if (build_fused_plan()) return 1;  // (again after a change of the "fuse" option: the tile lists are small)
   if (C->n_fl == 0) return 0;
+  if (C->nranks > 1 && !C->L.peers.empty() && C->fl[C->n_fl - 1].n_bnd == 0) { C->n_fl = 0; return 0; }
   if (build_remote_store_tables()) return 1;
   C->fz_state = 1;
   return 0;
+}
+
+int ensure_fused() {
+  if (C->fz_state) return 0;
+  C->fz_state = -1;
+  const int rc = ensure_fused_local();
+  if (C->nranks > 1 && C->p2p_ok) {  // the peers wait for this rank's flags: every rank runs the fused path or none does
+    int all = 0;
+    if (all_ranks_agree(rc == 0 && C->fz_state == 1, all)) return 1;
+    if (!all) { C->fz_state = -1; C->n_fl = 0; }
+  }
+  return rc;
 }
 
 int upload_fused_tables() {
@@ -534,60 +563,65 @@ int upload_fused_tables() {
   return 0;
 }
 
-template <int UM, bool STEADY, int FORM>
-void launch_fused_one(const StageParams &S, const double *pin, double *pout) {
+// one launch of the plan; P2P selects the kernel instance with the in-kernel halo exchange (only the launch that holds the
+// boundary tiles needs it: the other instances carry none of its registers)
+template <int UM, bool STEADY, int FORM, bool P2P>
+int launch_fused_part(FusedLaunch &fl, int k, int part_off, const StageParams &S, const double *pin, double *pout) {
+  auto k3 = k_stage_fused<UM, STEADY, FORM, 3, P2P>;
+  auto k2 = k_stage_fused<UM, STEADY, FORM, 2, P2P>;  // more registers, for launches that only fit two CTAs per SM anyway
+  const size_t smem = fused_cta_bytes(fl.meta);
+  const void *key = (const void *)k3;
+  ensure_smem_attr(k3, smem);
+  ensure_smem_attr(k2, smem);
+  if (fl.attr_key != key) {  // occupancy of this launch configuration, once per kernel instance
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fl.per3, k3, kPipeThreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fl.per2, k2, kPipeThreads, smem);
+    fl.attr_key = key;
+    if (getenv("FVS2D_DEBUG")) fprintf(stderr, "[fvs2d] k_stage_fused launch %d: %zu B smem/CTA, CTAs/SM %d (128 regs) / %d%s\n", k, smem, fl.per3, fl.per2, P2P ? ", in-kernel halo exchange" : "");
+  }
+  const bool use3 = fl.per3 >= 3 && (C->opt_ctas == 0 || C->opt_ctas >= 3);
+  int per_sm = std::max(1, use3 ? fl.per3 : fl.per2);
+  if (C->opt_ctas > 0) per_sm = std::min(per_sm, C->opt_ctas);
+  const int grid = std::min(fl.meta.ntiles, C->nsm * per_sm);
+  HaloP2P hx{};
+  if (P2P) {
+    const int which = pout == C->p_buf[0] ? 0 : 1;
+    hx.n_peers = (int)C->L.peers.size();
+    hx.n_bnd = fl.n_bnd; hx.n_bnd_ctas = std::min(fl.n_bnd, grid);
+    hx.stage = S.stage; hx.clk = C->clk;
+    for (int q = 0; q < hx.n_peers; q++) {
+      hx.peer_out[q] = C->peer_p[q][which];
+      hx.peer_np[q] = C->peer_np[q];
+      hx.peer_flag[q] = C->peer_flag[q];
+      hx.my_flag[q] = C->flags + C->L.peers[q];
+    }
+    hx.rs_word = C->d_rs_word; hx.rs_ent = C->d_rs_ent; hx.done_ctr = C->done_ctr;
+  }
+  if (grid > 0)
+    (use3 ? k3 : k2)<<<grid, kPipeThreads, smem, C->st>>>(C->dm, fl.meta, C->phys, S, pin, C->bc, C->q, C->f, pout, C->dtl,
+                                                          C->partial + 4 * (size_t)part_off, hx);
+  C->last_launches++;
+  return grid;
+}
+
+template <int UM, bool STEADY>
+void launch_fused_form(const StageParams &S, const double *pin, double *pout) {
+  const bool gg = C->L.g_form == 0;
   int part_off = 0;
   for (int k = 0; k < C->n_fl; k++) {
     FusedLaunch &fl = C->fl[k];
-    auto k3 = k_stage_fused<UM, STEADY, FORM, 3>;
-    auto k2 = k_stage_fused<UM, STEADY, FORM, 2>;  // more registers, for launches that only fit two CTAs per SM anyway
-    const size_t smem = fused_cta_bytes(fl.meta);
-    const void *key = (const void *)k3;
-    if (fl.attr_key != key) {  // per context and kernel instance: function attributes are per device
-      cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fl.per3, k3, kPipeThreads, smem);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fl.per2, k2, kPipeThreads, smem);
-      fl.attr_key = key;
-      if (getenv("FVS2D_DEBUG")) fprintf(stderr, "[fvs2d] k_stage_fused launch %d: %zu B smem/CTA, CTAs/SM %d (128 regs) / %d\n", k, smem, fl.per3, fl.per2);
-    }
-    const bool use3 = fl.per3 >= 3 && (C->opt_ctas == 0 || C->opt_ctas >= 3);
-    int per_sm = std::max(1, use3 ? fl.per3 : fl.per2);
-    if (C->opt_ctas > 0) per_sm = std::min(per_sm, C->opt_ctas);
-    const int grid = std::min(fl.meta.ntiles, C->nsm * per_sm);
-    HaloP2P hx{};
-    if (C->nranks > 1 && fl.n_bnd > 0) {
-      const int which = pout == C->p_buf[0] ? 0 : 1;
-      hx.n_peers = (int)C->L.peers.size();
-      hx.n_bnd = fl.n_bnd; hx.n_bnd_ctas = std::min(fl.n_bnd, grid);
-      hx.stage = S.stage; hx.clk = C->clk;
-      for (int q = 0; q < hx.n_peers; q++) {
-        hx.peer_out[q] = C->peer_p[q][which];
-        hx.peer_np[q] = C->peer_np[q];
-        hx.peer_flag[q] = C->peer_flag[q];
-        hx.my_flag[q] = C->flags + C->L.peers[q];
-      }
-      hx.rs_word = C->d_rs_word; hx.rs_ent = C->d_rs_ent; hx.done_ctr = C->done_ctr;
-    }
-    if (grid > 0)
-      (use3 ? k3 : k2)<<<grid, kPipeThreads, smem, C->st>>>(C->dm, fl.meta, C->phys, S, pin, C->bc, C->q, C->f, pout, C->dtl,
-                                                            C->partial + 4 * (size_t)part_off, hx);
-    part_off += grid;
-    C->last_launches++;
+    const bool p2p = C->nranks > 1 && fl.n_bnd > 0;
+    if (p2p) part_off += gg ? launch_fused_part<UM, STEADY, 0, true>(fl, k, part_off, S, pin, pout) : launch_fused_part<UM, STEADY, 1, true>(fl, k, part_off, S, pin, pout);
+    else part_off += gg ? launch_fused_part<UM, STEADY, 0, false>(fl, k, part_off, S, pin, pout) : launch_fused_part<UM, STEADY, 1, false>(fl, k, part_off, S, pin, pout);
   }
   C->nparts = part_off;
 }
 
 int launch_fused(int um, const StageParams &S, const double *pin, double *pout) {
   Span sp(2);
-  const bool steady = C->cfg.steady != 0, gg = C->L.g_form == 0;
-  if (um == UM_RK) {
-    if (steady) { if (gg) launch_fused_one<UM_RK, true, 0>(S, pin, pout); else launch_fused_one<UM_RK, true, 1>(S, pin, pout); }
-    else { if (gg) launch_fused_one<UM_RK, false, 0>(S, pin, pout); else launch_fused_one<UM_RK, false, 1>(S, pin, pout); }
-  } else {
-    if (steady) { if (gg) launch_fused_one<UM_SSPRK, true, 0>(S, pin, pout); else launch_fused_one<UM_SSPRK, true, 1>(S, pin, pout); }
-    else { if (gg) launch_fused_one<UM_SSPRK, false, 0>(S, pin, pout); else launch_fused_one<UM_SSPRK, false, 1>(S, pin, pout); }
-  }
+  const bool steady = C->cfg.steady != 0;
+  if (um == UM_RK) { if (steady) launch_fused_form<UM_RK, true>(S, pin, pout); else launch_fused_form<UM_RK, false>(S, pin, pout); }
+  else { if (steady) launch_fused_form<UM_SSPRK, true>(S, pin, pout); else launch_fused_form<UM_SSPRK, false>(S, pin, pout); }
   return 0;
 }
 
@@ -1037,6 +1071,9 @@ int fvs2d_gpu_compute_residual(double time, double *resid, double *ws_nrml) {
 
 int fvs2d_gpu_get_aux(double *pvar, double *grad, double *phi_lim) {
   NEED(C && C->has_state, "fvs2d_gpu_get_aux: no state");
+  // pvar, grad and phi_lim of ONE state, the current one (as if compute_residual had just been called on it): the fused
+  // stage kernel never writes gradients to global memory, and the two-pass path leaves those of the last stage's input
+  if ((grad || phi_lim) && launch_gradient(C->pa)) return 1;
   if (pvar && download_aos(C->pa, 4, pvar, 1, 0)) return 1;
   if (phi_lim && download_aos(C->phi, 1, phi_lim)) return 1;
   if (grad) {  // Fortran grad(ivar,ic,idim): two planes of (4,ncells); device g holds gx0-3, gy0-3 pair-interleaved
@@ -1130,12 +1167,27 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
     // at least 4096 rows (0.5 MB): the step graph is tied to this buffer, so growing it from call to call would
     // force a re-capture inside the caller's time loop
     const size_t cap = std::max<size_t>((size_t)nsub, 4096);
+    dev_free(C->logbuf, per * C->log_cap * sizeof(double));
+    dev_free(C->logid, C->log_cap * sizeof(int));
     if (dev_alloc(C->logbuf, per * cap) || dev_alloc(C->logid, cap)) return 1;
     C->log_cap = cap;
   }
   C->last_launches = 0;
-  C->ev_used = 0;
+  C->ev_used = 0; C->ev_dropped = 0;
   for (auto &s : C->ev_spans) s.clear();
+  double span_ms[3] = {0.0, 0.0, 0.0};
+  // option "timing": the event pool holds ~300 steps' worth of spans; it is drained (one stream synchronisation) whenever it
+  // runs low, so the per-phase times of a long call are complete
+  auto drain_spans = [&]() -> int {
+    CUDA_OK(cudaStreamSynchronize(C->st));
+    if (C->sx) CUDA_OK(cudaStreamSynchronize(C->sx));
+    for (int b = 0; b < 3; b++) {
+      for (auto &pr : C->ev_spans[b]) { float t = 0; cudaEventElapsedTime(&t, C->ev_pool[pr.first], C->ev_pool[pr.second]); span_ms[b] += t; }
+      C->ev_spans[b].clear();
+    }
+    C->ev_used = 0;
+    return 0;
+  };
   const bool overlap = C->nranks > 1 && C->opt_overlap && C->tile_ok && C->opt_tile == 2;
   bool p_pending = false;
   if (C->opt_fuse && ensure_fused()) return 1;
@@ -1237,7 +1289,10 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
     for (; done < nsub; done++) CUDA_OK(cudaGraphLaunch(C->graph_exec, C->st));
     C->last_launches = per_step * nsub;
   } else {
-    for (; done < nsub; done++) if (run_step()) return 1;
+    for (; done < nsub; done++) {
+      if (C->opt_timing && C->ev_used + 128 > C->ev_pool.size() && drain_spans()) return 1;
+      if (run_step()) return 1;
+    }
   }
   if (p_pending) CUDA_OK(cudaStreamWaitEvent(C->st, C->e_p, 0));  // the last exchange belongs to this call
   if (fused && C->nranks > 1) {
@@ -1262,11 +1317,8 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   float ms = 0;
   CUDA_OK(cudaEventElapsedTime(&ms, C->ev0, C->ev1));
   C->last_ms[0] = ms;
-  for (int b = 0; b < 3; b++) {
-    double acc = 0;
-    for (auto &pr : C->ev_spans[b]) { float t = 0; cudaEventElapsedTime(&t, C->ev_pool[pr.first], C->ev_pool[pr.second]); acc += t; }
-    C->last_ms[b == 0 ? 3 : b] = acc;
-  }
+  if (drain_spans()) return 1;
+  for (int b = 0; b < 3; b++) C->last_ms[b == 0 ? 3 : b] = span_ms[b];
   if (nsub == 0 || !(res_l2 || vortex_err || vortex_err_xy)) return 0;
 
   // ---- combine across ranks (sums / maxima are tiny: 17 doubles per step)

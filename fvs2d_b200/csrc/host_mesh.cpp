@@ -208,11 +208,15 @@ struct BucketGrid {
     double x1 = -1e300, y1 = -1e300;
     x0 = y0 = 1e300;
     for (int i = 0; i < n; i++) { x0 = std::min(x0, x[i]); x1 = std::max(x1, x[i]); y0 = std::min(y0, y[i]); y1 = std::max(y1, y[i]); }
-    const double area = std::max((x1 - x0) * (y1 - y0), 1e-300);
-    h = std::sqrt(area / std::max(1.0, n / 2.0));
-    nx = std::max(1, std::min(1 << 14, (int)((x1 - x0) / h) + 1));
-    ny = std::max(1, std::min(1 << 14, (int)((y1 - y0) / h) + 1));
-    h = std::max((x1 - x0) / nx, (y1 - y0) / ny) * (1.0 + 1e-12) + 1e-300;
+    // ~2 centroids per bucket; a degenerate bounding box (one row or column of cells) becomes a 1-D grid along the
+    // longer extent.  The bucket counts are formed and clamped in double before the conversion to int.
+    const double ex = x1 - x0, ey = y1 - y0, emax = std::max(ex, ey);
+    const double area = ex * ey;
+    h = area > 1e-12 * emax * emax ? std::sqrt(area / std::max(1.0, n / 2.0)) : emax / std::max(1.0, n / 2.0);
+    if (!(h > 0.0)) h = 1.0;  // every centroid at one point
+    nx = (int)std::max(1.0, std::min(16384.0, std::floor(ex / h) + 1.0));
+    ny = (int)std::max(1.0, std::min(16384.0, std::floor(ey / h) + 1.0));
+    h = std::max(ex / nx, ey / ny) * (1.0 + 1e-12) + 1e-300;
     ptr.assign((size_t)nx * ny + 1, 0);
     std::vector<int> b(n);
     for (int i = 0; i < n; i++) { b[i] = bucket(x[i], y[i]); ptr[b[i] + 1]++; }
@@ -221,8 +225,8 @@ struct BucketGrid {
     std::vector<int> fill(ptr.begin(), ptr.end() - 1);
     for (int i = 0; i < n; i++) item[fill[b[i]]++] = i;
   }
-  int bx(double x) const { return std::max(0, std::min(nx - 1, (int)((x - x0) / h))); }
-  int by(double y) const { return std::max(0, std::min(ny - 1, (int)((y - y0) / h))); }
+  int bx(double x) const { return (int)std::max(0.0, std::min((double)(nx - 1), std::floor((x - x0) / h))); }
+  int by(double y) const { return (int)std::max(0.0, std::min((double)(ny - 1), std::floor((y - y0) / h))); }
   int bucket(double x, double y) const { return by(y) * nx + bx(x); }
 };
 struct Near { double d2; int idx; };

@@ -90,7 +90,7 @@ __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <int UM, bool STEADY, int FORM, int CTAS>
+template <int UM, bool STEADY, int FORM, int CTAS, bool P2P>
 __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused(const DevMesh m, const FusedMeta fm, const Phys P, const StageParams S,
                                                                      const double *__restrict__ p, const double *__restrict__ bc,
                                                                      double *__restrict__ q, double *__restrict__ f,
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused(const DevMes
     };
     auto tile_id = [&](int j) { return fm.tile_list ? __ldg(&fm.tile_list[j]) : j; };
     if ((int)blockIdx.x < fm.ntiles) fetch_meta(tile_id(blockIdx.x));
-    if (hx.n_peers > 0 && (int)blockIdx.x < hx.n_bnd) {
+    if ((P2P && hx.n_peers > 0) && (int)blockIdx.x < hx.n_bnd) {
       // boundary tiles come first: before the first ghost is read, every peer must have delivered the previous stage
       const unsigned need = hx.clk->epoch0 + 4u * (unsigned)hx.clk->istep + (unsigned)hx.stage;
       if (lane < hx.n_peers) while ((int)(ld_acquire_sys(hx.my_flag[lane]) - need) < 0) __nanosleep(64);
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused(const DevMes
   // ================================== consumer warps ==================================
   double dq2[4] = {0.0, 0.0, 0.0, 0.0};
   const int hst0 = 2 * fm.FW * kBlock;  // first double2 of the ring-1 face states inside X
-  bool bnd_open = hx.n_peers > 0 && (int)blockIdx.x < hx.n_bnd;  // this CTA still owes its "boundary tiles done"
+  bool bnd_open = (P2P && hx.n_peers > 0) && (int)blockIdx.x < hx.n_bnd;  // this CTA still owes its "boundary tiles done"
   auto signal_peers = [&]() {
     __threadfence_system();  // this thread's stores to peer memory are visible system-wide ...
     asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");  // ... for all consumer threads of the CTA
@@ -239,9 +239,9 @@ __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused(const DevMes
     if (live) {
       stage_load<UM, STEADY>(S, i, np, q, f, dtl, q0, fo, dl);
       ivol = m.ivol[i];
-      if (hx.n_peers > 0 && j < hx.n_bnd) rsw = __ldg(&hx.rs_word[(size_t)j * kBlock + tid]);
+      if ((P2P && hx.n_peers > 0) && j < hx.n_bnd) rsw = __ldg(&hx.rs_word[(size_t)j * kBlock + tid]);
     }
-    if (hx.n_peers > 0 && bnd_open && j >= hx.n_bnd) { bnd_open = false; signal_peers(); }  // first interior tile of this CTA
+    if ((P2P && hx.n_peers > 0) && bnd_open && j >= hx.n_bnd) { bnd_open = false; signal_peers(); }  // first interior tile of this CTA
     double2 *sx = st_x(s), *scg = st_cg(s);
     const double2 *sph = st_ph(s), *sxy = st_xy(s), *e2 = st_e2(s);
     const double *sea = st_ea(s);
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused(const DevMes
       }
     }
   }
-  if (hx.n_peers > 0 && bnd_open) signal_peers();  // this CTA had boundary tiles only
+  if ((P2P && hx.n_peers > 0) && bnd_open) signal_peers();  // this CTA had boundary tiles only
   if (S.last) {
     __shared__ double red[4][kBlock / 32];
 #pragma unroll

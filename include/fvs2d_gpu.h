@@ -98,8 +98,12 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
  * ws_nrml(ncells) (may be NULL) in the original numbering. */
 int fvs2d_gpu_compute_residual(double time, double *resid, double *ws_nrml);
 
-/* Side products of the last residual evaluation (src/data_solution.f90:16-21): pvar(4,nc),
- * grad(4,nc,2) in Fortran order [idim][ic][ivar], phi_lim(nc).  Any pointer may be NULL. */
+/* Side products of a residual evaluation (src/data_solution.f90:16-21) for the CURRENT state: pvar(4,nc),
+ * grad(4,nc,2) in Fortran order [idim][ic][ivar], phi_lim(nc).  Any pointer may be NULL.  The gradients and the limiter are
+ * re-evaluated from the current primitive state by the call (pass A), so the three arrays always belong to one state --
+ * right after fvs2d_gpu_compute_residual they are that call's; after fvs2d_gpu_time_integration they belong to the final
+ * state (the reference leaves those of the last stage's input state there).  First-order reconstruction: grad = 0, as
+ * src/gradient.f90:49 leaves it. */
 int fvs2d_gpu_get_aux(double *pvar, double *grad, double *phi_lim);
 
 /* test_resid (src/test.f90:481-519): one compute_residual(0) and the L2/Linf norms of
