@@ -226,8 +226,12 @@ __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused(const DevMes
     }
   };
   int it = 0;
+  // the id of a tile is loaded one iteration ahead: the addresses of the cell's Runge-Kutta data depend on it, and an L2
+  // round trip at the top of every tile was the largest single long-scoreboard stall of the kernel
+  int t_next = ((int)blockIdx.x < fm.ntiles && fm.tile_list) ? __ldg(&fm.tile_list[blockIdx.x]) : (int)blockIdx.x;
   for (int j = blockIdx.x; j < fm.ntiles; j += gridDim.x, it++) {
-    const int t = fm.tile_list ? __ldg(&fm.tile_list[j]) : j;
+    const int t = t_next;
+    if (j + (int)gridDim.x < fm.ntiles) t_next = fm.tile_list ? __ldg(&fm.tile_list[j + gridDim.x]) : j + (int)gridDim.x;
     const int s = it % kStages;
     const uint32_t ph = (it / kStages) & 1;
     const int c0 = t * kBlock;

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 from fvs2d_b200 import config, meshgen, meshio, solver  # noqa: E402
 
 OUT = os.path.join(ROOT, "gpurun_out", "fused_check.txt")
-FUSE = tuple(int(x) for x in os.environ.get("FUSE", "2,4,5").split(","))
+FUSE = tuple(int(x) for x in os.environ.get("FUSE", "-1,2").split(","))
 os.makedirs(os.path.dirname(OUT), exist_ok=True)
 
 
@@ -84,6 +84,7 @@ def timing(which):
             gpu.set_option("fuse", fuse)
             gpu.set_option("timing", 0)
             gpu.time_integration(0.0, 5, logs=False)
+            time.sleep(1.0)                       # start every measurement from an idle GPU (power state)
             gpu.time_integration(0.0, 20, logs=False)
             ms = gpu.last_timing()["total_ms"] / 20
             gpu.set_option("timing", 1)   # event pair around every launch (eager path)
