@@ -19,7 +19,7 @@ _LIB = None
 
 # every symbol include/fvs2d_gpu.h declares (tests check that the .so exports them all)
 SYMBOLS = [
-    "fvs2d_gpu_init", "fvs2d_gpu_comm_unique_id", "fvs2d_gpu_comm_init", "fvs2d_gpu_set_mesh",
+    "fvs2d_gpu_init", "fvs2d_gpu_comm_unique_id", "fvs2d_gpu_comm_init", "fvs2d_gpu_set_mesh", "fvs2d_gpu_set_lsq",
     "fvs2d_gpu_initialize_solution", "fvs2d_gpu_set_state", "fvs2d_gpu_get_state", "fvs2d_gpu_set_state_local",
     "fvs2d_gpu_get_state_local",
     "fvs2d_gpu_time_integration", "fvs2d_gpu_compute_residual", "fvs2d_gpu_get_aux", "fvs2d_gpu_test_resid",
@@ -48,6 +48,7 @@ def lib():
     L.fvs2d_gpu_comm_unique_id.argtypes = [vp]
     L.fvs2d_gpu_comm_init.argtypes = [ci, ci, vp]
     L.fvs2d_gpu_set_mesh.argtypes = [ci, ci, ci, vp, vp, vp, ci, vp, vp, vp]
+    L.fvs2d_gpu_set_lsq.argtypes = [vp, vp, vp, vp]
     L.fvs2d_host_build.argtypes = [cfgp, ci, ci, ci, ci, ci, vp, vp, vp, ci, vp, vp, vp]
     L.fvs2d_gpu_initialize_solution.argtypes = []
     L.fvs2d_gpu_set_state.argtypes = [vp]

@@ -818,6 +818,8 @@ int fvs2d_gpu_comm_init(int rank, int nranks, const char id[128]) {
 }  // extern "C"
 
 namespace {
+int build_partition();
+int device_upload();
 // host half of set_mesh: connectivity, geometry, gradient operator, renumbering, layout (no CUDA calls)
 int host_build(int nnodes, int ntri, int nquad, const double *node_xy, const int *cell_ptr, const int *cell_node,
                int nb, const int *b_ncells, const int *b_type, const int *b_cell) {
@@ -853,6 +855,13 @@ int host_build(int nnodes, int ntri, int nquad, const double *node_xy, const int
   if (!err.empty()) return fail("%s", err.c_str());
   err = build_gradient(m, C->cfg.grad_method, C->cfg.lsq_stencil, C->cfg.lsq_pow, C->grad);
   if (!err.empty()) return fail("%s", err.c_str());
+  return build_partition();
+}
+
+// renumbering + this rank's layout from the mesh and the gradient operator (again after fvs2d_gpu_set_lsq)
+int build_partition() {
+  HostMesh &m = C->mesh;
+  std::string err;
   std::vector<int> perm;
   hilbert_order(m, perm);
   // several ranks + the fused stage kernel: one more ghost layer (the stencils of the face-neighbour ghosts); the
@@ -886,8 +895,43 @@ int fvs2d_gpu_set_mesh(int nnodes, int ntri, int nquad, const double *node_xy, c
   NEED(C && C->inited, "fvs2d_gpu_set_mesh: call fvs2d_gpu_init first");
   free_device();
   if (host_build(nnodes, ntri, nquad, node_xy, cell_ptr, cell_node, nb, b_ncells, b_type, b_cell)) return 1;
-  C->has_mesh = false;
+  return device_upload();
+}
 
+/* Replaces the least-squares operator built by fvs2d_gpu_set_mesh with the caller's (the reference's public `lsq` table,
+ * src/gradient_lsq.f90:16-27: lsq(ic)%ncells, %cell, %w, %coef), so that the Fortran host's own coefficients -- kd-tree
+ * tie-breaks included -- are used bit for bit.  CSR over the cells in the ORIGINAL numbering, 0-based cell ids. */
+int fvs2d_gpu_set_lsq(const int *ptr, const int *cell, const double *w, const double *coef) {
+  NEED(C && C->inited && C->has_mesh, "fvs2d_gpu_set_lsq: call fvs2d_gpu_init and fvs2d_gpu_set_mesh first");
+  NEED(C->cfg.grad_method == 3, "fvs2d_gpu_set_lsq: the run does not use the least-squares gradient (grad_method 3)");
+  NEED(ptr && cell && w && coef, "fvs2d_gpu_set_lsq: null array");
+  const int nc = C->mesh.ncells;
+  NEED(ptr[0] == 0, "fvs2d_gpu_set_lsq: ptr[0] must be 0");
+  GradOp g;
+  g.form = 1; g.method = 3; g.lsq_pow = C->cfg.lsq_pow;
+  g.ptr.resize((size_t)nc + 1);
+  for (int i = 0; i <= nc; i++) g.ptr[i] = ptr[i];
+  for (int i = 0; i < nc; i++) NEED(ptr[i + 1] >= ptr[i] && ptr[i + 1] - ptr[i] <= kMaxStencil, "fvs2d_gpu_set_lsq: bad ptr");
+  const int64_t n = g.ptr[nc];
+  g.idx.assign(cell, cell + n);
+  for (int64_t k = 0; k < n; k++) NEED(cell[k] >= 0 && cell[k] < nc, "fvs2d_gpu_set_lsq: cell id out of range");
+  g.user_cx.resize(n); g.user_cy.resize(n);
+  for (int64_t k = 0; k < n; k++) {  // grad = sum coef(:,k) * (p_j - p_i) * w(k): the product as src/gradient_lsq.f90:397 forms it
+    g.user_cx[k] = coef[2 * k] * w[k];
+    g.user_cy[k] = coef[2 * k + 1] * w[k];
+  }
+  C->grad = std::move(g);
+  free_device();
+  C->has_mesh = C->has_state = false;
+  if (build_partition()) return 1;
+  return device_upload();
+}
+
+}  // extern "C"
+
+namespace {
+int device_upload() {
+  C->has_mesh = false;
   // ---- upload
   const Layout &L = C->L;
   DevMesh &d = C->dm;
@@ -962,6 +1006,9 @@ int fvs2d_gpu_set_mesh(int nnodes, int ntri, int nquad, const double *node_xy, c
   C->has_mesh = true;
   return 0;
 }
+}  // namespace
+
+extern "C" {
 
 int fvs2d_gpu_set_state(const double *cvar) {
   NEED(C && C->has_mesh, "fvs2d_gpu_set_state: no mesh");

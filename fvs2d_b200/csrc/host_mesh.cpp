@@ -433,6 +433,16 @@ double grad_cell_coeffs(const HostMesh &m, const GradOp &g, int ic, double *cx, 
     c0x /= vol; c0y /= vol;
     return 0.0;
   }
+  if (!g.user_cx.empty()) {  // the caller's own least-squares table; the linear-exactness check is the reference's
+    double dfx = 0, dfy = 0;
+    for (int i = 0; i < n; i++) {
+      cx[i] = g.user_cx[b + i]; cy[i] = g.user_cy[b + i];
+      const int jc = g.idx[b + i];
+      const double diff = 1.0 * m.yc[jc] + 2.0 * m.xc[jc] - (1.0 * yc + 2.0 * xc);
+      dfx += cx[i] * diff; dfy += cy[i] * diff;
+    }
+    return std::max(std::fabs(dfx - 2.0), std::fabs(dfy - 1.0));
+  }
   // least squares: normal equations per cell (src/gradient_lsq.f90:137-203 / 281-347), w folded in
   double g11 = 0, g12 = 0, g21 = 0, g22 = 0;
   double dxw[kMaxStencil], dyw[kMaxStencil], w[kMaxStencil];

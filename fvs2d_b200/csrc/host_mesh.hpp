@@ -62,6 +62,7 @@ struct GradOp {
   std::vector<int64_t> ptr;  // ncells+1
   std::vector<int> idx;      // the LSQ stencil is also the limiter's min/max set (src/gradient_limiter.f90:54-58)
   std::vector<double> idw;   // GGNB: node weights 1 / sum_c 1/|x_c - x_v| (src/gradient_ggnb.f90:59-80)
+  std::vector<double> user_cx, user_cy;  // least squares supplied by the caller (fvs2d_gpu_set_lsq): coef * w per entry
 };
 
 // grad_method 1 GGCB (src/gradient_ggcb.f90:48-110), 2 GGNB (src/gradient_ggnb.f90:49-177),

@@ -51,6 +51,17 @@ class Fvs2dGpu:
         self.ncells = mesh.ncells
         return self
 
+    def set_lsq(self, ptr, cell, w, coef):
+        """Use the caller's least-squares table (the reference's public ``lsq(:)``, src/gradient_lsq.f90:16-27) instead of
+        the library's: CSR over the cells in the original numbering, 0-based ids, ``coef`` shaped [entries, 2]."""
+        ptr = np.ascontiguousarray(ptr, dtype=np.int32)
+        cell = np.ascontiguousarray(cell, dtype=np.int32)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        assert ptr.size == self.ncells + 1 and cell.size == w.size == ptr[-1] and coef.size == 2 * ptr[-1]
+        capi.check(self.L.fvs2d_gpu_set_lsq(capi.ptr(ptr), capi.ptr(cell), capi.ptr(w), capi.ptr(coef)))
+        return self
+
     def sizes(self) -> dict:
         out = np.zeros(10, dtype=np.int32)
         capi.check(self.L.fvs2d_gpu_sizes(capi.ptr(out)))

@@ -66,6 +66,16 @@ int fvs2d_gpu_set_mesh(int nnodes, int ncells_tri, int ncells_quad, const double
                        const int *bndry_ncells, const int *bndry_type /* FVS2D_BC_* */,
                        const int *bndry_cell /* concatenated */);
 
+/* Optional, after fvs2d_gpu_set_mesh (grad_method 3 only): replace the library's least-squares operator by the caller's --
+ * the reference's public table `lsq(:)` (src/gradient_lsq.f90:16-27: %ncells, %cell, %w, %coef(2,:)) flattened to CSR in the
+ * ORIGINAL cell numbering with 0-based cell ids: entries ptr[ic] .. ptr[ic+1]-1 belong to cell ic, coef holds coef(1,k),
+ * coef(2,k) per entry.  The Fortran host's own coefficients (kd-tree tie-breaks of the boundary stencils included) are then
+ * used bit for bit: grad = sum_k coef(:,k) * w(k) * (p(cell(k)) - p(ic)), src/gradient_lsq.f90:393-401.  The stencil is also
+ * the limiter's min/max set (src/gradient_limiter.f90:54-58).  The call repeats the partitioning and the device upload of
+ * fvs2d_gpu_set_mesh; the state must be set (again) afterwards.  The reference's linear-exactness check
+ * (src/gradient_lsq.f90:490-529, 1e-10) is applied to the supplied table. */
+int fvs2d_gpu_set_lsq(const int *ptr /* ncells+1 */, const int *cell, const double *w, const double *coef /* 2 per entry */);
+
 /* Replaces: initialize_solution for ntstart<=1 (src/initialize.f90:35-53,79-84): freestream, isentropic
  * vortex at t=(ntstart-1)*dt, or the manufactured solution (ntstart==0).  Restart (ntstart>1) is
  * fvs2d_gpu_set_state with the cvar read from cont.s8. */

@@ -122,3 +122,42 @@ def test_fallback_kernel_matches_pipeline_bitwise():
         gpu.close()
     for a, b in zip(*out):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("stencil,limiter", [("fn", 0), ("nn", 1)])
+def test_set_lsq_uses_the_callers_table(stencil, limiter):
+    """fvs2d_gpu_set_lsq: the reference's public lsq(:) table -- here the oracle's, with its own kd-tree
+    choices for the boundary stencils -- replaces the library's; residual, gradients and limiter equal the oracle's, and a
+    deliberately different table (every weight doubled, coefficient halved: the same operator) gives the same numbers."""
+    from fvs2d_b200 import config, meshgen, solver
+    from oracle.oracle import Oracle
+    mesh = meshgen.vortex_mixed_mesh(40)
+    cfg = config.RunInput(grad_cellcntr_imethd=3, grad_cellcntr_lsq_nghbr=stencil, grad_cellcntr_lsq_pow=1.0, grad_limiter_imethd=limiter,
+                          lvortex=True, dt=0.005).to_config()
+    orc = Oracle(mesh, cfg)
+    orc.initialize_solution()
+    r_o = orc.compute_residual(0.2).copy()
+    g_o, ph_o = orc.array("grad").reshape(2, -1, 4), orc.array("phi_lim")
+    ptr, cell, w, coef = orc.array("lsq_ptr"), orc.array("lsq_cell"), orc.array("lsq_w"), orc.array("lsq_coef").reshape(-1, 2)
+    gpu = solver.Fvs2dGpu(cfg, device=0)
+    gpu.set_mesh(mesh)
+    gpu.initialize_solution()
+    r_lib = gpu.compute_residual(0.2)
+    for ww, cc in ((w, coef), (2.0 * w, 0.5 * coef)):
+        gpu.set_lsq(ptr, cell, ww, cc)
+        gpu.initialize_solution()
+        r = gpu.compute_residual(0.2)
+        _, gr, ph = gpu.get_aux()
+        scale = np.abs(r_o).max(axis=0)
+        assert (np.abs(r - r_o) / scale).max() <= 1e-11
+        assert np.abs(gr - g_o).max() / np.abs(g_o).max() <= 1e-12
+        assert np.abs(ph - ph_o).max() <= 1e-9
+        assert (np.abs(r - r_lib) / scale).max() <= 1e-11
+    res, _, _ = gpu.time_integration(0.0, 3)       # the time loop runs on the supplied operator as well
+    res_o, _, _ = orc.time_integration(0.0, 3)
+    assert float((np.abs(res - res_o) / np.abs(res_o)).max()) <= 1e-9
+    # a table that is not linearly exact is rejected like the reference's grad_lsq_verify does (src/gradient_lsq.f90:490-529)
+    from fvs2d_b200 import capi
+    with pytest.raises(capi.Fvs2dError, match="LSQ coefficients"):
+        gpu.set_lsq(ptr, cell, w, 1.1 * coef)
+    gpu.close()
