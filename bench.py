@@ -373,7 +373,8 @@ def main():
     sustained = None
     if args.sustain_s > 0:
         ks = max(K, 20)
-        reps = max(1, int(np.ceil(args.sustain_s / (max(tm["total_ms"], 1e-3) * 1e-3 * ks / K))))
+        # (every rank must make the same number of calls: the count comes from the max-over-ranks time, not the local one)
+        reps = max(1, int(np.ceil(args.sustain_s / (max(max_over_ranks(tm["total_ms"]), 1e-3) * 1e-3 * ks / K))))
         with ClockSampler(local_rank) as clk_s:
             barrier()
             ms_s = 0.0

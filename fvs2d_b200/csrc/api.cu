@@ -114,6 +114,7 @@ struct Ctx {
   int peer_np[kMaxPeers] = {}, peer_recv_begin[kMaxPeers] = {};
   unsigned *peer_flag[kMaxPeers] = {};
   unsigned *flags = nullptr, *done_ctr = nullptr;  // flags[r]: stages rank r has delivered to this rank
+  int *p2p_timed_out = nullptr;                    // device flag: a wait for a peer gave up
   std::vector<void *> ipc_open;
   std::map<const void *, size_t> smem_attr;  // kernel -> dynamic shared memory it is configured for (per context: function
                                              // attributes are per device)
@@ -211,7 +212,7 @@ void free_device() {
   C->d_n2c_ptr = C->d_n2c = nullptr; C->d_idw = nullptr; C->d_fnode = nullptr;
   C->d_be_cell = nullptr; C->d_be_xy = C->d_be_nxy = nullptr; C->d_be_out = nullptr;
   C->fz_state = 0; C->n_fl = 0; C->fz_tables = 0;
-  C->flags = nullptr; C->done_ctr = nullptr; C->d_rs_word = nullptr; C->d_rs_ent = nullptr;
+  C->flags = nullptr; C->done_ctr = nullptr; C->p2p_timed_out = nullptr; C->d_rs_word = nullptr; C->d_rs_ent = nullptr;
 }
 
 // ---- event-based kernel timing (option "timing") ------------------------------------------------
@@ -668,7 +669,8 @@ int setup_p2p() {
   if (C->nranks == 1) return 0;
   const Layout &L = C->L;
   const int nr = C->nranks, npeer = (int)L.peers.size();
-  if (dev_alloc(C->flags, (size_t)kMaxRanks) || dev_alloc(C->done_ctr, 1)) return 1;
+  if (dev_alloc(C->flags, (size_t)kMaxRanks) || dev_alloc(C->done_ctr, 1) || dev_alloc(C->p2p_timed_out, 1)) return 1;
+  CUDA_OK(cudaMemset(C->p2p_timed_out, 0, sizeof(int)));
   CUDA_OK(cudaMemset(C->flags, 0, kMaxRanks * sizeof(unsigned)));
   CUDA_OK(cudaMemset(C->done_ctr, 0, sizeof(unsigned)));
   P2PInfo mine{};
@@ -725,8 +727,8 @@ int setup_p2p() {
 
 // spins (one warp) until every peer has delivered stage `epoch`: the ghost slots are complete when this kernel retires
 struct PeerList { int n; int r[kMaxPeers]; };
-__global__ void k_wait_peers(const unsigned *__restrict__ flags, const PeerList pl, unsigned epoch) {
-  if ((int)threadIdx.x < pl.n) while ((int)(ld_acquire_sys(flags + pl.r[threadIdx.x]) - epoch) < 0) __nanosleep(128);
+__global__ void k_wait_peers(const unsigned *__restrict__ flags, const PeerList pl, unsigned epoch, int *timed_out) {
+  if ((int)threadIdx.x < pl.n) wait_flag(flags + pl.r[threadIdx.x], epoch, timed_out);
 }
 
 // one residual evaluation's worth of pass A (+ halo) for state p
@@ -1341,6 +1343,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
       if (run_step()) return 1;
     }
   }
+  int p2p_timed_out = 0;
   if (p_pending) CUDA_OK(cudaStreamWaitEvent(C->st, C->e_p, 0));  // the last exchange belongs to this call
   if (fused && C->nranks > 1) {
     // the peers' last stage lands in this rank's ghost slots: complete before the call returns (compute_residual,
@@ -1349,7 +1352,8 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
     PeerList pl{};
     pl.n = (int)C->L.peers.size();
     for (int k = 0; k < pl.n; k++) pl.r[k] = C->L.peers[k];
-    if (nsub > 0) k_wait_peers<<<1, 32, 0, C->st>>>(C->flags, pl, C->epoch_total);
+    if (nsub > 0) k_wait_peers<<<1, 32, 0, C->st>>>(C->flags, pl, C->epoch_total, C->p2p_timed_out);
+    CUDA_OK(cudaMemcpyAsync(&p2p_timed_out, C->p2p_timed_out, sizeof(int), cudaMemcpyDeviceToHost, C->st));
   }
   CUDA_OK(cudaEventRecord(C->ev1, C->st));
   CUDA_OK(cudaGetLastError());
@@ -1361,6 +1365,8 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
     CUDA_OK(cudaMemcpyAsync(ids.data(), C->logid, ids.size() * 4, cudaMemcpyDeviceToHost, C->st));
   }
   CUDA_OK(cudaStreamSynchronize(C->st));
+  NEED(!p2p_timed_out, "in-kernel halo exchange timed out after 20 s: a peer never delivered a stage -- the ranks do not make the "
+                       "same sequence of fvs2d_gpu_time_integration calls, or a peer has failed");
   float ms = 0;
   CUDA_OK(cudaEventElapsedTime(&ms, C->ev0, C->ev1));
   C->last_ms[0] = ms;

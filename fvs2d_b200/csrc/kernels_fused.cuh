@@ -67,6 +67,15 @@ __host__ __device__ inline size_t fused_stage_bytes(const FusedMeta &f) {
 // more than an interior phase behind.  No kernel of the time loop depends on the host, so the step replays as a CUDA
 // graph on several ranks too.  (SURVEY 8e variant 2a: with the deep ghost layers only the state travels, once per stage.)
 constexpr int kMaxPeers = 8;
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 struct HaloP2P {
   int n_peers;                     // 0: single rank, nothing of the above happens
   int n_bnd;                       // the first n_bnd entries of tile_list are the boundary tiles
@@ -80,16 +89,25 @@ struct HaloP2P {
   const uint32_t *rs_word;         // per boundary tile (position in tile_list) and thread: first entry << 3 | count
   const int2 *rs_ent;              // (peer slot, ghost index at the peer)
   unsigned *done_ctr;              // CTAs done with their boundary tiles (reset by the last one)
+  int *timed_out;                  // set when a wait gave up (the ranks do not run the same sequence of calls): the host
+                                   // turns it into an error instead of a hung GPU
 };
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+constexpr unsigned long long kPeerWaitNs = 20ull * 1000000000ull;  // no exchange of a correct run takes 20 s
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
-__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// spin until *flag has reached `need` (counters wrap: signed distance); gives up after kPeerWaitNs
+__device__ __forceinline__ void wait_flag(const unsigned *flag, unsigned need, int *timed_out) {
+  if ((int)(ld_acquire_sys(flag) - need) >= 0) return;
+  if (*reinterpret_cast<volatile int *>(timed_out)) return;  // already given up once: do not wait 20 s per stage
+  const unsigned long long t0 = global_ns();
+  while ((int)(ld_acquire_sys(flag) - need) < 0) {
+    __nanosleep(64);
+    if (global_ns() - t0 > kPeerWaitNs) { *timed_out = 1; return; }
+  }
 }
-
 template <int UM, bool STEADY, int FORM, int CTAS, bool P2P>
 __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused(const DevMesh m, const FusedMeta fm, const Phys P, const StageParams S,
                                                                      const double *__restrict__ p, const double *__restrict__ bc,
@@ -141,7 +159,7 @@ __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused(const DevMes
     if ((P2P && hx.n_peers > 0) && (int)blockIdx.x < hx.n_bnd) {
       // boundary tiles come first: before the first ghost is read, every peer must have delivered the previous stage
       const unsigned need = hx.clk->epoch0 + 4u * (unsigned)hx.clk->istep + (unsigned)hx.stage;
-      if (lane < hx.n_peers) while ((int)(ld_acquire_sys(hx.my_flag[lane]) - need) < 0) __nanosleep(64);
+      if (lane < hx.n_peers) wait_flag(hx.my_flag[lane], need, hx.timed_out);
       __syncwarp();
     }
     int it = 0;
