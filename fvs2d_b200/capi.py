@@ -90,7 +90,7 @@ def ptr(a):
 _INT_ARRAYS = {"en1", "en2", "ec1", "ec2", "cedge", "nghbre", "cell_intr", "b_edge", "b_edge_ptr", "grad_ptr", "grad_idx",
                "perm", "f_off", "f_nbr", "f_edge", "g_off", "g_idx", "orig_id", "loc2new", "bf_type", "bf_edge", "peers",
                "send_ptr", "send_idx", "recv_begin", "recv_count", "tile_es", "tile_ne", "tile_hc_ptr", "tile_he_ptr",
-               "tile_hc_idx", "tile_he_idx", "f_bf", "tile_hdr", "t_bf", "fz_hdr", "fz_h2_idx", "fz_info", "fz_tile_int", "fz_tile_bnd", "gh_ptr", "gh_idx"}
+               "tile_hc_idx", "tile_he_idx", "f_bf", "tile_hdr", "t_bf", "fz_hdr", "fz_h2_idx", "fz_info", "fz_tile_int", "fz_tile_bnd", "gh_ptr", "gh_idx", "sub_orig", "sub_new_id"}
 _U32_ARRAYS = {"f_pack", "t_pack", "fz_pack2", "fz_hf", "fz_uf"}
 _U16_ARRAYS = {"fz_gslot"}
 _BYTE_ARRAYS = {"is_intr"}

@@ -1,5 +1,6 @@
 // api.cu -- context and C-ABI of libfvs2d_gpu.so (include/fvs2d_gpu.h).
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -60,6 +61,12 @@ struct FusedLaunch {  // one launch of k_stage_fused over a subset of the tiles
   int per3 = 0, per2 = 0;
 };
 
+struct GlobalInfo {  // counts and sums of the WHOLE mesh (a partition-local build knows only its share until they are reduced)
+  int nnodes = 0, ncells = 0, nedges = 0, nedges_intr = 0, nedges_bndr = 0, ncells_intr = 0, ncells_bndr = 0;
+  double heff1 = 0, heff2 = 0, vol_sum = 0, vol_green = 0, xy_cell0[2] = {0, 0};
+  bool partial_sums = false;
+};
+
 struct Ctx {
   bool inited = false, has_mesh = false, has_state = false;
   fvs2d_config cfg{};
@@ -69,7 +76,9 @@ struct Ctx {
   int rank = 0, nranks = 1;
   ncclComm_t comm = nullptr;
   // host products
-  HostMesh mesh;
+  HostMesh mesh;          // the whole mesh, or (several ranks) this rank's submesh
+  SubMesh sub;            // numbering of that submesh (its HostMesh is moved into `mesh`)
+  GlobalInfo gi;
   GradOp grad;
   Layout L;
   // device
@@ -81,7 +90,7 @@ struct Ctx {
   int recon = RC_K0;
   double *q = nullptr, *f = nullptr, *pa = nullptr, *pb = nullptr, *g = nullptr, *phi = nullptr, *dtl = nullptr;
   double *resid = nullptr, *ws = nullptr, *bc = nullptr, *partial = nullptr, *vpartial = nullptr;
-  int *vbest = nullptr;
+  int *vbest = nullptr, *vbest_loc = nullptr;
   double *stage_aos = nullptr;  // nc_global*8 doubles staging for AoS <-> SoA
   size_t stage_aos_len = 0;
   double *logbuf = nullptr; int *logid = nullptr; size_t log_cap = 0;
@@ -321,24 +330,45 @@ int ensure_stage(size_t ndoubles) {
   return 0;
 }
 
-// device SoA (local numbering, owned cells) -> caller AoS (original numbering)
+// device SoA (local numbering, owned cells) -> caller AoS (original numbering).  One rank: permuted on the device.  Several
+// ranks: only the owned cells cross PCIe (local order), the host scatters them into the caller's global array.
 int download_aos(const double *soa, int nvar, double *host_out, int pair = 0, int v0 = 0) {
-  const size_t ng = (size_t)C->L.nc_global * nvar;
-  if (ensure_stage(ng)) return 1;
-  k_gather_out<<<cdiv(C->L.n_own, 256), 256, 0, C->st>>>(C->L.n_own, C->np, nvar, C->dm.orig_id, soa, C->stage_aos, pair, v0);
-  CUDA_OK(cudaGetLastError());
+  const int n_own = C->L.n_own;
   if (C->nranks == 1) {
+    const size_t ng = (size_t)C->L.nc_global * nvar;
+    if (ensure_stage(ng)) return 1;
+    k_gather_out<<<cdiv(n_own, 256), 256, 0, C->st>>>(n_own, C->np, nvar, C->dm.orig_id, soa, C->stage_aos, pair, v0);
+    CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpyAsync(host_out, C->stage_aos, ng * 8, cudaMemcpyDeviceToHost, C->st));
     CUDA_OK(cudaStreamSynchronize(C->st));
-  } else {
-    std::vector<double> tmp(ng);
-    CUDA_OK(cudaMemcpyAsync(tmp.data(), C->stage_aos, ng * 8, cudaMemcpyDeviceToHost, C->st));
-    CUDA_OK(cudaStreamSynchronize(C->st));
-    for (int i = 0; i < C->L.n_own; i++) {
-      const size_t o = C->L.orig_id[i];
-      for (int v = 0; v < nvar; v++) host_out[o * nvar + v] = tmp[o * nvar + v];
-    }
+    return 0;
   }
+  const size_t nl = (size_t)n_own * nvar;
+  if (ensure_stage(nl)) return 1;
+  k_gather_out<<<cdiv(n_own, 256), 256, 0, C->st>>>(n_own, C->np, nvar, nullptr, soa, C->stage_aos, pair, v0);
+  CUDA_OK(cudaGetLastError());
+  std::vector<double> tmp(nl);
+  CUDA_OK(cudaMemcpyAsync(tmp.data(), C->stage_aos, nl * 8, cudaMemcpyDeviceToHost, C->st));
+  CUDA_OK(cudaStreamSynchronize(C->st));
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n_own; i++) {
+    const size_t o = C->L.orig_id[i];
+    for (int v = 0; v < nvar; v++) host_out[o * nvar + v] = tmp[(size_t)i * nvar + v];
+  }
+  return 0;
+}
+
+// conserved state of the LOCAL cells (owned + ghosts, library order, 4 doubles per cell) -> device q and primitive pa
+int upload_local_state(const double *cv_loc) {
+  const int n_loc = C->L.n_loc;
+  const size_t n = (size_t)n_loc * 4;
+  if (ensure_stage(n)) return 1;
+  CUDA_OK(cudaMemcpyAsync(C->stage_aos, cv_loc, n * 8, cudaMemcpyHostToDevice, C->st));
+  k_scatter_in<<<cdiv(n_loc, 256), 256, 0, C->st>>>(n_loc, C->np, 4, nullptr, C->stage_aos, C->q, 0);
+  k_prim<<<cdiv(n_loc, 256), 256, 0, C->st>>>(n_loc, C->np, C->cfg.gamma, C->q, C->pa);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(C->st));
+  C->has_state = true;
   return 0;
 }
 
@@ -822,6 +852,67 @@ int fvs2d_gpu_comm_init(int rank, int nranks, const char id[128]) {
 namespace {
 int build_partition();
 int device_upload();
+
+// ---- Hilbert keys + stable radix sort on the device (set-up only; HilbertSorter of host_mesh.hpp) -------------------
+// The same key arithmetic as the host loop of hilbert_order_raw (sums in node order, IEEE division, no contraction
+// possible in (s - x0) * scale), CUB's LSD radix sort is stable like the host's: the permutation is identical.
+__global__ void k_hilbert_keys(const int nc, const int *__restrict__ cptr, const int *__restrict__ cnode, const double *__restrict__ xn,
+                               const double *__restrict__ yn, const int xs, const HilbertFrame f, uint64_t *__restrict__ key,
+                               int *__restrict__ val) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  double sx = 0, sy = 0;
+  const int s0 = cptr[i], s1 = cptr[i + 1];
+  for (int s = s0; s < s1; s++) { const size_t v = (size_t)cnode[s] * xs; sx = __dadd_rn(sx, xn[v]); sy = __dadd_rn(sy, yn[v]); }
+  const double nv = (double)(s1 - s0);
+  sx = __ddiv_rn(sx, nv); sy = __ddiv_rn(sy, nv);
+  const uint32_t ix = (uint32_t)__dmul_rn(__dsub_rn(sx, f.x0), f.scale_x), iy = (uint32_t)__dmul_rn(__dsub_rn(sy, f.y0), f.scale_y);
+  key[i] = hilbert_d(ix, iy, f.bits);
+  val[i] = i;
+}
+
+bool device_hilbert_sort(const HilbertFrame &f, int nc, const int *cptr, const int *cnode, const double *xn, const double *yn, int xs,
+                         std::vector<int> &perm) {
+  if (!C || !C->inited || getenv("FVS2D_HOST_SORT")) return false;
+  const size_t nslots = (size_t)cptr[nc];
+  int nn = 0;  // node count = largest id + 1 (only the entries the cells use are read)
+#pragma omp parallel for schedule(static) reduction(max : nn)
+  for (size_t s = 0; s < nslots; s++) nn = std::max(nn, cnode[s] + 1);
+  int *d_cptr = nullptr, *d_cnode = nullptr, *d_val = nullptr, *d_val2 = nullptr;
+  double *d_x = nullptr, *d_y = nullptr;
+  uint64_t *d_key = nullptr, *d_key2 = nullptr;
+  void *d_tmp = nullptr;
+  bool ok = true;
+  auto A = [&](void **p, size_t bytes) { if (ok && cudaMalloc(p, std::max<size_t>(bytes, 16)) != cudaSuccess) { ok = false; cudaGetLastError(); } };
+  const size_t nxy = xs == 2 ? 2 * (size_t)nn : (size_t)nn;
+  A((void **)&d_cptr, ((size_t)nc + 1) * 4); A((void **)&d_cnode, nslots * 4); A((void **)&d_x, nxy * 8);
+  if (xs == 1) A((void **)&d_y, nxy * 8);
+  A((void **)&d_key, (size_t)nc * 8); A((void **)&d_key2, (size_t)nc * 8); A((void **)&d_val, (size_t)nc * 4); A((void **)&d_val2, (size_t)nc * 4);
+  size_t tmp_bytes = 0;
+  if (ok) {
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key, d_key2, d_val, d_val2, nc, 0, 2 * f.bits, C->st);
+    A(&d_tmp, tmp_bytes);
+  }
+  if (ok) {
+    ok = cudaMemcpyAsync(d_cptr, cptr, ((size_t)nc + 1) * 4, cudaMemcpyHostToDevice, C->st) == cudaSuccess &&
+         cudaMemcpyAsync(d_cnode, cnode, nslots * 4, cudaMemcpyHostToDevice, C->st) == cudaSuccess &&
+         cudaMemcpyAsync(d_x, xn, nxy * 8, cudaMemcpyHostToDevice, C->st) == cudaSuccess &&
+         (xs == 2 || cudaMemcpyAsync(d_y, yn, nxy * 8, cudaMemcpyHostToDevice, C->st) == cudaSuccess);
+  }
+  if (ok) {
+    k_hilbert_keys<<<cdiv(nc, 256), 256, 0, C->st>>>(nc, d_cptr, d_cnode, d_x, xs == 2 ? d_x + 1 : d_y, xs, f, d_key, d_val);
+    ok = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_key, d_key2, d_val, d_val2, nc, 0, 2 * f.bits, C->st) == cudaSuccess;
+    perm.resize(nc);
+    ok = ok && cudaMemcpyAsync(perm.data(), d_val2, (size_t)nc * 4, cudaMemcpyDeviceToHost, C->st) == cudaSuccess &&
+         cudaStreamSynchronize(C->st) == cudaSuccess;
+  }
+  for (void *p : {(void *)d_cptr, (void *)d_cnode, (void *)d_x, (void *)d_y, (void *)d_key, (void *)d_key2, (void *)d_val, (void *)d_val2, d_tmp})
+    if (p) cudaFree(p);
+  if (!ok) cudaGetLastError();
+  return ok;
+}
+const HilbertSorter g_device_sorter = device_hilbert_sort;
+
 // host half of set_mesh: connectivity, geometry, gradient operator, renumbering, layout (no CUDA calls)
 int host_build(int nnodes, int ntri, int nquad, const double *node_xy, const int *cell_ptr, const int *cell_node,
                int nb, const int *b_ncells, const int *b_type, const int *b_cell) {
@@ -837,40 +928,110 @@ int host_build(int nnodes, int ntri, int nquad, const double *node_xy, const int
   HostMesh &m = C->mesh;
   m = HostMesh();
   const int nc = ntri + nquad;
-  m.nnodes = nnodes; m.ntri = ntri; m.nquad = nquad; m.ncells = nc;
-  m.xn.resize(nnodes); m.yn.resize(nnodes);
-  for (int i = 0; i < nnodes; i++) { m.xn[i] = node_xy[2 * (size_t)i]; m.yn[i] = node_xy[2 * (size_t)i + 1]; }
-  m.cptr.assign(cell_ptr, cell_ptr + nc + 1);
-  NEED(m.cptr[0] == 0 && m.cptr[nc] == 3 * ntri + 4 * nquad, "fvs2d_gpu_set_mesh: cell_ptr inconsistent with ncells_tri/ncells_quad");
-  m.cnode.assign(cell_node, cell_node + m.cptr[nc]);
-  m.nb = nb;
-  m.b_ncells.assign(b_ncells, b_ncells + nb);
-  m.b_type.assign(b_type, b_type + nb);
-  size_t nbc = 0;
-  for (int ib = 0; ib < nb; ib++) {
+  NEED(cell_ptr[0] == 0 && cell_ptr[nc] == 3 * ntri + 4 * nquad, "fvs2d_gpu_set_mesh: cell_ptr inconsistent with ncells_tri/ncells_quad");
+  for (int ib = 0; ib < nb; ib++)
     NEED(b_type[ib] == FVS2D_BC_FREESTREAM || b_type[ib] == FVS2D_BC_SLIP_WALL || b_type[ib] == FVS2D_BC_DIRICHLET,
          "Boundary condition not implemented (src/residual.f90:206-216)");
-    nbc += b_ncells[ib];
+  C->sub = SubMesh();
+  GlobalInfo &gi = C->gi;
+  gi = GlobalInfo();
+  // Several ranks: partition-local pre-processing -- only this rank's cells and two rings around them are ever connected
+  // (extract_submesh).  The least-squares stencil over face neighbours completes boundary stencils from the nearest
+  // centroids of the WHOLE mesh (src/gradient_lsq.f90:98-123), so that scheme keeps the global build.
+  const double t_begin = omp_get_wtime();
+  auto lap = [&](const char *what) {
+    if (getenv("FVS2D_DEBUG")) fprintf(stderr, "[fvs2d] rank %d host build: %-28s %.2f s since start\n", C->rank, what, omp_get_wtime() - t_begin);
+  };
+  const bool local_build = C->nranks > 1 && !(C->cfg.grad_method == 3 && C->cfg.lsq_stencil == 0) && !getenv("FVS2D_GLOBAL_BUILD");
+  std::string err;
+  if (local_build) {
+    err = extract_submesh(nnodes, ntri, nquad, node_xy, cell_ptr, cell_node, nb, b_ncells, b_type, b_cell, C->rank, C->nranks, 2, C->sub,
+                          &g_device_sorter);
+    if (!err.empty()) return fail("%s", err.c_str());
+    m = std::move(C->sub.m);
+    C->sub.m = HostMesh();
+    lap("submesh extracted");
+  } else {
+    m.nnodes = nnodes; m.ntri = ntri; m.nquad = nquad; m.ncells = nc;
+    m.xn.resize(nnodes); m.yn.resize(nnodes);
+    for (int i = 0; i < nnodes; i++) { m.xn[i] = node_xy[2 * (size_t)i]; m.yn[i] = node_xy[2 * (size_t)i + 1]; }
+    m.cptr.assign(cell_ptr, cell_ptr + nc + 1);
+    m.cnode.assign(cell_node, cell_node + m.cptr[nc]);
+    m.nb = nb;
+    m.b_ncells.assign(b_ncells, b_ncells + nb);
+    m.b_type.assign(b_type, b_type + nb);
+    size_t nbc = 0;
+    for (int ib = 0; ib < nb; ib++) nbc += b_ncells[ib];
+    m.b_cell.assign(b_cell, b_cell + nbc);
   }
-  m.b_cell.assign(b_cell, b_cell + nbc);
-  std::string err = build_mesh(m);
+  err = build_mesh(m);
   if (!err.empty()) return fail("%s", err.c_str());
+  lap("connectivity + geometry");
   err = build_gradient(m, C->cfg.grad_method, C->cfg.lsq_stencil, C->cfg.lsq_pow, C->grad);
   if (!err.empty()) return fail("%s", err.c_str());
-  return build_partition();
+  lap("gradient stencils");
+  if (!local_build) {
+    gi.nnodes = m.nnodes; gi.ncells = m.ncells; gi.nedges = m.nedges; gi.nedges_intr = m.nedges_intr; gi.nedges_bndr = m.nedges_bndr;
+    gi.ncells_intr = m.ncells_intr; gi.ncells_bndr = m.ncells_bndr;
+    gi.heff1 = m.heff1; gi.heff2 = m.heff2; gi.vol_sum = m.vol_sum; gi.vol_green = m.vol_green;
+    gi.xy_cell0[0] = m.xc[0]; gi.xy_cell0[1] = m.yc[0];
+  } else {
+    // this rank's share of the global counts and sums (an edge counts for the owner of its c1 cell; owned cells have no
+    // cut faces); fvs2d_gpu_set_mesh adds the shares up over the communicator
+    const SubMesh &sb = C->sub;
+    gi.nnodes = nnodes; gi.ncells = nc;
+    gi.xy_cell0[0] = sb.xy_cell0[0]; gi.xy_cell0[1] = sb.xy_cell0[1];
+    auto owned = [&](int mc) { return sb.new_id[mc] >= sb.b0 && sb.new_id[mc] < sb.b1; };
+    long long ne = 0, neb = 0, ci = 0, cb = 0;
+    double vs = 0, vsq = 0, vg = 0;
+    for (int ie = 0; ie < m.nedges; ie++) if (owned(m.ec1[ie])) { ne++; neb += m.ec2[ie] < 0; }
+    for (int ic = 0; ic < m.ncells; ic++) {
+      if (!owned(ic)) continue;
+      bool intr = true;
+      double v = 0;
+      for (int sl = m.cptr[ic]; sl < m.cptr[ic + 1]; sl++) {
+        intr = intr && m.nghbre[sl] >= 0;
+        const int je = m.cedge[sl];
+        const EdgeGeom eg = edge_geom(m, je);
+        v += eg.nx * (m.ec1[je] == ic ? 1.0 : -1.0) * eg.x * eg.a;
+      }
+      (intr ? ci : cb)++;
+      vs += m.vol[ic]; vsq += std::sqrt(m.vol[ic]); vg += v;
+    }
+    gi.nedges = (int)ne; gi.nedges_bndr = (int)neb; gi.nedges_intr = (int)(ne - neb); gi.ncells_intr = (int)ci; gi.ncells_bndr = (int)cb;
+    gi.vol_sum = vs; gi.heff2 = vsq; gi.vol_green = vg;   // sums; heff1 / heff2 are formed after the reduction
+    gi.partial_sums = true;
+  }
+  const int rc = build_partition();
+  lap("renumbering + layout");
+  return rc;
 }
 
 // renumbering + this rank's layout from the mesh and the gradient operator (again after fvs2d_gpu_set_lsq)
 int build_partition() {
   HostMesh &m = C->mesh;
   std::string err;
-  std::vector<int> perm;
-  hilbert_order(m, perm);
+  CellNumbering num;
+  if (m.partial) {
+    const SubMesh &sb = C->sub;
+    num.nc_global = sb.nc_global;
+    num.new_id = sb.new_id;
+    num.orig = sb.orig.data();
+    num.order.resize(m.ncells);
+    for (int i = 0; i < m.ncells; i++) num.order[i] = i;
+    std::sort(num.order.begin(), num.order.end(), [&](int x, int y) { return sb.new_id[x] < sb.new_id[y]; });
+  } else {
+    num.nc_global = m.ncells;
+    hilbert_order(m, num.order, &g_device_sorter);
+    num.new_id.resize(m.ncells);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < m.ncells; i++) num.new_id[num.order[i]] = i;
+  }
   // several ranks + the fused stage kernel: one more ghost layer (the stencils of the face-neighbour ghosts); the
   // environment variable lets the CPU-side verification (fvs2d_host_build) ask for it
   // (decided before the tables exist: if they turn out not to fit, the two-pass path runs on the deeper layout)
   const bool deep = C->nranks > 1 && ((C->opt_fuse != 0 && C->recon == RC_K0 && !getenv("FVS2D_NO_P2P")) || getenv("FVS2D_DEEP_GHOSTS") != nullptr);
-  err = build_layout(m, C->grad, perm, C->rank, C->nranks, C->L, deep);
+  err = build_layout(m, C->grad, num, C->rank, C->nranks, C->L, deep);
   if (!err.empty()) return fail("%s", err.c_str());
   C->has_mesh = true;
   return 0;
@@ -907,20 +1068,40 @@ int fvs2d_gpu_set_lsq(const int *ptr, const int *cell, const double *w, const do
   NEED(C && C->inited && C->has_mesh, "fvs2d_gpu_set_lsq: call fvs2d_gpu_init and fvs2d_gpu_set_mesh first");
   NEED(C->cfg.grad_method == 3, "fvs2d_gpu_set_lsq: the run does not use the least-squares gradient (grad_method 3)");
   NEED(ptr && cell && w && coef, "fvs2d_gpu_set_lsq: null array");
-  const int nc = C->mesh.ncells;
+  const int nc = C->gi.ncells;   // the caller's table covers the whole mesh, original numbering
   NEED(ptr[0] == 0, "fvs2d_gpu_set_lsq: ptr[0] must be 0");
+  for (int i = 0; i < nc; i++) NEED(ptr[i + 1] >= ptr[i] && ptr[i + 1] - ptr[i] <= kMaxStencil, "fvs2d_gpu_set_lsq: bad ptr");
+  for (int64_t k = 0; k < ptr[nc]; k++) NEED(cell[k] >= 0 && cell[k] < nc, "fvs2d_gpu_set_lsq: cell id out of range");
   GradOp g;
   g.form = 1; g.method = 3; g.lsq_pow = C->cfg.lsq_pow;
-  g.ptr.resize((size_t)nc + 1);
-  for (int i = 0; i <= nc; i++) g.ptr[i] = ptr[i];
-  for (int i = 0; i < nc; i++) NEED(ptr[i + 1] >= ptr[i] && ptr[i + 1] - ptr[i] <= kMaxStencil, "fvs2d_gpu_set_lsq: bad ptr");
-  const int64_t n = g.ptr[nc];
-  g.idx.assign(cell, cell + n);
-  for (int64_t k = 0; k < n; k++) NEED(cell[k] >= 0 && cell[k] < nc, "fvs2d_gpu_set_lsq: cell id out of range");
-  g.user_cx.resize(n); g.user_cy.resize(n);
-  for (int64_t k = 0; k < n; k++) {  // grad = sum coef(:,k) * (p_j - p_i) * w(k): the product as src/gradient_lsq.f90:397 forms it
-    g.user_cx[k] = coef[2 * k] * w[k];
-    g.user_cy[k] = coef[2 * k + 1] * w[k];
+  const HostMesh &m = C->mesh;
+  const std::vector<int> &orig = C->sub.orig;   // empty: m is the whole mesh; else m-cell -> original id (ascending)
+  g.ptr.assign((size_t)m.ncells + 1, 0);
+  for (int mc = 0; mc < m.ncells; mc++) {
+    const int o = orig.empty() ? mc : orig[mc];
+    int n = 0;
+    for (int k = ptr[o]; k < ptr[o + 1]; k++) n += orig.empty() || std::binary_search(orig.begin(), orig.end(), cell[k]);
+    // (a submesh cell whose stencil leaves the submesh lies in its outermost ring: its gradient is never formed)
+    g.ptr[mc + 1] = g.ptr[mc] + n;
+  }
+  const int64_t n = g.ptr[m.ncells];
+  g.idx.resize(n); g.user_cx.resize(n); g.user_cy.resize(n);
+#pragma omp parallel for schedule(static)
+  for (int mc = 0; mc < m.ncells; mc++) {
+    const int o = orig.empty() ? mc : orig[mc];
+    int64_t e = g.ptr[mc];
+    for (int k = ptr[o]; k < ptr[o + 1]; k++) {
+      int j = cell[k];
+      if (!orig.empty()) {
+        const auto it = std::lower_bound(orig.begin(), orig.end(), j);
+        if (it == orig.end() || *it != j) continue;
+        j = (int)(it - orig.begin());
+      }
+      g.idx[e] = j;
+      g.user_cx[e] = coef[2 * (size_t)k] * w[k];      // grad = sum coef(:,k) * (p_j - p_i) * w(k), src/gradient_lsq.f90:397
+      g.user_cy[e] = coef[2 * (size_t)k + 1] * w[k];
+      e++;
+    }
   }
   C->grad = std::move(g);
   free_device();
@@ -977,7 +1158,7 @@ int device_upload() {
   if (dev_alloc(C->bc, 4 * (size_t)std::max(1, L.nbf))) return 1;
   if (dev_alloc(C->clk, 1)) return 1;
   if (C->graph_exec) { cudaGraphExecDestroy(C->graph_exec); C->graph_exec = nullptr; }
-  if (dev_alloc(C->partial, (size_t)C->nblocks * 4) || dev_alloc(C->vpartial, (size_t)C->nblocks * 13) || dev_alloc(C->vbest, (size_t)C->nblocks)) return 1;
+  if (dev_alloc(C->partial, (size_t)C->nblocks * 4) || dev_alloc(C->vpartial, (size_t)C->nblocks * 13) || dev_alloc(C->vbest, (size_t)C->nblocks) || dev_alloc(C->vbest_loc, (size_t)C->nblocks)) return 1;
   CUDA_OK(cudaMemset(C->q, 0, 4 * np * 8));
   CUDA_OK(cudaMemset(C->f, 0, 4 * np * 8));
   CUDA_OK(cudaMemset(C->pa, 0, 4 * np * 8));
@@ -1001,6 +1182,21 @@ int device_upload() {
     if (dev_alloc(C->sendbuf, (size_t)std::max(1, nsend) * 9)) return 1;
   }
   if (setup_p2p()) return 1;
+  if (C->gi.partial_sums && C->comm) {  // partition-local build: add the ranks' shares of the global counts and sums up
+    GlobalInfo &gi = C->gi;
+    double h[7] = {(double)gi.nedges, (double)gi.nedges_bndr, (double)gi.ncells_intr, (double)gi.ncells_bndr, gi.vol_sum, gi.heff2, gi.vol_green};
+    double *d = nullptr;
+    CUDA_OK(cudaMalloc(&d, sizeof h));
+    CUDA_OK(cudaMemcpyAsync(d, h, sizeof h, cudaMemcpyHostToDevice, C->st));
+    NCCL_OK(g_nccl.AllReduce(d, d, 7, ncclDouble, ncclSum, C->comm, C->st));
+    CUDA_OK(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, C->st));
+    CUDA_OK(cudaStreamSynchronize(C->st));
+    cudaFree(d);
+    gi.nedges = (int)h[0]; gi.nedges_bndr = (int)h[1]; gi.nedges_intr = gi.nedges - gi.nedges_bndr;
+    gi.ncells_intr = (int)h[2]; gi.ncells_bndr = (int)h[3];
+    gi.vol_sum = h[4]; gi.heff1 = std::sqrt(h[4] / (double)gi.ncells); gi.heff2 = h[5] / (double)gi.ncells; gi.vol_green = h[6];
+    gi.partial_sums = false;
+  }
   if (C->ev_pool.empty()) {  // once per context (a second set_mesh reuses them)
     C->ev_pool.assign(8192, nullptr);
     for (auto &e : C->ev_pool) CUDA_OK(cudaEventCreate(&e));
@@ -1015,6 +1211,16 @@ extern "C" {
 int fvs2d_gpu_set_state(const double *cvar) {
   NEED(C && C->has_mesh, "fvs2d_gpu_set_state: no mesh");
   NEED(cvar != nullptr, "fvs2d_gpu_set_state: null cvar");
+  if (C->nranks > 1) {  // only the entries of the cells this rank stores (owned + ghosts) are read and uploaded
+    const int n_loc = C->L.n_loc;
+    std::vector<double> loc((size_t)n_loc * 4);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n_loc; i++) {
+      const size_t o = C->L.orig_id[i];
+      for (int v = 0; v < 4; v++) loc[(size_t)i * 4 + v] = cvar[o * 4 + v];
+    }
+    return upload_local_state(loc.data());
+  }
   const size_t ng = (size_t)C->L.nc_global * 4;
   if (ensure_stage(ng)) return 1;
   CUDA_OK(cudaMemcpyAsync(C->stage_aos, cvar, ng * 8, cudaMemcpyHostToDevice, C->st));
@@ -1066,15 +1272,16 @@ int fvs2d_gpu_initialize_solution(void) {
   NEED(C && C->has_mesh, "fvs2d_gpu_initialize_solution: no mesh");
   const fvs2d_config &c = C->cfg;
   NEED(c.ntstart <= 1, "fvs2d_gpu_initialize_solution: ntstart>1 is a restart; pass cont.s8's cvar to fvs2d_gpu_set_state");
-  const HostMesh &m = C->mesh;
-  const int nc = m.ncells;
+  // evaluated for the cells this rank stores (owned + ghosts), in the library's order: no global array is formed
+  const Layout &L = C->L;
+  const int nc = L.n_loc;
   std::vector<double> cv(4 * (size_t)nc);
   const double pi = std::acos(-1.0), g = c.gamma;
   const double t0 = (double)(c.ntstart - 1) * c.dt;
 #pragma omp parallel for schedule(static)
   for (int ic = 0; ic < nc; ic++) {
     double pv[4];
-    const double x = m.xc[ic], y = m.yc[ic];
+    const double x = L.xc[ic], y = L.yc[ic];
     if (c.ntstart == 1 && c.lvortex) {  // src/mms.f90:219-265
       const double ri = c.vortex_inf[0], ui = c.vortex_inf[1], vi = c.vortex_inf[2], p_i = c.vortex_inf[3];
       const double dx = x - (c.vortex_pos[0] + ui * t0), dy = y - (c.vortex_pos[1] + vi * t0);
@@ -1093,7 +1300,7 @@ int fvs2d_gpu_initialize_solution(void) {
     q[0] = pv[0]; q[1] = pv[0] * pv[1]; q[2] = pv[0] * pv[2];
     q[3] = pv[3] / (g - 1.0) + 0.5 * pv[0] * (pv[1] * pv[1] + pv[2] * pv[2]);
   }
-  return fvs2d_gpu_set_state(cv.data());
+  return upload_local_state(cv.data());
 }
 
 int fvs2d_gpu_compute_residual(double time, double *resid, double *ws_nrml) {
@@ -1210,8 +1417,8 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   const int um = c.ssprk ? UM_SSPRK : UM_RK;
   const double dt = c.dt;
   const bool vort = c.lvortex != 0;
-  // device log: per step 4 sums of squares, 13 vortex numbers, 1 id
-  const size_t per = 4 + 13;
+  // device log: per step 4 sums of squares, 13 vortex numbers + the centroid of the largest density error, 1 id
+  const size_t per = 4 + 13 + 2;
   if (C->log_cap < (size_t)nsub) {
     // at least 4096 rows (0.5 MB): the step graph is tied to this buffer, so growing it from call to call would
     // force a re-capture inside the caller's time loop
@@ -1301,10 +1508,10 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
       int vgrid = 0;
       if (vort) {
         vgrid = std::min(C->nblocks, C->nsm * kVortexCtas);
-        k_vortex_err<<<vgrid, kBlock, 0, C->st>>>(C->dm, C->phys, C->clk, C->q, C->vpartial, C->vbest);
+        k_vortex_err<<<vgrid, kBlock, 0, C->st>>>(C->dm, C->phys, C->clk, C->q, C->vpartial, C->vbest, C->vbest_loc);
         C->last_launches++;
       }
-      k_finish_step<<<1, kFinishThreads, 0, C->st>>>(C->partial, C->nparts, C->vpartial, C->vbest, vgrid, C->logbuf, (int)per,
+      k_finish_step<<<1, kFinishThreads, 0, C->st>>>(C->partial, C->nparts, C->vpartial, C->vbest, C->vbest_loc, C->dm.xy, vgrid, C->logbuf, (int)per,
                                                       C->logid, C->clk);
       C->last_launches++;
     }
@@ -1390,15 +1597,15 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
     CUDA_OK(cudaMemcpyAsync(allid.data(), dallid, allid.size() * 4, cudaMemcpyDeviceToHost, C->st));
     CUDA_OK(cudaStreamSynchronize(C->st));
   } else { all = lg; allid = ids; }
-  const double ncg = (double)C->L.nc_global, nin = (double)C->mesh.ncells_intr;
+  const double ncg = (double)C->L.nc_global, nin = (double)C->gi.ncells_intr;
   for (int s = 0; s < nsub; s++) {
-    double sum4[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, best = -1.0;
+    double sum4[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, best = -1.0, bx = 0, by = 0;
     int bid = 0x7fffffff;
     for (int r = 0; r < nr; r++) {
       const double *a = &all[((size_t)r * nsub + s) * per];
       for (int v = 0; v < 4; v++) { sum4[v] += a[v]; mx[v] = std::max(mx[v], a[4 + v]); s1[v] += a[8 + v]; s2[v] += a[12 + v]; }
       const int id = allid[(size_t)r * nsub + s];
-      if (a[16] > best || (a[16] == best && id < bid)) { best = a[16]; bid = id; }
+      if (a[16] > best || (a[16] == best && id < bid)) { best = a[16]; bid = id; bx = a[17]; by = a[18]; }
     }
     if (res_l2) for (int v = 0; v < 4; v++) res_l2[4 * s + v] = std::sqrt(sum4[v] / ncg);  // src/runge_kutta.f90:172-181
     if (vort && vortex_err) {  // the 14 columns of src/mms.f90:357-361
@@ -1410,9 +1617,9 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
     }
     if (vort && vortex_err_xy) {
       // maxloc(erho) (src/mms.f90:363): first cell of the maximum; cell 1 when every error is zero
-      const int cell = (best > 0.0 && bid != 0x7fffffff) ? bid : 0;
-      vortex_err_xy[2 * s] = C->mesh.xc[cell];
-      vortex_err_xy[2 * s + 1] = C->mesh.yc[cell];
+      const bool found = best > 0.0 && bid != 0x7fffffff;
+      vortex_err_xy[2 * s] = found ? bx : C->gi.xy_cell0[0];
+      vortex_err_xy[2 * s + 1] = found ? by : C->gi.xy_cell0[1];
     }
   }
   return 0;
@@ -1461,7 +1668,7 @@ int fvs2d_gpu_test_resid(int corrected, double l2[4], double linf[4]) {
 
 int fvs2d_gpu_sizes(int s[10]) {
   NEED(C && C->has_mesh, "fvs2d_gpu_sizes: no mesh");
-  const HostMesh &m = C->mesh;
+  const GlobalInfo &m = C->gi;
   s[0] = m.nnodes; s[1] = m.ncells; s[2] = m.nedges; s[3] = m.nedges_intr; s[4] = m.nedges_bndr;
   s[5] = m.ncells_intr; s[6] = m.ncells_bndr; s[7] = C->L.n_own; s[8] = C->L.n_loc; s[9] = C->L.nedges;
   return 0;
@@ -1469,7 +1676,7 @@ int fvs2d_gpu_sizes(int s[10]) {
 
 int fvs2d_gpu_scalars(double s[6]) {
   NEED(C && C->has_mesh, "fvs2d_gpu_scalars: no mesh");
-  const HostMesh &m = C->mesh;
+  const GlobalInfo &m = C->gi;
   s[0] = m.heff1; s[1] = m.heff2; s[2] = m.vol_sum; s[3] = m.vol_green; s[4] = C->L.lsq_verify_err; s[5] = (double)C->bytes;
   return 0;
 }
@@ -1511,7 +1718,7 @@ long fvs2d_gpu_mesh_array(const char *name, void *out) {
   RET("tile_es", C->L.tile_es) RET("tile_ne", C->L.tile_ne) RET("tile_hc_ptr", C->L.tile_hc_ptr) RET("tile_he_ptr", C->L.tile_he_ptr)
   RET("tile_hdr", C->L.tile_hdr) RET("t_pack", C->L.t_pack) RET("t_bf", C->L.t_bf)
   RET("tile_hc_idx", C->L.tile_hc_idx) RET("tile_he_idx", C->L.tile_he_idx) RET("f_pack", C->L.f_pack) RET("f_bf", C->L.f_bf)
-  RET("grad_idx", C->grad.idx)
+  RET("grad_idx", C->grad.idx) RET("sub_orig", C->sub.orig) RET("sub_new_id", C->sub.new_id)
   if (n.rfind("fz_", 0) == 0) {  // tables of the fused stage kernel, built on first request (single rank)
     const std::string err = build_fused_tables(C->L);
     if (!err.empty()) { fail("%s", err.c_str()); return -1; }

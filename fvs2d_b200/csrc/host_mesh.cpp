@@ -14,6 +14,8 @@
 #include <cstring>
 #include <numeric>
 
+#include <omp.h>
+
 namespace fvs2d {
 
 static inline double tri_area(double x1, double x2, double x3, double y1, double y2, double y3) {
@@ -142,7 +144,7 @@ std::string build_mesh(HostMesh &m) {
   m.ncells_bndr = nc - m.ncells_intr;
   m.b_cell_ptr.assign(m.nb + 1, 0);
   for (int ib = 0; ib < m.nb; ib++) m.b_cell_ptr[ib + 1] = m.b_cell_ptr[ib] + m.b_ncells[ib];
-  if (m.ncells_bndr != m.b_cell_ptr[m.nb]) {
+  if (!m.partial && m.ncells_bndr != m.b_cell_ptr[m.nb]) {
     char buf[160];
     snprintf(buf, sizeof buf, "#s of boundary cells does not match (determined %d, .bc file %d)", m.ncells_bndr, m.b_cell_ptr[m.nb]);
     return buf;
@@ -169,13 +171,14 @@ std::string build_mesh(HostMesh &m) {
     }
     m.b_edge_ptr[ib + 1] = (int)m.b_edge.size();
   }
-  if ((int)m.b_edge.size() != m.nedges_bndr) {
+  if (!m.partial && (int)m.b_edge.size() != m.nedges_bndr) {
     char buf[160];
     snprintf(buf, sizeof buf, "#s of boundary edges/faces does not match (determined %d, read %d)", m.nedges_bndr, (int)m.b_edge.size());
     return buf;
   }
-  for (int ie = 0; ie < ne; ie++)
-    if (m.ec2[ie] < 0 && m.edge_bc[ie] < 0) return "build_mesh: a boundary edge belongs to no boundary of the .bc file";
+  if (!m.partial)
+    for (int ie = 0; ie < ne; ie++)
+      if (m.ec2[ie] < 0 && m.edge_bc[ie] < 0) return "build_mesh: a boundary edge belongs to no boundary of the .bc file";
 
   // -- Green-theorem volume (src/grid_procs.f90:831-840), logged only
   double vg = 0;
@@ -474,63 +477,220 @@ double grad_cell_coeffs(const HostMesh &m, const GradOp &g, int ic, double *cx, 
 // ------------------------------------------------------------------------------------------------
 // Hilbert ordering
 // ------------------------------------------------------------------------------------------------
-static inline uint64_t hilbert_d(uint32_t x, uint32_t y, int bits) {
-  uint64_t d = 0;
-  const uint32_t n1 = (1u << bits) - 1;
-  for (uint32_t s = 1u << (bits - 1); s > 0; s >>= 1) {
-    const uint32_t rx = (x & s) ? 1 : 0, ry = (y & s) ? 1 : 0;
-    d += (uint64_t)s * s * ((3 * rx) ^ ry);
-    if (ry == 0) {  // rotate the quadrant; only the bits below s are looked at afterwards
-      if (rx == 1) { x = n1 - x; y = n1 - y; }
-      const uint32_t t = x; x = y; y = t;
-    }
+// LSD radix sort of (key, value) by the low `bits` bits of key, 14 bits per pass, stable (ties keep the input order), with
+// per-thread histograms so that the passes run on all the cores the rank has
+static void radix_sort_pairs(std::vector<uint64_t> &key, std::vector<int> &val, int bits) {
+  const size_t n = key.size();
+  std::vector<uint64_t> key2(n);
+  std::vector<int> val2(n);
+  constexpr int RB = 14, NB = 1 << RB;
+  int nthr = 1;
+#pragma omp parallel
+  {
+#pragma omp single
+    nthr = omp_get_num_threads();
   }
-  return d;
+  std::vector<size_t> hist((size_t)nthr * NB);
+  for (int sh = 0; sh < bits; sh += RB) {
+    std::fill(hist.begin(), hist.end(), (size_t)0);
+#pragma omp parallel num_threads(nthr)
+    {
+      const int t = omp_get_thread_num();
+      const size_t lo = n * (size_t)t / nthr, hi = n * (size_t)(t + 1) / nthr;
+      size_t *h = &hist[(size_t)t * NB];
+      for (size_t i = lo; i < hi; i++) h[(key[i] >> sh) & (NB - 1)]++;
+#pragma omp barrier
+#pragma omp single
+      {
+        size_t run = 0;
+        for (int b = 0; b < NB; b++)
+          for (int tt = 0; tt < nthr; tt++) { const size_t c = hist[(size_t)tt * NB + b]; hist[(size_t)tt * NB + b] = run; run += c; }
+      }
+      for (size_t i = lo; i < hi; i++) {
+        const size_t pos = h[(key[i] >> sh) & (NB - 1)]++;
+        key2[pos] = key[i]; val2[pos] = val[i];
+      }
+    }
+    key.swap(key2); val.swap(val2);
+  }
 }
 
-void hilbert_order(const HostMesh &m, std::vector<int> &perm) {
-  const int nc = m.ncells;
-  const int bits = 20;
+// Hilbert order from the raw arrays (no HostMesh needed: the partition-local pre-processing orders the GLOBAL cells
+// without building any global connectivity).  xn / yn with stride `xs` (1: separate arrays, 2: interleaved node_xy).
+// Step 1 (host, one light pass): the key transformation.  Step 2: keys + stable sort -- on the device when a sorter is
+// supplied (fvs2d_gpu_set_mesh: 69 M keys sort in milliseconds there, seconds on two host threads), else on the host;
+// both give the same permutation (same key arithmetic, both sorts stable in the original id).
+HilbertFrame hilbert_frame(int nc, const int *cptr, const int *cnode, const double *xn, const double *yn, int xs) {
   double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
-  for (int i = 0; i < nc; i++) { x0 = std::min(x0, m.xc[i]); x1 = std::max(x1, m.xc[i]); y0 = std::min(y0, m.yc[i]); y1 = std::max(y1, m.yc[i]); }
   // Anisotropy: the curve should be compact in CELL COUNTS, not in physical distance (a 128-cell tile of a
   // mesh with 8:1 cells would otherwise be a 2-row strip with a huge halo).  Each axis is measured in units of
   // the mean cell extent along it.
-  double ex = 0, ey = 0;
-#pragma omp parallel for schedule(static) reduction(+ : ex, ey)
-  for (int i = 0; i < nc; i++) {
-    double xa = 1e300, xb = -1e300, ya = 1e300, yb = -1e300;
-    for (int s = m.cptr[i]; s < m.cptr[i + 1]; s++) {
-      const int v = m.cnode[s];
-      xa = std::min(xa, m.xn[v]); xb = std::max(xb, m.xn[v]); ya = std::min(ya, m.yn[v]); yb = std::max(yb, m.yn[v]);
+  // (the extent sums are formed per fixed chunk of cells and added up in chunk order: every rank must get the same
+  // bits whatever its thread count, because every rank derives the same global order from them)
+  constexpr int kChunk = 1 << 16;
+  const int nchunk = (nc + kChunk - 1) / kChunk;
+  std::vector<double> cex(nchunk, 0.0), cey(nchunk, 0.0);
+#pragma omp parallel for schedule(dynamic, 1) reduction(min : x0, y0) reduction(max : x1, y1)
+  for (int c = 0; c < nchunk; c++) {
+    double sex = 0, sey = 0;
+    for (int i = c * kChunk; i < std::min(nc, (c + 1) * kChunk); i++) {
+      double xa = 1e300, xb = -1e300, ya = 1e300, yb = -1e300, sx = 0, sy = 0;
+      for (int s = cptr[i]; s < cptr[i + 1]; s++) {
+        const size_t v = (size_t)cnode[s] * xs;
+        xa = std::min(xa, xn[v]); xb = std::max(xb, xn[v]); ya = std::min(ya, yn[v]); yb = std::max(yb, yn[v]);
+        sx = sx + xn[v]; sy = sy + yn[v];
+      }
+      const double nv = (double)(cptr[i + 1] - cptr[i]);
+      sx /= nv; sy /= nv;
+      x0 = std::min(x0, sx); x1 = std::max(x1, sx); y0 = std::min(y0, sy); y1 = std::max(y1, sy);
+      sex += xb - xa; sey += yb - ya;
     }
-    ex += xb - xa; ey += yb - ya;
+    cex[c] = sex; cey[c] = sey;
   }
+  double ex = 0, ey = 0;
+  for (int c = 0; c < nchunk; c++) { ex += cex[c]; ey += cey[c]; }
   ex = std::max(ex / nc, 1e-300); ey = std::max(ey / nc, 1e-300);
+  HilbertFrame f;
+  f.bits = 20;
   const double span = std::max(std::max((x1 - x0) / ex, (y1 - y0) / ey), 1e-300);
-  const double scale = ((double)(1u << bits) - 1.0) / span;
-  const double scale_x = scale / ex, scale_y = scale / ey;
-  std::vector<uint64_t> key(nc), key2(nc);
-  std::vector<int> idx2(nc);
+  const double scale = ((double)(1u << f.bits) - 1.0) / span;
+  f.x0 = x0; f.y0 = y0; f.scale_x = scale / ex; f.scale_y = scale / ey;
+  return f;
+}
+
+void hilbert_order_raw(int nc, const int *cptr, const int *cnode, const double *xn, const double *yn, int xs, std::vector<int> &perm,
+                       const HilbertSorter *device_sort) {
+  const HilbertFrame f = hilbert_frame(nc, cptr, cnode, xn, yn, xs);
+  if (device_sort && *device_sort && (*device_sort)(f, nc, cptr, cnode, xn, yn, xs, perm)) return;
+  std::vector<uint64_t> key(nc);
   perm.resize(nc);
 #pragma omp parallel for schedule(static)
   for (int i = 0; i < nc; i++) {
-    const uint32_t ix = (uint32_t)((m.xc[i] - x0) * scale_x), iy = (uint32_t)((m.yc[i] - y0) * scale_y);
-    key[i] = hilbert_d(ix, iy, bits);
+    double sx = 0, sy = 0;
+    for (int s = cptr[i]; s < cptr[i + 1]; s++) { const size_t v = (size_t)cnode[s] * xs; sx = sx + xn[v]; sy = sy + yn[v]; }
+    const double nv = (double)(cptr[i + 1] - cptr[i]);
+    sx /= nv; sy /= nv;
+    const uint32_t ix = (uint32_t)((sx - f.x0) * f.scale_x), iy = (uint32_t)((sy - f.y0) * f.scale_y);
+    key[i] = hilbert_d(ix, iy, f.bits);
     perm[i] = i;
   }
-  // LSD radix sort, 5 passes of 8 bits over the 40-bit key; stable, so ties keep the original order
-  for (int pass = 0; pass < 5; pass++) {
-    const int sh = 8 * pass;
-    size_t cnt[257] = {0};
-    for (int i = 0; i < nc; i++) cnt[((key[i] >> sh) & 255) + 1]++;
-    for (int b = 0; b < 256; b++) cnt[b + 1] += cnt[b];
-    for (int i = 0; i < nc; i++) {
-      const size_t p = cnt[(key[i] >> sh) & 255]++;
-      key2[p] = key[i]; idx2[p] = perm[i];
-    }
-    key.swap(key2); perm.swap(idx2);
+  radix_sort_pairs(key, perm, 2 * f.bits);
+}
+
+void hilbert_order(const HostMesh &m, std::vector<int> &perm, const HilbertSorter *device_sort) {
+  hilbert_order_raw(m.ncells, m.cptr.data(), m.cnode.data(), m.xn.data(), m.yn.data(), 1, perm, device_sort);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Partition-local pre-processing (several ranks): this rank's cells plus `rings` layers of node-adjacent cells, cut out
+// of the caller's global arrays.  Only O(global) work: the Hilbert keys + their sort, and one pass over the global
+// cell -> node list per ring against a node bitmap; no global connectivity is ever built.  The submesh keeps the global
+// relative order of cells and nodes (ascending original ids), so build_mesh numbers its edges in the reference's relative
+// order, and the boundary lists keep the .bc order.
+// ------------------------------------------------------------------------------------------------
+std::string extract_submesh(int nnodes, int ntri, int nquad, const double *node_xy, const int *cptr, const int *cnode, int nb,
+                            const int *b_ncells, const int *b_type, const int *b_cell, int rank, int nranks, int rings, SubMesh &out,
+                            const HilbertSorter *device_sort) {
+  const int nc = ntri + nquad;
+  out = SubMesh();
+  out.nc_global = nc; out.nn_global = nnodes;
+  for (int ic = 0; ic < nc; ic++) {
+    const int nv = cptr[ic + 1] - cptr[ic];
+    if (nv != (ic < ntri ? 3 : 4)) return "build_mesh: cells must be listed triangles first, then quads";
   }
+  {
+    int bad = 0;
+    const int nslots = cptr[nc];
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+    for (int s = 0; s < nslots; s++) bad += cnode[s] < 0 || cnode[s] >= nnodes;
+    if (bad) return "build_mesh: node id out of range";
+  }
+  const double t0 = omp_get_wtime();
+  auto lap = [&](const char *what) { if (getenv("FVS2D_DEBUG")) fprintf(stderr, "[fvs2d]   extract_submesh: %-24s %.2f s\n", what, omp_get_wtime() - t0); };
+  std::vector<int> perm;
+  hilbert_order_raw(nc, cptr, cnode, node_xy, node_xy + 1, 2, perm, device_sort);
+  lap("hilbert order");
+  auto range_begin = [&](int r) { return r >= nranks ? nc : (int)((int64_t)nc * r / nranks / 128 * 128); };
+  const int b0 = out.b0 = range_begin(rank), b1 = out.b1 = range_begin(rank + 1);
+  // ring 0 = owned cells; level[c] = ring + 1, 0 = outside
+  std::vector<unsigned char> level(nc, 0), nmark(nnodes, 0);
+#pragma omp parallel for schedule(static)
+  for (int i = b0; i < b1; i++) level[perm[i]] = 1;
+  for (int r = 0; r <= rings; r++) {
+    // mark the nodes of ring r, then (r < rings) every unmarked cell that touches a marked node becomes ring r + 1
+#pragma omp parallel for schedule(static)
+    for (int ic = 0; ic < nc; ic++)
+      if (level[ic] == r + 1)
+        for (int s = cptr[ic]; s < cptr[ic + 1]; s++) nmark[cnode[s]] = 1;  // (concurrent writes store the same value)
+    if (r == rings) break;
+#pragma omp parallel for schedule(static)
+    for (int ic = 0; ic < nc; ic++) {
+      if (level[ic]) continue;
+      bool hit = false;
+      for (int s = cptr[ic]; s < cptr[ic + 1] && !hit; s++) hit = nmark[cnode[s]] != 0;
+      if (hit) level[ic] = (unsigned char)(r + 2);
+    }
+  }
+  lap("rings");
+  // Hilbert id of every original cell is needed for the submesh cells only: scatter it through a transient global array
+  std::vector<int> new_of(nc);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < nc; i++) new_of[perm[i]] = i;
+  perm.clear(); perm.shrink_to_fit();
+  // submesh cells / nodes in ascending original id
+  std::vector<int> &orig = out.orig;
+  for (int ic = 0; ic < nc; ic++) if (level[ic]) orig.push_back(ic);
+  const int ns = (int)orig.size();
+  std::vector<int> node_loc(nnodes, -1);
+  int nn = 0;
+  for (int v = 0; v < nnodes; v++) if (nmark[v]) node_loc[v] = nn++;
+  HostMesh &m = out.m;
+  m.partial = true;
+  m.nnodes = nn;
+  m.xn.resize(nn); m.yn.resize(nn);
+  out.node_orig.resize(nn);
+#pragma omp parallel for schedule(static)
+  for (int v = 0; v < nnodes; v++)
+    if (node_loc[v] >= 0) { m.xn[node_loc[v]] = node_xy[2 * (size_t)v]; m.yn[node_loc[v]] = node_xy[2 * (size_t)v + 1]; out.node_orig[node_loc[v]] = v; }
+  m.ntri = (int)(std::lower_bound(orig.begin(), orig.end(), ntri) - orig.begin());
+  m.nquad = ns - m.ntri;
+  m.ncells = ns;
+  m.cptr.resize(ns + 1);
+  m.cptr[0] = 0;
+  for (int k = 0; k < ns; k++) m.cptr[k + 1] = m.cptr[k] + (cptr[orig[k] + 1] - cptr[orig[k]]);
+  m.cnode.resize(m.cptr[ns]);
+  out.new_id.resize(ns);
+  out.ring.resize(ns);
+#pragma omp parallel for schedule(static)
+  for (int k = 0; k < ns; k++) {
+    const int o = orig[k];
+    for (int s = 0; s < cptr[o + 1] - cptr[o]; s++) m.cnode[m.cptr[k] + s] = node_loc[cnode[cptr[o] + s]];
+    out.new_id[k] = new_of[o];
+    out.ring[k] = (unsigned char)(level[o] - 1);
+  }
+  lap("submesh arrays");
+  // boundary lists restricted to the submesh, .bc order kept (level doubles as the "in submesh" test; ids via binary search)
+  m.nb = nb;
+  m.b_type.assign(b_type, b_type + nb);
+  m.b_ncells.assign(nb, 0);
+  size_t off = 0;
+  long long nbc_global = 0;
+  for (int ib = 0; ib < nb; ib++) {
+    for (int i = 0; i < b_ncells[ib]; i++) {
+      const int c = b_cell[off + i];
+      if (c < 0 || c >= nc) return "build_mesh: boundary cell id out of range";
+      if (level[c]) { m.b_cell.push_back((int)(std::lower_bound(orig.begin(), orig.end(), c) - orig.begin())); m.b_ncells[ib]++; }
+    }
+    off += b_ncells[ib];
+    nbc_global += b_ncells[ib];
+  }
+  out.nbcells_global = nbc_global;
+  {  // centroid of original cell 0 (maxloc of an all-zero error field points at it, src/mms.f90:363)
+    double sx = 0, sy = 0;
+    for (int s = cptr[0]; s < cptr[1]; s++) { sx = sx + node_xy[2 * (size_t)cnode[s]]; sy = sy + node_xy[2 * (size_t)cnode[s] + 1]; }
+    out.xy_cell0[0] = sx / (double)(cptr[1] - cptr[0]); out.xy_cell0[1] = sy / (double)(cptr[1] - cptr[0]);
+  }
+  return "";
 }
 
 }  // namespace fvs2d

@@ -4,6 +4,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -29,6 +30,10 @@ struct HostMesh {
   std::vector<int> b_edge_ptr, b_edge;  // boundary edge lists in .bc order then local-edge order
   std::vector<int> edge_bc;             // per edge: -1 interior, else boundary index ib
   double heff1 = 0, heff2 = 0, vol_sum = 0, vol_green = 0;
+  // partial == true: the mesh is one rank's submesh (extract_submesh); cells of its outermost ring miss neighbours that
+  // lie outside ("cut" edges look like boundary edges but belong to no boundary), so the .bc consistency checks of
+  // grid_data are not applied and global sums are formed over the owned cells by the caller
+  bool partial = false;
 
   int nvrt(int ic) const { return cptr[ic + 1] - cptr[ic]; }
   // nghbr(slot) of the reference: slot k holds the neighbour across local edge (k-2) (src/grid_procs.f90:330-366)
@@ -73,6 +78,45 @@ double grad_cell_coeffs(const HostMesh &m, const GradOp &g, int ic, double *cx, 
 // Hilbert-curve ordering of the cell centroids (perm[new] = old), measured in cell counts per axis so that
 // anisotropic meshes still give compact tiles.  (Tried and rejected on B200: scanline order inside each
 // 128-cell tile -- 4-10 % slower pass B than the plain curve.)
-void hilbert_order(const HostMesh &m, std::vector<int> &perm);
+struct HilbertFrame { double x0, y0, scale_x, scale_y; int bits; };  // centroid -> integer lattice of the curve
+// Optional device implementation of "keys + stable sort" (api.cu: CUB radix sort); returns false to fall back to the host.
+typedef std::function<bool(const HilbertFrame &, int nc, const int *cptr, const int *cnode, const double *xn, const double *yn, int xs,
+                           std::vector<int> &perm)> HilbertSorter;
+void hilbert_order(const HostMesh &m, std::vector<int> &perm, const HilbertSorter *device_sort = nullptr);
+void hilbert_order_raw(int nc, const int *cptr, const int *cnode, const double *xn, const double *yn, int xs, std::vector<int> &perm,
+                       const HilbertSorter *device_sort = nullptr);
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint64_t hilbert_d(uint32_t x, uint32_t y, int bits) {
+  uint64_t d = 0;
+  const uint32_t n1 = (1u << bits) - 1;
+  for (uint32_t s = 1u << (bits - 1); s > 0; s >>= 1) {
+    const uint32_t rx = (x & s) ? 1 : 0, ry = (y & s) ? 1 : 0;
+    d += (uint64_t)s * s * ((3 * rx) ^ ry);
+    if (ry == 0) {  // rotate the quadrant; only the bits below s are looked at afterwards
+      if (rx == 1) { x = n1 - x; y = n1 - y; }
+      const uint32_t t = x; x = y; y = t;
+    }
+  }
+  return d;
+}
+
+
+// One rank's part of a mesh: its cells (a contiguous range [b0, b1) of the global Hilbert order) plus rings of
+// node-adjacent cells, as a HostMesh with local ids that keep the original relative order.
+struct SubMesh {
+  HostMesh m;
+  std::vector<int> orig;        // submesh cell -> original cell id (ascending)
+  std::vector<int> new_id;      // submesh cell -> Hilbert id in the global order
+  std::vector<unsigned char> ring;  // 0 owned, 1 / 2 ... node-adjacency ring around the owned cells
+  std::vector<int> node_orig;   // submesh node -> original node id
+  int nc_global = 0, nn_global = 0, b0 = 0, b1 = 0;
+  long long nbcells_global = 0;
+  double xy_cell0[2] = {0, 0};
+};
+std::string extract_submesh(int nnodes, int ntri, int nquad, const double *node_xy, const int *cptr, const int *cnode, int nb,
+                            const int *b_ncells, const int *b_type, const int *b_cell, int rank, int nranks, int rings, SubMesh &out,
+                            const HilbertSorter *device_sort = nullptr);
 
 }  // namespace fvs2d

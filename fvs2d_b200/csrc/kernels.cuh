@@ -954,14 +954,14 @@ constexpr int kVortexCtas = 6;  // resident CTAs per SM of k_vortex_err; its gri
 // best_id[b] = original id of the first cell attaining it.
 __global__ void __launch_bounds__(kBlock, kVortexCtas) k_vortex_err(const DevMesh m, const Phys P, const StepClock *__restrict__ clk,
                                                           const double *__restrict__ q, double *__restrict__ partial,
-                                                          int *__restrict__ best_id) {
+                                                          int *__restrict__ best_id, int *__restrict__ best_loc) {
   const double time = clock_told(clk) + clk->off_end;
   // grid-stride over the owned cells with a fixed grid (one resident wave): the partial count is small and the
   // summation order is a function of the launch configuration only (deterministic)
   const int np = m.np;
   double dmx[4] = {0, 0, 0, 0}, ds1[4] = {0, 0, 0, 0}, ds2[4] = {0, 0, 0, 0};
   double bv = -1.0;
-  int bi = 0x7fffffff;
+  int bi = 0x7fffffff, bl = 0;  // best: value, original id (tie-break: the reference's maxloc takes the first), local id
   for (int i = blockIdx.x * kBlock + threadIdx.x; i < m.n_own; i += gridDim.x * kBlock) {
     // all loads of the cell are issued together; boundary cells (few) are computed and masked out
     const bool in = m.is_intr[i] != 0;
@@ -981,18 +981,18 @@ __global__ void __launch_bounds__(kBlock, kVortexCtas) k_vortex_err(const DevMes
       for (int v = 0; v < 4; v++) { dmx[v] = fmax(dmx[v], d[v]); ds1[v] += d[v]; ds2[v] += d[v] * d[v]; }
       if (d[0] >= bv) {  // rare after the first few cells: only then is the original id needed
         const int oid = m.orig_id[i];
-        if (d[0] > bv || oid < bi) { bv = d[0]; bi = oid; }
+        if (d[0] > bv || oid < bi) { bv = d[0]; bi = oid; bl = i; }
       }
     }
   }
   __shared__ double smx[4][kBlock / 32], s1[4][kBlock / 32], s2[4][kBlock / 32], sb[kBlock / 32];
-  __shared__ int sid[kBlock / 32];
+  __shared__ int sid[kBlock / 32], sil[kBlock / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const double ov = __shfl_down_sync(0xffffffffu, bv, o);
-    const int oi = __shfl_down_sync(0xffffffffu, bi, o);
-    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    const int oi = __shfl_down_sync(0xffffffffu, bi, o), ol = __shfl_down_sync(0xffffffffu, bl, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bl = ol; }
   }
 #pragma unroll
   for (int v = 0; v < 4; v++) {
@@ -1005,7 +1005,7 @@ __global__ void __launch_bounds__(kBlock, kVortexCtas) k_vortex_err(const DevMes
     }
     if (lane == 0) { smx[v][wid] = mx; s1[v][wid] = a; s2[v][wid] = b; }
   }
-  if (lane == 0) { sb[wid] = bv; sid[wid] = bi; }
+  if (lane == 0) { sb[wid] = bv; sid[wid] = bi; sil[wid] = bl; }
   __syncthreads();
   if (threadIdx.x < 4) {
     const int v = threadIdx.x;
@@ -1016,11 +1016,12 @@ __global__ void __launch_bounds__(kBlock, kVortexCtas) k_vortex_err(const DevMes
     partial[(size_t)blockIdx.x * 13 + 8 + v] = b;
   }
   if (threadIdx.x == 0) {
-    double bb = sb[0]; int ii = sid[0];
+    double bb = sb[0]; int ii = sid[0], ll = sil[0];
     for (int w = 1; w < kBlock / 32; w++)
-      if (sb[w] > bb || (sb[w] == bb && sid[w] < ii)) { bb = sb[w]; ii = sid[w]; }
+      if (sb[w] > bb || (sb[w] == bb && sid[w] < ii)) { bb = sb[w]; ii = sid[w]; ll = sil[w]; }
     partial[(size_t)blockIdx.x * 13 + 12] = bb;
     best_id[blockIdx.x] = ii;
+    best_loc[blockIdx.x] = ll;
   }
 }
 
@@ -1029,10 +1030,12 @@ __global__ void __launch_bounds__(kBlock, kVortexCtas) k_vortex_err(const DevMes
 // there is no block-wide synchronisation until the clock update:
 //   warps 0..3   row[v]      = sum_b partial[b*4+v]        Sigma (q-q0)^2 of the step (src/runge_kutta.f90:169-184)
 //   warps 4..15  row[4+v]    = max (v<4) / sum of vpartial[b*13+v]                     (src/mms.f90:315-361)
-//   warp  16     row[16], logid = largest rho error and the original id of the first cell attaining it
+//   warp  16     row[16], logid = largest rho error and the original id of the first cell attaining it;
+//                row[17], row[18] = that cell's centroid (src/mms.f90:363), so the host needs no global coordinate array
 constexpr int kFinishThreads = 17 * 32;
 __global__ void __launch_bounds__(kFinishThreads) k_finish_step(const double *__restrict__ partial, const int nparts,
                                                                 const double *__restrict__ vpartial, const int *__restrict__ vbest,
+                                                                const int *__restrict__ vbest_loc, const double2 *__restrict__ xy,
                                                                 const int nvparts, double *__restrict__ logbuf, const int stride,
                                                                 int *__restrict__ logid, StepClock *__restrict__ clk) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1061,19 +1064,22 @@ __global__ void __launch_bounds__(kFinishThreads) k_finish_step(const double *__
     }
   } else if (nvparts > 0) {
     double bv = -1.0;
-    int bi = 0x7fffffff;
+    int bi = 0x7fffffff, bl = 0;
     for (int b = lane; b < nvparts; b += 32) {
       const double x = vpartial[(size_t)b * 13 + 12];
       const int id = vbest[b];
-      if (x > bv || (x == bv && id < bi)) { bv = x; bi = id; }
+      if (x > bv || (x == bv && id < bi)) { bv = x; bi = id; bl = vbest_loc[b]; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const double x = __shfl_down_sync(0xffffffffu, bv, o);
-      const int id = __shfl_down_sync(0xffffffffu, bi, o);
-      if (x > bv || (x == bv && id < bi)) { bv = x; bi = id; }
+      const int id = __shfl_down_sync(0xffffffffu, bi, o), il = __shfl_down_sync(0xffffffffu, bl, o);
+      if (x > bv || (x == bv && id < bi)) { bv = x; bi = id; bl = il; }
     }
-    if (lane == 0) { row[16] = bv; logid[istep] = bi; }
+    if (lane == 0) {
+      const double2 c = xy[bl];
+      row[16] = bv; row[17] = c.x; row[18] = c.y; logid[istep] = bi;
+    }
   }
   __syncthreads();  // every warp has read istep
   if (threadIdx.x == 0) clk->istep = istep + 1;

@@ -14,78 +14,81 @@ struct FaceTmp {
 };
 }  // namespace
 
-std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<int> &perm, int rank, int nranks, Layout &L,
+std::string build_layout(const HostMesh &m, const GradOp &g, const CellNumbering &num, int rank, int nranks, Layout &L,
                          bool deep) {
-  const int nc = m.ncells;
+  // `m` holds the cells this call may touch: the whole mesh (one rank, or the global build) or this rank's submesh
+  // (extract_submesh).  m-cell ids index m's arrays; num.new_id maps them to the global Hilbert order, num.order lists
+  // them by ascending Hilbert id, num.orig (or identity) gives the original ids the caller's arrays use.
+  const int nc = num.nc_global, ncm = m.ncells;
   L = Layout();
   L.deep = deep && nranks > 1;
   deep = L.deep != 0;
   L.rank = rank; L.nranks = nranks; L.nc_global = nc;
-  L.perm = perm;
-  std::vector<int> iperm(nc);
-#pragma omp parallel for schedule(static)
-  for (int i = 0; i < nc; i++) iperm[perm[i]] = i;
+  if (!num.orig) L.perm = num.order;  // whole mesh: new id -> original id (output path, verification)
+  const std::vector<int> &order = num.order, &new_id = num.new_id;
   // rank boundaries on tile boundaries of the global order (tiles are sorted internally by hilbert_order)
   auto range_begin = [&](int r) { return r >= nranks ? nc : (int)((int64_t)nc * r / nranks / kTile * kTile); };
+  auto pos_of = [&](int newid) {  // first entry of `order` whose Hilbert id is >= newid
+    return (int)(std::lower_bound(order.begin(), order.end(), newid, [&](int mc, int v) { return new_id[mc] < v; }) - order.begin());
+  };
   const int b0 = range_begin(rank), b1 = range_begin(rank + 1);
+  const int k0 = pos_of(b0), k1 = pos_of(b1);
+  if (k1 - k0 != b1 - b0) return "build_layout: the mesh handed in does not hold all of this rank's cells";
   L.own_begin = b0;
   L.n_own = b1 - b0;
   L.g_form = g.form;
+  auto owned = [&](int mc) { return new_id[mc] >= b0 && new_id[mc] < b1; };
 
   // ---- ghosts: everything an owned cell reads that it does not own
-  std::vector<int> new2loc;
-  std::vector<int> ghosts;
+  std::vector<int> ghosts;   // m-cells, ascending Hilbert id
+  std::vector<int> loc_of;   // m-cell -> local id (owned first, then ghosts), -1: not stored by this rank
   if (nranks > 1) {
-    std::vector<unsigned char> mark(nc, 0);  // bit 0: ghost, bit 1: face-neighbour ghost (concurrent writes store the same bits)
+    std::vector<unsigned char> mark(ncm, 0);  // bit 0: ghost, bit 1: face-neighbour ghost (concurrent writes store the same bits)
 #pragma omp parallel for schedule(static)
-    for (int i = b0; i < b1; i++) {
-      const int o = perm[i];
+    for (int k = k0; k < k1; k++) {
+      const int o = order[k];
       for (int s = m.cptr[o]; s < m.cptr[o + 1]; s++) {
         const int j = m.nghbre[s];
-        if (j >= 0) { const int jn = iperm[j]; if (jn < b0 || jn >= b1) mark[jn] = 3; }
+        if (j >= 0 && !owned(j)) mark[j] = 3;
       }
     }
 #pragma omp parallel for schedule(static)
-    for (int i = b0; i < b1; i++) {
-      const int o = perm[i];
+    for (int k = k0; k < k1; k++) {
+      const int o = order[k];
       for (int64_t t = g.ptr[o]; t < g.ptr[o + 1]; t++) {
-        const int jn = iperm[g.idx[t]];
-        if ((jn < b0 || jn >= b1) && !mark[jn]) mark[jn] = 1;
+        const int j = g.idx[t];
+        if (!owned(j) && !mark[j]) mark[j] = 1;
       }
     }
     if (deep) {  // the stencils of the face-neighbour ghosts must be local too
       std::vector<int> g1;
-      for (int i = 0; i < nc; i++) if (mark[i] & 2) g1.push_back(i);
-      for (int jn : g1) {
-        const int o = perm[jn];
-        for (int64_t t = g.ptr[o]; t < g.ptr[o + 1]; t++) {
-          const int kn = iperm[g.idx[t]];
-          if ((kn < b0 || kn >= b1) && !mark[kn]) mark[kn] = 1;
+      for (int i = 0; i < ncm; i++) if (mark[i] & 2) g1.push_back(i);
+      for (int j : g1)
+        for (int64_t t = g.ptr[j]; t < g.ptr[j + 1]; t++) {
+          const int kk = g.idx[t];
+          if (!owned(kk) && !mark[kk]) mark[kk] = 1;
         }
-      }
     }
-    for (int i = 0; i < nc; i++) if (mark[i]) ghosts.push_back(i);
+    for (int i = 0; i < ncm; i++) if (mark[i]) ghosts.push_back(i);
+    std::sort(ghosts.begin(), ghosts.end(), [&](int x, int y) { return new_id[x] < new_id[y]; });
+    loc_of.assign(ncm, -1);
+    for (int k = k0; k < k1; k++) loc_of[order[k]] = new_id[order[k]] - b0;
+    for (size_t k = 0; k < ghosts.size(); k++) loc_of[ghosts[k]] = L.n_own + (int)k;
     if (deep) {
       // gradient operator of the face-neighbour ghosts (local ids; the members are local by construction)
       const int ng = (int)ghosts.size();
       L.gh_ptr.assign(ng + 1, 0);
-      for (int k = 0; k < ng; k++) L.gh_ptr[k + 1] = L.gh_ptr[k] + ((mark[ghosts[k]] & 2) ? (int)(g.ptr[perm[ghosts[k]] + 1] - g.ptr[perm[ghosts[k]]]) : 0);
+      for (int k = 0; k < ng; k++) L.gh_ptr[k + 1] = L.gh_ptr[k] + ((mark[ghosts[k]] & 2) ? (int)(g.ptr[ghosts[k] + 1] - g.ptr[ghosts[k]]) : 0);
       L.gh_idx.resize(L.gh_ptr[ng]); L.gh_cx.resize(L.gh_ptr[ng]); L.gh_cy.resize(L.gh_ptr[ng]);
       L.gh_c0x.assign(ng, 0.0); L.gh_c0y.assign(ng, 0.0);
     }
   }
   L.n_loc = L.n_own + (int)ghosts.size();
   L.loc2new.resize(L.n_loc);
-  for (int i = 0; i < L.n_own; i++) L.loc2new[i] = b0 + i;
-  for (size_t k = 0; k < ghosts.size(); k++) L.loc2new[L.n_own + k] = ghosts[k];
-  auto to_local = [&](int newid) -> int {
-    if (newid >= b0 && newid < b1) return newid - b0;
-    return new2loc[newid];
-  };
-  if (nranks > 1) {
-    new2loc.assign(nc, -1);
-    for (size_t k = 0; k < ghosts.size(); k++) new2loc[ghosts[k]] = L.n_own + (int)k;
-  }
+  std::vector<int> loc2m(L.n_loc);  // local id -> m-cell
+  for (int i = 0; i < L.n_own; i++) { loc2m[i] = order[k0 + i]; L.loc2new[i] = b0 + i; }
+  for (size_t k = 0; k < ghosts.size(); k++) { loc2m[L.n_own + k] = ghosts[k]; L.loc2new[L.n_own + k] = new_id[ghosts[k]]; }
+  auto to_local = [&](int mc) -> int { return nranks > 1 ? loc_of[mc] : new_id[mc] - b0; };
   if (deep) {
     const int ng = (int)ghosts.size();
     int bad = 0;
@@ -93,11 +96,13 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
     for (int k = 0; k < ng; k++) {
       const int n = L.gh_ptr[k + 1] - L.gh_ptr[k];
       if (n == 0) continue;
-      const int o = perm[ghosts[k]];
+      const int o = ghosts[k];
       double cx[kMaxStencil], cy[kMaxStencil], c0x = 0, c0y = 0;
       if (grad_cell_coeffs(m, g, o, cx, cy, c0x, c0y) < 0) bad++;
       for (int e = 0; e < n; e++) {
-        L.gh_idx[L.gh_ptr[k] + e] = to_local(iperm[g.idx[g.ptr[o] + e]]);
+        const int l = to_local(g.idx[g.ptr[o] + e]);
+        if (l < 0) bad++;
+        L.gh_idx[L.gh_ptr[k] + e] = l;
         L.gh_cx[L.gh_ptr[k] + e] = cx[e];
         L.gh_cy[L.gh_ptr[k] + e] = cy[e];
       }
@@ -110,13 +115,13 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
   L.orig_id.resize(L.n_loc); L.xc.resize(L.n_loc); L.yc.resize(L.n_loc);
 #pragma omp parallel for schedule(static)
   for (int i = 0; i < L.n_loc; i++) {
-    const int o = perm[L.loc2new[i]];
-    L.orig_id[i] = o; L.xc[i] = m.xc[o]; L.yc[i] = m.yc[o];
+    const int o = loc2m[i];
+    L.orig_id[i] = num.orig ? num.orig[o] : o; L.xc[i] = m.xc[o]; L.yc[i] = m.yc[o];
   }
   L.vol.resize(L.n_own); L.is_intr.resize(L.n_own);
 #pragma omp parallel for schedule(static)
   for (int i = 0; i < L.n_own; i++) {
-    const int o = L.orig_id[i];
+    const int o = loc2m[i];
     L.vol[i] = m.vol[o];
     bool intr = true;
     for (int s = m.cptr[o]; s < m.cptr[o + 1]; s++) intr = intr && m.nghbre[s] >= 0;
@@ -135,7 +140,7 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
       ne_loc = (ne_loc + 1) & ~1;
       L.tile_es[i / kTile] = ne_loc;
     }
-    const int o = L.orig_id[i];
+    const int o = loc2m[i];
     for (int s = m.cptr[o]; s < m.cptr[o + 1]; s++) {
       const int je = m.cedge[s];
       if (edge_loc[je] < 0) edge_loc[je] = ne_loc++;
@@ -159,7 +164,7 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
   for (int s = 0; s < nsl; s++) {
     int wf = 0, wg = 0;
     for (int i = 32 * s; i < std::min(L.n_own, 32 * s + 32); i++) {
-      const int o = L.orig_id[i];
+      const int o = loc2m[i];
       wf = std::max(wf, m.cptr[o + 1] - m.cptr[o]);
       wg = std::max(wg, (int)(g.ptr[o + 1] - g.ptr[o]));
     }
@@ -175,14 +180,14 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
   // boundary-face ids: sequential in cell order
   std::vector<int> bf_start(L.n_own + 1, 0);
   for (int i = 0; i < L.n_own; i++) {
-    const int o = L.orig_id[i];
+    const int o = loc2m[i];
     int c = 0;
     for (int s = m.cptr[o]; s < m.cptr[o + 1]; s++) c += m.nghbre[s] < 0;
     bf_start[i + 1] = bf_start[i] + c;
   }
 #pragma omp parallel for schedule(static)
   for (int i = 0; i < L.n_own; i++) {
-    const int o = L.orig_id[i];
+    const int o = loc2m[i];
     const int nv = m.cptr[o + 1] - m.cptr[o];
     FaceTmp f[4];
     for (int k = 0; k < nv; k++) {
@@ -198,7 +203,7 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
       const int le = edge_loc[f[k].edge];
       L.f_edge[e] = 2 * le + (m.ec1[f[k].edge] == o ? 0 : 1);
       if (f[k].nbr >= 0) {
-        L.f_nbr[e] = to_local(iperm[f[k].nbr]);
+        L.f_nbr[e] = to_local(f[k].nbr);
       } else {
         L.f_nbr[e] = -1 - bf;
         L.bf_type[bf] = m.b_type[m.edge_bc[f[k].edge]];
@@ -314,7 +319,7 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
     for (int lane = 0; lane < 32; lane++) {
       const int i = 32 * s + lane;
       const bool live = i < L.n_own;
-      const int o = live ? L.orig_id[i] : 0;
+      const int o = live ? loc2m[i] : 0;
       const int n = live ? (int)(g.ptr[o + 1] - g.ptr[o]) : 0;
       double c0x = 0, c0y = 0;
       if (live) {
@@ -324,7 +329,7 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
       for (int k = 0; k < w; k++) {
         const int e = L.g_off[s] + 32 * k + lane;
         if (k < n) {
-          L.g_idx[e] = to_local(iperm[g.idx[g.ptr[o] + k]]);
+          L.g_idx[e] = to_local(g.idx[g.ptr[o] + k]);
           L.g_cx[e] = cx[k];
           L.g_cy[e] = cy[k];
         } else {
@@ -344,41 +349,43 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<i
     for (int p = 0; p < nranks; p++) {
       if (p == rank) continue;
       const int p0 = range_begin(p), p1 = range_begin(p + 1);
+      const int q0 = pos_of(p0), q1 = pos_of(p1);   // p's cells that `m` holds (all of them in the global build)
       std::vector<unsigned char> &mask = need[p];
       mask.assign(L.n_own, 0);
       bool any = false;
+      auto of_p = [&](int mc) { return new_id[mc] >= p0 && new_id[mc] < p1; };
 #pragma omp parallel for schedule(static) reduction(|| : any)
-      for (int i = p0; i < p1; i++) {
-        const int o = perm[i];
+      for (int q = q0; q < q1; q++) {
+        const int o = order[q];
         for (int s = m.cptr[o]; s < m.cptr[o + 1]; s++) {
           const int j = m.nghbre[s];
-          if (j >= 0) { const int jn = iperm[j]; if (jn >= b0 && jn < b1) { mask[jn - b0] = 1; any = true; } }
+          if (j >= 0 && owned(j)) { mask[new_id[j] - b0] = 1; any = true; }
         }
         for (int64_t t = g.ptr[o]; t < g.ptr[o + 1]; t++) {
-          const int jn = iperm[g.idx[t]];
-          if (jn >= b0 && jn < b1) { mask[jn - b0] = 1; any = true; }
+          const int j = g.idx[t];
+          if (owned(j)) { mask[new_id[j] - b0] = 1; any = true; }
         }
         if (deep)  // p also stores the stencil members of its face-neighbour ghosts
           for (int s = m.cptr[o]; s < m.cptr[o + 1]; s++) {
             const int j = m.nghbre[s];
-            if (j < 0) continue;
-            const int jn = iperm[j];
-            if (jn >= p0 && jn < p1) continue;
+            if (j < 0 || of_p(j)) continue;
             for (int64_t t = g.ptr[j]; t < g.ptr[j + 1]; t++) {
-              const int kn = iperm[g.idx[t]];
-              if (kn >= b0 && kn < b1) { mask[kn - b0] = 1; any = true; }
+              const int kk = g.idx[t];
+              if (owned(kk)) { mask[new_id[kk] - b0] = 1; any = true; }
             }
           }
       }
       if (!any) mask.clear();
     }
     L.send_ptr.push_back(0);
+    auto ghost_pos = [&](int newid) {
+      return (int)(std::lower_bound(ghosts.begin(), ghosts.end(), newid, [&](int mc, int v) { return new_id[mc] < v; }) - ghosts.begin());
+    };
     for (int p = 0; p < nranks; p++) {
       if (p == rank) continue;
       const int p0 = range_begin(p), p1 = range_begin(p + 1);
       // ghosts owned by p: contiguous run of the sorted ghost list
-      const int gb = (int)(std::lower_bound(ghosts.begin(), ghosts.end(), p0) - ghosts.begin());
-      const int ge = (int)(std::lower_bound(ghosts.begin(), ghosts.end(), p1) - ghosts.begin());
+      const int gb = ghost_pos(p0), ge = ghost_pos(p1);
       const bool sends = !need[p].empty();
       if (ge == gb && !sends) continue;
       L.peers.push_back(p);

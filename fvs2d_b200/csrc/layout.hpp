@@ -28,7 +28,7 @@ struct Layout {
   int nc_global = 0;
   int n_own = 0, n_loc = 0;        // owned cells, owned + ghost cells
   int own_begin = 0;               // first owned new id
-  std::vector<int> perm;           // global: new id -> original id
+  std::vector<int> perm;           // new id -> original id (whole-mesh builds only; empty after a partition-local build)
   std::vector<int> loc2new;        // local id -> new id (owned: own_begin + i)
   std::vector<int> orig_id;        // local id -> original id
   // per local cell
@@ -105,8 +105,16 @@ struct Layout {
   std::vector<uint32_t> fz_pack2, fz_hf;
 };
 
+// How the cells of a HostMesh relate to the global mesh: the whole mesh (orig == null: m-cell id = original id, order = the
+// Hilbert permutation) or one rank's submesh (extract_submesh).
+struct CellNumbering {
+  int nc_global = 0;
+  std::vector<int> order;      // m-cells by ascending Hilbert id
+  std::vector<int> new_id;     // m-cell -> Hilbert id
+  const int *orig = nullptr;   // m-cell -> original id (null: identity)
+};
 // Builds the layout of `rank` out of `nranks` (equal contiguous chunks of the Hilbert order).
-std::string build_layout(const HostMesh &m, const GradOp &g, const std::vector<int> &perm, int rank, int nranks, Layout &L,
+std::string build_layout(const HostMesh &m, const GradOp &g, const CellNumbering &num, int rank, int nranks, Layout &L,
                          bool deep = false);
 
 // Adds the fz_* tables of the fused stage kernel to a single-rank layout (on demand: they are only needed when the

@@ -28,54 +28,75 @@ def make_mesh(nx: int, ny: int, lx: float = 20.0, ly: float = 10.0, quad_band=No
         raise ValueError("need at least 2x2 background quads")
     hx, hy = lx / nx, ly / ny
     ii, jj = np.meshgrid(np.arange(nx + 1, dtype=np.int32), np.arange(ny + 1, dtype=np.int32), indexing="xy")  # (ny+1, nx+1)
-    xy = np.stack([ii * hx, jj * hy], axis=-1).astype(np.float64).reshape(-1, 2)
+    xy = np.empty(((nx + 1) * (ny + 1), 2), dtype=np.float64)
+    xy[:, 0] = (ii * hx).reshape(-1)
+    xy[:, 1] = (jj * hy).reshape(-1)
     if jitter > 0:
         rng = np.random.default_rng(seed)
         d = rng.uniform(-jitter, jitter, size=xy.shape)
         d[:, 0] *= hx
         d[:, 1] *= hy
         interior = ((ii > 0) & (ii < nx) & (jj > 0) & (jj < ny)).reshape(-1)
-        xy[interior] += d[interior]
+        d *= interior[:, None]          # boundary nodes stay put (x + 0.0 == x: the same bits as adding to the interior only)
+        xy += d
         del d, interior
     if (nx + 1) * (ny + 1) >= 2**31:
         raise ValueError("mesh too large for 32-bit node ids")
-    node = lambda i, j: (j * np.int32(nx + 1) + i).astype(np.int32)
     del ii, jj
-    qi, qj = np.meshgrid(np.arange(nx, dtype=np.int32), np.arange(ny, dtype=np.int32), indexing="xy")
-    qi, qj = qi.reshape(-1), qj.reshape(-1)
-    n00, n10, n11, n01 = node(qi, qj), node(qi + 1, qj), node(qi + 1, qj + 1), node(qi, qj + 1)
-    is_quad = (qi >= b0) & (qi < b1)
-    is_tri = ~is_quad
-    flip = ((qi == nx - 1) & (qj == 0)) | ((qi == 0) & (qj == ny - 1))
-    # two triangles per split quad: "lower" then "upper"
-    t_lo = np.where(flip[:, None], np.stack([n00, n10, n01], 1), np.stack([n00, n10, n11], 1))
-    t_hi = np.where(flip[:, None], np.stack([n10, n11, n01], 1), np.stack([n00, n11, n01], 1))
-    tri = np.empty((2 * int(is_tri.sum()), 3), dtype=np.int32)
-    tri[0::2] = t_lo[is_tri]
-    tri[1::2] = t_hi[is_tri]
-    del t_lo, t_hi
-    quad = np.stack([n00[is_quad], n10[is_quad], n11[is_quad], n01[is_quad]], 1).astype(np.int32)
+    # cells: only the quads of each kind are ever expanded (a 69 M-cell mesh is built in seconds); numbering = background
+    # quads in row-major order, two triangles ("lower", "upper") per split quad
+    q_all = np.arange(nx * ny, dtype=np.int64)
+    qi_all = (q_all % nx).astype(np.int32)
+    is_quad = (qi_all >= b0) & (qi_all < b1)
+    tq, qq = np.flatnonzero(~is_quad), np.flatnonzero(is_quad)
+    del q_all, qi_all, is_quad
+
+    def corners(q):
+        i, j = q % nx, q // nx
+        n00 = (j * (nx + 1) + i).astype(np.int32)
+        return n00, n00 + np.int32(1), n00 + np.int32(nx + 2), n00 + np.int32(nx + 1)
+    n00, n10, n11, n01 = corners(tq)
+    tri = np.empty((2 * tq.size, 3), dtype=np.int32)
+    tri[0::2, 0], tri[0::2, 1], tri[0::2, 2] = n00, n10, n11      # lower: bottom, right
+    tri[1::2, 0], tri[1::2, 1], tri[1::2, 2] = n00, n11, n01      # upper: top, left
     del n00, n10, n11, n01
+    ncol_tri = nx - (b1 - b0)                                      # split quads per row
+
+    def tri_rank(i, j):   # position of quad (i, j) among the split quads
+        i = np.asarray(i, dtype=np.int64)
+        return np.asarray(j, dtype=np.int64) * ncol_tri + np.where(i < b0, i, i - (b1 - b0))
+
+    def quad_rank(i, j):
+        return np.asarray(j, dtype=np.int64) * (b1 - b0) + (np.asarray(i, dtype=np.int64) - b0)
+    flips = [(nx - 1, 0), (0, ny - 1)]
+    for fi, fj in flips:                                            # the two corner quads with the other diagonal
+        r = int(tri_rank(fi, fj))
+        c00 = fj * (nx + 1) + fi
+        c10, c11, c01 = c00 + 1, c00 + nx + 2, c00 + nx + 1
+        tri[2 * r] = (c00, c10, c01)                                # lower: bottom, left
+        tri[2 * r + 1] = (c10, c11, c01)                            # upper: right, top
+    n00, n10, n11, n01 = corners(qq)
+    quad = np.empty((qq.size, 4), dtype=np.int32)
+    quad[:, 0], quad[:, 1], quad[:, 2], quad[:, 3] = n00, n10, n11, n01
+    del n00, n10, n11, n01, tq, qq
     ntri = tri.shape[0]
-    # cell id of a background quad's pieces
-    tri_rank = np.cumsum(is_tri, dtype=np.int32) - 1
-    quad_rank = np.cumsum(is_quad, dtype=np.int32) - 1
-    lo_id = np.where(is_tri, 2 * tri_rank, ntri + quad_rank)      # piece holding the bottom edge (and, unflipped, the right edge)
-    hi_id = np.where(is_tri, 2 * tri_rank + 1, ntri + quad_rank)  # piece holding the top edge (and, unflipped, the left edge)
-    Q = lambda i, j: j * nx + i
+
     # which piece holds which side of the background quad
     #   unflipped: lo=(n00,n10,n11): bottom,right ; hi=(n00,n11,n01): top,left
     #   flipped:   lo=(n00,n10,n01): bottom,left  ; hi=(n10,n11,n01): right,top
     def side_cell(i, j, side):
-        q = Q(i, j)
-        f = flip[q]
+        i, j = np.asarray(i, dtype=np.int64), np.asarray(j, dtype=np.int64)
+        isq = (i >= b0) & (i < b1)
+        lo = np.where(isq, ntri + quad_rank(i, j), 2 * tri_rank(i, j))
+        hi = np.where(isq, ntri + quad_rank(i, j), 2 * tri_rank(i, j) + 1)
+        f = ((i == nx - 1) & (j == 0)) | ((i == 0) & (j == ny - 1))
         if side == "bottom":
-            return lo_id[q]
+            return lo
         if side == "top":
-            return hi_id[q]
+            return hi
         if side == "right":
-            return np.where(f, hi_id[q], lo_id[q])
-        return np.where(f, lo_id[q], hi_id[q])  # left
+            return np.where(f, hi, lo)
+        return np.where(f, lo, hi)  # left
     i_all, j_all = np.arange(nx), np.arange(ny)
     walk = np.concatenate([
         side_cell(i_all, np.zeros(nx, int), "bottom"),

@@ -47,13 +47,14 @@ class Mesh:
 
     def csr(self):
         """(cell_ptr[ncells+1], cell_node[3*ntri+4*nquad]) int32, triangles first."""
-        ptr = np.empty(self.ncells + 1, dtype=np.int64)
-        ptr[0] = 0
-        ptr[1:self.ntri + 1] = 3 * np.arange(1, self.ntri + 1, dtype=np.int64)
-        ptr[self.ntri + 1:] = 3 * self.ntri + 4 * np.arange(1, self.nquad + 1, dtype=np.int64)
-        assert ptr[-1] < 2**31
-        node = np.concatenate([self.tri.reshape(-1), self.quad.reshape(-1)]).astype(np.int32)
-        return ptr.astype(np.int32), node
+        assert 3 * self.ntri + 4 * self.nquad < 2**31
+        ptr = np.empty(self.ncells + 1, dtype=np.int32)
+        ptr[:self.ntri + 1] = np.arange(0, 3 * self.ntri + 1, 3, dtype=np.int32)
+        ptr[self.ntri:] = np.arange(3 * self.ntri, 3 * self.ntri + 4 * self.nquad + 1, 4, dtype=np.int32)
+        node = np.empty(3 * self.ntri + 4 * self.nquad, dtype=np.int32)
+        node[:3 * self.ntri] = self.tri.reshape(-1)
+        node[3 * self.ntri:] = self.quad.reshape(-1)
+        return ptr, node
 
     def bc_arrays(self):
         """(bndry_ncells, bndry_type_enum, bndry_cell_concat) int32."""

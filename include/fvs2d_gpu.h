@@ -150,6 +150,10 @@ int fvs2d_gpu_scalars(double scalars[6]);
  * and of the device layout (local numbering, sliced ELL; see fvs2d_b200/csrc/layout.hpp):
  *   int: f_off f_nbr f_edge g_off g_idx orig_id loc2new bf_type bf_edge peers send_ptr send_idx
  *        recv_begin recv_count;  double: g_cx g_cy lex ley;  unsigned char: is_intr
+ * Several ranks (except the least-squares stencil over face neighbours): the pre-processing is partition-local -- the
+ * "reference numbering" arrays above then describe this rank's SUBMESH (its cells plus two rings of node-adjacent cells,
+ * ids local to it, in ascending original id); int sub_orig / sub_new_id give the original id and the global Hilbert id
+ * of every submesh cell (both empty after a whole-mesh build).
  * Call with out==NULL to get the element count. Returns the count, or -1 for an unknown name. */
 long fvs2d_gpu_mesh_array(const char *name, void *out);
 

@@ -59,8 +59,12 @@ def _worker(rank, world, port, out):
             for kk in range((g_off[sl + 1] - g_off[sl]) >> 5):
                 e = g_off[sl] + 32 * kk + lane
                 acc[i] += g_cx[e] * a[1, g_idx[e]]
-        ptr, idx, cx = A("grad_ptr"), A("grad_idx"), A("grad_cx")
-        ref = np.array([sum(cx[t] * float(idx[t]) for t in range(ptr[o], ptr[o + 1])) for o in orig[:n_own]])
+        # the operator in the pre-processing's own numbering: a partition-local build numbers this rank's submesh
+        ptr, idx, cx, sub = A("grad_ptr"), A("grad_idx"), A("grad_cx"), A("sub_orig")
+        assert len(sub) > 0 and len(sub) < mesh.ncells, "several ranks: the pre-processing must be partition-local"
+        mc = np.searchsorted(sub, orig[:n_own])
+        assert np.array_equal(sub[mc], orig[:n_own])
+        ref = np.array([sum(cx[t] * float(sub[idx[t]]) for t in range(ptr[o], ptr[o + 1])) for o in mc])
         ok_stencil = bool(np.allclose(acc, ref, rtol=1e-13, atol=1e-9))
         res = torch.tensor([float(ok_ghosts), float(ok_stencil), float(n_own)], dtype=torch.float64)
         gathered = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]

@@ -154,8 +154,11 @@ def test_partition_and_halo_plan(nranks):
     cfg = config.RunInput(grad_cellcntr_imethd=3, grad_cellcntr_lsq_nghbr="nn", lvortex=True).to_config()
     plans = []
     for r in range(nranks):
-        n_own, n_loc = _layout_checks(mesh, cfg, r, nranks)
+        solver.host_build(cfg, mesh, r, nranks)
         A = capi.mesh_array
+        sz = np.zeros(10, dtype=np.int32); capi.lib().fvs2d_gpu_sizes(capi.ptr(sz))
+        n_own, n_loc = int(sz[7]), int(sz[8])
+        assert len(A("sub_orig")) < mesh.ncells, "several ranks: partition-local pre-processing"
         plans.append(dict(n_own=n_own, n_loc=n_loc, loc2new=A("loc2new").copy(), peers=A("peers").copy(), send_ptr=A("send_ptr").copy(),
                           send_idx=A("send_idx").copy(), recv_begin=A("recv_begin").copy(), recv_count=A("recv_count").copy(),
                           g_idx=A("g_idx").copy(), f_nbr=A("f_nbr").copy(), gh_idx=A("gh_idx").copy()))
@@ -176,6 +179,39 @@ def test_partition_and_halo_plan(nranks):
             sent_new = p["loc2new"][p["send_idx"][p["send_ptr"][k]:p["send_ptr"][k + 1]]]
             recv_new = q["loc2new"][q["recv_begin"][kk]:q["recv_begin"][kk] + q["recv_count"][kk]]
             assert np.array_equal(sent_new, recv_new)
+
+
+LAYOUT_ARRAYS = ["orig_id", "loc2new", "f_off", "f_nbr", "f_edge", "lex", "ley", "lea", "lenx", "leny", "lxc", "lyc", "lvol", "g_off", "g_idx",
+                 "g_cx", "g_cy", "bf_type", "bf_edge", "peers", "send_ptr", "send_idx", "recv_begin", "recv_count", "tile_hdr", "t_pack", "t_bf",
+                 "tile_hc_idx", "tile_he_idx", "is_intr", "gh_ptr", "gh_idx", "fz_tile_int", "fz_tile_bnd", "fz_hdr", "fz_h2_idx",
+                 "fz_gslot", "fz_pack2", "fz_hf", "fz_gc"]
+
+
+@pytest.mark.parametrize("grad,stencil,nranks", [(1, "fn", 2), (1, "fn", 5), (2, "fn", 3), (3, "nn", 4)])
+def test_partition_local_build_equals_whole_mesh_build(grad, stencil, nranks, monkeypatch):
+    """SURVEY 8 row f1 on several ranks: a rank pre-processes only its Hilbert chunk plus two rings of node-adjacent cells
+    cut out of the caller's global arrays (no global connectivity).  Everything that reaches the device -- local
+    numbering, faces, local edges and their geometry, gradient operator, boundary faces, tiles, halo plan, the fused
+    kernel's tables -- must be bit-identical to what the whole-mesh pre-processing (the round-1 path, still used for the
+    least-squares stencil over face neighbours) gives for the same rank; the whole-mesh path itself is checked against the
+    oracle's grid_data restatement above."""
+    from fvs2d_b200 import capi, config, meshgen, solver
+    mesh = meshgen.vortex_mixed_mesh(48)
+    cfg = config.RunInput(grad_cellcntr_imethd=grad, grad_cellcntr_lsq_nghbr=stencil, lvortex=True).to_config()
+    A = capi.mesh_array
+    for rank in range(nranks):
+        monkeypatch.delenv("FVS2D_GLOBAL_BUILD", raising=False)
+        solver.host_build(cfg, mesh, rank, nranks)
+        assert 0 < len(A("sub_orig")) < mesh.ncells
+        sz = np.zeros(10, dtype=np.int32); capi.lib().fvs2d_gpu_sizes(capi.ptr(sz))
+        part = {k: A(k).copy() for k in LAYOUT_ARRAYS}
+        monkeypatch.setenv("FVS2D_GLOBAL_BUILD", "1")
+        solver.host_build(cfg, mesh, rank, nranks)
+        assert len(A("sub_orig")) == 0
+        sz2 = np.zeros(10, dtype=np.int32); capi.lib().fvs2d_gpu_sizes(capi.ptr(sz2))
+        assert np.array_equal(sz[7:], sz2[7:]) and sz[0] == sz2[0] and sz[1] == sz2[1]     # (the other counts are per-rank shares until reduced)
+        for k in LAYOUT_ARRAYS:
+            assert np.array_equal(part[k], A(k)), f"rank {rank}/{nranks}: {k} differs between the partition-local and the whole-mesh build"
 
 
 def test_input_and_mesh_files_round_trip(tmp_path, vortex_mesh):
