@@ -3,6 +3,9 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
+
+#include <omp.h>
 
 namespace fvs2d {
 
@@ -20,6 +23,8 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const CellNumbering
   // (extract_submesh).  m-cell ids index m's arrays; num.new_id maps them to the global Hilbert order, num.order lists
   // them by ascending Hilbert id, num.orig (or identity) gives the original ids the caller's arrays use.
   const int nc = num.nc_global, ncm = m.ncells;
+  const double t_begin = omp_get_wtime();
+  auto lap = [&](const char *what) { if (getenv("FVS2D_DEBUG")) fprintf(stderr, "[fvs2d]   build_layout: %-22s %.2f s\n", what, omp_get_wtime() - t_begin); };
   L = Layout();
   L.deep = deep && nranks > 1;
   deep = L.deep != 0;
@@ -111,6 +116,7 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const CellNumbering
     if (bad) return "gradient_lsq: singular least-squares system";
   }
 
+  lap("ghosts");
   // ---- per-cell data
   L.orig_id.resize(L.n_loc); L.xc.resize(L.n_loc); L.yc.resize(L.n_loc);
 #pragma omp parallel for schedule(static)
@@ -157,6 +163,7 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const CellNumbering
     if (l >= 0) { const EdgeGeom eg = edge_geom(m, je); L.ex[l] = eg.x; L.ey[l] = eg.y; L.ea[l] = eg.a; L.enx[l] = eg.nx; L.eny[l] = eg.ny; }
   }
 
+  lap("local edges");
   // ---- faces as sliced ELL
   const int nsl = L.nslices = (L.n_own + 31) / 32;
   L.f_off.assign(nsl + 1, 0);
@@ -213,6 +220,7 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const CellNumbering
     }
   }
 
+  lap("faces");
   // ---- tile metadata for the shared-memory pass-B kernel
   {
     const int nt = L.ntiles;
@@ -305,6 +313,7 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const CellNumbering
     if (L.tile_hc_max + kTile >= 0xFFFE || L.tile_e_max >= 0x7FFF) L.tile_hc_max = -1;  // no tile kernel for this mesh
   }
 
+  lap("tiles");
   // ---- gradient stencil as sliced ELL (padding: the cell itself with zero weight)
   L.g_idx.resize(L.g_off[nsl]);
   L.g_cx.assign(L.g_off[nsl], 0.0);
@@ -343,6 +352,7 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const CellNumbering
   if (singular) return "gradient_lsq: singular least-squares system";
   if (g.form == 1 && !(verr <= 1.0e-10)) return " LSQ coefficients are not correct";
 
+  lap("gradient operator");
   // ---- halo plan
   if (nranks > 1) {
     std::vector<std::vector<unsigned char>> need(nranks);

@@ -161,3 +161,20 @@ def test_set_lsq_uses_the_callers_table(stencil, limiter):
     with pytest.raises(capi.Fvs2dError, match="LSQ coefficients"):
         gpu.set_lsq(ptr, cell, w, 1.1 * coef)
     gpu.close()
+
+
+def test_device_hilbert_sort_equals_host_sort(monkeypatch):
+    """set-up: the Hilbert keys and their stable radix sort run on the device in fvs2d_gpu_set_mesh; the
+    permutation must be the host's (fvs2d_host_build / FVS2D_HOST_SORT=1), bit for bit, because every rank derives its
+    partition from it."""
+    from fvs2d_b200 import capi, config, meshgen, solver
+    mesh = meshgen.vortex_mixed_mesh(96)
+    cfg = config.RunInput(grad_cellcntr_imethd=1, lvortex=True, dt=0.005).to_config()
+    gpu = solver.Fvs2dGpu(cfg, device=0)
+    gpu.set_mesh(mesh)
+    dev = capi.mesh_array("perm").copy()
+    monkeypatch.setenv("FVS2D_HOST_SORT", "1")
+    gpu.set_mesh(mesh)
+    host = capi.mesh_array("perm").copy()
+    gpu.close()
+    assert np.array_equal(np.sort(dev), np.arange(mesh.ncells)) and np.array_equal(dev, host)
