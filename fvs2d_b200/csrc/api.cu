@@ -626,7 +626,7 @@ int launch_fused_part(FusedLaunch &fl, int k, int part_off, const StageParams &S
       hx.peer_flag[q] = C->peer_flag[q];
       hx.my_flag[q] = C->flags + C->L.peers[q];
     }
-    hx.rs_word = C->d_rs_word; hx.rs_ent = C->d_rs_ent; hx.done_ctr = C->done_ctr;
+    hx.rs_word = C->d_rs_word; hx.rs_ent = C->d_rs_ent; hx.done_ctr = C->done_ctr; hx.timed_out = C->p2p_timed_out;
   }
   if (grid > 0)
     (use3 ? k3 : k2)<<<grid, kPipeThreads, smem, C->st>>>(C->dm, fl.meta, C->phys, S, pin, C->bc, C->q, C->f, pout, C->dtl,
