@@ -577,6 +577,30 @@ void hilbert_order_raw(int nc, const int *cptr, const int *cnode, const double *
   radix_sort_pairs(key, perm, 2 * f.bits);
 }
 
+// Cut the Hilbert order into `nranks` contiguous chunks of equal estimated COST, on 128-cell tile boundaries.  A
+// quadrilateral costs about 1.4 triangles in the stage kernel (four faces instead of three, and its tiles run at two CTAs
+// per SM instead of three; measured 0.108 vs 0.0765 ns per cell-stage on B200), so equal cell counts leave the ranks that
+// hold the quadrilateral band of a mixed mesh 25-30 % slower than the all-triangle ones -- and a time step takes as long as
+// the slowest rank.  perm[new] = original id; original ids below ntri are triangles.
+std::vector<int> partition_cuts(const std::vector<int> &perm, int ntri, int nranks) {
+  const int nc = (int)perm.size();
+  std::vector<int> cuts(nranks + 1, nc);
+  cuts[0] = 0;
+  if (nranks == 1) return cuts;
+  constexpr long long kTri = 5, kQuad = 7;
+  long long total = 0;
+#pragma omp parallel for schedule(static) reduction(+ : total)
+  for (int i = 0; i < nc; i++) total += perm[i] < ntri ? kTri : kQuad;
+  long long run = 0;
+  int r = 1;
+  for (int i = 0; i < nc && r < nranks; i++) {
+    if ((i & 127) == 0 && run * nranks >= total * r) cuts[r++] = i;   // first tile boundary at or past r / nranks of the cost
+    run += perm[i] < ntri ? kTri : kQuad;
+  }
+  for (int k = 1; k <= nranks; k++) cuts[k] = std::max(cuts[k], cuts[k - 1]);
+  return cuts;
+}
+
 void hilbert_order(const HostMesh &m, std::vector<int> &perm, const HilbertSorter *device_sort) {
   hilbert_order_raw(m.ncells, m.cptr.data(), m.cnode.data(), m.xn.data(), m.yn.data(), 1, perm, device_sort);
 }
@@ -610,8 +634,8 @@ std::string extract_submesh(int nnodes, int ntri, int nquad, const double *node_
   std::vector<int> perm;
   hilbert_order_raw(nc, cptr, cnode, node_xy, node_xy + 1, 2, perm, device_sort);
   lap("hilbert order");
-  auto range_begin = [&](int r) { return r >= nranks ? nc : (int)((int64_t)nc * r / nranks / 128 * 128); };
-  const int b0 = out.b0 = range_begin(rank), b1 = out.b1 = range_begin(rank + 1);
+  out.cuts = partition_cuts(perm, ntri, nranks);
+  const int b0 = out.b0 = out.cuts[rank], b1 = out.b1 = out.cuts[rank + 1];
   // ring 0 = owned cells; level[c] = ring + 1, 0 = outside
   std::vector<unsigned char> level(nc, 0), nmark(nnodes, 0);
 #pragma omp parallel for schedule(static)

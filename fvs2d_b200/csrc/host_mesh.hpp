@@ -78,6 +78,7 @@ double grad_cell_coeffs(const HostMesh &m, const GradOp &g, int ic, double *cx, 
 // Hilbert-curve ordering of the cell centroids (perm[new] = old), measured in cell counts per axis so that
 // anisotropic meshes still give compact tiles.  (Tried and rejected on B200: scanline order inside each
 // 128-cell tile -- 4-10 % slower pass B than the plain curve.)
+std::vector<int> partition_cuts(const std::vector<int> &perm, int ntri, int nranks);
 struct HilbertFrame { double x0, y0, scale_x, scale_y; int bits; };  // centroid -> integer lattice of the curve
 // Optional device implementation of "keys + stable sort" (api.cu: CUB radix sort); returns false to fall back to the host.
 typedef std::function<bool(const HilbertFrame &, int nc, const int *cptr, const int *cnode, const double *xn, const double *yn, int xs,
@@ -112,6 +113,7 @@ struct SubMesh {
   std::vector<unsigned char> ring;  // 0 owned, 1 / 2 ... node-adjacency ring around the owned cells
   std::vector<int> node_orig;   // submesh node -> original node id
   int nc_global = 0, nn_global = 0, b0 = 0, b1 = 0;
+  std::vector<int> cuts;        // Hilbert ids where the ranks' chunks begin (nranks + 1 entries)
   long long nbcells_global = 0;
   double xy_cell0[2] = {0, 0};
 };

@@ -254,13 +254,9 @@ __global__ void __launch_bounds__(256) k_prim(int n, int np, double gamma, const
 //   FORM 1: grad = sum c_k (p_k - p_i)    (LSQ src/gradient_lsq.f90:393-401)
 //   LIM: phi_i = min over vars and faces (src/gradient_limiter.f90:47-91); min/max over the stencil
 template <int FORM, bool LIM>
-__global__ void __launch_bounds__(kBlock) k_gradient(const DevMesh m, const int limiter_type, const double *__restrict__ p,
-                                                     double *__restrict__ g, double *__restrict__ phi,
-                                                     const int *__restrict__ tile_list) {
-  // one CTA = one 128-cell tile; tile_list (or null = all tiles in order) selects the interior / boundary subset
-  const int i = (tile_list ? __ldg(&tile_list[blockIdx.x]) : (int)blockIdx.x) * kBlock + threadIdx.x;
-  if (i >= m.n_own) return;
-  const int np = m.np, lane = threadIdx.x & 31, sl = i >> 5;
+__device__ __forceinline__ void gradient_cell(const DevMesh &m, const int limiter_type, const double *__restrict__ p,
+                                              double *__restrict__ g, double *__restrict__ phi, const int i) {
+  const int np = m.np, lane = i & 31, sl = i >> 5;
   const int off = __ldg(&m.g_off[sl]);
   const int w = (__ldg(&m.g_off[sl + 1]) - off) >> 5;
   const double2 *p2 = reinterpret_cast<const double2 *>(p);
@@ -327,14 +323,20 @@ __global__ void __launch_bounds__(kBlock) k_gradient(const DevMesh m, const int 
   }
 }
 
+template <int FORM, bool LIM>
+__global__ void __launch_bounds__(kBlock) k_gradient(const DevMesh m, const int limiter_type, const double *__restrict__ p,
+                                                     double *__restrict__ g, double *__restrict__ phi,
+                                                     const int *__restrict__ tile_list) {
+  // one CTA = one 128-cell tile; tile_list (or null = all tiles in order) selects the interior / boundary subset
+  const int i = (tile_list ? __ldg(&tile_list[blockIdx.x]) : (int)blockIdx.x) * kBlock + threadIdx.x;
+  if (i >= m.n_own) return;
+  gradient_cell<FORM, LIM>(m, limiter_type, p, g, phi, i);
+}
+
 // ------------------------------------------------------------------------------------------------
 // ghost states of the boundary faces that do not depend on the interior state
 // (src/residual.f90:195-217: freestream -> pvar_inf, dirichlet -> vortex(t) or MMS at the face centre)
-__global__ void __launch_bounds__(128) k_bc_state(const DevMesh m, const Phys P, const StepClock *__restrict__ clk, const int stage,
-                                                  double *__restrict__ bc /* [4][nbf] */) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= m.nbf) return;
-  const double time = clock_told(clk) + clk->off[stage];
+__device__ __forceinline__ void bc_state_one(const DevMesh &m, const Phys &P, const double time, const int b, double *__restrict__ bc) {
   const int type = m.bf_type[b];
   double pv[4] = {0, 0, 0, 0};
   if (type == 1) {
@@ -348,6 +350,12 @@ __global__ void __launch_bounds__(128) k_bc_state(const DevMesh m, const Phys P,
   }
 #pragma unroll
   for (int v = 0; v < 4; v++) bc[v * m.nbf + b] = pv[v];
+}
+__global__ void __launch_bounds__(128) k_bc_state(const DevMesh m, const Phys P, const StepClock *__restrict__ clk, const int stage,
+                                                  double *__restrict__ bc /* [4][nbf] */) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= m.nbf) return;
+  bc_state_one(m, P, clock_told(clk) + clk->off[stage], b, bc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -530,6 +538,66 @@ __device__ __forceinline__ void stage_update(const Phys &P, const StageParams &S
 // ------------------------------------------------------------------------------------------------
 // pass B, direct-gather variant: neighbour data straight from global memory (works for any mesh
 // numbering; also the fallback when a tile's halo does not fit the packed 16-bit slots).
+// one cell of the direct-gather pass B: faces from global memory, then the stage update
+template <int UM, bool STEADY, int RC>
+__device__ __forceinline__ void flux_rk_cell(const DevMesh &m, const Phys &P, const StageParams &S, const double *__restrict__ p,
+                                             const double *__restrict__ g, const double *__restrict__ phi, const double *__restrict__ bc,
+                                             double *__restrict__ q, double *__restrict__ f, double *__restrict__ pout,
+                                             double *__restrict__ dtl, double *__restrict__ resid_out, double *__restrict__ ws_out,
+                                             const int i, double dq2[4]) {
+  const int np = m.np, lane = i & 31;
+  const double2 *p2 = reinterpret_cast<const double2 *>(p), *g2 = reinterpret_cast<const double2 *>(g);
+  const int sl = i >> 5;
+  const int off = __ldg(&m.f_off[sl]);
+  const int w = (__ldg(&m.f_off[sl + 1]) - off) >> 5;
+  double p0[4], g0x[4], g0y[4];
+  load4(p2, np, i, p0);
+  if (RC != RC_FIRST) { load4(g2, np, i, g0x); load4(g2 + 2 * (size_t)np, np, i, g0y); }
+  const double2 c0 = m.xy[i];
+  const double phi0 = (RC >= RC_K0_PHI) ? phi[i] : 1.0;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0}, wsacc = 0.0;
+  for (int k = 0; k < w; k++) {
+    const int e = off + 32 * k + lane;
+    const int nb = __ldg(&m.f_nbr[e]);
+    if (nb == kPadNbr) continue;
+    const int fe = __ldg(&m.f_edge[e]);
+    const int ed = fe >> 1;
+    const bool self_c1 = (fe & 1) == 0;
+    const double2 fc = __ldg(&m.exy[ed]), fn = __ldg(&m.enxy[ed]);
+    const double af = __ldg(&m.ea[ed]);
+    double me[4] = {0.0, 0.0, 0.0, 0.0};  // this cell's reconstruction increment (x_f - x_c) . grad p (RC_K0: the state)
+    if (RC != RC_FIRST) {
+      const double dx = fc.x - c0.x, dy = fc.y - c0.y;
+#pragma unroll
+      for (int v = 0; v < 4; v++) me[v] = RC == RC_K0 ? recon_k0(p0[v], g0x[v], g0y[v], dx, dy) : dx * g0x[v] + dy * g0y[v];
+    }
+    if (nb >= 0) {
+      double pj[4], ot[4] = {0.0, 0.0, 0.0, 0.0};
+      load4(p2, np, nb, pj);
+      double phij = 1.0;
+      if (RC != RC_FIRST) {
+        double gjx[4], gjy[4];
+        load4(g2, np, nb, gjx);
+        load4(g2 + 2 * (size_t)np, np, nb, gjy);
+        const double2 cj = m.xy[nb];
+        const double dx = fc.x - cj.x, dy = fc.y - cj.y;
+#pragma unroll
+        for (int v = 0; v < 4; v++) ot[v] = RC == RC_K0 ? recon_k0(pj[v], gjx[v], gjy[v], dx, dy) : dx * gjx[v] + dy * gjy[v];
+        if (RC >= RC_K0_PHI) phij = phi[nb];
+      }
+      interior_face<RC>(P, self_c1, p0, me, phi0, pj, ot, phij, fn.x, fn.y, af, acc, wsacc);
+    } else {
+      const int b = -1 - nb;
+      const int type = __ldg(&m.bf_type[b]);
+      double bcv[4];
+#pragma unroll
+      for (int v = 0; v < 4; v++) bcv[v] = bc[v * m.nbf + b];  // (plain load: the cooperative step kernel writes bc itself)
+      boundary_face<RC>(P, type, p0, me, phi0, bcv, fn.x, fn.y, af, acc, wsacc);
+    }
+  }
+  stage_update<UM, STEADY>(P, S, i, np, m.ivol[i], m.vol, acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
+}
+
 template <int UM, bool STEADY, int RC>
 __global__ void __launch_bounds__(kBlock) k_flux_rk(const DevMesh m, const Phys P, const StageParams S,
                                                     const double *__restrict__ p, const double *__restrict__ g,
@@ -538,61 +606,8 @@ __global__ void __launch_bounds__(kBlock) k_flux_rk(const DevMesh m, const Phys 
                                                     double *__restrict__ dtl, double *__restrict__ resid_out,
                                                     double *__restrict__ ws_out, double *__restrict__ partial) {
   const int i = blockIdx.x * kBlock + threadIdx.x;
-  const bool live = i < m.n_own;
-  const int np = m.np, lane = threadIdx.x & 31;
-  const double2 *p2 = reinterpret_cast<const double2 *>(p), *g2 = reinterpret_cast<const double2 *>(g);
   double dq2[4] = {0.0, 0.0, 0.0, 0.0};
-  if (live) {
-    const int sl = i >> 5;
-    const int off = __ldg(&m.f_off[sl]);
-    const int w = (__ldg(&m.f_off[sl + 1]) - off) >> 5;
-    double p0[4], g0x[4], g0y[4];
-    load4(p2, np, i, p0);
-    if (RC != RC_FIRST) { load4(g2, np, i, g0x); load4(g2 + 2 * (size_t)np, np, i, g0y); }
-    const double2 c0 = m.xy[i];
-    const double phi0 = (RC >= RC_K0_PHI) ? phi[i] : 1.0;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0}, wsacc = 0.0;
-    for (int k = 0; k < w; k++) {
-      const int e = off + 32 * k + lane;
-      const int nb = __ldg(&m.f_nbr[e]);
-      if (nb == kPadNbr) continue;
-      const int fe = __ldg(&m.f_edge[e]);
-      const int ed = fe >> 1;
-      const bool self_c1 = (fe & 1) == 0;
-      const double2 fc = __ldg(&m.exy[ed]), fn = __ldg(&m.enxy[ed]);
-      const double af = __ldg(&m.ea[ed]);
-      double me[4] = {0.0, 0.0, 0.0, 0.0};  // this cell's reconstruction increment (x_f - x_c) . grad p (RC_K0: the state)
-      if (RC != RC_FIRST) {
-        const double dx = fc.x - c0.x, dy = fc.y - c0.y;
-#pragma unroll
-        for (int v = 0; v < 4; v++) me[v] = RC == RC_K0 ? recon_k0(p0[v], g0x[v], g0y[v], dx, dy) : dx * g0x[v] + dy * g0y[v];
-      }
-      if (nb >= 0) {
-        double pj[4], ot[4] = {0.0, 0.0, 0.0, 0.0};
-        load4(p2, np, nb, pj);
-        double phij = 1.0;
-        if (RC != RC_FIRST) {
-          double gjx[4], gjy[4];
-          load4(g2, np, nb, gjx);
-          load4(g2 + 2 * (size_t)np, np, nb, gjy);
-          const double2 cj = m.xy[nb];
-          const double dx = fc.x - cj.x, dy = fc.y - cj.y;
-#pragma unroll
-          for (int v = 0; v < 4; v++) ot[v] = RC == RC_K0 ? recon_k0(pj[v], gjx[v], gjy[v], dx, dy) : dx * gjx[v] + dy * gjy[v];
-          if (RC >= RC_K0_PHI) phij = phi[nb];
-        }
-        interior_face<RC>(P, self_c1, p0, me, phi0, pj, ot, phij, fn.x, fn.y, af, acc, wsacc);
-      } else {
-        const int b = -1 - nb;
-        const int type = __ldg(&m.bf_type[b]);
-        double bcv[4];
-#pragma unroll
-        for (int v = 0; v < 4; v++) bcv[v] = __ldg(&bc[v * m.nbf + b]);
-        boundary_face<RC>(P, type, p0, me, phi0, bcv, fn.x, fn.y, af, acc, wsacc);
-      }
-    }
-    stage_update<UM, STEADY>(P, S, i, np, m.ivol[i], m.vol, acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
-  }
+  if (i < m.n_own) flux_rk_cell<UM, STEADY, RC>(m, P, S, p, g, phi, bc, q, f, pout, dtl, resid_out, ws_out, i, dq2);
   if (UM != UM_RESID && S.last) block_sum_store<4>(dq2, partial);
 }
 

@@ -32,7 +32,8 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const CellNumbering
   if (!num.orig) L.perm = num.order;  // whole mesh: new id -> original id (output path, verification)
   const std::vector<int> &order = num.order, &new_id = num.new_id;
   // rank boundaries on tile boundaries of the global order (tiles are sorted internally by hilbert_order)
-  auto range_begin = [&](int r) { return r >= nranks ? nc : (int)((int64_t)nc * r / nranks / kTile * kTile); };
+  if ((int)num.cuts.size() != nranks + 1) return "build_layout: partition cuts missing";
+  auto range_begin = [&](int r) { return r >= nranks ? nc : num.cuts[r]; };
   auto pos_of = [&](int newid) {  // first entry of `order` whose Hilbert id is >= newid
     return (int)(std::lower_bound(order.begin(), order.end(), newid, [&](int mc, int v) { return new_id[mc] < v; }) - order.begin());
   };

@@ -112,8 +112,9 @@ struct CellNumbering {
   std::vector<int> order;      // m-cells by ascending Hilbert id
   std::vector<int> new_id;     // m-cell -> Hilbert id
   const int *orig = nullptr;   // m-cell -> original id (null: identity)
+  std::vector<int> cuts;       // Hilbert ids where the ranks' chunks begin (partition_cuts; nranks + 1 entries)
 };
-// Builds the layout of `rank` out of `nranks` (equal contiguous chunks of the Hilbert order).
+// Builds the layout of `rank` out of `nranks` (contiguous chunks of the Hilbert order of equal estimated cost).
 std::string build_layout(const HostMesh &m, const GradOp &g, const CellNumbering &num, int rank, int nranks, Layout &L,
                          bool deep = false);
 
