@@ -490,7 +490,9 @@ def main():
         return
 
     peak, peak_src = load_peaks()
-    n_own = sizes["ncells_own"]
+    # cells per rank for the per-kernel figures: the mean (the ranks' chunks have equal estimated cost, not equal counts,
+    # on mixed meshes; the kernel time is the max over ranks)
+    n_own = ncells / world
     roof = {"bound": "hbm", "kernel": "k_flux_pipe (pass B: face-flux gather + residual + RK update; persistent TMA/cp.async smem pipeline)",
             "achieved": bB * n_own / (flux_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
             "alg_bytes_per_cell": bB, "avg_launch_ms": flux_ms, "traffic": None,
@@ -522,7 +524,7 @@ def main():
     line = {"metric": metric, "value": value, "unit": "cell-stage updates/s", "n_gpus": ngpus, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": desc, "ncells": ncells, "ncells_per_gpu": n_own, "dt": dt, "l2": "inputs larger than L2 "
+            "config": {"workload": desc, "ncells": ncells, "ncells_per_gpu": n_own, "ncells_rank0": sizes["ncells_own"], "dt": dt, "l2": "inputs larger than L2 "
                        f"({scal['device_bytes'] / 1e9:.2f} GB resident per GPU vs 126 MB L2)", "parallelism": f"dd{ngpus}",
                        "setup_s": round(t_setup, 1)},
             "roofline": roof, "stage_roofline": stage, "gradient_kernel": gradk,

@@ -21,7 +21,6 @@
 #include "host_mesh.hpp"
 #include "kernels.cuh"
 #include "kernels_fused.cuh"
-#include "kernels_coop.cuh"
 #include "layout.hpp"
 
 using namespace fvs2d;
@@ -106,8 +105,6 @@ struct Ctx {
   const void *graph_logbuf = nullptr;  // the graph is tied to these
   int graph_um = -1;
   int opt_ctas = 0;      // persistent pass-B CTAs per SM: 0 = as many as shared memory allows (max 3)
-  int opt_coop = 1;      // small meshes (every tile has a resident CTA): whole calls of time_integration as ONE cooperative kernel
-  unsigned long long *coop_bar = nullptr;
   int opt_overlap = 1;   // multi-GPU: overlap the halo exchanges with interior-tile work (second stream)
   int opt_smem_pad = 0;  // experiment: extra dynamic shared memory (KB) per pass-B CTA (shrinks the L1 carve-out)
   int opt_carveout = -1; // experiment: preferred shared-memory carve-out of the pass-B kernel in KB (-1: driver default)
@@ -224,7 +221,6 @@ void free_device() {
   C->d_n2c_ptr = C->d_n2c = nullptr; C->d_idw = nullptr; C->d_fnode = nullptr;
   C->d_be_cell = nullptr; C->d_be_xy = C->d_be_nxy = nullptr; C->d_be_out = nullptr;
   C->fz_state = 0; C->n_fl = 0; C->fz_tables = 0;
-  C->coop_bar = nullptr;
   C->flags = nullptr; C->done_ctr = nullptr; C->p2p_timed_out = nullptr; C->d_rs_word = nullptr; C->d_rs_ent = nullptr;
 }
 
@@ -658,42 +654,6 @@ int launch_fused(int um, const StageParams &S, const double *pin, double *pout) 
   if (um == UM_RK) { if (steady) launch_fused_form<UM_RK, true>(S, pin, pout); else launch_fused_form<UM_RK, false>(S, pin, pout); }
   else { if (steady) launch_fused_form<UM_SSPRK, true>(S, pin, pout); else launch_fused_form<UM_SSPRK, false>(S, pin, pout); }
   return 0;
-}
-
-// ---- small meshes: all nsub steps of a call in one cooperative launch (kernels_coop.cuh) -----------------------------
-template <int FORM, bool LIM, int UM, bool STEADY, int RC>
-int launch_coop_one(const CoopArgs &A, bool query_only, int &capacity) {
-  auto k = k_step_coop<FORM, LIM, UM, STEADY, RC>;
-  int per_sm = 0;
-  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kBlock, 0));
-  capacity = per_sm * C->nsm;
-  if (query_only || C->nblocks > capacity) return 0;
-  void *args[] = {(void *)&C->dm, (void *)&C->phys, (void *)&A};
-  CUDA_OK(cudaLaunchCooperativeKernel((const void *)k, dim3(C->nblocks), dim3(kBlock), args, 0, C->st));
-  C->last_launches++;
-  return 0;
-}
-template <int FORM, bool LIM, int UM, bool STEADY>
-int launch_coop_rc(const CoopArgs &A, bool q, int &cap) {
-  switch (C->recon) {
-    case RC_FIRST: return LIM ? 0 : launch_coop_one<0, false, UM, STEADY, RC_FIRST>(A, q, cap);
-    case RC_K0: return LIM ? 0 : launch_coop_one<FORM, false, UM, STEADY, RC_K0>(A, q, cap);
-    case RC_K0_PHI: return LIM ? launch_coop_one<FORM, true, UM, STEADY, RC_K0_PHI>(A, q, cap) : 0;
-    default: return launch_coop_one<FORM, LIM, UM, STEADY, RC_GENERAL>(A, q, cap);
-  }
-}
-// query_only: just the number of CTAs that can be co-resident (capacity); else launch when the mesh fits
-int launch_coop(int um, const CoopArgs &A, bool query_only, int &capacity) {
-  const bool lim = C->cfg.limiter > 0 && C->recon != RC_FIRST, steady = C->cfg.steady != 0, gg = C->L.g_form == 0;
-  capacity = 0;
-#define COOP_DISPATCH(F, L_)                                                                                     \
-  (um == UM_RK ? (steady ? launch_coop_rc<F, L_, UM_RK, true>(A, query_only, capacity)                          \
-                         : launch_coop_rc<F, L_, UM_RK, false>(A, query_only, capacity))                        \
-               : (steady ? launch_coop_rc<F, L_, UM_SSPRK, true>(A, query_only, capacity)                       \
-                         : launch_coop_rc<F, L_, UM_SSPRK, false>(A, query_only, capacity)))
-  if (gg) return lim ? COOP_DISPATCH(0, true) : COOP_DISPATCH(0, false);
-  return lim ? COOP_DISPATCH(1, true) : COOP_DISPATCH(1, false);
-#undef COOP_DISPATCH
 }
 
 int launch_bc(int stage) {
@@ -1499,34 +1459,6 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
     CUDA_OK(cudaStreamSynchronize(C->st));  // hc is a stack variable
   }
   CUDA_OK(cudaEventRecord(C->ev0, C->st));
-  // Small meshes: the whole call as one cooperative kernel (every tile has its own resident CTA, phases separated by
-  // grid-wide barriers) -- no launch latency between the ~10 dependent phases of a step.
-  bool coop_done = false;
-  if (C->opt_coop && C->nranks == 1 && !C->opt_timing && nsub > 0 && C->nblocks <= 4 * C->nsm) {
-    CoopArgs A{};
-    A.pa = C->pa; A.pb = C->pb; A.g = C->g; A.phi = C->phi; A.bc = C->bc; A.q = C->q; A.f = C->f; A.dtl = C->dtl;
-    A.partial = C->partial; A.vpartial = C->vpartial; A.vbest = C->vbest; A.vbest_loc = C->vbest_loc;
-    A.logbuf = C->logbuf; A.logid = C->logid; A.clk = C->clk;
-    for (int rk = 0; rk < 4; rk++) {
-      StageParams &S = A.S[rk];
-      S.stage = rk; S.last = rk == 3; S.c = C->rk_coef[rk]; S.dt = dt;
-      if (c.steady) S.h = c.ssprk ? (rk == 3 ? 1.0 / 4.0 : 1.0 / 3.0) : (rk == 2 ? 1.0 : rk == 3 ? 1.0 / 6.0 : 1.0 / 2.0);
-      else S.h = C->h_rk[rk];
-    }
-    A.nsteps = nsub; A.limiter_type = c.limiter; A.log_stride = (int)per; A.vort = vort ? 1 : 0;
-    A.bc_time_dep = c.lvortex != 0; A.bc_done = C->bc_static_done ? 1 : 0;
-    if (!C->coop_bar && dev_alloc(C->coop_bar, 1)) return 1;
-    A.bar = C->coop_bar;
-    int capacity = 0;
-    if (launch_coop(um, A, true, capacity)) return 1;
-    if (C->nblocks <= capacity) {
-      CUDA_OK(cudaMemsetAsync(C->coop_bar, 0, sizeof(unsigned long long), C->st));
-      if (launch_coop(um, A, false, capacity)) return 1;
-      C->bc_static_done = true;
-      C->nparts = C->nblocks;
-      coop_done = true;   // (4 stages per step: pa / pb end up where they started)
-    }
-  }
   // one time step = a fixed kernel sequence; nothing in it depends on the host-side step counter
   auto run_step = [&]() -> int {
     for (int rk = 0; rk < 4; rk++) {
@@ -1591,10 +1523,9 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   // configures the kernels), the remaining ones replay a CUDA graph captured from the same sequence.
   // (several ranks: only the fused path, whose halo exchange lives inside the stage kernel -- no NCCL call in the step)
   const bool use_graph = C->opt_graph && (C->nranks == 1 || fused) && !C->opt_timing && nsub >= 3;
-  int done = coop_done ? nsub : 0;
-  if (coop_done) {
-  } else if (nsub > 0) { if (run_step()) return 1; done = 1; }
-  if (use_graph && !coop_done) {
+  int done = 0;
+  if (nsub > 0) { if (run_step()) return 1; done = 1; }
+  if (use_graph) {
     if (C->graph_exec && (C->graph_logbuf != C->logbuf || C->graph_um != (fused ? 256 * ((C->opt_fuse & 3) + 1) : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas)) {
       cudaGraphExecDestroy(C->graph_exec);
       C->graph_exec = nullptr;
@@ -1831,7 +1762,6 @@ int fvs2d_gpu_set_option(const char *key, int value) {
   if (k == "ctas") { C->opt_ctas = value; return 0; }
   if (k == "overlap") { C->opt_overlap = value; return 0; }
   if (k == "graph") { C->opt_graph = value; return 0; }
-  if (k == "coop") { C->opt_coop = value; return 0; }
   if (k == "smem_pad") { C->opt_smem_pad = value; return 0; }
   if (k == "carveout") { C->opt_carveout = value; return 0; }
   if (k == "fuse") {

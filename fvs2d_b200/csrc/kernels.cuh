@@ -392,10 +392,9 @@ __device__ __forceinline__ void block_sum_store(double val[NV], double *__restri
 // neighbour's.  The flux is evaluated in the edge's own orientation (L = c1, R = c2).
 // RC_K0: me / ot are the reconstructed STATES (recon_k0), for the other modes the increments (x_f - x_c) . grad p.
 template <int RC>
-__device__ __forceinline__ void interior_face(const Phys &P, const bool self_c1, const double p0[4], const double me[4],
-                                              const double phi0, const double pj[4], const double ot[4], const double phij,
-                                              const double nx, const double ny, const double af, double acc[4], double &wsacc) {
-  double sL[4], sR[4];
+__device__ __forceinline__ void interior_states(const Phys &P, const bool self_c1, const double p0[4], const double me[4],
+                                                const double phi0, const double pj[4], const double ot[4], const double phij,
+                                                double sL[4], double sR[4]) {
   const double kap = P.kappa;
 #pragma unroll
   for (int v = 0; v < 4; v++) {
@@ -413,6 +412,13 @@ __device__ __forceinline__ void interior_face(const Phys &P, const bool self_c1,
       }
     }
   }
+}
+template <int RC>
+__device__ __forceinline__ void interior_face(const Phys &P, const bool self_c1, const double p0[4], const double me[4],
+                                              const double phi0, const double pj[4], const double ot[4], const double phij,
+                                              const double nx, const double ny, const double af, double acc[4], double &wsacc) {
+  double sL[4], sR[4];
+  interior_states<RC>(P, self_c1, p0, me, phi0, pj, ot, phij, sL, sR);
   double flux[4], ws;
   roe_flux2(P, sL, sR, nx, ny, flux, ws);
   const double ha = 0.5 * af, sa = self_c1 ? ha : -ha;
@@ -423,10 +429,8 @@ __device__ __forceinline__ void interior_face(const Phys &P, const bool self_c1,
 
 // boundary face: this cell is c1 (src/residual.f90:125-155); bcv = ghost state for freestream/dirichlet
 template <int RC>
-__device__ __forceinline__ void boundary_face(const Phys &P, const int type, const double p0[4], const double me[4],
-                                              const double phi0, const double bcv[4], const double nx, const double ny,
-                                              const double af, double acc[4], double &wsacc) {
-  double sL[4], sR[4];
+__device__ __forceinline__ void boundary_states(const int type, const double p0[4], const double me[4], const double phi0,
+                                                const double bcv[4], const double nx, const double ny, double sL[4], double sR[4]) {
 #pragma unroll
   for (int v = 0; v < 4; v++) sL[v] = (RC == RC_FIRST) ? p0[v] : (RC == RC_K0) ? me[v] : p0[v] + phi0 * me[v];
   if (type == 2) {  // slip wall: mirror the normal velocity
@@ -438,6 +442,13 @@ __device__ __forceinline__ void boundary_face(const Phys &P, const int type, con
 #pragma unroll
     for (int v = 0; v < 4; v++) sR[v] = bcv[v];
   }
+}
+template <int RC>
+__device__ __forceinline__ void boundary_face(const Phys &P, const int type, const double p0[4], const double me[4],
+                                              const double phi0, const double bcv[4], const double nx, const double ny,
+                                              const double af, double acc[4], double &wsacc) {
+  double sL[4], sR[4];
+  boundary_states<RC>(type, p0, me, phi0, bcv, nx, ny, sL, sR);
   double flux[4], ws;
   roe_flux2(P, sL, sR, nx, ny, flux, ws);
   const double ha = 0.5 * af;
@@ -555,12 +566,21 @@ __device__ __forceinline__ void flux_rk_cell(const DevMesh &m, const Phys &P, co
   if (RC != RC_FIRST) { load4(g2, np, i, g0x); load4(g2 + 2 * (size_t)np, np, i, g0y); }
   const double2 c0 = m.xy[i];
   const double phi0 = (RC >= RC_K0_PHI) ? phi[i] : 1.0;
+  // the cell's Runge-Kutta data and all of its face words are requested up front: one memory round trip instead of one per
+  // face (on meshes that live in L2 a stage is bound by these dependent latencies, not by bandwidth)
+  double q0[4], fo[4], dl;
+  stage_load<UM, STEADY>(S, i, np, q, f, dtl, q0, fo, dl);
+  const double ivol = m.ivol[i];
+  int nbv[4], fev[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    nbv[k] = k < w ? __ldg(&m.f_nbr[off + 32 * k + lane]) : kPadNbr;
+    fev[k] = k < w ? __ldg(&m.f_edge[off + 32 * k + lane]) : 0;
+  }
   double acc[4] = {0.0, 0.0, 0.0, 0.0}, wsacc = 0.0;
-  for (int k = 0; k < w; k++) {
-    const int e = off + 32 * k + lane;
-    const int nb = __ldg(&m.f_nbr[e]);
-    if (nb == kPadNbr) continue;
-    const int fe = __ldg(&m.f_edge[e]);
+  // twice the flux of face k in the edge's orientation, its wave speed, and the signed half length it is added with
+  auto face = [&](const int k, double fl[4], double &ws, double &ha, double &sa) {
+    const int nb = nbv[k], fe = fev[k];
     const int ed = fe >> 1;
     const bool self_c1 = (fe & 1) == 0;
     const double2 fc = __ldg(&m.exy[ed]), fn = __ldg(&m.enxy[ed]);
@@ -571,6 +591,7 @@ __device__ __forceinline__ void flux_rk_cell(const DevMesh &m, const Phys &P, co
 #pragma unroll
       for (int v = 0; v < 4; v++) me[v] = RC == RC_K0 ? recon_k0(p0[v], g0x[v], g0y[v], dx, dy) : dx * g0x[v] + dy * g0y[v];
     }
+    double sL[4], sR[4];
     if (nb >= 0) {
       double pj[4], ot[4] = {0.0, 0.0, 0.0, 0.0};
       load4(p2, np, nb, pj);
@@ -585,17 +606,50 @@ __device__ __forceinline__ void flux_rk_cell(const DevMesh &m, const Phys &P, co
         for (int v = 0; v < 4; v++) ot[v] = RC == RC_K0 ? recon_k0(pj[v], gjx[v], gjy[v], dx, dy) : dx * gjx[v] + dy * gjy[v];
         if (RC >= RC_K0_PHI) phij = phi[nb];
       }
-      interior_face<RC>(P, self_c1, p0, me, phi0, pj, ot, phij, fn.x, fn.y, af, acc, wsacc);
+      interior_states<RC>(P, self_c1, p0, me, phi0, pj, ot, phij, sL, sR);
+      sa = self_c1 ? 0.5 * af : -(0.5 * af);
     } else {
       const int b = -1 - nb;
       const int type = __ldg(&m.bf_type[b]);
       double bcv[4];
 #pragma unroll
       for (int v = 0; v < 4; v++) bcv[v] = bc[v * m.nbf + b];  // (plain load: the cooperative step kernel writes bc itself)
-      boundary_face<RC>(P, type, p0, me, phi0, bcv, fn.x, fn.y, af, acc, wsacc);
+      boundary_states<RC>(type, p0, me, phi0, bcv, fn.x, fn.y, sL, sR);
+      sa = 0.5 * af;
+    }
+    roe_flux2(P, sL, sR, fn.x, fn.y, fl, ws);
+    ha = 0.5 * af;
+  };
+  auto add = [&](const double fl[4], const double ws, const double ha, const double sa) {
+#pragma unroll
+    for (int v = 0; v < 4; v++) acc[v] += fl[v] * sa;
+    wsacc += ws * ha;
+  };
+  {
+    // two faces per basic block, so that their independent flux evaluations interleave; accumulated in face order
+    int k = 0;
+#pragma unroll 1
+    for (; k + 1 < w; k += 2) {
+      const bool v0 = nbv[k] != kPadNbr, v1 = nbv[k + 1] != kPadNbr;
+      if (v0 && v1) {
+        double fa[4], fb[4], wa, wb, ha, hb, sa_, sb_;
+        face(k, fa, wa, ha, sa_);
+        face(k + 1, fb, wb, hb, sb_);
+        add(fa, wa, ha, sa_);
+        add(fb, wb, hb, sb_);
+      } else if (v0 || v1) {
+        double fa[4], wa, ha, sa_;
+        face(v0 ? k : k + 1, fa, wa, ha, sa_);
+        add(fa, wa, ha, sa_);
+      }
+    }
+    if (k < w && nbv[k] != kPadNbr) {
+      double fa[4], wa, ha, sa_;
+      face(k, fa, wa, ha, sa_);
+      add(fa, wa, ha, sa_);
     }
   }
-  stage_update<UM, STEADY>(P, S, i, np, m.ivol[i], m.vol, acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
+  stage_update_pre<UM, STEADY>(P, S, i, np, ivol, m.vol, q0, fo, dl, acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
 }
 
 template <int UM, bool STEADY, int RC>

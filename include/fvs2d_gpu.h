@@ -185,9 +185,6 @@ int fvs2d_gpu_last_timing(double ms[4], long *launches);
  *              On several ranks the option must be set before fvs2d_gpu_set_mesh (it decides the ghost layers).
  *   "graph"    1 (default): steps 2..nsub of a call replay a captured CUDA graph (one GPU, or the fused path on several:
  *              its time step contains no NCCL call); 0: every step eager
- *   "coop"     1 (default): on one GPU, when every 128-cell tile of the mesh can have its own resident CTA (up to 592 tiles =
- *              75 776 cells on a B200: the reference's shipped examples), a whole call -- all nsub steps -- runs as ONE
- *              cooperative kernel with grid-wide barriers between the phases of a step; 0: always the launch sequence
  *   "overlap"  1 (default): multi-GPU halo exchange on a second stream, overlapped with interior-tile work
  *   "ctas"     resident CTAs per SM of k_flux_pipe (0 = occupancy API), "smem_pad" / "carveout": extra dynamic shared
  *              memory per CTA / preferred shared-memory carve-out of k_flux_pipe, both in KB (the L1 experiments of

@@ -178,43 +178,3 @@ def test_device_hilbert_sort_equals_host_sort(monkeypatch):
     host = capi.mesh_array("perm").copy()
     gpu.close()
     assert np.array_equal(np.sort(dev), np.arange(mesh.ncells)) and np.array_equal(dev, host)
-
-
-@pytest.mark.parametrize("case", ["c1-vortex-lsqfn", "c2-naca-venkat-steady", "naca-ggcb-rk4", "mixed-ggnb-umuscl", "tri-first-order"])
-def test_cooperative_step_kernel_matches_the_launch_sequence(case, vortex_mesh, naca_mesh):
-    """Small meshes (every tile has its own resident CTA) run a whole call as ONE cooperative kernel (option "coop", the
-    default): the state must be bitwise that of the kernel-per-phase sequence, log_res / vortex errors agree to 1e-13 (the
-    norm partials are per tile instead of per persistent CTA), and the call is a single launch."""
-    from fvs2d_b200 import config, meshgen, solver
-    from conftest import run_input
-    if case == "c1-vortex-lsqfn":
-        mesh, run = vortex_mesh, run_input("vortex")
-    elif case == "c2-naca-venkat-steady":
-        mesh, run = naca_mesh, run_input("naca")
-        run.grad_limiter_imethd = 1
-    elif case == "naca-ggcb-rk4":
-        mesh, run = naca_mesh, config.RunInput(grad_cellcntr_imethd=1, dt=1e-4, mach_inf=0.5)
-    elif case == "mixed-ggnb-umuscl":
-        mesh, run = meshgen.vortex_mixed_mesh(48), config.RunInput(grad_cellcntr_imethd=2, face_reconst_imethd=3, umuscl_cst=1.0 / 3.0, lvortex=True, dt=0.005)
-    else:
-        mesh, run = meshgen.vortex_tri_mesh(40), config.RunInput(grad_cellcntr_imethd=1, face_reconst_imethd=1, lvortex=True, dt=0.005)
-    cfg = run.to_config()
-    gpu = solver.Fvs2dGpu(cfg, device=0)
-    gpu.set_mesh(mesh)
-    out = {}
-    for coop in (0, 1):
-        gpu.set_option("coop", coop)
-        gpu.set_option("fuse", 0)
-        gpu.initialize_solution()
-        r1, v1, x1 = gpu.time_integration(0.0, 7)
-        r2, v2, x2 = gpu.time_integration(7 * run.dt, 5)          # a second call: the step clock and the buffers carry over
-        out[coop] = (gpu.get_state().copy(), np.concatenate([r1, r2]), None if v1 is None else np.concatenate([v1, v2]),
-                     None if x1 is None else np.concatenate([x1, x2]), gpu.last_timing()["launches"])
-    gpu.close()
-    q0, r0, v0, x0, l0 = out[0]
-    q1, r1, v1, x1, l1 = out[1]
-    assert np.array_equal(q0, q1)
-    assert np.allclose(r1, r0, rtol=1e-13, atol=0.0)
-    if v0 is not None:
-        assert np.allclose(v1, v0, rtol=1e-12, atol=0.0) and np.array_equal(x0, x1)
-    assert l1 == 1 and l0 > 5 * 9
