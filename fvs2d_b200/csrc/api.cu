@@ -105,6 +105,8 @@ struct Ctx {
   const void *graph_logbuf = nullptr;  // the graph is tied to these
   int graph_um = -1;
   int opt_ctas = 0;      // persistent pass-B CTAs per SM: 0 = as many as shared memory allows (max 3)
+  int opt_pair = -1;     // small meshes on one GPU: two threads per cell in both passes (k_gradient2 / k_flux_rk2); -1 automatic
+                         // (meshes that leave most thread slots of the machine empty with one thread per cell), 0 never, 1 always
   int opt_overlap = 1;   // multi-GPU: overlap the halo exchanges with interior-tile work (second stream)
   int opt_smem_pad = 0;  // experiment: extra dynamic shared memory (KB) per pass-B CTA (shrinks the L1 carve-out)
   int opt_carveout = -1; // experiment: preferred shared-memory carve-out of the pass-B kernel in KB (-1: driver default)
@@ -372,12 +374,30 @@ int upload_local_state(const double *cv_loc) {
   return 0;
 }
 
+// two threads per cell: meshes that would leave most of the machine's thread slots empty (one GPU, whole-mesh launches)
+bool use_pair_kernels() {
+  if (C->nranks != 1 || C->opt_pair == 0) return false;
+  return C->opt_pair > 0 || C->L.n_own <= C->nsm * 1024;   // B200: 151 552 cells
+}
+
 int launch_gradient(const double *p, const int *list = nullptr, int nlist = 0, bool force = false) {
   if (C->recon == RC_FIRST && !force) return 0;  // src/gradient.f90:49
   const int nb = list ? nlist : C->nblocks;
   if (nb == 0) return 0;
   Span sp(1);
   const bool lim = C->cfg.limiter > 0;
+  if (!list && use_pair_kernels()) {
+    const int nb2 = cdiv(2 * C->L.n_own, kBlock);
+    if (C->L.g_form == 0) {
+      if (lim) k_gradient2<0, true><<<nb2, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi);
+      else k_gradient2<0, false><<<nb2, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi);
+    } else {
+      if (lim) k_gradient2<1, true><<<nb2, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi);
+      else k_gradient2<1, false><<<nb2, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi);
+    }
+    C->last_launches++;
+    return 0;
+  }
   if (C->L.g_form == 0) {
     if (lim) k_gradient<0, true><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi, list);
     else k_gradient<0, false><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi, list);
@@ -395,6 +415,13 @@ TileSel g_sel;
 template <int UM, bool STEADY, int RC>
 void launch_flux_one(const StageParams &S, const double *pin, double *pout) {
   const int nb = C->nblocks;
+  if (!g_sel.list && use_pair_kernels()) {
+    const int nb2 = cdiv(2 * C->L.n_own, kBlock);
+    k_flux_rk2<UM, STEADY, RC><<<nb2, kBlock, 0, C->st>>>(C->dm, C->phys, S, pin, C->g, C->phi, C->bc, C->q, C->f, pout, C->dtl, C->resid,
+                                                          C->ws, C->partial);
+    C->nparts = nb2;
+    return;
+  }
   if (C->tile_ok && C->opt_tile == 2) {
     const size_t smem = kStages * pipe_stage_bytes<RC>(C->pm.S, C->pm.E) + 2 * kStages * sizeof(uint64_t) + (size_t)C->opt_smem_pad * 1024;
     ensure_smem_attr(k_flux_pipe<UM, STEADY, RC>, smem);
@@ -1160,7 +1187,7 @@ int device_upload() {
   if (dev_alloc(C->bc, 4 * (size_t)std::max(1, L.nbf))) return 1;
   if (dev_alloc(C->clk, 1)) return 1;
   if (C->graph_exec) { cudaGraphExecDestroy(C->graph_exec); C->graph_exec = nullptr; }
-  if (dev_alloc(C->partial, (size_t)C->nblocks * 4) || dev_alloc(C->vpartial, (size_t)C->nblocks * 13) || dev_alloc(C->vbest, (size_t)C->nblocks) || dev_alloc(C->vbest_loc, (size_t)C->nblocks)) return 1;
+  if (dev_alloc(C->partial, (size_t)(2 * C->nblocks + 1) * 4) || dev_alloc(C->vpartial, (size_t)C->nblocks * 13) || dev_alloc(C->vbest, (size_t)C->nblocks) || dev_alloc(C->vbest_loc, (size_t)C->nblocks)) return 1;
   CUDA_OK(cudaMemset(C->q, 0, 4 * np * 8));
   CUDA_OK(cudaMemset(C->f, 0, 4 * np * 8));
   CUDA_OK(cudaMemset(C->pa, 0, 4 * np * 8));
@@ -1449,7 +1476,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   const bool overlap = C->nranks > 1 && C->opt_overlap && C->tile_ok && C->opt_tile == 2;
   bool p_pending = false;
   if (C->opt_fuse && ensure_fused()) return 1;
-  const bool fused = C->opt_fuse != 0 && C->fz_state == 1 && C->opt_tile == 2;
+  const bool fused = C->opt_fuse != 0 && C->fz_state == 1 && C->opt_tile == 2 && !(use_pair_kernels() && C->opt_fuse < 0);
   {  // device step clock (src/runge_kutta.f90:135-145, 218-221): stage times are told + off[stage]
     StepClock hc{};
     hc.t1 = t1; hc.dt = dt; hc.istep = 0; hc.epoch0 = C->epoch_total;
@@ -1526,7 +1553,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   int done = 0;
   if (nsub > 0) { if (run_step()) return 1; done = 1; }
   if (use_graph) {
-    if (C->graph_exec && (C->graph_logbuf != C->logbuf || C->graph_um != (fused ? 256 * ((C->opt_fuse & 3) + 1) : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas)) {
+    if (C->graph_exec && (C->graph_logbuf != C->logbuf || C->graph_um != (fused ? 256 * ((C->opt_fuse & 3) + 1) : 0) + (use_pair_kernels() ? 2048 : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas)) {
       cudaGraphExecDestroy(C->graph_exec);
       C->graph_exec = nullptr;
     }
@@ -1541,7 +1568,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
       CUDA_OK(cudaGraphInstantiate(&C->graph_exec, graph, 0));
       cudaGraphDestroy(graph);
       C->graph_logbuf = C->logbuf;
-      C->graph_um = (fused ? 256 * ((C->opt_fuse & 3) + 1) : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas;
+      C->graph_um = (fused ? 256 * ((C->opt_fuse & 3) + 1) : 0) + (use_pair_kernels() ? 2048 : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas;
     }
     const long per_step = C->last_launches;
     for (; done < nsub; done++) CUDA_OK(cudaGraphLaunch(C->graph_exec, C->st));
@@ -1762,6 +1789,7 @@ int fvs2d_gpu_set_option(const char *key, int value) {
   if (k == "ctas") { C->opt_ctas = value; return 0; }
   if (k == "overlap") { C->opt_overlap = value; return 0; }
   if (k == "graph") { C->opt_graph = value; return 0; }
+  if (k == "pair") { C->opt_pair = value; return 0; }
   if (k == "smem_pad") { C->opt_smem_pad = value; return 0; }
   if (k == "carveout") { C->opt_carveout = value; return 0; }
   if (k == "fuse") {

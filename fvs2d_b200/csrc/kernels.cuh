@@ -666,6 +666,185 @@ __global__ void __launch_bounds__(kBlock) k_flux_rk(const DevMesh m, const Phys 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Small meshes: TWO threads per cell.  A mesh of a few ten thousand cells fills only a fraction of the machine's
+// thread slots with one thread per cell, and a pass then lasts as long as the dependent chain of a single thread (C2:
+// ~10 us per pass, whatever launches it -- profiles/r2_small_meshes.md).  The two lanes of a pair split the chain:
+//   pass A  lane h takes the variable pair (rho,u) / (v,p) -- the pair-interleaved layout makes that one 16-byte load per
+//           stencil member -- and half of the limiter evaluations; phi = fmin of the two lanes' minima (exact);
+//   pass B  lane h takes the faces k = h, h + 2; lane 1's fluxes travel to lane 0 by shuffles and are added there in
+//           face order with the same fused multiply-adds as k_flux_rk, so the state is bitwise the one-thread kernel's;
+//           lane 0 applies the stage update.
+template <int FORM, bool LIM>
+__global__ void __launch_bounds__(kBlock) k_gradient2(const DevMesh m, const int limiter_type, const double *__restrict__ p,
+                                                      double *__restrict__ g, double *__restrict__ phi) {
+  const int t = blockIdx.x * kBlock + threadIdx.x, half = t & 1;
+  const bool live = (t >> 1) < m.n_own;
+  const int i = live ? t >> 1 : m.n_own - 1;  // (idle pairs redo the last cell and store nothing: the shuffles stay full-warp)
+  const int np = m.np, lane = i & 31, sl = i >> 5;
+  const int off = __ldg(&m.g_off[sl]);
+  const int w = (__ldg(&m.g_off[sl + 1]) - off) >> 5;
+  const double2 *p2 = reinterpret_cast<const double2 *>(p) + (size_t)half * np;
+  const double2 q0 = p2[i];
+  double ax0, ax1, ay0, ay1, mn0 = q0.x, mx0 = q0.x, mn1 = q0.y, mx1 = q0.y;
+  if (FORM == 0) {
+    const double c0x = m.c0x[i], c0y = m.c0y[i];
+    ax0 = c0x * q0.x; ay0 = c0y * q0.x; ax1 = c0x * q0.y; ay1 = c0y * q0.y;
+  } else {
+    ax0 = ax1 = ay0 = ay1 = 0.0;
+  }
+  for (int k = 0; k < w; k++) {
+    const int e = off + 32 * k + lane;
+    const int j = __ldg(&m.g_idx[e]);
+    const double cx = __ldg(&m.g_cx[e]), cy = __ldg(&m.g_cy[e]);
+    const double2 pj = p2[j];
+    const double d0 = FORM == 0 ? pj.x : pj.x - q0.x, d1 = FORM == 0 ? pj.y : pj.y - q0.y;
+    ax0 += cx * d0;
+    ay0 += cy * d0;
+    ax1 += cx * d1;
+    ay1 += cy * d1;
+    if (LIM) { mn0 = fmin(mn0, pj.x); mx0 = fmax(mx0, pj.x); mn1 = fmin(mn1, pj.y); mx1 = fmax(mx1, pj.y); }
+  }
+  if (live) {
+    double2 *g2 = reinterpret_cast<double2 *>(g);
+    g2[(size_t)half * np + i] = make_double2(ax0, ax1);
+    g2[(size_t)(2 + half) * np + i] = make_double2(ay0, ay1);
+  }
+  if (LIM) {
+    const double pi = 3.141592653589793238462643383279502884;
+    const double xc = m.xy[i].x, yc = m.xy[i].y;
+    const double h = 2.0 * sqrt(m.vol[i] / pi);
+    const double kh = (limiter_type == 1 ? 5.0 : 0.3) * h;
+    const double eps2 = kh * kh * kh;
+    const int foff = __ldg(&m.f_off[sl]);
+    const int fw = (__ldg(&m.f_off[sl + 1]) - foff) >> 5;
+    double ph = 1.0;
+    for (int k = 0; k < fw; k++) {
+      const int e = foff + 32 * k + lane;
+      if (__ldg(&m.f_nbr[e]) == kPadNbr) continue;
+      const int ed = __ldg(&m.f_edge[e]) >> 1;
+      const double2 ec = __ldg(&m.exy[ed]);
+      const double dx = ec.x - xc, dy = ec.y - yc;
+      {
+        const double pf = q0.x + dx * ax0 + dy * ay0;
+        const double diff = pf - q0.x;
+        double f = 1.0;
+        if (diff > 0.0) f = limiter_fn(limiter_type, mx0 - q0.x, diff, eps2);
+        else if (diff < 0.0) f = limiter_fn(limiter_type, mn0 - q0.x, diff, eps2);
+        ph = fmin(ph, f);
+      }
+      {
+        const double pf = q0.y + dx * ax1 + dy * ay1;
+        const double diff = pf - q0.y;
+        double f = 1.0;
+        if (diff > 0.0) f = limiter_fn(limiter_type, mx1 - q0.y, diff, eps2);
+        else if (diff < 0.0) f = limiter_fn(limiter_type, mn1 - q0.y, diff, eps2);
+        ph = fmin(ph, f);
+      }
+    }
+    ph = fmin(ph, __shfl_xor_sync(0xffffffffu, ph, 1));
+    if (live && half == 0) phi[i] = ph;
+  }
+}
+
+template <int UM, bool STEADY, int RC>
+__global__ void __launch_bounds__(kBlock) k_flux_rk2(const DevMesh m, const Phys P, const StageParams S,
+                                                     const double *__restrict__ p, const double *__restrict__ g,
+                                                     const double *__restrict__ phi, const double *__restrict__ bc,
+                                                     double *__restrict__ q, double *__restrict__ f, double *__restrict__ pout,
+                                                     double *__restrict__ dtl, double *__restrict__ resid_out,
+                                                     double *__restrict__ ws_out, double *__restrict__ partial) {
+  const int t = blockIdx.x * kBlock + threadIdx.x, half = t & 1;
+  const bool live = (t >> 1) < m.n_own;
+  const int i = live ? t >> 1 : m.n_own - 1;
+  const int np = m.np, lane = i & 31, sl = i >> 5;
+  const double2 *p2 = reinterpret_cast<const double2 *>(p), *g2 = reinterpret_cast<const double2 *>(g);
+  const int off = __ldg(&m.f_off[sl]);
+  const int w = (__ldg(&m.f_off[sl + 1]) - off) >> 5;
+  double q0[4], fo[4], dl = 0.0, ivol = 1.0;
+  if (half == 0) { stage_load<UM, STEADY>(S, i, np, q, f, dtl, q0, fo, dl); ivol = m.ivol[i]; }
+  double p0[4], g0x[4], g0y[4];
+  load4(p2, np, i, p0);
+  if (RC != RC_FIRST) { load4(g2, np, i, g0x); load4(g2 + 2 * (size_t)np, np, i, g0y); }
+  const double2 c0 = m.xy[i];
+  const double phi0 = (RC >= RC_K0_PHI) ? phi[i] : 1.0;
+  int nbv[2], fev[2];
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    const int k = 2 * r + half;
+    nbv[r] = k < w ? __ldg(&m.f_nbr[off + 32 * k + lane]) : kPadNbr;
+    fev[r] = k < w ? __ldg(&m.f_edge[off + 32 * k + lane]) : 0;
+  }
+  double acc[4] = {0.0, 0.0, 0.0, 0.0}, wsacc = 0.0;
+#pragma unroll
+  for (int r = 0; r < 2; r++) {  // round r: faces 2r (lane 0) and 2r + 1 (lane 1)
+    const int nb = nbv[r], fe = fev[r];
+    const bool valid = nb != kPadNbr;
+    double fl[4] = {0.0, 0.0, 0.0, 0.0}, ws = 0.0, ha = 0.0, sa = 0.0;
+    if (valid) {
+      const int ed = fe >> 1;
+      const bool self_c1 = (fe & 1) == 0;
+      const double2 fc = __ldg(&m.exy[ed]), fn = __ldg(&m.enxy[ed]);
+      const double af = __ldg(&m.ea[ed]);
+      double me[4] = {0.0, 0.0, 0.0, 0.0};
+      if (RC != RC_FIRST) {
+        const double dx = fc.x - c0.x, dy = fc.y - c0.y;
+#pragma unroll
+        for (int v = 0; v < 4; v++) me[v] = RC == RC_K0 ? recon_k0(p0[v], g0x[v], g0y[v], dx, dy) : dx * g0x[v] + dy * g0y[v];
+      }
+      double sL[4], sR[4];
+      if (nb >= 0) {
+        double pj[4], ot[4] = {0.0, 0.0, 0.0, 0.0};
+        load4(p2, np, nb, pj);
+        double phij = 1.0;
+        if (RC != RC_FIRST) {
+          double gjx[4], gjy[4];
+          load4(g2, np, nb, gjx);
+          load4(g2 + 2 * (size_t)np, np, nb, gjy);
+          const double2 cj = m.xy[nb];
+          const double dx = fc.x - cj.x, dy = fc.y - cj.y;
+#pragma unroll
+          for (int v = 0; v < 4; v++) ot[v] = RC == RC_K0 ? recon_k0(pj[v], gjx[v], gjy[v], dx, dy) : dx * gjx[v] + dy * gjy[v];
+          if (RC >= RC_K0_PHI) phij = phi[nb];
+        }
+        interior_states<RC>(P, self_c1, p0, me, phi0, pj, ot, phij, sL, sR);
+        sa = self_c1 ? 0.5 * af : -(0.5 * af);
+      } else {
+        const int b = -1 - nb;
+        const int type = __ldg(&m.bf_type[b]);
+        double bcv[4];
+#pragma unroll
+        for (int v = 0; v < 4; v++) bcv[v] = bc[v * m.nbf + b];
+        boundary_states<RC>(type, p0, me, phi0, bcv, fn.x, fn.y, sL, sR);
+        sa = 0.5 * af;
+      }
+      roe_flux2(P, sL, sR, fn.x, fn.y, fl, ws);
+      ha = 0.5 * af;
+    }
+    // lane 1's face joins lane 0's sum: face 2r first, then face 2r + 1 (a skipped face adds nothing, as in k_flux_rk)
+    double ofl[4];
+#pragma unroll
+    for (int v = 0; v < 4; v++) ofl[v] = __shfl_xor_sync(0xffffffffu, fl[v], 1);
+    const double ows = __shfl_xor_sync(0xffffffffu, ws, 1), oha = __shfl_xor_sync(0xffffffffu, ha, 1), osa = __shfl_xor_sync(0xffffffffu, sa, 1);
+    const bool ovalid = __shfl_xor_sync(0xffffffffu, valid ? 1 : 0, 1) != 0;
+    if (half == 0) {
+      if (valid) {
+#pragma unroll
+        for (int v = 0; v < 4; v++) acc[v] += fl[v] * sa;
+        wsacc += ws * ha;
+      }
+      if (ovalid) {
+#pragma unroll
+        for (int v = 0; v < 4; v++) acc[v] += ofl[v] * osa;
+        wsacc += ows * oha;
+      }
+    }
+  }
+  double dq2[4] = {0.0, 0.0, 0.0, 0.0};
+  if (live && half == 0) stage_update_pre<UM, STEADY>(P, S, i, np, ivol, m.vol, q0, fo, dl, acc, wsacc, q, f, pout, dtl, resid_out, ws_out, dq2);
+  if (UM != UM_RESID && S.last) block_sum_store<4>(dq2, partial);
+}
+
+// ------------------------------------------------------------------------------------------------
 // PTX helpers of the shared-memory pipeline: mbarrier, TMA bulk copy (cp.async.bulk), cp.async
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
