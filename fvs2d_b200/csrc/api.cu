@@ -377,7 +377,9 @@ int upload_local_state(const double *cv_loc) {
 // two threads per cell: meshes that would leave most of the machine's thread slots empty (one GPU, whole-mesh launches)
 bool use_pair_kernels() {
   if (C->nranks != 1 || C->opt_pair == 0) return false;
-  return C->opt_pair > 0 || C->L.n_own <= C->nsm * 1024;   // B200: 151 552 cells
+  // measured (profiles/r2_small_meshes.md): 7 k cells 47.1 -> 38.9 us per step, 65 k cells 86.0 -> 76.4 us: automatic while one
+  // thread per cell cannot fill the machine's thread slots (512 threads per SM at 128 registers)
+  return C->opt_pair > 0 || C->L.n_own <= C->nsm * 512;   // B200: 75 776 cells
 }
 
 int launch_gradient(const double *p, const int *list = nullptr, int nlist = 0, bool force = false) {

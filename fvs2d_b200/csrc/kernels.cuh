@@ -313,10 +313,10 @@ __device__ __forceinline__ void gradient_cell(const DevMesh &m, const int limite
       for (int v = 0; v < 4; v++) {
         const double pf = p0[v] + dx * ax[v] + dy * ay[v];
         const double diff = pf - p0[v];
-        double f = 1.0;
-        if (diff > 0.0) f = limiter_fn(limiter_type, pmax[v] - p0[v], diff, eps2);
-        else if (diff < 0.0) f = limiter_fn(limiter_type, pmin[v] - p0[v], diff, eps2);
-        ph = fmin(ph, f);
+        // one evaluation with the selected extremum instead of two divergent calls (the same function of the same
+        // arguments: bitwise the reference's value); diff == 0 -> 1 (src/gradient_limiter.f90:80-86)
+        const double f = limiter_fn(limiter_type, (diff > 0.0 ? pmax[v] : pmin[v]) - p0[v], diff, eps2);
+        ph = fmin(ph, diff != 0.0 ? f : 1.0);
       }
     }
     phi[i] = ph;
@@ -727,18 +727,14 @@ __global__ void __launch_bounds__(kBlock) k_gradient2(const DevMesh m, const int
       {
         const double pf = q0.x + dx * ax0 + dy * ay0;
         const double diff = pf - q0.x;
-        double f = 1.0;
-        if (diff > 0.0) f = limiter_fn(limiter_type, mx0 - q0.x, diff, eps2);
-        else if (diff < 0.0) f = limiter_fn(limiter_type, mn0 - q0.x, diff, eps2);
-        ph = fmin(ph, f);
+        const double f = limiter_fn(limiter_type, (diff > 0.0 ? mx0 : mn0) - q0.x, diff, eps2);
+        ph = fmin(ph, diff != 0.0 ? f : 1.0);
       }
       {
         const double pf = q0.y + dx * ax1 + dy * ay1;
         const double diff = pf - q0.y;
-        double f = 1.0;
-        if (diff > 0.0) f = limiter_fn(limiter_type, mx1 - q0.y, diff, eps2);
-        else if (diff < 0.0) f = limiter_fn(limiter_type, mn1 - q0.y, diff, eps2);
-        ph = fmin(ph, f);
+        const double f = limiter_fn(limiter_type, (diff > 0.0 ? mx1 : mn1) - q0.y, diff, eps2);
+        ph = fmin(ph, diff != 0.0 ? f : 1.0);
       }
     }
     ph = fmin(ph, __shfl_xor_sync(0xffffffffu, ph, 1));

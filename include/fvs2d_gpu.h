@@ -187,8 +187,9 @@ int fvs2d_gpu_last_timing(double ms[4], long *launches);
  *              its time step contains no NCCL call); 0: every step eager
  *   "pair"     two threads per cell in both passes (k_gradient2 / k_flux_rk2: the variable pairs in pass A, the faces in pass B, fluxes
  *              joined by shuffles in face order -- the state is bitwise the one-thread kernels'): -1 (default) automatic = on one
- *              GPU for meshes of up to 1024 cells per SM (151 552 on a B200: the reference's shipped examples), where one thread
- *              per cell leaves most thread slots empty and a pass lasts as long as one thread's dependent chain; 0 never; 1 always
+ *              GPU for meshes of up to 512 cells per SM (75 776 on a B200: the reference's shipped examples), where one thread
+ *              per cell cannot fill the machine's thread slots and a pass lasts as long as one thread's dependent chain (measured
+ *              47.1 -> 38.9 us per step at 7 k cells, 86.0 -> 76.4 us at 65 k cells); 0 never; 1 always
  *   "overlap"  1 (default): multi-GPU halo exchange on a second stream, overlapped with interior-tile work
  *   "ctas"     resident CTAs per SM of k_flux_pipe (0 = occupancy API), "smem_pad" / "carveout": extra dynamic shared
  *              memory per CTA / preferred shared-memory carve-out of k_flux_pipe, both in KB (the L1 experiments of

@@ -178,3 +178,48 @@ def test_device_hilbert_sort_equals_host_sort(monkeypatch):
     host = capi.mesh_array("perm").copy()
     gpu.close()
     assert np.array_equal(np.sort(dev), np.arange(mesh.ncells)) and np.array_equal(dev, host)
+
+
+@pytest.mark.parametrize("case", ["c1-vortex-lsqfn", "c2-naca-venkat-steady", "naca-ggcb-rk4", "mixed-ggnb-umuscl", "tri-first-order", "mixed-lsqnn-barth"])
+def test_two_threads_per_cell_kernels_match_one_thread_kernels(case, vortex_mesh, naca_mesh):
+    """Small meshes run both passes with two threads per cell (option "pair", automatic up to 1024 cells per SM): the state,
+    gradients and limiter must be bitwise those of the one-thread-per-cell kernels; log_res / vortex errors agree to 1e-13
+    (the norm partials are grouped per 64 cells instead of per persistent CTA)."""
+    from fvs2d_b200 import config, meshgen, solver
+    from conftest import run_input
+    if case == "c1-vortex-lsqfn":
+        mesh, run = vortex_mesh, run_input("vortex")
+    elif case == "c2-naca-venkat-steady":
+        mesh, run = naca_mesh, run_input("naca")
+        run.grad_limiter_imethd = 1
+    elif case == "naca-ggcb-rk4":
+        mesh, run = naca_mesh, config.RunInput(grad_cellcntr_imethd=1, dt=1e-4, mach_inf=0.5)
+    elif case == "mixed-ggnb-umuscl":
+        mesh, run = meshgen.vortex_mixed_mesh(47), config.RunInput(grad_cellcntr_imethd=2, face_reconst_imethd=3, umuscl_cst=1.0 / 3.0, lvortex=True, dt=0.005)
+    elif case == "mixed-lsqnn-barth":
+        mesh, run = meshgen.vortex_mixed_mesh(40), config.RunInput(grad_cellcntr_imethd=3, grad_cellcntr_lsq_nghbr="nn", grad_limiter_imethd=2, lvortex=True, dt=0.005)
+    else:
+        mesh, run = meshgen.vortex_tri_mesh(40), config.RunInput(grad_cellcntr_imethd=1, face_reconst_imethd=1, lvortex=True, dt=0.005)
+    cfg = run.to_config()
+    gpu = solver.Fvs2dGpu(cfg, device=0)
+    gpu.set_mesh(mesh)
+    out = {}
+    for pair in (0, 1):
+        gpu.set_option("pair", pair)
+        gpu.set_option("fuse", 0)
+        gpu.initialize_solution()
+        r1, v1, x1 = gpu.time_integration(0.0, 7)
+        r2, v2, x2 = gpu.time_integration(7 * run.dt, 5)          # a second call: graph replay with the same kernels
+        resid = gpu.compute_residual(12 * run.dt)
+        aux = gpu.get_aux()
+        out[pair] = (gpu.get_state().copy(), np.concatenate([r1, r2]), None if v1 is None else np.concatenate([v1, v2]),
+                     None if x1 is None else np.concatenate([x1, x2]), resid, aux)
+    gpu.close()
+    q0, r0, v0, x0, res0, aux0 = out[0]
+    q1, r1, v1, x1, res1, aux1 = out[1]
+    assert np.array_equal(q0, q1) and np.array_equal(res0, res1, equal_nan=True)
+    for a, b in zip(aux0, aux1):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert np.allclose(r1, r0, rtol=1e-13, atol=0.0)
+    if v0 is not None:
+        assert np.allclose(v1, v0, rtol=1e-12, atol=0.0) and np.array_equal(x0, x1)
