@@ -107,6 +107,8 @@ struct Ctx {
   int opt_ctas = 0;      // persistent pass-B CTAs per SM: 0 = as many as shared memory allows (max 3)
   int opt_pair = -1;     // small meshes on one GPU: two threads per cell in both passes (k_gradient2 / k_flux_rk2); -1 automatic
                          // (meshes that leave most thread slots of the machine empty with one thread per cell), 0 never, 1 always
+  int opt_pdl = 1;       // programmatic dependent launch between the kernels of a time step (one GPU)
+  bool pdl_on = false;   // set while fvs2d_gpu_time_integration issues / captures its step sequence
   int opt_overlap = 1;   // multi-GPU: overlap the halo exchanges with interior-tile work (second stream)
   int opt_smem_pad = 0;  // experiment: extra dynamic shared memory (KB) per pass-B CTA (shrinks the L1 carve-out)
   int opt_carveout = -1; // experiment: preferred shared-memory carve-out of the pass-B kernel in KB (-1: driver default)
@@ -139,6 +141,8 @@ struct Ctx {
   bool bc_static_done = false;
   double rk_coef[4], h_rk[4], dts[4], dte[4];
   // output path, uploaded on first use: node -> cell lists with inverse-distance weights, boundary-edge tables
+  std::vector<int> out_nodes;            // original ids of the nodes this rank interpolates to (the nodes of its owned cells)
+  std::vector<int> be_ptr, be_pos;       // owned boundary edges per boundary; their positions in the caller's edge lists
   const int *d_n2c_ptr = nullptr, *d_n2c = nullptr;
   const double *d_idw = nullptr;
   double *d_fnode = nullptr;
@@ -224,6 +228,20 @@ void free_device() {
   C->d_be_cell = nullptr; C->d_be_xy = C->d_be_nxy = nullptr; C->d_be_out = nullptr;
   C->fz_state = 0; C->n_fl = 0; C->fz_tables = 0;
   C->flags = nullptr; C->done_ctr = nullptr; C->p2p_timed_out = nullptr; C->d_rs_word = nullptr; C->d_rs_ent = nullptr;
+}
+
+// launch of a kernel of the time-step chain: with programmatic stream serialisation while a step sequence is being issued
+// (C->pdl_on: one GPU, no per-launch timing), so that the kernel may be scheduled while its predecessor drains
+// (pdl_entry() in the kernels); a plain launch otherwise
+template <class... KArgs, class... Args>
+void launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = C->st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = C->pdl_on ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 // ---- event-based kernel timing (option "timing") ------------------------------------------------
@@ -391,21 +409,21 @@ int launch_gradient(const double *p, const int *list = nullptr, int nlist = 0, b
   if (!list && use_pair_kernels()) {
     const int nb2 = cdiv(2 * C->L.n_own, kBlock);
     if (C->L.g_form == 0) {
-      if (lim) k_gradient2<0, true><<<nb2, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi);
-      else k_gradient2<0, false><<<nb2, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi);
+      if (lim) launch_chain(k_gradient2<0, true>, dim3(nb2), dim3(kBlock), 0, C->dm, C->cfg.limiter, p, C->g, C->phi);
+      else launch_chain(k_gradient2<0, false>, dim3(nb2), dim3(kBlock), 0, C->dm, C->cfg.limiter, p, C->g, C->phi);
     } else {
-      if (lim) k_gradient2<1, true><<<nb2, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi);
-      else k_gradient2<1, false><<<nb2, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi);
+      if (lim) launch_chain(k_gradient2<1, true>, dim3(nb2), dim3(kBlock), 0, C->dm, C->cfg.limiter, p, C->g, C->phi);
+      else launch_chain(k_gradient2<1, false>, dim3(nb2), dim3(kBlock), 0, C->dm, C->cfg.limiter, p, C->g, C->phi);
     }
     C->last_launches++;
     return 0;
   }
   if (C->L.g_form == 0) {
-    if (lim) k_gradient<0, true><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi, list);
-    else k_gradient<0, false><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi, list);
+    if (lim) launch_chain(k_gradient<0, true>, dim3(nb), dim3(kBlock), 0, C->dm, C->cfg.limiter, p, C->g, C->phi, list);
+    else launch_chain(k_gradient<0, false>, dim3(nb), dim3(kBlock), 0, C->dm, C->cfg.limiter, p, C->g, C->phi, list);
   } else {
-    if (lim) k_gradient<1, true><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi, list);
-    else k_gradient<1, false><<<nb, kBlock, 0, C->st>>>(C->dm, C->cfg.limiter, p, C->g, C->phi, list);
+    if (lim) launch_chain(k_gradient<1, true>, dim3(nb), dim3(kBlock), 0, C->dm, C->cfg.limiter, p, C->g, C->phi, list);
+    else launch_chain(k_gradient<1, false>, dim3(nb), dim3(kBlock), 0, C->dm, C->cfg.limiter, p, C->g, C->phi, list);
   }
   C->last_launches++;
   return 0;
@@ -419,7 +437,7 @@ void launch_flux_one(const StageParams &S, const double *pin, double *pout) {
   const int nb = C->nblocks;
   if (!g_sel.list && use_pair_kernels()) {
     const int nb2 = cdiv(2 * C->L.n_own, kBlock);
-    k_flux_rk2<UM, STEADY, RC><<<nb2, kBlock, 0, C->st>>>(C->dm, C->phys, S, pin, C->g, C->phi, C->bc, C->q, C->f, pout, C->dtl, C->resid,
+    launch_chain(k_flux_rk2<UM, STEADY, RC>, dim3(nb2), dim3(kBlock), 0, C->dm, C->phys, S, pin, C->g, C->phi, C->bc, C->q, C->f, pout, C->dtl, C->resid,
                                                           C->ws, C->partial);
     C->nparts = nb2;
     return;
@@ -438,11 +456,11 @@ void launch_flux_one(const StageParams &S, const double *pin, double *pout) {
     if (g_sel.list) { pm.tile_list = g_sel.list; pm.ntiles = g_sel.n; }
     const int grid = std::min(pm.ntiles, C->nsm * per_sm);
     if (grid > 0)
-      k_flux_pipe<UM, STEADY, RC><<<grid, kPipeThreads, smem, C->st>>>(C->dm, pm, C->phys, S, pin, C->g, C->phi, C->bc, C->q, C->f, pout,
+      launch_chain(k_flux_pipe<UM, STEADY, RC>, dim3(grid), dim3(kPipeThreads), smem, C->dm, pm, C->phys, S, pin, C->g, C->phi, C->bc, C->q, C->f, pout,
                                                                        C->dtl, C->resid, C->ws, C->partial + 4 * (size_t)g_sel.part_off);
     C->nparts = g_sel.part_off + grid;
   } else {
-    k_flux_rk<UM, STEADY, RC><<<nb, kBlock, 0, C->st>>>(C->dm, C->phys, S, pin, C->g, C->phi, C->bc, C->q, C->f, pout, C->dtl, C->resid,
+    launch_chain(k_flux_rk<UM, STEADY, RC>, dim3(nb), dim3(kBlock), 0, C->dm, C->phys, S, pin, C->g, C->phi, C->bc, C->q, C->f, pout, C->dtl, C->resid,
                                                         C->ws, C->partial);
     C->nparts = nb;
   }
@@ -658,7 +676,7 @@ int launch_fused_part(FusedLaunch &fl, int k, int part_off, const StageParams &S
     hx.rs_word = C->d_rs_word; hx.rs_ent = C->d_rs_ent; hx.done_ctr = C->done_ctr; hx.timed_out = C->p2p_timed_out;
   }
   if (grid > 0)
-    (use3 ? k3 : k2)<<<grid, kPipeThreads, smem, C->st>>>(C->dm, fl.meta, C->phys, S, pin, C->bc, C->q, C->f, pout, C->dtl,
+    launch_chain(use3 ? k3 : k2, dim3(grid), dim3(kPipeThreads), smem, C->dm, fl.meta, C->phys, S, pin, C->bc, C->q, C->f, pout, C->dtl,
                                                           C->partial + 4 * (size_t)part_off, hx);
   C->last_launches++;
   return grid;
@@ -690,7 +708,7 @@ int launch_bc(int stage) {
   const bool time_dep = C->cfg.lvortex != 0;
   if (!time_dep && C->bc_static_done) return 0;
   Span sp(0);
-  k_bc_state<<<cdiv(C->L.nbf, 128), 128, 0, C->st>>>(C->dm, C->phys, C->clk, stage, C->bc);
+  launch_chain(k_bc_state, dim3(cdiv(C->L.nbf, 128)), dim3(128), 0, C->dm, C->phys, C->clk, stage, C->bc);
   C->last_launches++;
   C->bc_static_done = true;
   return 0;
@@ -1371,64 +1389,129 @@ int fvs2d_gpu_get_aux(double *pvar, double *grad, double *phi_lim) {
   return 0;
 }
 
+// m-cell (id in C->mesh: the whole mesh or this rank's submesh) -> local id of the cells this rank stores, -1 otherwise
+static std::vector<int> mcell_to_local() {
+  const HostMesh &m = C->mesh;
+  const std::vector<int> &orig = C->sub.orig;
+  std::vector<int> m2l(m.ncells, -1);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < C->L.n_loc; i++) {
+    const int o = C->L.orig_id[i];
+    m2l[orig.empty() ? o : (int)(std::lower_bound(orig.begin(), orig.end(), o) - orig.begin())] = i;
+  }
+  return m2l;
+}
+
 int fvs2d_gpu_interpolate_cell2node(const int select[4], double *fnode) {
   NEED(C && C->has_state, "fvs2d_gpu_interpolate_cell2node: no state");
   NEED(select && fnode, "fvs2d_gpu_interpolate_cell2node: null argument");
-  NEED(C->nranks == 1, "fvs2d_gpu_interpolate_cell2node: single GPU only (a node's cells may live on several ranks)");
   const HostMesh &m = C->mesh;
   int mask = 0, nsel = 0;
   for (int v = 0; v < 4; v++) if (select[v]) { mask |= 1 << v; nsel++; }
   if (nsel == 0) return 0;
-  if (!C->d_n2c_ptr) {  // first use: node -> cell lists in local ids and the weights of cell2node_idw_setup
-    std::vector<int> iperm(m.ncells), n2c(m.n2c.size());
-    std::vector<double> idw(m.n2c.size());
+  if (!C->d_n2c_ptr) {
+    // first use: the nodes of this rank's OWNED cells, their node -> cell lists restricted to owned cells (local ids,
+    // ascending original id) and the weights of cell2node_idw_setup (src/interpolation.f90:62-101).  The weight of a cell
+    // is normalised by ALL cells around the node (their geometry is in the rank's submesh even where their state is not),
+    // so on several ranks a node's value is the SUM of the ranks' shares.
+    const std::vector<int> m2l = mcell_to_local();
+    const int n_own = C->L.n_own;
+    std::vector<unsigned char> used(m.nnodes, 0);
+    for (int mc = 0; mc < m.ncells; mc++)
+      if (m2l[mc] >= 0 && m2l[mc] < n_own)
+        for (int sl = m.cptr[mc]; sl < m.cptr[mc + 1]; sl++) used[m.cnode[sl]] = 1;
+    std::vector<int> &nodes = C->out_nodes;
+    nodes.clear();
+    for (int in = 0; in < m.nnodes; in++) if (used[in]) nodes.push_back(in);
+    const int nl = (int)nodes.size();
+    std::vector<int> ptr(nl + 1, 0);
+    for (int k = 0; k < nl; k++) {
+      int cnt = 0;
+      for (int j = m.n2c_ptr[nodes[k]]; j < m.n2c_ptr[nodes[k] + 1]; j++) cnt += m2l[m.n2c[j]] >= 0 && m2l[m.n2c[j]] < n_own;
+      ptr[k + 1] = ptr[k] + cnt;
+    }
+    std::vector<int> n2c(ptr[nl]);
+    std::vector<double> idw(ptr[nl]);
 #pragma omp parallel for schedule(static)
-    for (int i = 0; i < m.ncells; i++) iperm[C->L.perm[i]] = i;
-#pragma omp parallel for schedule(static)
-    for (int in = 0; in < m.nnodes; in++) {  // src/interpolation.f90:62-101
+    for (int k = 0; k < nl; k++) {
+      const int in = nodes[k];
       double idt = 0.0;
       for (int j = m.n2c_ptr[in]; j < m.n2c_ptr[in + 1]; j++) {
         const int ic = m.n2c[j];
         const double dx = m.xc[ic] - m.xn[in], dy = m.yc[ic] - m.yn[in];
-        idw[j] = std::sqrt(dx * dx + dy * dy);
-        idt = idt + 1.0 / idw[j];
-        n2c[j] = iperm[ic];
+        idt = idt + 1.0 / std::sqrt(dx * dx + dy * dy);
       }
-      for (int j = m.n2c_ptr[in]; j < m.n2c_ptr[in + 1]; j++) idw[j] = 1.0 / idw[j] / idt;
+      int e = ptr[k];
+      for (int j = m.n2c_ptr[in]; j < m.n2c_ptr[in + 1]; j++) {
+        const int ic = m.n2c[j], l = m2l[ic];
+        if (l < 0 || l >= n_own) continue;
+        const double dx = m.xc[ic] - m.xn[in], dy = m.yc[ic] - m.yn[in];
+        n2c[e] = l;
+        idw[e] = 1.0 / std::sqrt(dx * dx + dy * dy) / idt;
+        e++;
+      }
     }
-    if (dev_upload(C->d_n2c, n2c) || dev_upload(C->d_idw, idw) || dev_alloc(C->d_fnode, 4 * (size_t)m.nnodes)) return 1;
-    if (dev_upload(C->d_n2c_ptr, m.n2c_ptr)) return 1;
+    if (!C->sub.node_orig.empty()) for (int &v : nodes) v = C->sub.node_orig[v];  // original node ids of the caller's array
+    if (dev_upload(C->d_n2c, n2c) || dev_upload(C->d_idw, idw) || dev_alloc(C->d_fnode, 4 * (size_t)std::max(1, nl))) return 1;
+    if (dev_upload(C->d_n2c_ptr, ptr)) return 1;
   }
+  const int nl = (int)C->out_nodes.size();
+  const size_t nn = (size_t)C->gi.nnodes;
   // C->pa is the primitive state of the current cvar (cvar2pvar of write_inst_ios, src/io.f90:135)
-  k_cell2node<<<cdiv(m.nnodes, 256), 256, 0, C->st>>>(m.nnodes, C->np, mask, C->d_n2c_ptr, C->d_n2c, C->d_idw, C->pa, C->d_fnode);
+  if (nl) k_cell2node<<<cdiv(nl, 256), 256, 0, C->st>>>(nl, C->np, mask, C->d_n2c_ptr, C->d_n2c, C->d_idw, C->pa, C->d_fnode);
   CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaMemcpyAsync(fnode, C->d_fnode, (size_t)nsel * m.nnodes * 8, cudaMemcpyDeviceToHost, C->st));
+  if (C->nranks == 1 && (size_t)nl == nn) {  // every node belongs to some cell: the records are the caller's, in place
+    CUDA_OK(cudaMemcpyAsync(fnode, C->d_fnode, (size_t)nsel * nn * 8, cudaMemcpyDeviceToHost, C->st));
+    CUDA_OK(cudaStreamSynchronize(C->st));
+    return 0;
+  }
+  std::vector<double> tmp((size_t)nsel * std::max(1, nl));
+  CUDA_OK(cudaMemcpyAsync(tmp.data(), C->d_fnode, tmp.size() * 8, cudaMemcpyDeviceToHost, C->st));
   CUDA_OK(cudaStreamSynchronize(C->st));
+  std::fill(fnode, fnode + (size_t)nsel * nn, 0.0);
+  for (int k = 0; k < nsel; k++)
+    for (int i = 0; i < nl; i++) fnode[(size_t)k * nn + C->out_nodes[i]] = tmp[(size_t)k * nl + i];
   return 0;
 }
 
 int fvs2d_gpu_wall_values(int ib, double *vals) {
   NEED(C && C->has_state, "fvs2d_gpu_wall_values: no state");
   NEED(vals != nullptr, "fvs2d_gpu_wall_values: null argument");
-  NEED(C->nranks == 1, "fvs2d_gpu_wall_values: single GPU only");
   const HostMesh &m = C->mesh;
   NEED(ib >= 0 && ib < m.nb, "fvs2d_gpu_wall_values: boundary index out of range");
-  const int nbe = (int)m.b_edge.size();
-  if (!C->d_be_cell) {  // first use: every boundary edge in bndry(:)%edge order -> its cell (edge%c1) and geometry
-    std::vector<int> iperm(m.ncells), cell(nbe);
-    std::vector<double2> exy(nbe), enxy(nbe);
-    for (int i = 0; i < m.ncells; i++) iperm[C->L.perm[i]] = i;
-    for (int i = 0; i < nbe; i++) {
-      const int je = m.b_edge[i];
-      const EdgeGeom eg = edge_geom(m, je);
-      cell[i] = iperm[m.ec1[je]];
-      exy[i] = make_double2(eg.x, eg.y);
-      enxy[i] = make_double2(eg.nx, eg.ny);
+  if (!C->d_be_cell) {
+    // first use: the boundary edges whose cell this rank OWNS, per boundary in bndry(ib)%edge order: cell (edge%c1, local
+    // id), geometry, and the position of the edge in the caller's list
+    const std::vector<int> m2l = mcell_to_local();
+    const bool part = !C->sub.orig.empty();
+    std::vector<int> cell, &pos = C->be_pos, &ptr = C->be_ptr;
+    std::vector<double2> exy, enxy;
+    pos.clear();
+    ptr.assign(m.nb + 1, 0);
+    for (int b = 0; b < m.nb; b++) {
+      for (int k = m.b_edge_ptr[b]; k < m.b_edge_ptr[b + 1]; k++) {
+        const int je = m.b_edge[k], l = m2l[m.ec1[je]];
+        if (l < 0 || l >= C->L.n_own) continue;
+        if (part) {  // the caller's list position of the CELL: valid when every listed cell has one boundary edge, as
+                     // the reference's own boundary loop assumes (src/residual.f90:112-125 indexes cell(i) and edge(i) alike)
+          const int src = m.b_edge_src[k];
+          NEED((k == m.b_edge_ptr[b] || m.b_edge_src[k - 1] != src) && (k + 1 == m.b_edge_ptr[b + 1] || m.b_edge_src[k + 1] != src),
+               "fvs2d_gpu_wall_values on several ranks needs one boundary edge per listed boundary cell");
+          pos.push_back(C->sub.b_pos[src]);
+        } else {
+          pos.push_back(k - m.b_edge_ptr[b]);
+        }
+        const EdgeGeom eg = edge_geom(m, je);
+        cell.push_back(l);
+        exy.push_back(make_double2(eg.x, eg.y));
+        enxy.push_back(make_double2(eg.nx, eg.ny));
+      }
+      ptr[b + 1] = (int)cell.size();
     }
     if (dev_upload(C->d_be_cell, cell) || dev_upload(C->d_be_xy, exy) || dev_upload(C->d_be_nxy, enxy) ||
-        dev_alloc(C->d_be_out, 4 * (size_t)std::max(1, nbe))) return 1;
+        dev_alloc(C->d_be_out, 4 * std::max<size_t>(1, cell.size()))) return 1;
   }
-  const int e0 = m.b_edge_ptr[ib], n = m.b_edge_ptr[ib + 1] - e0;
+  const int e0 = C->be_ptr[ib], n = C->be_ptr[ib + 1] - e0;
   if (n == 0) return 0;
   // gradient_cellcntr_1var (src/gradient.f90:74-96): the unlimited gradient of the selected scheme, also for
   // first-order reconstruction, of the current primitive state
@@ -1436,8 +1519,16 @@ int fvs2d_gpu_wall_values(int ib, double *vals) {
   k_wall_values<<<cdiv(n, 128), 128, 0, C->st>>>(n, C->np, C->d_be_cell + e0, C->d_be_xy + e0, C->d_be_nxy + e0, C->dm.xy, C->pa, C->g,
                                                  C->d_be_out);
   CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaMemcpyAsync(vals, C->d_be_out, (size_t)n * 32, cudaMemcpyDeviceToHost, C->st));
+  if (C->nranks == 1) {  // every edge of the boundary, in order
+    CUDA_OK(cudaMemcpyAsync(vals, C->d_be_out, (size_t)n * 32, cudaMemcpyDeviceToHost, C->st));
+    CUDA_OK(cudaStreamSynchronize(C->st));
+    return 0;
+  }
+  std::vector<double> tmp(4 * (size_t)n);
+  CUDA_OK(cudaMemcpyAsync(tmp.data(), C->d_be_out, tmp.size() * 8, cudaMemcpyDeviceToHost, C->st));
   CUDA_OK(cudaStreamSynchronize(C->st));
+  for (int i = 0; i < n; i++)
+    for (int v = 0; v < 4; v++) vals[4 * (size_t)C->be_pos[e0 + i] + v] = tmp[4 * (size_t)i + v];
   return 0;
 }
 
@@ -1539,10 +1630,10 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
       int vgrid = 0;
       if (vort) {
         vgrid = std::min(C->nblocks, C->nsm * kVortexCtas);
-        k_vortex_err<<<vgrid, kBlock, 0, C->st>>>(C->dm, C->phys, C->clk, C->q, C->vpartial, C->vbest, C->vbest_loc);
+        launch_chain(k_vortex_err, dim3(vgrid), dim3(kBlock), 0, C->dm, C->phys, C->clk, C->q, C->vpartial, C->vbest, C->vbest_loc);
         C->last_launches++;
       }
-      k_finish_step<<<1, kFinishThreads, 0, C->st>>>(C->partial, C->nparts, C->vpartial, C->vbest, C->vbest_loc, C->dm.xy, vgrid, C->logbuf, (int)per,
+      launch_chain(k_finish_step, dim3(1), dim3(kFinishThreads), 0, C->partial, C->nparts, C->vpartial, C->vbest, C->vbest_loc, C->dm.xy, vgrid, C->logbuf, (int)per,
                                                       C->logid, C->clk);
       C->last_launches++;
     }
@@ -1552,10 +1643,12 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
   // configures the kernels), the remaining ones replay a CUDA graph captured from the same sequence.
   // (several ranks: only the fused path, whose halo exchange lives inside the stage kernel -- no NCCL call in the step)
   const bool use_graph = C->opt_graph && (C->nranks == 1 || fused) && !C->opt_timing && nsub >= 3;
+  struct PdlScope { ~PdlScope() { C->pdl_on = false; } } pdl_scope;   // off again on every way out of the call
+  C->pdl_on = C->opt_pdl && C->nranks == 1 && !C->opt_timing;
   int done = 0;
   if (nsub > 0) { if (run_step()) return 1; done = 1; }
   if (use_graph) {
-    if (C->graph_exec && (C->graph_logbuf != C->logbuf || C->graph_um != (fused ? 256 * ((C->opt_fuse & 3) + 1) : 0) + (use_pair_kernels() ? 2048 : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas)) {
+    if (C->graph_exec && (C->graph_logbuf != C->logbuf || C->graph_um != (fused ? 256 * ((C->opt_fuse & 3) + 1) : 0) + (use_pair_kernels() ? 2048 : 0) + (C->pdl_on ? 4096 : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas)) {
       cudaGraphExecDestroy(C->graph_exec);
       C->graph_exec = nullptr;
     }
@@ -1570,7 +1663,7 @@ int fvs2d_gpu_time_integration(double t1, int nsub, double *res_l2, double *vort
       CUDA_OK(cudaGraphInstantiate(&C->graph_exec, graph, 0));
       cudaGraphDestroy(graph);
       C->graph_logbuf = C->logbuf;
-      C->graph_um = (fused ? 256 * ((C->opt_fuse & 3) + 1) : 0) + (use_pair_kernels() ? 2048 : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas;
+      C->graph_um = (fused ? 256 * ((C->opt_fuse & 3) + 1) : 0) + (use_pair_kernels() ? 2048 : 0) + (C->pdl_on ? 4096 : 0) + um * 16 + C->opt_tile * 4 + C->opt_ctas;
     }
     const long per_step = C->last_launches;
     for (; done < nsub; done++) CUDA_OK(cudaGraphLaunch(C->graph_exec, C->st));
@@ -1792,6 +1885,7 @@ int fvs2d_gpu_set_option(const char *key, int value) {
   if (k == "overlap") { C->opt_overlap = value; return 0; }
   if (k == "graph") { C->opt_graph = value; return 0; }
   if (k == "pair") { C->opt_pair = value; return 0; }
+  if (k == "pdl") { C->opt_pdl = value; return 0; }
   if (k == "smem_pad") { C->opt_smem_pad = value; return 0; }
   if (k == "carveout") { C->opt_carveout = value; return 0; }
   if (k == "fuse") {

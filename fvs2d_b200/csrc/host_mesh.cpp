@@ -157,6 +157,7 @@ std::string build_mesh(HostMesh &m) {
   m.edge_bc.assign(ne, -1);
   m.b_edge_ptr.assign(m.nb + 1, 0);
   m.b_edge.clear();
+  m.b_edge_src.clear();
   for (int ib = 0; ib < m.nb; ib++) {
     for (int i = m.b_cell_ptr[ib]; i < m.b_cell_ptr[ib + 1]; i++) {
       const int ic = m.b_cell[i];
@@ -165,6 +166,7 @@ std::string build_mesh(HostMesh &m) {
         const int je = m.cedge[s];
         if (m.ec1[je] == ic && m.ec2[je] < 0) {
           m.b_edge.push_back(je);
+          m.b_edge_src.push_back(i);
           m.edge_bc[je] = ib;
         }
       }
@@ -703,7 +705,11 @@ std::string extract_submesh(int nnodes, int ntri, int nquad, const double *node_
     for (int i = 0; i < b_ncells[ib]; i++) {
       const int c = b_cell[off + i];
       if (c < 0 || c >= nc) return "build_mesh: boundary cell id out of range";
-      if (level[c]) { m.b_cell.push_back((int)(std::lower_bound(orig.begin(), orig.end(), c) - orig.begin())); m.b_ncells[ib]++; }
+      if (level[c]) {
+        m.b_cell.push_back((int)(std::lower_bound(orig.begin(), orig.end(), c) - orig.begin()));
+        out.b_pos.push_back(i);
+        m.b_ncells[ib]++;
+      }
     }
     off += b_ncells[ib];
     nbc_global += b_ncells[ib];

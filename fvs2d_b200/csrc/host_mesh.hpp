@@ -28,6 +28,7 @@ struct HostMesh {
   int ncells_intr = 0, ncells_bndr = 0;
   std::vector<int> cell_intr;
   std::vector<int> b_edge_ptr, b_edge;  // boundary edge lists in .bc order then local-edge order
+  std::vector<int> b_edge_src;          // per b_edge entry: the index into b_cell of the list entry it comes from
   std::vector<int> edge_bc;             // per edge: -1 interior, else boundary index ib
   double heff1 = 0, heff2 = 0, vol_sum = 0, vol_green = 0;
   // partial == true: the mesh is one rank's submesh (extract_submesh); cells of its outermost ring miss neighbours that
@@ -112,6 +113,7 @@ struct SubMesh {
   std::vector<int> new_id;      // submesh cell -> Hilbert id in the global order
   std::vector<unsigned char> ring;  // 0 owned, 1 / 2 ... node-adjacency ring around the owned cells
   std::vector<int> node_orig;   // submesh node -> original node id
+  std::vector<int> b_pos;       // per entry of m.b_cell: its position inside its boundary's cell list in the caller's .bc order
   int nc_global = 0, nn_global = 0, b0 = 0, b1 = 0;
   std::vector<int> cuts;        // Hilbert ids where the ranks' chunks begin (nranks + 1 entries)
   long long nbcells_global = 0;

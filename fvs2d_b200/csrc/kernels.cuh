@@ -89,6 +89,15 @@ struct StageParams {
   double dt;        // global dt
 };
 
+// Programmatic dependent launch (the kernels of a time step form one dependent chain; on small meshes the ~2.5 us between
+// two kernels of a graph are a third of the step): every kernel of the chain waits here for its predecessor's results
+// before its first global access, and at once lets its own successor be scheduled, so that the successor's launch latency
+// and prologue hide behind this kernel.  Without the launch attribute both instructions do nothing.
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // variable v of cell i in a pair-interleaved array (as doubles)
 __host__ __device__ __forceinline__ size_t pidx(int v, int np, int i) { return ((size_t)(v >> 1) * np + i) * 2 + (v & 1); }
 __device__ __forceinline__ void load4(const double2 *__restrict__ a2, int np, int i, double out[4]) {
@@ -327,6 +336,7 @@ template <int FORM, bool LIM>
 __global__ void __launch_bounds__(kBlock) k_gradient(const DevMesh m, const int limiter_type, const double *__restrict__ p,
                                                      double *__restrict__ g, double *__restrict__ phi,
                                                      const int *__restrict__ tile_list) {
+  pdl_entry();
   // one CTA = one 128-cell tile; tile_list (or null = all tiles in order) selects the interior / boundary subset
   const int i = (tile_list ? __ldg(&tile_list[blockIdx.x]) : (int)blockIdx.x) * kBlock + threadIdx.x;
   if (i >= m.n_own) return;
@@ -353,6 +363,7 @@ __device__ __forceinline__ void bc_state_one(const DevMesh &m, const Phys &P, co
 }
 __global__ void __launch_bounds__(128) k_bc_state(const DevMesh m, const Phys P, const StepClock *__restrict__ clk, const int stage,
                                                   double *__restrict__ bc /* [4][nbf] */) {
+  pdl_entry();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= m.nbf) return;
   bc_state_one(m, P, clock_told(clk) + clk->off[stage], b, bc);
@@ -659,6 +670,7 @@ __global__ void __launch_bounds__(kBlock) k_flux_rk(const DevMesh m, const Phys 
                                                     double *__restrict__ q, double *__restrict__ f, double *__restrict__ pout,
                                                     double *__restrict__ dtl, double *__restrict__ resid_out,
                                                     double *__restrict__ ws_out, double *__restrict__ partial) {
+  pdl_entry();
   const int i = blockIdx.x * kBlock + threadIdx.x;
   double dq2[4] = {0.0, 0.0, 0.0, 0.0};
   if (i < m.n_own) flux_rk_cell<UM, STEADY, RC>(m, P, S, p, g, phi, bc, q, f, pout, dtl, resid_out, ws_out, i, dq2);
@@ -677,6 +689,7 @@ __global__ void __launch_bounds__(kBlock) k_flux_rk(const DevMesh m, const Phys 
 template <int FORM, bool LIM>
 __global__ void __launch_bounds__(kBlock) k_gradient2(const DevMesh m, const int limiter_type, const double *__restrict__ p,
                                                       double *__restrict__ g, double *__restrict__ phi) {
+  pdl_entry();
   const int t = blockIdx.x * kBlock + threadIdx.x, half = t & 1;
   const bool live = (t >> 1) < m.n_own;
   const int i = live ? t >> 1 : m.n_own - 1;  // (idle pairs redo the last cell and store nothing: the shuffles stay full-warp)
@@ -749,6 +762,7 @@ __global__ void __launch_bounds__(kBlock) k_flux_rk2(const DevMesh m, const Phys
                                                      double *__restrict__ q, double *__restrict__ f, double *__restrict__ pout,
                                                      double *__restrict__ dtl, double *__restrict__ resid_out,
                                                      double *__restrict__ ws_out, double *__restrict__ partial) {
+  pdl_entry();
   const int t = blockIdx.x * kBlock + threadIdx.x, half = t & 1;
   const bool live = (t >> 1) < m.n_own;
   const int i = live ? t >> 1 : m.n_own - 1;
@@ -928,6 +942,7 @@ __global__ void __launch_bounds__(kPipeThreads, FVS2D_PIPE_CTAS) k_flux_pipe(con
                                                                double *__restrict__ pout, double *__restrict__ dtl,
                                                                double *__restrict__ resid_out, double *__restrict__ ws_out,
                                                                double *__restrict__ partial) {
+  pdl_entry();
   constexpr int NC2 = pipe_nc2<RC>();
   constexpr bool PHI = RC >= RC_K0_PHI;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1199,6 +1214,7 @@ constexpr int kVortexCtas = 6;  // resident CTAs per SM of k_vortex_err; its gri
 __global__ void __launch_bounds__(kBlock, kVortexCtas) k_vortex_err(const DevMesh m, const Phys P, const StepClock *__restrict__ clk,
                                                           const double *__restrict__ q, double *__restrict__ partial,
                                                           int *__restrict__ best_id, int *__restrict__ best_loc) {
+  pdl_entry();
   const double time = clock_told(clk) + clk->off_end;
   // grid-stride over the owned cells with a fixed grid (one resident wave): the partial count is small and the
   // summation order is a function of the launch configuration only (deterministic)
@@ -1282,6 +1298,7 @@ __global__ void __launch_bounds__(kFinishThreads) k_finish_step(const double *__
                                                                 const int *__restrict__ vbest_loc, const double2 *__restrict__ xy,
                                                                 const int nvparts, double *__restrict__ logbuf, const int stride,
                                                                 int *__restrict__ logid, StepClock *__restrict__ clk) {
+  pdl_entry();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int istep = clk->istep;
   double *row = logbuf + (size_t)stride * istep;

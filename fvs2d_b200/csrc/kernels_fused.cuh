@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(kPipeThreads, CTAS) k_stage_fused(const DevMes
                                                                      double *__restrict__ q, double *__restrict__ f,
                                                                      double *__restrict__ pout, double *__restrict__ dtl,
                                                                      double *__restrict__ partial, const HaloP2P hx) {
+  pdl_entry();
   constexpr int F0 = FORM == 0 ? 1 : 0;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int H1 = fm.H1, HP = fm.HP, EE = fm.E, CG = fm.CG, np = m.np;

@@ -49,6 +49,7 @@ class Fvs2dGpu:
         capi.check(self.L.fvs2d_gpu_set_mesh(mesh.nnodes, mesh.ntri, mesh.nquad, capi.ptr(xy), capi.ptr(cptr),
                                              capi.ptr(cnode), len(bn), capi.ptr(bn), capi.ptr(bt), capi.ptr(bc)))
         self.ncells = mesh.ncells
+        self._bndry_ncells = [len(c) for c in mesh.bndry_cell]
         return self
 
     def set_lsq(self, ptr, cell, w, coef):
@@ -139,8 +140,11 @@ class Fvs2dGpu:
 
     def wall_values(self, ib: int) -> np.ndarray:
         """-> [nedges(ib), 4] = x_f, p_w, p_cell, u_n per edge of boundary ``ib`` (src/io.f90:340-449)."""
-        bptr = capi.mesh_array("b_edge_ptr")
-        n = int(bptr[ib + 1] - bptr[ib]) if 0 <= ib < len(bptr) - 1 else 0   # out of range: the library reports it
+        if self.nranks == 1:
+            bptr = capi.mesh_array("b_edge_ptr")
+            n = int(bptr[ib + 1] - bptr[ib]) if 0 <= ib < len(bptr) - 1 else 0   # out of range: the library reports it
+        else:   # one edge per listed cell (see include/fvs2d_gpu.h); entries of edges other ranks own stay zero
+            n = self._bndry_ncells[ib] if 0 <= ib < len(self._bndry_ncells) else 0
         out = np.zeros((max(n, 1), 4))
         capi.check(self.L.fvs2d_gpu_wall_values(int(ib), capi.ptr(out)))
         return out[:n]

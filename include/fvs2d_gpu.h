@@ -127,14 +127,20 @@ int fvs2d_gpu_test_resid(int corrected, double l2[4], double linf[4]);
  * (src/interpolation.f90:62-123: linear inverse-distance weights, summed over node%cell in ascending cell id) for
  * every primitive variable v (0 rho, 1 u, 2 v, 3 p) with select[v] != 0 -- the lw_inst flags of fvs2d.input
  * line 17.  fnode holds nselected records of nnodes doubles in variable order, ready for writed
- * (src/ios_unstrc.f90:300-404).  Only the node records cross PCIe instead of cvar(4,ncells).  Single GPU only. */
+ * (src/ios_unstrc.f90:300-404).  Only the node records cross PCIe instead of cvar(4,ncells).
+ * Under a communicator every rank gets its SHARE of every node value -- the weighted sum over the cells it owns, with
+ * weights normalised by all cells around the node -- and zeros elsewhere: the node values are the sum of the ranks' arrays
+ * (MPI_Allreduce / MPI_Reduce with MPI_SUM on the host side), which differs from the one-rank result only by the summation
+ * order at nodes on partition interfaces. */
 int fvs2d_gpu_interpolate_cell2node(const int select[4], double *fnode /* nselected * nnodes */);
 
 /* Replaces: the numerical part of write_inst_cp_un (src/io.f90:340-449) for boundary ib (0-based, .bc order): the
  * unlimited gradient of the current primitive state (gradient_cellcntr_1var, src/gradient.f90:74-96) and, per edge i
  * of bndry(ib)%edge, vals[4*i..4*i+3] = x_f, p_w, p_cell, u_n (pressure and normal velocity extrapolated to the edge
  * centre from the edge's cell, the cell pressure).  cp, the |V_n| norms and cl/cd are sums of these in edge order, left
- * to the caller exactly as the reference forms them.  Single GPU only. */
+ * to the caller exactly as the reference forms them.  Under a communicator a rank fills the entries of the edges whose cell it
+ * owns and leaves the others untouched (zero the array first and sum over the ranks); this needs one boundary edge per
+ * listed boundary cell, which the reference's own boundary loop assumes as well (src/residual.f90:112-125). */
 int fvs2d_gpu_wall_values(int ib, double *vals /* 4 * nedges(ib) */);
 
 /* ---- queries ----------------------------------------------------------------------------- */
@@ -190,6 +196,9 @@ int fvs2d_gpu_last_timing(double ms[4], long *launches);
  *              GPU for meshes of up to 512 cells per SM (75 776 on a B200: the reference's shipped examples), where one thread
  *              per cell cannot fill the machine's thread slots and a pass lasts as long as one thread's dependent chain (measured
  *              47.1 -> 38.9 us per step at 7 k cells, 86.0 -> 76.4 us at 65 k cells); 0 never; 1 always
+ *   "pdl"      1 (default): on one GPU the kernels of a time step are launched with programmatic stream serialisation -- each one
+ *              waits for its predecessor's results at its first instruction (griddepcontrol.wait) and lets its successor be
+ *              scheduled at once, so launch latency hides behind the running kernel; 0: plain launches
  *   "overlap"  1 (default): multi-GPU halo exchange on a second stream, overlapped with interior-tile work
  *   "ctas"     resident CTAs per SM of k_flux_pipe (0 = occupancy API), "smem_pad" / "carveout": extra dynamic shared
  *              memory per CTA / preferred shared-memory carve-out of k_flux_pipe, both in KB (the L1 experiments of

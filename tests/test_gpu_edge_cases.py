@@ -223,3 +223,33 @@ def test_two_threads_per_cell_kernels_match_one_thread_kernels(case, vortex_mesh
     assert np.allclose(r1, r0, rtol=1e-13, atol=0.0)
     if v0 is not None:
         assert np.allclose(v1, v0, rtol=1e-12, atol=0.0) and np.array_equal(x0, x1)
+
+
+@pytest.mark.parametrize("case", ["c1-vortex-lsqfn", "c2-naca-venkat-steady", "mixed-ggcb-fused-264k"])
+def test_programmatic_dependent_launch_changes_nothing(case, vortex_mesh, naca_mesh):
+    """option "pdl" (default on, one GPU): the kernels of a step are launched with programmatic stream serialisation and
+    wait for their predecessor at their first instruction -- state and logs must be bitwise those of plain launches, on the
+    launch-bound examples and on a mesh whose stage kernels run several waves of tiles."""
+    from fvs2d_b200 import config, meshgen, solver
+    from conftest import run_input
+    if case == "c1-vortex-lsqfn":
+        mesh, run, n = vortex_mesh, run_input("vortex"), 40
+    elif case == "c2-naca-venkat-steady":
+        mesh, run, n = naca_mesh, run_input("naca"), 12
+        run.grad_limiter_imethd = 1
+    else:
+        mesh, run, n = meshgen.vortex_mixed_mesh(420), config.RunInput(grad_cellcntr_imethd=1, lvortex=True, dt=0.002), 12
+    cfg = run.to_config()
+    gpu = solver.Fvs2dGpu(cfg, device=0)
+    gpu.set_mesh(mesh)
+    out = {}
+    for pdl in (0, 1):
+        gpu.set_option("pdl", pdl)
+        gpu.initialize_solution()
+        r1, v1, _ = gpu.time_integration(0.0, n)
+        r2, v2, _ = gpu.time_integration(n * run.dt, n)
+        out[pdl] = (gpu.get_state().copy(), np.concatenate([r1, r2]), None if v1 is None else np.concatenate([v1, v2]))
+    gpu.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    if out[0][2] is not None:
+        assert np.array_equal(out[0][2], out[1][2])
