@@ -33,6 +33,8 @@ def main():
         ("mixed ggnb umuscl", meshgen.vortex_mixed_mesh(48),
          config.RunInput(grad_cellcntr_imethd=2, face_reconst_imethd=3, umuscl_cst=1.0 / 3.0, lvortex=True, dt=0.005), 6),
     ]
+    cases.append(("tri lsq-fn rk4 (whole-mesh pre-processing: boundary stencils need the global nearest-centroid search)",
+                  meshgen.vortex_tri_mesh(48), config.RunInput(grad_cellcntr_imethd=3, grad_cellcntr_lsq_nghbr="fn", lvortex=True, dt=0.005), 6))
     naca = meshio.load_npz(os.path.join(ROOT, "tests", "golden", "naca_mesh.npz"))
     cases.append(("naca ggcb ssprk steady (slip wall + freestream; wall values)", naca,
                   config.RunInput(grad_cellcntr_imethd=1, lsteady=True, cfl_user=1.25, rk_order=2, lSSPRK=True, mach_inf=0.8), 5))
