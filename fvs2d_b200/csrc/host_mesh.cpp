@@ -647,7 +647,10 @@ std::string extract_submesh(int nnodes, int ntri, int nquad, const double *node_
 #pragma omp parallel for schedule(static)
     for (int ic = 0; ic < nc; ic++)
       if (level[ic] == r + 1)
-        for (int s = cptr[ic]; s < cptr[ic + 1]; s++) nmark[cnode[s]] = 1;  // (concurrent writes store the same value)
+        for (int s = cptr[ic]; s < cptr[ic + 1]; s++) {
+#pragma omp atomic write
+          nmark[cnode[s]] = 1;
+        }
     if (r == rings) break;
 #pragma omp parallel for schedule(static)
     for (int ic = 0; ic < nc; ic++) {

@@ -55,7 +55,10 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const CellNumbering
       const int o = order[k];
       for (int s = m.cptr[o]; s < m.cptr[o + 1]; s++) {
         const int j = m.nghbre[s];
-        if (j >= 0 && !owned(j)) mark[j] = 3;
+        if (j >= 0 && !owned(j)) {
+#pragma omp atomic write
+          mark[j] = 3;
+        }
       }
     }
 #pragma omp parallel for schedule(static)
@@ -63,7 +66,14 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const CellNumbering
       const int o = order[k];
       for (int64_t t = g.ptr[o]; t < g.ptr[o + 1]; t++) {
         const int j = g.idx[t];
-        if (!owned(j) && !mark[j]) mark[j] = 1;
+        if (owned(j)) continue;
+        unsigned char seen;
+#pragma omp atomic read
+        seen = mark[j];
+        if (!seen) {
+#pragma omp atomic write
+          mark[j] = 1;
+        }
       }
     }
     if (deep) {  // the stencils of the face-neighbour ghosts must be local too
@@ -370,11 +380,19 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const CellNumbering
         const int o = order[q];
         for (int s = m.cptr[o]; s < m.cptr[o + 1]; s++) {
           const int j = m.nghbre[s];
-          if (j >= 0 && owned(j)) { mask[new_id[j] - b0] = 1; any = true; }
+          if (j >= 0 && owned(j)) {
+#pragma omp atomic write
+            mask[new_id[j] - b0] = 1;
+            any = true;
+          }
         }
         for (int64_t t = g.ptr[o]; t < g.ptr[o + 1]; t++) {
           const int j = g.idx[t];
-          if (owned(j)) { mask[new_id[j] - b0] = 1; any = true; }
+          if (owned(j)) {
+#pragma omp atomic write
+            mask[new_id[j] - b0] = 1;
+            any = true;
+          }
         }
         if (deep)  // p also stores the stencil members of its face-neighbour ghosts
           for (int s = m.cptr[o]; s < m.cptr[o + 1]; s++) {
@@ -382,7 +400,11 @@ std::string build_layout(const HostMesh &m, const GradOp &g, const CellNumbering
             if (j < 0 || of_p(j)) continue;
             for (int64_t t = g.ptr[j]; t < g.ptr[j + 1]; t++) {
               const int kk = g.idx[t];
-              if (owned(kk)) { mask[new_id[kk] - b0] = 1; any = true; }
+              if (owned(kk)) {
+#pragma omp atomic write
+            mask[new_id[kk] - b0] = 1;
+            any = true;
+          }
             }
           }
       }
