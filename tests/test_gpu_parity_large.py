@@ -134,3 +134,33 @@ def test_c5_mms_sweep_32_to_512_with_order_table(capsys):
     assert np.abs(order[:, 0] - order[:, 1]).max() <= 1e-8
     assert (np.abs(order[:, 0, 0, 0]) < 0.05).all()          # typo kept: the continuity row never converges
     assert (order[0, 0, 1] > 0.3).all() and (order[:, 0, 1] > 0.0).all()   # corrected: converging, stalling with refinement
+
+
+def test_c1_shipped_example_4000_steps(vortex_mesh):
+    """the isentropic-vortex example exactly as shipped (LSQ-fn, RK4, dt = 0.01), the whole run of 4 000 steps in
+    the save-interval pattern of its fvs2d.input (50 calls of 80 steps): fields, the complete log_res.plt history and
+    log_vortex_err.plt against the oracle.  (The vortex is smooth: round-off differences stay at 1e-13 over 4 000 steps.)"""
+    from conftest import run_input
+    from fvs2d_b200 import solver
+    from oracle.oracle import Oracle
+    run = run_input("vortex")
+    cfg = run.to_config()
+    nsub = run.nsubsteps()
+    assert sum(nsub) == 4000 and len(nsub) == 50
+    gpu = solver.Fvs2dGpu(cfg, device=0)
+    gpu.set_mesh(vortex_mesh)
+    gpu.initialize_solution()
+    res, ve, t = [], [], 0.0
+    for n in nsub:
+        r, v, _ = gpu.time_integration(t, n)
+        res.append(r); ve.append(v)
+        t += n * run.dt
+    q = gpu.get_state()
+    gpu.close()
+    res, ve = np.concatenate(res), np.concatenate(ve)
+    orc = Oracle(vortex_mesh, cfg)
+    orc.initialize_solution()
+    res_o, ve_o, _ = orc.time_integration(0.0, 4000)
+    assert _rel(q, orc.cvar) <= TOL
+    assert float((np.abs(res - res_o) / np.abs(res_o)).max()) <= TOL
+    assert float((np.abs(ve - ve_o) / np.maximum(np.abs(ve_o), 1e-300)).max()) <= 1e-8
