@@ -312,15 +312,18 @@ def main():
 
     t_setup = time.perf_counter()
     mesh, run, desc, (bA, bB) = make_workload(args.workload, args.mesh_for_gpus or ngpus, args.scale)
+    t_meshgen = time.perf_counter() - t_setup         # the synthetic-mesh generator (numpy; stands in for reading a .grid file)
     cfg = run.to_config(ngpus)
     gpu = solver.Fvs2dGpu(cfg, device=local_rank, comm=comm)
     for k, v in opts:
         gpu.set_option(k, v)
+    t_lib = time.perf_counter()
     gpu.set_mesh(mesh)
     ncells = mesh.ncells
     del mesh                                          # the library holds its own copy
     gpu.initialize_solution()
     sizes, scal = gpu.sizes(), gpu.scalars()
+    t_lib = time.perf_counter() - t_lib               # fvs2d_gpu_set_mesh + fvs2d_gpu_initialize_solution (the library's share)
     t_setup = time.perf_counter() - t_setup
     from fvs2d_b200 import capi
     vol_own = capi.mesh_array("lvol")[:sizes["ncells_own"]]
@@ -528,7 +531,8 @@ def main():
             "data": "synthetic" if args.workload in ("c3", "c4") or args.workload.startswith("x:") else "the reference's example mesh, freestream / vortex initial state",
             "config": {"workload": desc, "ncells": ncells, "ncells_per_gpu": n_own, "ncells_rank0": sizes["ncells_own"], "dt": dt, "l2": "inputs larger than L2 "
                        f"({scal['device_bytes'] / 1e9:.2f} GB resident per GPU vs 126 MB L2)", "parallelism": f"dd{ngpus}",
-                       "setup_s": round(t_setup, 1)},
+                       "setup_s": round(t_setup, 1),
+                       "setup_breakdown_s": {"synthetic_mesh_generator": round(t_meshgen, 1), "set_mesh_and_initial_condition": round(t_lib, 1)}},
             "roofline": roof, "stage_roofline": stage, "gradient_kernel": gradk,
             "wall_ms_per_step": wall * 1e3 / K, "gpu_launches": launches, "clocks": clk.summary(), "e2e": e2e,
             "parity": parity, "state_check": state_check, "sustained": sustained}
