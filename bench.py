@@ -195,6 +195,32 @@ def cpu_baseline(name: str, run, steps: int, warmup: int = 0, full: bool = False
     return out, dt / steps * 1e3
 
 
+def bind_to_gpu_cpus(local_rank: int):
+    """Several ranks on one host: run this rank on the CPUs next to its GPU (NVML's ideal-CPU mask, as a job launcher's NUMA
+    binding would), so that its pinned host buffers are first touched on the memory node the GPU's PCIe link hangs off.
+    Without it the e2e leg (553 MB over PCIe per rank and step) crosses the socket interconnect for about half of the ranks.
+    Never fatal: returns the CPU list it bound to, or None when NVML gives no usable mask inside the allowed CPU set."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local_rank)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        allowed = os.sched_getaffinity(0)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(max(allowed) + 1, os.cpu_count() or 1) + 63) // 64)
+        ideal = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        use = ideal & allowed
+        if not use or use == allowed:
+            return None
+        os.sched_setaffinity(0, use)
+        return sorted(use)
+    except Exception:
+        return None
+
+
 def parity_block(workload: str, world: int, rank: int, local_rank: int, new_comm, opts):
     """GPU (all `world` ranks) against the CPU oracle (parity build, rank 0) on a sibling of the workload small enough for
     the oracle, same generator / seed / scheme, state and log_res after `steps` RK4 steps.  c4 / c3: the 1/16-size sibling
@@ -290,6 +316,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    cpu_binding = bind_to_gpu_cpus(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -531,6 +558,7 @@ def main():
             "data": "synthetic" if args.workload in ("c3", "c4") or args.workload.startswith("x:") else "the reference's example mesh, freestream / vortex initial state",
             "config": {"workload": desc, "ncells": ncells, "ncells_per_gpu": n_own, "ncells_rank0": sizes["ncells_own"], "dt": dt, "l2": "inputs larger than L2 "
                        f"({scal['device_bytes'] / 1e9:.2f} GB resident per GPU vs 126 MB L2)", "parallelism": f"dd{ngpus}",
+                       "cpu_binding": (f"rank 0 bound to {len(cpu_binding)} CPUs next to its GPU (NVML ideal-CPU mask)" if cpu_binding else "none"),
                        "setup_s": round(t_setup, 1),
                        "setup_breakdown_s": {"synthetic_mesh_generator": round(t_meshgen, 1), "set_mesh_and_initial_condition": round(t_lib, 1)}},
             "roofline": roof, "stage_roofline": stage, "gradient_kernel": gradk,
