@@ -110,8 +110,6 @@ struct Ctx {
   int opt_pdl = 1;       // programmatic dependent launch between the kernels of a time step (one GPU)
   bool pdl_on = false;   // set while fvs2d_gpu_time_integration issues / captures its step sequence
   int opt_overlap = 1;   // multi-GPU: overlap the halo exchanges with interior-tile work (second stream)
-  int opt_smem_pad = 0;  // experiment: extra dynamic shared memory (KB) per pass-B CTA (shrinks the L1 carve-out)
-  int opt_carveout = -1; // experiment: preferred shared-memory carve-out of the pass-B kernel in KB (-1: driver default)
   int opt_fuse = -1;     // one kernel per stage (k_stage_fused) where it applies -- second-order upwind reconstruction without
                          // limiter, gradient tables that fit shared memory: -1 automatic (default), 0 never (two-pass path),
                          // 2 force a single launch per stage (no split by shared-memory need)
@@ -443,10 +441,8 @@ void launch_flux_one(const StageParams &S, const double *pin, double *pout) {
     return;
   }
   if (C->tile_ok && C->opt_tile == 2) {
-    const size_t smem = kStages * pipe_stage_bytes<RC>(C->pm.S, C->pm.E) + 2 * kStages * sizeof(uint64_t) + (size_t)C->opt_smem_pad * 1024;
+    const size_t smem = kStages * pipe_stage_bytes<RC>(C->pm.S, C->pm.E) + 2 * kStages * sizeof(uint64_t);
     ensure_smem_attr(k_flux_pipe<UM, STEADY, RC>, smem);
-    if (C->opt_carveout >= 0)
-      cudaFuncSetAttribute(k_flux_pipe<UM, STEADY, RC>, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(100, C->opt_carveout * 100 / 228 + 1));
     int per_sm = 0;  // persistent kernel: exactly as many CTAs as are co-resident
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flux_pipe<UM, STEADY, RC>, kPipeThreads, smem);
     per_sm = std::max(1, per_sm);
@@ -1886,8 +1882,6 @@ int fvs2d_gpu_set_option(const char *key, int value) {
   if (k == "graph") { C->opt_graph = value; return 0; }
   if (k == "pair") { C->opt_pair = value; return 0; }
   if (k == "pdl") { C->opt_pdl = value; return 0; }
-  if (k == "smem_pad") { C->opt_smem_pad = value; return 0; }
-  if (k == "carveout") { C->opt_carveout = value; return 0; }
   if (k == "fuse") {
     if (value != C->opt_fuse) C->fz_state = 0;  // plan again under the new setting
     C->opt_fuse = value;

@@ -200,9 +200,7 @@ int fvs2d_gpu_last_timing(double ms[4], long *launches);
  *              waits for its predecessor's results at its first instruction (griddepcontrol.wait) and lets its successor be
  *              scheduled at once, so launch latency hides behind the running kernel; 0: plain launches
  *   "overlap"  1 (default): multi-GPU halo exchange on a second stream, overlapped with interior-tile work
- *   "ctas"     resident CTAs per SM of k_flux_pipe (0 = occupancy API), "smem_pad" / "carveout": extra dynamic shared
- *              memory per CTA / preferred shared-memory carve-out of k_flux_pipe, both in KB (the L1 experiments of
- *              DESIGN.md section 5) */
+ *   "ctas"     resident CTAs per SM of the persistent kernels (0 = as many as the occupancy API reports, at most 3) */
 int fvs2d_gpu_set_option(const char *key, int value);
 
 const char *fvs2d_gpu_last_error(void);
