@@ -9,7 +9,9 @@
  * numeric golden vectors and cannot be compiled in this image (no Fortran compiler).  The oracle
  * is pinned only through the reference's own analytic self-checks (LSQ linear exactness
  * src/gradient_lsq.f90:490-529, sum-of-volumes src/grid_procs.f90:824-840, boundary counts
- * src/grid_procs.f90:722-728,785-791) -- see tests/test_oracle_pins.py.
+ * src/grid_procs.f90:722-728,785-791) -- see tests/test_oracle_pins.py -- and, since round 2, against an independent
+ * numpy transcription of the same Fortran sources (tests/golden/ref_numpy.py, fixtures tests/golden/ref_*.npz,
+ * tests/test_oracle_vs_ref_numpy.py: fields <= 1e-12, log_res <= 1e-10).  Nothing here is an output of the reference itself.
  *
  * Serial, IEEE fp64, compiled with -ffp-contract=off.  Loop order follows the reference
  * (edge-scatter residual, per-cell stencils).  All indices are 0-based here; "no neighbour /
