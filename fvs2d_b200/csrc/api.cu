@@ -93,6 +93,8 @@ struct Ctx {
   int *vbest = nullptr, *vbest_loc = nullptr;
   double *stage_aos = nullptr;  // nc_global*8 doubles staging for AoS <-> SoA
   size_t stage_aos_len = 0;
+  double *h_stage = nullptr;    // pinned host staging (several ranks: the caller's global arrays are permuted on the host)
+  size_t h_stage_len = 0;
   double *logbuf = nullptr; int *logid = nullptr; size_t log_cap = 0;
   int *send_idx = nullptr; double *sendbuf = nullptr;
   PipeMeta pm{};
@@ -221,6 +223,8 @@ void free_device() {
   C->allocs.clear();
   C->bytes = 0;
   C->stage_aos = nullptr; C->stage_aos_len = 0;
+  if (C->h_stage) cudaFreeHost(C->h_stage);
+  C->h_stage = nullptr; C->h_stage_len = 0;
   C->logbuf = nullptr; C->log_cap = 0;
   C->d_n2c_ptr = C->d_n2c = nullptr; C->d_idw = nullptr; C->d_fnode = nullptr;
   C->d_be_cell = nullptr; C->d_be_xy = C->d_be_nxy = nullptr; C->d_be_out = nullptr;
@@ -335,6 +339,16 @@ int halo_exchange(const HaloItem *items, int nitems, cudaStream_t st = nullptr) 
   return 0;
 }
 
+// pinned host buffer of at least `ndoubles` (grown, never shrunk; freed with the device arrays)
+int ensure_host_stage(size_t ndoubles) {
+  if (C->h_stage_len >= ndoubles) return 0;
+  if (C->h_stage) cudaFreeHost(C->h_stage);
+  C->h_stage = nullptr; C->h_stage_len = 0;
+  CUDA_OK(cudaMallocHost((void **)&C->h_stage, std::max<size_t>(ndoubles, 1) * sizeof(double)));
+  C->h_stage_len = ndoubles;
+  return 0;
+}
+
 int ensure_stage(size_t ndoubles) {
   if (C->stage_aos_len >= ndoubles) return 0;
   if (C->stage_aos) {
@@ -365,8 +379,9 @@ int download_aos(const double *soa, int nvar, double *host_out, int pair = 0, in
   if (ensure_stage(nl)) return 1;
   k_gather_out<<<cdiv(n_own, 256), 256, 0, C->st>>>(n_own, C->np, nvar, nullptr, soa, C->stage_aos, pair, v0);
   CUDA_OK(cudaGetLastError());
-  std::vector<double> tmp(nl);
-  CUDA_OK(cudaMemcpyAsync(tmp.data(), C->stage_aos, nl * 8, cudaMemcpyDeviceToHost, C->st));
+  if (ensure_host_stage(nl)) return 1;
+  const double *tmp = C->h_stage;
+  CUDA_OK(cudaMemcpyAsync(C->h_stage, C->stage_aos, nl * 8, cudaMemcpyDeviceToHost, C->st));
   CUDA_OK(cudaStreamSynchronize(C->st));
 #pragma omp parallel for schedule(static)
   for (int i = 0; i < n_own; i++) {
@@ -1258,13 +1273,14 @@ int fvs2d_gpu_set_state(const double *cvar) {
   NEED(cvar != nullptr, "fvs2d_gpu_set_state: null cvar");
   if (C->nranks > 1) {  // only the entries of the cells this rank stores (owned + ghosts) are read and uploaded
     const int n_loc = C->L.n_loc;
-    std::vector<double> loc((size_t)n_loc * 4);
+    if (ensure_host_stage((size_t)n_loc * 4)) return 1;
+    double *loc = C->h_stage;
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < n_loc; i++) {
       const size_t o = C->L.orig_id[i];
       for (int v = 0; v < 4; v++) loc[(size_t)i * 4 + v] = cvar[o * 4 + v];
     }
-    return upload_local_state(loc.data());
+    return upload_local_state(loc);
   }
   const size_t ng = (size_t)C->L.nc_global * 4;
   if (ensure_stage(ng)) return 1;
